@@ -1,0 +1,170 @@
+"""CPU tests of the oracle (oracle/oracle.cpp): known-answer vectors, cross-check against the independent
+pure-Python spec (tests/pyspec.py), property tests (hypothesis), and the reference's doc invariant."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import oracle
+import pyspec
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_murmur3_known_answers():
+    vecs = json.load(open(os.path.join(GOLD, "murmur3_kat.json")))["vectors"]
+    assert sum(v["provenance"] == "published" for v in vecs) >= 4
+    for v in vecs:
+        h1, h2 = oracle.murmur3_x64_128(v["input"].encode(), v["seed"])
+        assert (h1, h2) == (int(v["h1"], 16), int(v["h2"], 16)), v
+        assert pyspec.murmur3_x64_128(v["input"].encode(), v["seed"]) == (h1, h2)
+
+
+@given(st.binary(min_size=0, max_size=70), st.integers(0, 2**32 - 1))
+@settings(max_examples=300, deadline=None)
+def test_murmur3_matches_pyspec(data, seed):
+    assert oracle.murmur3_x64_128(data, seed) == pyspec.murmur3_x64_128(data, seed)
+
+
+def test_normalize_table():
+    raw = b"ACGTacgtuUnN.~- \t\r\nRYKMSWBDHVryx*0"
+    assert oracle.normalize(raw) == b"ACGTACGTTTNN---" + b"N" * 15
+    assert oracle.normalize(raw) == pyspec.normalize(raw)
+    assert oracle.normalize(b"") == b""
+
+
+def test_canonical_kats():
+    # TTTT..T canonicalises to AAAA..A; ACGTACGTACGTACGT is its own reverse complement (tie branch)
+    a = oracle.kmer_hashes(b"T" * 16, 16, 0)
+    assert a.tolist() == [0x37BD7653D0D19D9A]
+    assert oracle.kmer_hashes(b"A" * 16, 16, 0).tolist() == a.tolist()
+    assert oracle.kmer_hashes(b"ACGTACGTACGTACGT", 16, 0).tolist() == [0xE183B34678E6D5B6]
+    assert oracle.kmer_hashes(b"ACGTACGTACGTACGT", 16, 42).tolist() == [0x4152541EAC055887]
+    # shorter than k: nothing
+    assert oracle.kmer_hashes(b"ACGT", 16, 0).size == 0
+    # an N breaks windows; whitespace is stripped so windows continue across it
+    s = b"ACGTTGCAAGGCTTAACC"
+    assert oracle.kmer_hashes(s[:9] + b"\n" + s[9:], 16, 0).tolist() == oracle.kmer_hashes(s, 16, 0).tolist()
+    assert oracle.kmer_hashes(s[:9] + b"N" + s[9:], 16, 0).size == 0
+
+
+dna_dirty = st.text(alphabet="ACGTacgtNnRYu-. \n", min_size=0, max_size=120).map(str.encode)
+
+
+@given(dna_dirty, st.sampled_from([4, 7, 11, 16, 17, 21, 31, 32]), st.sampled_from([0, 42]))
+@settings(max_examples=200, deadline=None)
+def test_kmer_hashes_match_pyspec(seq, k, seed):
+    assert oracle.kmer_hashes(seq, k, seed).tolist() == pyspec.canonical_kmer_hashes(seq, k, seed)
+
+
+@given(st.lists(st.text(alphabet="ACGTN", min_size=0, max_size=80).map(str.encode), min_size=0, max_size=5),
+       st.sampled_from([3, 5, 16]), st.integers(1, 40))
+@settings(max_examples=200, deadline=None)
+def test_streaming_sketcher_equals_closed_form(records, k, s):
+    """finch heap+map form == 's smallest distinct hashes with exact counts' (SURVEY.md Appendix A.4)."""
+    sk = oracle.Sketcher(s, k, 0)
+    for r in records:
+        sk.process(r)
+    h, c = sk.to_vec()
+    eh, ec, eb, ek = pyspec.bottom_s(records, k, s, 0)
+    assert h.tolist() == eh and c.tolist() == ec
+    assert sk.totals() == (eb, ek)
+    assert all(h[i] < h[i + 1] for i in range(len(h) - 1))
+
+
+def _rand_dna(rng, n):
+    return bytes(rng.choice(b"ACGT") for _ in range(n))
+
+
+def test_sketch_groups_order_and_threads():
+    rng = random.Random(5)
+    recs = [_rand_dna(rng, rng.randint(0, 400)) for _ in range(11)]
+    groups = [0, 0, 1, 3, 3, 3, 4, 5, 5, 6, 6]  # group 2 is an empty file
+    a, ab, ak = oracle.sketch_groups(recs, groups, 7, 16, 50, 0, nthreads=1)
+    b, bb, bk = oracle.sketch_groups(recs, groups, 7, 16, 50, 0, nthreads=4)
+    for g in range(7):
+        mine = [r for r, gg in zip(recs, groups) if gg == g]
+        eh, ec, eb, ek = pyspec.bottom_s(mine, 16, 50, 0)
+        assert a[g][0].tolist() == eh and a[g][1].tolist() == ec
+        assert b[g][0].tolist() == eh
+        assert (int(ab[g]), int(ak[g])) == (eb, ek) == (int(bb[g]), int(bk[g]))
+    assert a[2][0].size == 0
+
+
+@given(st.lists(st.integers(0, 60), max_size=40), st.lists(st.integers(0, 60), max_size=40))
+@settings(max_examples=300, deadline=None)
+def test_common_hashes_is_set_intersection_for_strictly_increasing(a, b):
+    a, b = sorted(set(a)), sorted(set(b))
+    got = oracle.common_hashes(np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64))
+    assert got == len(set(a) & set(b))
+    # the scaled tail (src/sketchy.rs:441-457) never changes the count
+    assert oracle.common_hashes(np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64), 0.001) == got
+
+
+def test_self_shared_equals_s():
+    """docs/index.md:148-149: a sketch vs itself shares s hashes."""
+    rng = random.Random(1)
+    g = _rand_dna(rng, 20000)
+    (res,), _, _ = oracle.sketch_groups([g], [0], 1, 16, 1000, 0)
+    assert res[0].size == 1000
+    assert oracle.common_hashes(res[0], res[0]) == 1000
+
+
+def _small_world(seed=3, n_ref=9, glen=3000, s=64, n_reads=25, rlen=300):
+    rng = random.Random(seed)
+    base = [_rand_dna(rng, glen) for _ in range(3)]
+    genomes = []
+    for i in range(n_ref):
+        g = bytearray(base[i % 3])
+        for _ in range(glen // 100):
+            g[rng.randrange(glen)] = rng.choice(b"ACGT")
+        genomes.append(bytes(g))
+    sk, _, _ = oracle.sketch_groups(genomes, list(range(n_ref)), n_ref, 16, s, 0)
+    rows = [h for h, _ in sk]
+    off = np.zeros(n_ref + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    reads = []
+    for _ in range(n_reads):
+        g = genomes[rng.randrange(n_ref)]
+        p = rng.randrange(glen - rlen)
+        reads.append(g[p:p + rlen])
+    return genomes, rows, ref, off, reads
+
+
+def test_predict_stream_matches_pyspec_and_ties():
+    genomes, rows, ref, off, reads = _small_world()
+    reads = [b"ACGT"] + reads  # first read shorter than k: all sums 0 -> top = first refs in file order
+    idx, sm, sums = oracle.predict_stream(ref, off, reads, 16, 64, 0, 5)
+    exp, esums = pyspec.predict_stream([r.tolist() for r in rows], reads, 16, 64, 0, 5)
+    assert idx.shape == (len(reads), 5)
+    assert idx[0].tolist() == [0, 1, 2, 3, 4] and sm[0].tolist() == [0] * 5
+    for r in range(len(reads)):
+        assert [(int(i), int(s)) for i, s in zip(idx[r], sm[r])] == exp[r]
+    assert sums.tolist() == esums
+    # limit (src/sketchy.rs:350-353) and carried sums
+    idx2, sm2, s2 = oracle.predict_stream(ref, off, reads, 16, 64, 0, 5, limit=7)
+    assert idx2.shape[0] == 7 and (idx2 == idx[:7]).all()
+    idx3, sm3, s3 = oracle.predict_stream(ref, off, reads[7:], 16, 64, 0, 5, sums=s2)
+    assert (idx3 == idx[7:]).all() and (sm3 == sm[7:]).all() and (s3 == sums).all()
+    with pytest.raises(ValueError):
+        oracle.predict_stream(ref, off, reads, 16, 64, 0, len(rows) + 1)
+
+
+def test_predict_readset_and_shared_matrix():
+    genomes, rows, ref, off, reads = _small_world(seed=8)
+    n, idx, sh, allc = oracle.predict_readset(ref, off, reads, 16, 64, 0, 4)
+    assert n == len(reads)
+    q, _, _, _ = pyspec.bottom_s(reads, 16, 64, 0)
+    exp = [len(set(q) & set(r.tolist())) for r in rows]
+    assert allc.tolist() == exp
+    order = sorted(range(len(rows)), key=lambda i: (-exp[i], i))[:4]
+    assert idx.tolist() == order and sh.tolist() == [exp[i] for i in order]
+    n2, *_ = oracle.predict_readset(ref, off, reads, 16, 64, 0, 4, limit=3)
+    assert n2 == 3
+    m = oracle.shared_matrix(ref, off, ref, off)
+    assert (np.diag(m) == [r.size for r in rows]).all()
+    assert (m == m.T).all()
