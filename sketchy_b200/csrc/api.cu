@@ -1,0 +1,1005 @@
+// api.cu — context, pinned 2-bit batch packer, pass orchestration and the exported C ABI (include/sketchy_b200.h).
+// No CPU fallback lives here: every compute entry point launches the sm_100a kernels or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+#include "kernels.h"
+
+#define SKB_VERSION_STR "sketchy_b200 0.1.0 (sm_100a)"
+
+// ---------------------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  // grows keeping the first `keep` bytes
+  cudaError_t ensure(size_t bytes, size_t keep) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t ncap = std::max(bytes, cap * 2);
+    void* np = nullptr;
+    cudaError_t e = cudaHostAlloc(&np, ncap, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e;
+    if (p && keep) std::memcpy(np, p, keep);
+    if (p) cudaFreeHost(p);
+    p = np; cap = ncap;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+// needletail normalize(false) folded into the 2-bit packer: 0..3 = ACGT code, 4 = breaks k-mers, 5 = removed
+struct PackLut {
+  uint8_t t[256];
+  PackLut() {
+    std::memset(t, 4, sizeof t);
+    t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2;
+    t['T'] = t['t'] = t['U'] = t['u'] = 3;
+    t[' '] = t['\t'] = t['\r'] = t['\n'] = 5;
+  }
+};
+const PackLut kPackLut;
+
+// Pack one record at base position P (multiple of 32); everything up to Pnext (multiple of 32) not covered by a
+// valid base is marked invalid. The words touched belong to this record alone.
+void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uint32_t* codes, uint32_t* nmask) {
+  uint64_t pos = P;
+  uint32_t cw = 0, mw = 0;
+  for (uint64_t i = 0; i < len; ++i) {
+    const uint32_t v = kPackLut.t[s[i]];
+    if (v == 5) continue;
+    if (v < 4) cw |= v << (2 * (pos & 15));
+    else mw |= 1u << (pos & 31);
+    ++pos;
+    if ((pos & 15) == 0) { codes[(pos >> 4) - 1] = cw; cw = 0; }
+    if ((pos & 31) == 0) { nmask[(pos >> 5) - 1] = mw; mw = 0; }
+  }
+  // finish the current 32-base block as invalid, then whole invalid blocks
+  while (pos < Pnext && (pos & 31)) {
+    mw |= 1u << (pos & 31);
+    ++pos;
+    if ((pos & 15) == 0) { codes[(pos >> 4) - 1] = cw; cw = 0; }
+    if ((pos & 31) == 0) { nmask[(pos >> 5) - 1] = mw; mw = 0; }
+  }
+  for (; pos < Pnext; pos += 32) {
+    codes[pos >> 4] = 0; codes[(pos >> 4) + 1] = 0;
+    nmask[pos >> 5] = 0xFFFFFFFFu;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// context / batch
+// ---------------------------------------------------------------------------------------------------------
+struct ProfEvent { int id; cudaEvent_t a, b; };
+
+struct skb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // reference shard
+  DevBuf ref, row_off;
+  uint64_t ref_len = 0;
+  uint32_t n_rows = 0, row_base = 0, uniform_len = 0;
+  uint64_t hmax = 0;
+  bool has_ref = false;
+  DevBuf sums[2];
+  int sums_cur = 0;
+  DevBuf tracked, tracked_next;
+  uint32_t tracked_top = 0;  // 0 = invalid
+  // per-group scratch (hash/select)
+  DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, cand_pool;
+  DevBuf sk_hashes, sk_counts;
+  // predict scratch
+  DevBuf q_off, qh, qread, counts, lb_sum, lb_idx, cand, cand_sorted, cand_cnt, cand_off, cand_fill, scal;
+  DevBuf t_keys, t_cnt, t_start, t_fill, t_reads, t_slot, t_bloom;
+  uint32_t t_cap = 0, t_maxkeys = 0;
+  DevBuf out_idx, out_sum, misc;
+  uint32_t pass_max = 2048, pass_cur = 64;
+  uint32_t cand_cap = 0;
+  // stats / profiling
+  bool prof_on = false;
+  std::vector<ProfEvent> pending;
+  double prof_ms[SKB_K_COUNT] = {0};
+  uint64_t prof_n[SKB_K_COUNT] = {0};
+  uint64_t launches = 0;
+  uint64_t st_ref_bytes = 0, st_passes = 0, st_qhashes = 0, st_cands = 0;
+  uint32_t* h_scal = nullptr;  // pinned, 64 bytes
+};
+
+struct skb_batch {
+  skb_ctx* ctx = nullptr;
+  PinBuf codes, nmask;
+  uint64_t cur = 0;  // packed length in bases (multiple of 32)
+  std::vector<uint64_t> rec_pos, rec_len;
+  std::vector<uint64_t> g_first, g_end;  // chunk ranges
+  std::vector<uint64_t> g_raw, g_packed; // raw bytes, packed bases
+  uint64_t total_raw = 0;
+  // device mirror
+  bool staged = false;
+  DevBuf d_codes, d_nmask, d_seg_group, d_seg_chunk0, d_seg_n;
+  uint32_t nseg = 0;
+};
+
+namespace {
+
+int fail(skb_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+
+#define CU(c, call)                                                                                  \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail((c), e__ == cudaErrorMemoryAllocation ? SKB_ERR_OOM : SKB_ERR_CUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e__));                                                          \
+  } while (0)
+
+struct ProfScope {
+  skb_ctx* c; int id; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(skb_ctx* ctx, int kid, int n_launches) : c(ctx), id(kid) {
+    c->launches += n_launches;
+    c->prof_n[id] += n_launches;
+    if (c->prof_on) {
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~ProfScope() {
+    if (c->prof_on) {
+      cudaEventRecord(b, c->stream);
+      c->pending.push_back({id, a, b});
+    }
+  }
+};
+
+void prof_resolve(skb_ctx* c) {
+  if (c->pending.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : c->pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.id] += ms;
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  c->pending.clear();
+}
+
+int check_launch(skb_ctx* c, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, SKB_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+  return SKB_OK;
+}
+
+int stage_batch(skb_batch* b) {
+  skb_ctx* c = b->ctx;
+  if (b->staged) return SKB_OK;
+  const uint64_t ncode = b->cur / 16 + 4, nmask = b->cur / 32 + 2;
+  CU(c, b->codes.ensure(ncode * 4, (b->cur / 16) * 4));
+  CU(c, b->nmask.ensure(nmask * 4, (b->cur / 32) * 4));
+  for (uint64_t i = b->cur / 16; i < ncode; ++i) b->codes.as<uint32_t>()[i] = 0;
+  for (uint64_t i = b->cur / 32; i < nmask; ++i) b->nmask.as<uint32_t>()[i] = 0xFFFFFFFFu;
+  // segments: <= 32 chunks of one group each
+  std::vector<uint32_t> sg, sc;
+  std::vector<uint8_t> sn;
+  for (size_t g = 0; g < b->g_first.size(); ++g) {
+    for (uint64_t ch = b->g_first[g]; ch < b->g_end[g]; ch += 32) {
+      sg.push_back((uint32_t)g);
+      sc.push_back((uint32_t)ch);
+      sn.push_back((uint8_t)std::min<uint64_t>(32, b->g_end[g] - ch));
+    }
+  }
+  b->nseg = (uint32_t)sg.size();
+  CU(c, b->d_codes.ensure(ncode * 4));
+  CU(c, b->d_nmask.ensure(nmask * 4));
+  CU(c, b->d_seg_group.ensure(std::max<size_t>(4, sg.size() * 4)));
+  CU(c, b->d_seg_chunk0.ensure(std::max<size_t>(4, sc.size() * 4)));
+  CU(c, b->d_seg_n.ensure(std::max<size_t>(4, sn.size())));
+  CU(c, cudaMemcpyAsync(b->d_codes.p, b->codes.p, ncode * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(b->d_nmask.p, b->nmask.p, nmask * 4, cudaMemcpyHostToDevice, c->stream));
+  if (!sg.empty()) {
+    CU(c, cudaMemcpyAsync(b->d_seg_group.p, sg.data(), sg.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(b->d_seg_chunk0.p, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(b->d_seg_n.p, sn.data(), sn.size(), cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  b->staged = true;
+  return SKB_OK;
+}
+
+SkbPackedView view_of(const skb_batch* b) {
+  SkbPackedView v;
+  v.codes = b->d_codes.as<uint32_t>();
+  v.nmask = b->d_nmask.as<uint32_t>();
+  v.seg_group = b->d_seg_group.as<uint32_t>();
+  v.seg_chunk0 = b->d_seg_chunk0.as<uint32_t>();
+  v.seg_n = b->d_seg_n.as<uint8_t>();
+  v.nseg = b->nseg;
+  return v;
+}
+
+// ---- hash + select with the exactness loop ---------------------------------------------------------------
+// mode sketch : tau per group from the group's size; groups that end with < s distinct hashes under a finite tau
+//               are redone with a larger tau; out = [G*s] (+counts)
+// mode query  : tau = hmax for every group, no underfill check; output stays in the candidate pool
+struct SelectPlan {
+  std::vector<uint64_t> tau, base;
+  std::vector<uint32_t> cap;
+};
+
+int run_hash_select(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s, uint64_t seed, bool query_mode,
+                    uint64_t query_tau, uint64_t* d_out_hashes, uint32_t* d_out_counts,
+                    std::vector<uint32_t>& h_out_n, std::vector<uint64_t>& h_kmers, SelectPlan& plan) {
+  const uint32_t G = (uint32_t)b->g_first.size();
+  plan.tau.assign(G, 0); plan.base.assign(G, 0); plan.cap.assign(G, 0);
+  h_out_n.assign(G, 0); h_kmers.assign(G, 0);
+  if (G == 0) return SKB_OK;
+  const double two64 = 18446744073709551616.0;
+  uint64_t pool = 0;
+  for (uint32_t g = 0; g < G; ++g) {
+    const double n = (double)std::max<uint64_t>(b->g_packed[g], 1);
+    double est;
+    if (query_mode) {
+      plan.tau[g] = query_tau;
+      est = n * (((double)query_tau + 1.0) / two64);
+      est = 4.0 * est + 16.0;
+    } else {
+      const double m = 1.25 * ((double)s + 8.0 * std::sqrt((double)s) + 32.0);
+      if (n <= 2.0 * m) { plan.tau[g] = SKB_EMPTY_KEY; est = n; }
+      else { plan.tau[g] = (uint64_t)std::min(two64 * (m / n), 18446744073709549568.0); est = 2.0 * m; }
+    }
+    est = std::min(est, n);
+    plan.cap[g] = (uint32_t)skb_next_pow2((uint64_t)std::max(32.0, est));
+    plan.base[g] = pool;
+    pool += plan.cap[g];
+  }
+  CU(c, c->g_tau.ensure(G * 8)); CU(c, c->g_base.ensure(G * 8)); CU(c, c->g_cap.ensure(G * 4));
+  CU(c, c->g_cnt.ensure(G * 4)); CU(c, c->g_kmers.ensure(G * 8)); CU(c, c->g_active.ensure(G));
+  CU(c, c->g_outn.ensure(G * 4)); CU(c, c->g_status.ensure(G * 4));
+  CU(c, c->cand_pool.ensure(std::max<uint64_t>(pool, 1) * 8));
+  CU(c, cudaMemsetAsync(c->g_cnt.p, 0, G * 4, c->stream));
+  CU(c, cudaMemsetAsync(c->g_kmers.p, 0, G * 8, c->stream));
+  CU(c, cudaMemsetAsync(c->g_active.p, 1, G, c->stream));
+  CU(c, cudaMemsetAsync(c->g_status.p, 0, G * 4, c->stream));
+
+  std::vector<uint32_t> status(G), cnt(G);
+  std::vector<uint8_t> active(G, 1);
+  uint64_t pool_used = pool;
+  uint32_t max_cap = 32;
+  for (uint32_t g = 0; g < G; ++g) max_cap = std::max(max_cap, plan.cap[g]);
+  for (int iter = 0; iter < 12; ++iter) {
+    CU(c, cudaMemcpyAsync(c->g_tau.p, plan.tau.data(), G * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->g_base.p, plan.base.data(), G * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->g_cap.p, plan.cap.data(), G * 4, cudaMemcpyHostToDevice, c->stream));
+    uint64_t* cur_pool = c->cand_pool.as<uint64_t>();
+    SkbHashArgs ha{};
+    ha.pv = view_of(b); ha.k = k; ha.seed = seed;
+    ha.tau = c->g_tau.as<uint64_t>(); ha.active = c->g_active.as<uint8_t>();
+    ha.cand = cur_pool; ha.cand_base = c->g_base.as<uint64_t>(); ha.cand_cap = c->g_cap.as<uint32_t>();
+    ha.cand_cnt = c->g_cnt.as<uint32_t>(); ha.kmers = c->g_kmers.as<unsigned long long>();
+    { ProfScope ps(c, SKB_K_HASH, 1); skb_launch_hash(ha, c->stream); }
+    if (int rc = check_launch(c, "hash")) return rc;
+    SkbSelectArgs sa{};
+    sa.n_groups = G; sa.cand = cur_pool; sa.cand_base = ha.cand_base; sa.cand_cap = ha.cand_cap;
+    sa.cand_cnt = ha.cand_cnt; sa.active = ha.active; sa.tau = ha.tau; sa.s = s;
+    sa.check_underfill = query_mode ? 0 : 1;
+    sa.out_hashes = query_mode ? cur_pool : d_out_hashes;
+    sa.out_off = query_mode ? ha.cand_base : nullptr;
+    sa.out_counts = query_mode ? nullptr : d_out_counts;
+    sa.out_n = c->g_outn.as<uint32_t>(); sa.status = c->g_status.as<uint32_t>();
+    // the sort runs in shared memory when a group's candidates fit; bigger groups sort in place in global memory
+    const uint32_t want = (uint32_t)std::min<uint64_t>(16384, skb_next_pow2(max_cap));
+    if (want <= 256) { sa.threads = 32; sa.smem_elems = 256; }
+    else if (want <= 2048) { sa.threads = 256; sa.smem_elems = want; }
+    else { sa.threads = 512; sa.smem_elems = want; }
+    { ProfScope ps(c, SKB_K_SELECT, 1); skb_launch_select(sa, c->stream); }
+    if (int rc = check_launch(c, "select")) return rc;
+    CU(c, cudaMemcpyAsync(status.data(), c->g_status.p, G * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(cnt.data(), c->g_cnt.p, G * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> failed;
+    for (uint32_t g = 0; g < G; ++g)
+      if (active[g] && status[g] != SKB_ST_OK) failed.push_back(g);
+    if (failed.empty()) break;
+    if (iter == 11)
+      return fail(c, SKB_ERR_INTERNAL, "bottom-s selection did not converge for %zu groups", failed.size());
+    // redo only the failed groups with a corrected threshold / capacity, in fresh space at the end of the pool
+    std::vector<uint32_t> outn(G);
+    CU(c, cudaMemcpy(outn.data(), c->g_outn.p, G * 4, cudaMemcpyDeviceToHost));
+    std::fill(active.begin(), active.end(), 0);
+    const uint64_t pool_before = pool_used;
+    max_cap = 32;
+    for (uint32_t g : failed) {
+      active[g] = 1;
+      double expect = (double)cnt[g];
+      if (status[g] == SKB_ST_UNDERFILL) {
+        const double d = (double)outn[g];
+        const double ratio = d < 1.0 ? 64.0 : std::max(2.0, 1.5 * (double)s / d);
+        const double nt = (double)plan.tau[g] * ratio;
+        plan.tau[g] = nt >= 18446744073709549568.0 ? SKB_EMPTY_KEY : (uint64_t)nt;
+        expect = plan.tau[g] == SKB_EMPTY_KEY ? (double)b->g_packed[g] : expect * ratio * 1.5 + 64.0;
+      }
+      expect = std::min(expect, (double)std::max<uint64_t>(b->g_packed[g], 1));
+      plan.cap[g] = (uint32_t)skb_next_pow2((uint64_t)std::max(32.0, expect));
+      max_cap = std::max(max_cap, plan.cap[g]);
+      plan.base[g] = pool_used;
+      pool_used += plan.cap[g];
+    }
+    if (pool_used * 8 > c->cand_pool.cap) {  // grow, keeping the finished groups' data
+      DevBuf nb;
+      CU(c, nb.ensure(pool_used * 8));
+      CU(c, cudaMemcpy(nb.p, c->cand_pool.p, pool_before * 8, cudaMemcpyDeviceToDevice));
+      c->cand_pool.release();
+      c->cand_pool = nb;
+    }
+    CU(c, cudaMemcpyAsync(c->g_active.p, active.data(), G, cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint32_t> z(G);
+    std::vector<uint64_t> hk(G);
+    CU(c, cudaMemcpy(z.data(), c->g_cnt.p, G * 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(hk.data(), c->g_kmers.p, G * 8, cudaMemcpyDeviceToHost));
+    for (uint32_t g : failed) { z[g] = 0; hk[g] = 0; }
+    CU(c, cudaMemcpy(c->g_cnt.p, z.data(), G * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->g_kmers.p, hk.data(), G * 8, cudaMemcpyHostToDevice));
+  }
+  CU(c, cudaMemcpyAsync(h_out_n.data(), c->g_outn.p, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(h_kmers.data(), c->g_kmers.p, G * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
+int ensure_table(skb_ctx* c, uint32_t max_keys) {
+  if (max_keys <= c->t_maxkeys) return SKB_OK;
+  const uint32_t mk = (uint32_t)skb_next_pow2(std::max<uint32_t>(max_keys, 1u << 16));
+  const uint32_t cap = mk * 2;
+  CU(c, c->t_keys.ensure(((size_t)cap + 1) * 8));
+  CU(c, c->t_cnt.ensure(((size_t)cap + 1) * 4));
+  CU(c, c->t_start.ensure(((size_t)cap + 1) * 4));
+  CU(c, c->t_fill.ensure(((size_t)cap + 1) * 4));
+  CU(c, c->t_reads.ensure((size_t)mk * 4));
+  CU(c, c->t_slot.ensure((size_t)mk * 4));
+  CU(c, c->t_bloom.ensure((size_t)SKB_BLOOM_WORDS * 4));
+  c->t_cap = cap;
+  c->t_maxkeys = mk;
+  return SKB_OK;
+}
+
+SkbTable table_of(skb_ctx* c) {
+  SkbTable t;
+  t.keys = c->t_keys.as<uint64_t>(); t.cnt = c->t_cnt.as<uint32_t>(); t.start = c->t_start.as<uint32_t>();
+  t.fill = c->t_fill.as<uint32_t>(); t.reads = c->t_reads.as<uint32_t>(); t.slot_of = c->t_slot.as<uint32_t>();
+  t.bloom = c->t_bloom.as<uint32_t>();
+  t.cursor = c->scal.as<uint32_t>() + 4;
+  t.cap = c->t_cap;
+  uint32_t l = 0;
+  while ((1u << l) < t.cap) ++l;
+  t.log2cap = l;
+  return t;
+}
+
+int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const uint64_t* off, uint32_t n_rows,
+                      uint32_t global_row_base) {
+  if (!off && n_rows) return fail(c, SKB_ERR_INVALID_ARG, "off is null");
+  const uint64_t len = n_rows ? off[n_rows] : 0;
+  if (n_rows && off[0] != 0) return fail(c, SKB_ERR_INVALID_ARG, "off[0] must be 0");
+  for (uint32_t i = 0; i < n_rows; ++i)
+    if (off[i + 1] < off[i]) return fail(c, SKB_ERR_INVALID_ARG, "row offsets must be non-decreasing");
+  if (len && !hashes) return fail(c, SKB_ERR_INVALID_ARG, "hashes is null");
+  c->has_ref = false;
+  const uint64_t padded = round_up(len + 2, 2048);
+  CU(c, c->ref.ensure(padded * 8));
+  CU(c, c->row_off.ensure(((size_t)n_rows + 1) * 8));
+  if (len)
+    CU(c, cudaMemcpyAsync(c->ref.p, hashes, len * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                          c->stream));
+  CU(c, cudaMemsetAsync(c->ref.as<uint64_t>() + len, 0xFF, (padded - len) * 8, c->stream));
+  if (n_rows) {
+    CU(c, cudaMemcpyAsync(c->row_off.p, off, ((size_t)n_rows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CU(c, cudaMemsetAsync(c->row_off.p, 0, 8, c->stream));
+  }
+  CU(c, c->scal.ensure(256));
+  CU(c, cudaMemsetAsync(c->scal.p, 0, 256, c->stream));
+  uint32_t* d_bad = c->scal.as<uint32_t>();
+  unsigned long long* d_hmax = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 8);
+  { ProfScope ps(c, SKB_K_MISC, 1);
+    skb_launch_ref_check(c->ref.as<uint64_t>(), c->row_off.as<uint64_t>(), n_rows, d_bad, d_hmax, c->stream); }
+  if (int rc = check_launch(c, "ref_check")) return rc;
+  uint32_t bad = 0;
+  unsigned long long hmax = 0;
+  CU(c, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(&hmax, d_hmax, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (bad) return fail(c, SKB_ERR_REF_NOT_SORTED, "a reference row is not strictly increasing");
+  c->ref_len = len; c->n_rows = n_rows; c->row_base = global_row_base; c->hmax = hmax;
+  uint32_t ul = n_rows ? (uint32_t)std::min<uint64_t>(off[1] - off[0], 0xFFFFFFFFull) : 0;
+  for (uint32_t i = 0; i < n_rows && ul; ++i)
+    if (off[i + 1] - off[i] != ul) ul = 0;
+  c->uniform_len = ul;
+  CU(c, c->sums[0].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
+  CU(c, c->sums[1].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
+  CU(c, cudaMemsetAsync(c->sums[0].p, 0, std::max<size_t>(8, (size_t)n_rows * 8), c->stream));
+  c->sums_cur = 0;
+  c->tracked_top = 0;
+  c->pass_cur = std::min<uint32_t>(64, c->pass_max);
+  CU(c, c->tracked.ensure(SKB_MAX_TOP * 4));
+  CU(c, c->tracked_next.ensure(SKB_MAX_TOP * 4));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->has_ref = true;
+  return SKB_OK;
+}
+
+void fill_pad(std::vector<uint32_t>& idx, std::vector<uint64_t>& sum) {
+  std::fill(idx.begin(), idx.end(), 0xFFFFFFFFu);
+  std::fill(sum.begin(), sum.end(), 0ull);
+}
+
+int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top, int pad,
+                   uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
+  if (k < 1 || k > SKB_MAX_K) return fail(c, SKB_ERR_UNSUPPORTED_K, "k=%u unsupported (1..%d)", k, SKB_MAX_K);
+  if (top < 1 || top > SKB_MAX_TOP) return fail(c, SKB_ERR_INVALID_ARG, "top=%u unsupported (1..%d)", top, SKB_MAX_TOP);
+  if (top > c->n_rows && !pad)
+    return fail(c, SKB_ERR_TOP_GT_N, "top (%u) exceeds the number of reference sketches (%u)", top, c->n_rows);
+  if (s_query < 1) return fail(c, SKB_ERR_INVALID_ARG, "s_query must be >= 1");
+  if (int rc = stage_batch(b)) return rc;
+  const uint32_t R = (uint32_t)b->g_first.size();
+  c->st_passes = 0; c->st_qhashes = 0; c->st_cands = 0; c->st_ref_bytes = c->ref_len * 8;
+  if (R == 0) return SKB_OK;
+  if (c->n_rows == 0) {
+    CU(c, cudaMemsetAsync(d_out_idx, 0xFF, (size_t)R * top * 4, c->stream));
+    CU(c, cudaMemsetAsync(d_out_sum, 0, (size_t)R * top * 8, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return SKB_OK;
+  }
+  // ---- per-read query sets: hashes <= hmax, distinct, ascending, at most s_query
+  std::vector<uint32_t> qn;
+  std::vector<uint64_t> kmers;
+  SelectPlan plan;
+  if (int rc = run_hash_select(c, b, k, s_query, seed, true, c->hmax, nullptr, nullptr, qn, kmers, plan)) return rc;
+  std::vector<uint64_t> q_off(R + 1, 0);
+  uint32_t qmax = 0;
+  for (uint32_t r = 0; r < R; ++r) { q_off[r + 1] = q_off[r] + qn[r]; qmax = std::max(qmax, qn[r]); }
+  if (qmax > 65535u)
+    return fail(c, SKB_ERR_INVALID_ARG, "a read keeps %u query hashes under the reference maximum; limit is 65535", qmax);
+  const uint64_t QN = q_off[R];
+  c->st_qhashes = QN;
+  CU(c, c->q_off.ensure((R + 1) * 8));
+  CU(c, c->qh.ensure(std::max<uint64_t>(QN, 1) * 8));
+  CU(c, c->qread.ensure(std::max<uint64_t>(QN, 1) * 4));
+  CU(c, cudaMemcpyAsync(c->q_off.p, q_off.data(), (R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  {
+    ProfScope ps(c, SKB_K_SELECT, 1);
+    skb_launch_compact_queries(c->cand_pool.as<uint64_t>(), c->g_base.as<uint64_t>(), c->g_outn.as<uint32_t>(), c->q_off.as<uint64_t>(),
+                               R, c->qh.as<uint64_t>(), c->qread.as<uint32_t>(), c->stream);
+  }
+  if (int rc = check_launch(c, "compact")) return rc;
+
+  // ---- rows tracked for the lower bounds: the current top rows
+  const uint32_t n_tracked = std::min(top, c->n_rows);
+  unsigned long long* sums_in = c->sums[c->sums_cur].as<unsigned long long>();
+  if (c->tracked_top != top) {
+    ProfScope ps(c, SKB_K_RANK, 1);
+    skb_launch_rank_full(sums_in, c->n_rows, n_tracked, 0, nullptr, nullptr, c->tracked.as<uint32_t>(), c->stream);
+    c->tracked_top = top;
+  }
+  c->cand_cap = (uint32_t)std::max<uint64_t>(4u << 20, 2ull * c->n_rows);
+  CU(c, c->cand.ensure((size_t)c->cand_cap * sizeof(SkbCand)));
+  CU(c, c->cand_sorted.ensure((size_t)c->cand_cap * sizeof(SkbCand)));
+  CU(c, c->scal.ensure(256));
+  uint32_t* d_cand_total = c->scal.as<uint32_t>() + 8;
+
+  uint32_t r = 0;
+  uint32_t* h_total = c->h_scal;
+  int rc_final = SKB_OK;
+  while (r < R) {
+    uint32_t B = std::min<uint32_t>(std::min(c->pass_cur, c->pass_max), R - r);
+    // keep the pass's key count inside the filter's design load (and the table)
+    const uint64_t key_budget = 1u << 17;
+    while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
+    const uint32_t nkeys = (uint32_t)(q_off[r + B] - q_off[r]);
+    if (int rc = ensure_table(c, nkeys)) { rc_final = rc; break; }
+    const uint32_t stride = (uint32_t)round_up(B, 8);
+    const size_t count_bytes = (size_t)c->n_rows * stride * 2;
+    cudaError_t e;
+    if ((e = c->counts.ensure(count_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
+        (e = c->lb_idx.ensure((size_t)B * 4)) != cudaSuccess || (e = c->cand_cnt.ensure((size_t)B * 4)) != cudaSuccess ||
+        (e = c->cand_off.ensure(((size_t)B + 1) * 4)) != cudaSuccess ||
+        (e = c->cand_fill.ensure((size_t)B * 4)) != cudaSuccess) {
+      rc_final = fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
+      break;
+    }
+    SkbTable t = table_of(c);
+    { ProfScope ps(c, SKB_K_TABLE, nkeys ? 3 : 0);
+      skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->stream); }
+    cudaMemsetAsync(c->counts.p, 0, count_bytes, c->stream);
+    SkbStreamArgs sa{};
+    sa.ref = c->ref.as<uint64_t>(); sa.ref_len = c->ref_len; sa.row_off = c->row_off.as<uint64_t>();
+    sa.n_rows = c->n_rows; sa.uniform_len = c->uniform_len; sa.table = t;
+    sa.counts = c->counts.as<uint16_t>(); sa.row_stride = stride; sa.num_ctas = c->num_sms;
+    if (nkeys && c->ref_len) { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_stream(sa, c->stream); }
+    cudaMemsetAsync(d_cand_total, 0, 4, c->stream);
+    cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)B * 4, c->stream);
+    cudaMemsetAsync(c->cand_fill.p, 0, (size_t)B * 4, c->stream);
+    SkbRankArgs ra{};
+    ra.counts = sa.counts; ra.row_stride = stride; ra.n_rows = c->n_rows; ra.n_reads = B; ra.row_base = c->row_base;
+    ra.sums_in = c->sums[c->sums_cur].as<unsigned long long>();
+    ra.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
+    ra.tracked = c->tracked.as<uint32_t>(); ra.n_tracked = n_tracked;
+    ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>();
+    ra.cand = c->cand.as<SkbCand>(); ra.cand_cap = c->cand_cap; ra.cand_total = d_cand_total;
+    ra.cand_cnt = c->cand_cnt.as<uint32_t>(); ra.cand_off = c->cand_off.as<uint32_t>();
+    ra.cand_fill = c->cand_fill.as<uint32_t>(); ra.cand_sorted = c->cand_sorted.as<SkbCand>();
+    ra.top = top; ra.out_idx = d_out_idx + (size_t)r * top;
+    ra.out_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)r * top;
+    ra.tracked_next = c->tracked_next.as<uint32_t>();
+    { ProfScope ps(c, SKB_K_RANK, 5);
+      skb_launch_rank_bounds(ra, c->stream);
+      skb_launch_rank_scan(ra, c->stream);
+      skb_launch_rank_group(ra, c->stream);
+      skb_launch_rank_select(ra, c->stream); }
+    if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
+    if ((e = cudaMemcpyAsync(h_total, d_cand_total, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
+      rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e));
+      break;
+    }
+    c->st_passes += 1;
+    if (*h_total > c->cand_cap) {
+      if (B == 1) { rc_final = fail(c, SKB_ERR_INTERNAL, "candidate overflow with a single read"); break; }
+      c->pass_cur = std::max(1u, B / 2);  // too many contenders for the bound: redo with fewer reads
+      continue;
+    }
+    c->st_cands += *h_total;
+    c->sums_cur ^= 1;
+    cudaMemcpyAsync(c->tracked.p, c->tracked_next.p, (size_t)n_tracked * 4, cudaMemcpyDeviceToDevice, c->stream);
+    r += B;
+    if (*h_total < c->cand_cap / 4) c->pass_cur = std::min(c->pass_max, std::max(B, c->pass_cur) * 2);
+  }
+  if (rc_final) return rc_final;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// exported C ABI
+// =========================================================================================================
+extern "C" {
+
+const char* skb_version(void) { return SKB_VERSION_STR; }
+
+int skb_create(int device, skb_ctx** out) {
+  if (!out) return SKB_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return SKB_ERR_NO_DEVICE;
+  if (device < 0 || device >= n) return SKB_ERR_INVALID_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return SKB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SKB_ERR_CUDA;
+  if (prop.major != 10) return SKB_ERR_NO_DEVICE;  // built for sm_100a only
+  skb_ctx* c = new skb_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SKB_ERR_CUDA; }
+  if (cudaHostAlloc((void**)&c->h_scal, 64, cudaHostAllocDefault) != cudaSuccess) {
+    cudaStreamDestroy(c->stream); delete c; return SKB_ERR_OOM;
+  }
+  *out = c;
+  return SKB_OK;
+}
+
+void skb_destroy(skb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  DevBuf* bufs[] = {&c->ref, &c->row_off, &c->sums[0], &c->sums[1], &c->tracked, &c->tracked_next, &c->g_tau, &c->g_cap,
+                    &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->cand_pool,
+                    &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->lb_sum,
+                    &c->lb_idx, &c->cand, &c->cand_sorted, &c->cand_cnt, &c->cand_off, &c->cand_fill, &c->scal,
+                    &c->t_keys, &c->t_cnt, &c->t_start, &c->t_fill, &c->t_reads, &c->t_slot, &c->t_bloom, &c->out_idx,
+                    &c->out_sum, &c->misc};
+  for (DevBuf* b : bufs) b->release();
+  if (c->h_scal) cudaFreeHost(c->h_scal);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* skb_last_error(const skb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void* skb_stream(skb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int skb_synchronize(skb_ctx* c) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
+// ---- batch ------------------------------------------------------------------------------------------------
+int skb_batch_create(skb_ctx* c, skb_batch** out) {
+  if (!c || !out) return SKB_ERR_INVALID_ARG;
+  skb_batch* b = new skb_batch();
+  b->ctx = c;
+  *out = b;
+  return SKB_OK;
+}
+
+void skb_batch_destroy(skb_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  b->codes.release(); b->nmask.release();
+  b->d_codes.release(); b->d_nmask.release(); b->d_seg_group.release(); b->d_seg_chunk0.release(); b->d_seg_n.release();
+  delete b;
+}
+
+int skb_batch_clear(skb_batch* b) {
+  if (!b) return SKB_ERR_INVALID_ARG;
+  b->cur = 0; b->rec_pos.clear(); b->rec_len.clear();
+  b->g_first.clear(); b->g_end.clear(); b->g_raw.clear(); b->g_packed.clear();
+  b->total_raw = 0; b->staged = false; b->nseg = 0;
+  return SKB_OK;
+}
+
+int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, const uint32_t* groups, uint64_t n,
+                  uint32_t nthreads) {
+  if (!b) return SKB_ERR_INVALID_ARG;
+  skb_ctx* c = b->ctx;
+  if (b->staged) return fail(c, SKB_ERR_STATE, "batch already staged; clear it before adding");
+  if (n == 0) return SKB_OK;
+  if (!offsets || (!blob && offsets[n] != offsets[0])) return fail(c, SKB_ERR_INVALID_ARG, "null blob/offsets");
+  for (uint64_t r = 0; r < n; ++r)
+    if (offsets[r + 1] < offsets[r]) return fail(c, SKB_ERR_INVALID_ARG, "record offsets must be non-decreasing");
+  if (groups) {
+    const uint64_t ng = b->g_first.size();
+    if (ng && groups[0] + 1 < ng) return fail(c, SKB_ERR_INVALID_ARG, "groups must continue from the last group");
+    for (uint64_t r = 1; r < n; ++r)
+      if (groups[r] < groups[r - 1]) return fail(c, SKB_ERR_INVALID_ARG, "groups must be non-decreasing");
+  }
+  const uint64_t first_rec = b->rec_pos.size();
+  uint64_t cur = b->cur;
+  for (uint64_t r = 0; r < n; ++r) {
+    const uint64_t len = offsets[r + 1] - offsets[r];
+    const uint64_t next = round_up(cur + len + 1, 32);
+    const uint64_t gid = groups ? groups[r] : b->g_first.size();
+    while (b->g_first.size() <= gid) {  // open new (possibly empty) groups
+      b->g_first.push_back(cur / 32); b->g_end.push_back(cur / 32);
+      b->g_raw.push_back(0); b->g_packed.push_back(0);
+    }
+    b->g_end[gid] = next / 32;
+    b->g_raw[gid] += len; b->g_packed[gid] += len;
+    b->rec_pos.push_back(cur); b->rec_len.push_back(len);
+    b->total_raw += len;
+    cur = next;
+  }
+  if (cur / 32 >= 0xFFFFFFF0ull) return fail(c, SKB_ERR_INVALID_ARG, "batch too large (> 2^37 bases)");
+  CU(c, b->codes.ensure((cur / 16 + 4) * 4, (b->cur / 16) * 4));
+  CU(c, b->nmask.ensure((cur / 32 + 2) * 4, (b->cur / 32) * 4));
+  uint32_t* codes = b->codes.as<uint32_t>();
+  uint32_t* nmask = b->nmask.as<uint32_t>();
+  uint32_t T = nthreads ? nthreads : std::max(1u, std::thread::hardware_concurrency());
+  const uint64_t total_bytes = offsets[n] - offsets[0];
+  if (total_bytes < (1u << 20) || n < 2) T = 1;
+  T = (uint32_t)std::min<uint64_t>(T, n);
+  auto work = [&](uint64_t r0, uint64_t r1) {
+    for (uint64_t r = r0; r < r1; ++r) {
+      const uint64_t P = b->rec_pos[first_rec + r];
+      const uint64_t Pn = (first_rec + r + 1 < b->rec_pos.size()) ? b->rec_pos[first_rec + r + 1] : cur;
+      pack_record(blob + offsets[r], offsets[r + 1] - offsets[r], P, Pn, codes, nmask);
+    }
+  };
+  if (T <= 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> pool;
+    uint64_t r0 = 0;
+    for (uint32_t t = 0; t < T; ++t) {
+      // split by bytes so long and short records balance
+      const uint64_t target = offsets[0] + total_bytes * (t + 1) / T;
+      uint64_t r1 = (t + 1 == T) ? n : (uint64_t)(std::upper_bound(offsets + r0, offsets + n, target) - offsets);
+      if (r1 > n) r1 = n;
+      if (r1 < r0) r1 = r0;
+      pool.emplace_back(work, r0, r1);
+      r0 = r1;
+    }
+    for (auto& th : pool) th.join();
+  }
+  b->cur = cur;
+  return SKB_OK;
+}
+
+uint32_t skb_batch_num_groups(const skb_batch* b) { return b ? (uint32_t)b->g_first.size() : 0; }
+uint64_t skb_batch_num_records(const skb_batch* b) { return b ? b->rec_pos.size() : 0; }
+uint64_t skb_batch_num_bases(const skb_batch* b) { return b ? b->total_raw : 0; }
+uint64_t skb_batch_packed_len(const skb_batch* b) { return b ? b->cur : 0; }
+int skb_batch_record_start(const skb_batch* b, uint64_t record, uint64_t* packed_pos, uint64_t* packed_len) {
+  if (!b || record >= b->rec_pos.size()) return SKB_ERR_INVALID_ARG;
+  if (packed_pos) *packed_pos = b->rec_pos[record];
+  if (packed_len) *packed_len = b->rec_len[record];
+  return SKB_OK;
+}
+
+int skb_batch_stage(skb_batch* b) {
+  if (!b) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(b->ctx->device);
+  return stage_batch(b);
+}
+
+// ---- sketch -----------------------------------------------------------------------------------------------
+int skb_sketch(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s, uint64_t seed, uint64_t* out_hashes,
+               uint32_t* out_counts, uint32_t* out_n, uint64_t* out_bases, uint64_t* out_kmers) {
+  if (!c || !b || b->ctx != c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (k < 1 || k > SKB_MAX_K) return fail(c, SKB_ERR_UNSUPPORTED_K, "k=%u unsupported (1..%d)", k, SKB_MAX_K);
+  if (s < 1) return fail(c, SKB_ERR_INVALID_ARG, "sketch size must be >= 1");
+  const uint32_t G = (uint32_t)b->g_first.size();
+  if (G == 0) return SKB_OK;
+  if (!out_hashes || !out_n) return fail(c, SKB_ERR_INVALID_ARG, "null output");
+  if (int rc = stage_batch(b)) return rc;
+  CU(c, c->sk_hashes.ensure((size_t)G * s * 8));
+  CU(c, c->sk_counts.ensure((size_t)G * s * 4));
+  std::vector<uint32_t> n;
+  std::vector<uint64_t> kmers;
+  SelectPlan plan;
+  if (int rc = run_hash_select(c, b, k, s, seed, false, 0, c->sk_hashes.as<uint64_t>(), c->sk_counts.as<uint32_t>(), n,
+                               kmers, plan))
+    return rc;
+  CU(c, cudaMemcpyAsync(out_hashes, c->sk_hashes.p, (size_t)G * s * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (out_counts) CU(c, cudaMemcpyAsync(out_counts, c->sk_counts.p, (size_t)G * s * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t g = 0; g < G; ++g) {
+    out_n[g] = n[g];
+    if (out_bases) out_bases[g] = b->g_raw[g];
+    if (out_kmers) out_kmers[g] = kmers[g];
+  }
+  return SKB_OK;
+}
+
+// ---- reference --------------------------------------------------------------------------------------------
+int skb_ref_upload(skb_ctx* c, const uint64_t* hashes, const uint64_t* off, uint32_t n_rows, uint32_t global_row_base) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  return upload_ref_common(c, hashes, false, off, n_rows, global_row_base);
+}
+int skb_ref_upload_device(skb_ctx* c, const uint64_t* d_hashes, const uint64_t* off, uint32_t n_rows,
+                          uint32_t global_row_base) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  return upload_ref_common(c, d_hashes, true, off, n_rows, global_row_base);
+}
+uint32_t skb_ref_rows(const skb_ctx* c) { return c && c->has_ref ? c->n_rows : 0; }
+
+// ---- predict ----------------------------------------------------------------------------------------------
+int skb_predict_stream_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top,
+                              int pad, uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  if (!c || !b || b->ctx != c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (b->g_first.size() && (!d_out_idx || !d_out_sum)) return fail(c, SKB_ERR_INVALID_ARG, "null output");
+  return predict_device(c, b, k, s_query, seed, top, pad, d_out_idx, d_out_sum);
+}
+
+int skb_predict_stream(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top, int pad,
+                       uint32_t* out_idx, uint64_t* out_sum) {
+  if (!c || !b || b->ctx != c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  const size_t R = b->g_first.size();
+  if (R && (!out_idx || !out_sum)) return fail(c, SKB_ERR_INVALID_ARG, "null output");
+  if (top < 1 || top > SKB_MAX_TOP) return fail(c, SKB_ERR_INVALID_ARG, "top=%u unsupported (1..%d)", top, SKB_MAX_TOP);
+  CU(c, c->out_idx.ensure(std::max<size_t>(4, R * top * 4)));
+  CU(c, c->out_sum.ensure(std::max<size_t>(8, R * top * 8)));
+  if (int rc = predict_device(c, b, k, s_query, seed, top, pad, c->out_idx.as<uint32_t>(), c->out_sum.as<uint64_t>()))
+    return rc;
+  if (R) {
+    CU(c, cudaMemcpyAsync(out_idx, c->out_idx.p, R * top * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(out_sum, c->out_sum.p, R * top * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return SKB_OK;
+}
+
+int skb_sums_reset(skb_ctx* c) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
+  CU(c, cudaMemsetAsync(c->sums[c->sums_cur].p, 0, std::max<size_t>(8, (size_t)c->n_rows * 8), c->stream));
+  c->tracked_top = 0;
+  c->pass_cur = std::min<uint32_t>(64, c->pass_max);
+  return SKB_OK;
+}
+
+int skb_sums_download(skb_ctx* c, uint64_t* out) {
+  if (!c || !out) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
+  if (c->n_rows) CU(c, cudaMemcpyAsync(out, c->sums[c->sums_cur].p, (size_t)c->n_rows * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
+int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
+  if (!c || !in) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
+  if (c->n_rows) CU(c, cudaMemcpyAsync(c->sums[c->sums_cur].p, in, (size_t)c->n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->tracked_top = 0;
+  return SKB_OK;
+}
+
+int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  c->pass_max = m ? std::min<uint32_t>(m, 8192) : 2048;
+  c->pass_cur = std::min(c->pass_cur, c->pass_max);
+  return SKB_OK;
+}
+
+// ---- shared / rank ----------------------------------------------------------------------------------------
+int skb_shared_counts(skb_ctx* c, const uint64_t* q_hashes, const uint64_t* q_off, uint32_t Q, uint64_t* out) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
+  if (Q == 0 || c->n_rows == 0) return SKB_OK;
+  if (!q_off || !out) return fail(c, SKB_ERR_INVALID_ARG, "null argument");
+  const uint64_t qlen = q_off[Q];
+  if (qlen && !q_hashes) return fail(c, SKB_ERR_INVALID_ARG, "null query hashes");
+  for (uint32_t j = 0; j < Q; ++j) {
+    if (q_off[j + 1] < q_off[j]) return fail(c, SKB_ERR_INVALID_ARG, "query offsets must be non-decreasing");
+    for (uint64_t x = q_off[j]; x + 1 < q_off[j + 1]; ++x)
+      if (!(q_hashes[x] < q_hashes[x + 1])) return fail(c, SKB_ERR_REF_NOT_SORTED, "query sketch %u is not strictly increasing", j);
+  }
+  const size_t pairs = (size_t)c->n_rows * Q;
+  DevBuf dq, dqo, dout;
+  int rc = SKB_OK;
+  cudaError_t e;
+  if ((e = dq.ensure(std::max<uint64_t>(qlen, 1) * 8)) != cudaSuccess || (e = dqo.ensure(((size_t)Q + 1) * 8)) != cudaSuccess ||
+      (e = dout.ensure(pairs * 8)) != cudaSuccess) {
+    rc = fail(c, SKB_ERR_OOM, "shared buffers: %s", cudaGetErrorString(e));
+  } else {
+    if (qlen) cudaMemcpyAsync(dq.p, q_hashes, qlen * 8, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(dqo.p, q_off, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+    { ProfScope ps(c, SKB_K_SHARED, 1);
+      skb_launch_shared(c->ref.as<uint64_t>(), c->row_off.as<uint64_t>(), c->n_rows, dq.as<uint64_t>(), dqo.as<uint64_t>(), Q,
+                        dout.as<unsigned long long>(), c->stream); }
+    rc = check_launch(c, "shared");
+    if (!rc) {
+      cudaMemcpyAsync(out, dout.p, pairs * 8, cudaMemcpyDeviceToHost, c->stream);
+      e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) rc = fail(c, SKB_ERR_CUDA, "shared: %s", cudaGetErrorString(e));
+    }
+  }
+  dq.release(); dqo.release(); dout.release();
+  return rc;
+}
+
+int skb_rank_counts(skb_ctx* c, const uint64_t* counts, uint32_t n, uint32_t top, uint32_t* out_idx, uint64_t* out_sum) {
+  if (!c || !counts || !out_idx || !out_sum) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (top > n) return fail(c, SKB_ERR_TOP_GT_N, "top (%u) exceeds the number of reference sketches (%u)", top, n);
+  if (top < 1 || top > SKB_MAX_TOP) return fail(c, SKB_ERR_INVALID_ARG, "top=%u unsupported (1..%d)", top, SKB_MAX_TOP);
+  CU(c, c->misc.ensure((size_t)n * 8 + SKB_MAX_TOP * 16));
+  unsigned long long* dv = c->misc.as<unsigned long long>();
+  unsigned long long* dos = dv + n;
+  uint32_t* doi = reinterpret_cast<uint32_t*>(dos + SKB_MAX_TOP);
+  CU(c, cudaMemcpyAsync(dv, counts, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+  { ProfScope ps(c, SKB_K_RANK, 1); skb_launch_rank_full(dv, n, top, 0, doi, dos, nullptr, c->stream); }
+  if (int rc = check_launch(c, "rank_full")) return rc;
+  CU(c, cudaMemcpyAsync(out_idx, doi, (size_t)top * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(out_sum, dos, (size_t)top * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
+int skb_merge_topn_device(skb_ctx* c, const uint32_t* d_idx_parts, const uint64_t* d_sum_parts, uint32_t n_parts,
+                          uint64_t n_reads, uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (n_reads == 0) return SKB_OK;
+  if (!d_idx_parts || !d_sum_parts || !d_out_idx || !d_out_sum || n_parts == 0 || top == 0)
+    return fail(c, SKB_ERR_INVALID_ARG, "bad merge arguments");
+  { ProfScope ps(c, SKB_K_MERGE, 1);
+    skb_launch_merge_topn(d_idx_parts, reinterpret_cast<const unsigned long long*>(d_sum_parts), n_parts, n_reads, top,
+                          d_out_idx, reinterpret_cast<unsigned long long*>(d_out_sum), c->stream); }
+  if (int rc = check_launch(c, "merge")) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------------------
+int skb_prof_enable(skb_ctx* c, int on) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  prof_resolve(c);
+  c->prof_on = on != 0;
+  return SKB_OK;
+}
+int skb_prof_reset(skb_ctx* c) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  prof_resolve(c);
+  for (int i = 0; i < SKB_K_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+  return SKB_OK;
+}
+int skb_prof_get(skb_ctx* c, int id, double* total_ms, uint64_t* launches) {
+  if (!c || id < 0 || id >= SKB_K_COUNT) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  prof_resolve(c);
+  if (total_ms) *total_ms = c->prof_ms[id];
+  if (launches) *launches = c->prof_n[id];
+  return SKB_OK;
+}
+uint64_t skb_launch_count(const skb_ctx* c) { return c ? c->launches : 0; }
+int skb_last_predict_stats(const skb_ctx* c, uint64_t* ref_bytes_per_pass, uint64_t* passes, uint64_t* query_hashes,
+                           uint64_t* candidates) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  if (ref_bytes_per_pass) *ref_bytes_per_pass = c->st_ref_bytes;
+  if (passes) *passes = c->st_passes;
+  if (query_hashes) *query_hashes = c->st_qhashes;
+  if (candidates) *candidates = c->st_cands;
+  return SKB_OK;
+}
+
+// ---- debug ------------------------------------------------------------------------------------------------
+int skb_debug_kmer_hashes(skb_ctx* c, skb_batch* b, uint32_t k, uint64_t seed, uint64_t* out_hash, uint8_t* out_valid) {
+  if (!c || !b || b->ctx != c || !out_hash || !out_valid) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (k < 1 || k > SKB_MAX_K) return fail(c, SKB_ERR_UNSUPPORTED_K, "k=%u unsupported (1..%d)", k, SKB_MAX_K);
+  if (int rc = stage_batch(b)) return rc;
+  const uint64_t n = b->cur;
+  if (n == 0) return SKB_OK;
+  DevBuf dh, dv;
+  cudaError_t e;
+  int rc = SKB_OK;
+  if ((e = dh.ensure(n * 8)) != cudaSuccess || (e = dv.ensure(n)) != cudaSuccess) {
+    rc = fail(c, SKB_ERR_OOM, "debug buffers: %s", cudaGetErrorString(e));
+  } else {
+    cudaMemsetAsync(dh.p, 0, n * 8, c->stream);
+    cudaMemsetAsync(dv.p, 0, n, c->stream);
+    SkbHashArgs ha{};
+    ha.pv = view_of(b); ha.k = k; ha.seed = seed;
+    ha.dump_hash = dh.as<uint64_t>(); ha.dump_valid = dv.as<uint8_t>();
+    { ProfScope ps(c, SKB_K_HASH, 1); skb_launch_hash(ha, c->stream); }
+    rc = check_launch(c, "hash(dump)");
+    if (!rc) {
+      cudaMemcpyAsync(out_hash, dh.p, n * 8, cudaMemcpyDeviceToHost, c->stream);
+      cudaMemcpyAsync(out_valid, dv.p, n, cudaMemcpyDeviceToHost, c->stream);
+      e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) rc = fail(c, SKB_ERR_CUDA, "hash(dump): %s", cudaGetErrorString(e));
+    }
+  }
+  dh.release(); dv.release();
+  return rc;
+}
+
+}  // extern "C"

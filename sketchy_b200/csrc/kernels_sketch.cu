@@ -1,0 +1,335 @@
+// kernels_sketch.cu — K1 (canonical k-mer + MurmurHash3_x64_128.h1 + threshold filter) and K2 (bottom-s:
+// sort, dedup, occurrence counts, truncate). sm_100a.
+//
+// K1 replaces needletail `canonical_kmers` + finch `hash_f` reached through `sketcher.process(record)`
+// (reference src/sketchy.rs:296, 333, 477); K2 replaces finch `MashSketcher::push` / `to_vec()`
+// (src/sketchy.rs:302, 335, 480) using the closed form "s smallest distinct hashes with exact counts"
+// (SURVEY.md Appendix A.4).
+#include "kernels.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// MurmurHash3_x64_128, first 64 bits
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint64_t MM_C1 = 0x87c37b91114253d5ull;
+constexpr uint64_t MM_C2 = 0x4cf5ad432745937full;
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+__device__ __forceinline__ void mm3_block(uint64_t& h1, uint64_t& h2, uint64_t k1, uint64_t k2) {
+  k1 *= MM_C1; k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
+  h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ull;
+  k2 *= MM_C2; k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
+  h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ull;
+}
+
+__device__ __forceinline__ uint64_t mm3_finish_h1(uint64_t h1, uint64_t h2, uint64_t len) {
+  h1 ^= len; h2 ^= len;
+  h1 += h2; h2 += h1;
+  h1 = fmix64(h1); h2 = fmix64(h2);
+  return h1 + h2;
+}
+
+// k = 16: exactly one block, no tail.
+__device__ __forceinline__ uint64_t mm3_h1_k16(uint64_t k1, uint64_t k2, uint64_t seed) {
+  uint64_t h1 = seed, h2 = seed;
+  mm3_block(h1, h2, k1, k2);
+  return mm3_finish_h1(h1, h2, 16);
+}
+
+// generic length <= 32: w[i] holds bytes 8i..8i+7 little-endian, bytes >= len are zero.
+__device__ __forceinline__ uint64_t mm3_h1_upto32(const uint64_t w[4], uint32_t len, uint64_t seed) {
+  uint64_t h1 = seed, h2 = seed;
+  uint32_t tb = 0;
+  if (len >= 16) { mm3_block(h1, h2, w[0], w[1]); tb = 2; }
+  if (len == 32) { mm3_block(h1, h2, w[2], w[3]); tb = 4; }
+  const uint32_t t = len & 15u;
+  if (t > 8) {
+    uint64_t k2 = (tb == 0) ? w[1] : w[3];
+    k2 *= MM_C2; k2 = rotl64(k2, 33); k2 *= MM_C1; h2 ^= k2;
+  }
+  if (t > 0) {
+    uint64_t k1 = (tb == 0) ? w[0] : w[2];
+    k1 *= MM_C1; k1 = rotl64(k1, 31); k1 *= MM_C2; h1 ^= k1;
+  }
+  return mm3_finish_h1(h1, h2, len);
+}
+
+// 4 packed bases (one byte, base i at bits 2i) -> 4 ASCII bytes, byte i = "ACGT"[code_i]
+__device__ __forceinline__ uint32_t ascii4(uint32_t v) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r |= ((0x54474341u >> (8 * ((v >> (2 * i)) & 3u))) & 0xFFu) << (8 * i);
+  return r;
+}
+
+// OR of k consecutive bits: bit p of the result = any(m[p .. p+k))
+__device__ __forceinline__ uint64_t window_or(uint64_t m, uint32_t k) {
+  uint32_t r = 1;
+  while (2 * r <= k) { m |= m >> r; r *= 2; }
+  if (k > r) m |= m >> (k - r);
+  return m;
+}
+
+template <bool DUMP>
+__device__ __forceinline__ void emit_hash(const SkbHashArgs& a, uint32_t g, uint64_t tau, uint64_t base,
+                                          uint32_t cap, uint64_t pos, uint64_t h, bool valid) {
+  if (DUMP) {
+    a.dump_hash[pos] = valid ? h : 0ull;
+    a.dump_valid[pos] = valid ? 1 : 0;
+  } else if (valid && h <= tau) {
+    const uint32_t slot = atomicAdd(&a.cand_cnt[g], 1u);
+    if (slot < cap) a.cand[base + slot] = h;
+  }
+}
+
+// One warp per segment (<= 32 chunks of one group); one lane per chunk of 32 k-mer start positions.
+template <bool K16, bool DUMP>
+__global__ void __launch_bounds__(256) hash_kernel(const SkbHashArgs a) {
+  __shared__ uint32_t lut[256];
+  if (K16) {
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ascii4(i);
+    __syncthreads();
+  }
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= a.pv.nseg) return;
+  const uint32_t lane = skb_lane();
+  const uint32_t g = a.pv.seg_group[warp];
+  if (a.active && !a.active[g]) return;
+  const uint32_t nchunk = a.pv.seg_n[warp];
+  uint32_t nvalid = 0;
+  if (lane < nchunk) {
+    const uint64_t chunk = (uint64_t)a.pv.seg_chunk0[warp] + lane;
+    const uint32_t m0 = __ldg(a.pv.nmask + chunk), m1 = __ldg(a.pv.nmask + chunk + 1);
+    const uint64_t inv = window_or((uint64_t)m0 | ((uint64_t)m1 << 32), a.k);
+    const uint32_t valid = ~(uint32_t)inv;
+    nvalid = __popc(valid);
+    if (valid != 0u || DUMP) {
+      const uint64_t tau = DUMP ? 0 : a.tau[g];
+      const uint64_t base = DUMP ? 0 : a.cand_base[g];
+      const uint32_t cap = DUMP ? 0 : a.cand_cap[g];
+      const uint64_t pos0 = chunk * SKB_CHUNK;
+      const uint32_t* cw = a.pv.codes + chunk * 2;
+      if (K16) {
+        const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2);
+        uint32_t fwd_le = w0;
+        uint32_t x = __brev(fwd_le);
+        uint32_t fwd_be = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j > 0) {
+            const uint32_t lo = (j < 16) ? w0 : w1, hi = (j < 16) ? w1 : w2;
+            const int sh = 2 * (j & 15);
+            fwd_le = sh ? __funnelshift_r(lo, hi, sh) : lo;
+            fwd_be = (fwd_be << 2) | (fwd_le >> 30);
+          }
+          // reverse complement, first base most significant, is ~fwd_le; in the little-endian layout it is ~fwd_be
+          const bool use_rc = (~fwd_le) < fwd_be;
+          const uint32_t canon = use_rc ? ~fwd_be : fwd_le;
+          const uint64_t k1 = (uint64_t)lut[canon & 0xFFu] | ((uint64_t)lut[(canon >> 8) & 0xFFu] << 32);
+          const uint64_t k2 = (uint64_t)lut[(canon >> 16) & 0xFFu] | ((uint64_t)lut[canon >> 24] << 32);
+          const uint64_t h = mm3_h1_k16(k1, k2, a.seed);
+          emit_hash<DUMP>(a, g, tau, base, cap, pos0 + j, h, (valid >> j) & 1u);
+        }
+      } else {
+        const uint32_t k = a.k;
+        const uint64_t lo = (uint64_t)__ldg(cw) | ((uint64_t)__ldg(cw + 1) << 32);
+        const uint64_t hi = (uint64_t)__ldg(cw + 2) | ((uint64_t)__ldg(cw + 3) << 32);
+        const uint64_t kmask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
+        uint64_t fwd = 0, rc = 0;
+        // prime with the first k-1 bases, then one base per k-mer
+        for (uint32_t i = 0; i < 31 + k; ++i) {
+          const uint64_t c = (i < 32) ? ((lo >> (2 * i)) & 3ull) : ((hi >> (2 * (i - 32))) & 3ull);
+          fwd = ((fwd << 2) | c) & kmask;
+          rc = (rc >> 2) | ((3ull - c) << (2 * (k - 1)));
+          if (i + 1 >= k) {
+            const uint32_t j = i + 1 - k;
+            const uint64_t canon = fwd < rc ? fwd : rc;  // first base most significant == lexicographic
+            uint64_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (uint32_t b = 0; b < 32; ++b) {
+              if (b < k) {
+                const uint32_t code = (uint32_t)(canon >> (2 * (k - 1 - b))) & 3u;
+                w[b >> 3] |= (uint64_t)((0x54474341u >> (8 * code)) & 0xFFu) << (8 * (b & 7));
+              }
+            }
+            const uint64_t h = mm3_h1_upto32(w, k, a.seed);
+            emit_hash<DUMP>(a, g, tau, base, cap, pos0 + j, h, (valid >> j) & 1u);
+          }
+        }
+      }
+    }
+  }
+  if (!DUMP) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    if (lane == 0 && nvalid) atomicAdd(&a.kmers[g], (unsigned long long)nvalid);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: one CTA per group. Sort the group's candidates (bitonic; shared memory when they fit, else in place in
+// global memory), drop duplicates keeping occurrence counts, keep the s smallest.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cta_bitonic_sort(uint64_t* buf, uint32_t n2) {
+  for (uint32_t size = 2; size <= n2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        const uint32_t j = i + stride;
+        const bool up = (i & size) == 0;
+        const uint64_t x = buf[i], y = buf[j];
+        if ((x > y) == up) { buf[i] = y; buf[j] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// exclusive scan of one flag per thread across the CTA; returns this thread's offset, *total = CTA sum
+__device__ __forceinline__ uint32_t cta_scan_flag(bool flag, uint32_t* warp_sums, uint32_t* total) {
+  const uint32_t lane = skb_lane(), wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+  const uint32_t in_warp = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_sums[wid] = __popc(bal);
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+  for (uint32_t w = 0; w < nw; ++w) {
+    const uint32_t v = warp_sums[w];
+    if (w < wid) off += v;
+    tot += v;
+  }
+  __syncthreads();
+  *total = tot;
+  return off + in_warp;
+}
+
+__global__ void select_kernel(const SkbSelectArgs a) {
+  extern __shared__ __align__(16) uint64_t sbuf[];
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t start_s_sh;
+  const uint32_t g = blockIdx.x;
+  if (a.active && !a.active[g]) return;
+  const uint32_t cnt = a.cand_cnt[g], cap = a.cand_cap[g];
+  if (cnt > cap) {
+    if (threadIdx.x == 0) { a.status[g] = SKB_ST_OVERFLOW; a.out_n[g] = 0; }
+    return;
+  }
+  uint64_t* gbuf = a.cand + a.cand_base[g];
+  uint32_t n2 = 1;
+  while (n2 < cnt) n2 <<= 1;
+  const bool in_smem = n2 <= a.smem_elems;
+  uint64_t* buf = in_smem ? sbuf : gbuf;
+  if (in_smem) {
+    for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) sbuf[i] = i < cnt ? gbuf[i] : SKB_EMPTY_KEY;
+  } else {
+    for (uint32_t i = cnt + threadIdx.x; i < n2; i += blockDim.x) gbuf[i] = SKB_EMPTY_KEY;  // n2 <= cap (pow2)
+  }
+  if (threadIdx.x == 0) start_s_sh = cnt;
+  __syncthreads();
+  cta_bitonic_sort(buf, n2);
+
+  uint64_t* out = a.out_hashes + (a.out_off ? a.out_off[g] : (uint64_t)g * a.s);
+  uint32_t* cnt_out = a.out_counts ? a.out_counts + (uint64_t)g * a.s : nullptr;
+  uint32_t distinct = 0;
+  for (uint32_t base = 0; base < cnt; base += blockDim.x) {
+    const uint32_t i = base + threadIdx.x;
+    uint64_t v = 0;
+    bool head = false;
+    if (i < cnt) {
+      v = buf[i];
+      head = (i == 0) || (buf[i - 1] != v);
+    }
+    __syncthreads();  // all reads of this tile done before any in-place write
+    uint32_t tot;
+    const uint32_t rank = distinct + cta_scan_flag(head, warp_sums, &tot);
+    if (head) {
+      if (rank < a.s) {
+        out[rank] = v;
+        if (cnt_out) cnt_out[rank] = i;  // start index of the run; turned into a count below
+      } else if (rank == a.s) {
+        start_s_sh = i;
+      }
+    }
+    distinct += tot;
+    __syncthreads();
+  }
+  const uint32_t n_out = distinct < a.s ? distinct : a.s;
+  if (cnt_out) {
+    const uint32_t end_all = start_s_sh;  // start of run #s if it exists, else cnt
+    for (uint32_t base = 0; base < n_out; base += blockDim.x) {
+      const uint32_t r = base + threadIdx.x;
+      uint32_t st = 0, nx = 0;
+      if (r < n_out) {
+        st = cnt_out[r];
+        nx = (r + 1 < n_out) ? cnt_out[r + 1] : end_all;
+      }
+      __syncthreads();
+      if (r < n_out) cnt_out[r] = nx - st;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    a.out_n[g] = n_out;
+    a.status[g] = (a.check_underfill && distinct < a.s && a.tau[g] != SKB_EMPTY_KEY) ? SKB_ST_UNDERFILL : SKB_ST_OK;
+  }
+}
+
+__global__ void compact_queries_kernel(const uint64_t* __restrict__ cand, const uint64_t* __restrict__ cand_base,
+                                       const uint32_t* __restrict__ out_n, const uint64_t* __restrict__ q_off,
+                                       uint32_t n_reads, uint64_t* __restrict__ qh, uint32_t* __restrict__ qread) {
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_reads) return;
+  const uint32_t n = out_n[r];
+  const uint64_t src = cand_base[r], dst = q_off[r];
+  for (uint32_t j = skb_lane(); j < n; j += 32) {
+    qh[dst + j] = cand[src + j];
+    qread[dst + j] = r;
+  }
+}
+
+}  // namespace
+
+void skb_launch_hash(const SkbHashArgs& a, cudaStream_t st) {
+  if (a.pv.nseg == 0) return;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)(((uint64_t)a.pv.nseg * 32 + threads - 1) / threads);
+  const bool dump = a.dump_hash != nullptr;
+  if (a.k == 16) {
+    if (dump) hash_kernel<true, true><<<blocks, threads, 0, st>>>(a);
+    else hash_kernel<true, false><<<blocks, threads, 0, st>>>(a);
+  } else {
+    if (dump) hash_kernel<false, true><<<blocks, threads, 0, st>>>(a);
+    else hash_kernel<false, false><<<blocks, threads, 0, st>>>(a);
+  }
+}
+
+void skb_launch_select(const SkbSelectArgs& a, cudaStream_t st) {
+  if (a.n_groups == 0) return;
+  const size_t smem = (size_t)a.smem_elems * sizeof(uint64_t);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  select_kernel<<<a.n_groups, a.threads, smem, st>>>(a);
+}
+
+void skb_launch_compact_queries(const uint64_t* cand, const uint64_t* cand_base, const uint32_t* out_n,
+                                const uint64_t* q_off, uint32_t n_reads, uint64_t* qh, uint32_t* qread,
+                                cudaStream_t st) {
+  if (n_reads == 0) return;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)(((uint64_t)n_reads * 32 + threads - 1) / threads);
+  compact_queries_kernel<<<blocks, threads, 0, st>>>(cand, cand_base, out_n, q_off, n_reads, qh, qread);
+}

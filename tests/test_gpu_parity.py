@@ -1,0 +1,253 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+Bit-exact for every integer result (hashes, counts, totals, shared counts, top-N order with index tie-break)."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from sketchy_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sketchy_b200._lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _rand_dna(rng, n, alphabet=b"ACGT"):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+DIRTY = [
+    b"",
+    b"ACGT",
+    b"ACGTACGTACGTACGT",
+    b"T" * 16,
+    b"acgtacgtnnACGTTGCAAGGCTTAACCGGTTAACCGGTTuuUUacgtRYKMACGTTGCATGCATGCATGCAGGG",
+    b"ACGTTGCAAGGC\nTTAACCGGTT\r\nAACCGGTTACGTAGCTAGCTAGGATC  CGATCGATCG\tATCGATTTAGC",
+    b"N" * 40,
+    b"ACGTTGCAAGGCTTAAC-CGGTTAACCGG.TTACGTAGCTAGCT~AGGATCCGATCGATCGATCGATTTAGC",
+]
+
+
+@pytest.mark.parametrize("k", [16, 21, 11, 31, 32, 5, 1, 17])
+def test_kmer_hashes_positional(ctx, k):
+    """K1: every packed position's canonical k-mer hash == the oracle's emission order, record by record."""
+    rng = random.Random(100 + k)
+    recs = list(DIRTY) + [_rand_dna(rng, rng.randint(0, 700), b"ACGTACGTACGTN") for _ in range(40)]
+    recs += [_rand_dna(rng, 5000)]
+    b = ctx.batch().add_records(recs)
+    seed = 42 if k % 2 else 0
+    h, v = ctx.debug_kmer_hashes(b, k, seed)
+    covered = np.zeros(h.size, dtype=bool)
+    for r, rec in enumerate(recs):
+        pos, raw_len = b.record_start(r)
+        assert raw_len == len(rec)
+        ln = len(oracle.normalize(rec))
+        exp = oracle.kmer_hashes(rec, k, seed)
+        span = slice(pos, pos + max(ln, 0))
+        got = h[span][v[span] == 1]
+        assert got.tolist() == exp.tolist(), (r, rec[:40])
+        covered[span] = True
+    assert v[~covered].sum() == 0  # padding / separators never emit
+    b.close()
+
+
+def _files(rng):
+    big = _rand_dna(rng, 300_000)
+    rep = (_rand_dna(rng, 37) * 3000)  # heavy duplicates: forces candidate overflow + retry
+    files = [
+        [big[:150_000], big[150_000:]],
+        [],                                       # empty file
+        [b"ACGTACGTAC"],                          # shorter than k
+        [_rand_dna(rng, 700)],                    # fewer than s distinct k-mers
+        [rep],
+        [_rand_dna(rng, 50_000, b"ACGTN"), _rand_dna(rng, 10), _rand_dna(rng, 80_000)],
+        [big[1000:200_000].lower()],
+    ]
+    return files
+
+
+@pytest.mark.parametrize("k,s,seed", [(16, 1000, 0), (16, 100, 42), (21, 500, 42), (16, 10000, 0), (31, 64, 7)])
+def test_sketch_parity(ctx, k, s, seed):
+    """K1+K2 == finch MashSketcher per file: hashes, occurrence counts, total_bases, total_kmers."""
+    rng = random.Random(7)
+    files = _files(rng)
+    recs = [r for f in files for r in f]
+    groups = [g for g, f in enumerate(files) for _ in f]
+    exp, eb, ek = oracle.sketch_groups(recs, groups, len(files), k, s, seed, nthreads=4)
+    b = ctx.batch()
+    # last file has records; empty file in the middle is created by the group numbering
+    b.add_records(recs, np.asarray(groups, dtype=np.uint32))
+    assert b.num_groups == len(files)
+    got, gb, gk = ctx.sketch(b, k, s, seed)
+    for g in range(len(files)):
+        assert got[g][0].tolist() == exp[g][0].tolist(), g
+        assert got[g][1].tolist() == exp[g][1].tolist(), g
+        assert (int(gb[g]), int(gk[g])) == (int(eb[g]), int(ek[g])), g
+    b.close()
+
+
+def _world(seed, n_lineages, per_lineage, glen, s, n_reads, rlen, k=16, hseed=0, ragged=False):
+    base = [synth.random_genome(glen, seed * 1000 + l) for l in range(n_lineages)]
+    genomes = []
+    for g in range(n_lineages * per_lineage):   # lineages interleaved in file order
+        genomes.append(synth.mutate(base[g % n_lineages], 0.002, seed * 7919 + g))
+    if ragged:
+        genomes[3] = genomes[3][:s // 2 + k]     # a tiny genome: fewer than s k-mers, huge max hash
+        genomes[5] = genomes[5][:k - 1]          # no k-mers at all: empty row
+    sk, _, _ = oracle.sketch_groups([g.tobytes() for g in genomes], list(range(len(genomes))), len(genomes), k, s,
+                                    hseed, nthreads=8)
+    rows = [h for h, _ in sk]
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    blob, roff, src = synth.sample_reads(base, n_reads, rlen, seed + 5)
+    return ref, off, blob, roff
+
+
+def _check_predict(ctx, ref, off, blob, roff, k, s_query, hseed, top, pass_reads, chunks=1):
+    ctx.ref_upload(ref, off)
+    ctx.set_pass_reads(pass_reads)
+    n = roff.size - 1
+    ei, es, esums = oracle.predict_stream(ref, off, (blob, roff), k, s_query, hseed, top)
+    gi_all, gs_all = [], []
+    bounds = np.linspace(0, n, chunks + 1).astype(int)
+    for c in range(chunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        b = ctx.batch()
+        sub_off = roff[lo:hi + 1] - roff[lo]
+        b.add(blob[int(roff[lo]):int(roff[hi])] if hi > lo else np.zeros(1, np.uint8), sub_off)
+        gi, gs = ctx.predict_stream(b, k, s_query, hseed, top)
+        gi_all.append(gi)
+        gs_all.append(gs)
+        b.close()
+    gi = np.concatenate(gi_all)
+    gs = np.concatenate(gs_all)
+    assert gi.shape == ei.shape
+    bad = np.flatnonzero((gi != ei).any(axis=1) | (gs != es).any(axis=1))
+    assert bad.size == 0, (bad[:5], gi[bad[:2]], ei[bad[:2]], gs[bad[:2]], es[bad[:2]])
+    assert (ctx.sums_download() == esums).all()
+
+
+@pytest.mark.parametrize("pass_reads", [1, 7, 64, 0])
+def test_predict_stream_parity_uniform(ctx, pass_reads):
+    ref, off, blob, roff = _world(seed=3, n_lineages=6, per_lineage=20, glen=40_000, s=500, n_reads=300, rlen=1500)
+    # first reads shorter than k: all sums zero -> ranking = first `top` references in file order
+    blob = np.concatenate([np.frombuffer(b"ACGTACGT", np.uint8), blob])
+    roff = np.concatenate([[0], roff + 8]).astype(np.uint64)
+    _check_predict(ctx, ref, off, blob, roff, 16, 500, 0, 10, pass_reads)
+
+
+def test_predict_stream_parity_ragged_and_chunked(ctx):
+    ref, off, blob, roff = _world(seed=11, n_lineages=5, per_lineage=9, glen=30_000, s=300, n_reads=200, rlen=2000,
+                                  hseed=42, ragged=True)
+    assert len(set(np.diff(off).tolist())) > 1
+    _check_predict(ctx, ref, off, blob, roff, 16, 300, 42, 5, 32, chunks=3)
+
+
+def test_predict_stream_k21_top1_and_large_top(ctx):
+    ref, off, blob, roff = _world(seed=21, n_lineages=4, per_lineage=40, glen=20_000, s=200, n_reads=120, rlen=1000,
+                                  k=21, hseed=42)
+    _check_predict(ctx, ref, off, blob, roff, 21, 200, 42, 1, 0)
+    _check_predict(ctx, ref, off, blob, roff, 21, 200, 42, 100, 16)
+
+
+def test_predict_small_squery_truncates(ctx):
+    """s_query smaller than the read's k-mer count: the read sketch is its s smallest hashes."""
+    ref, off, blob, roff = _world(seed=31, n_lineages=3, per_lineage=5, glen=5_000, s=2000, n_reads=60, rlen=3000)
+    _check_predict(ctx, ref, off, blob, roff, 16, 50, 0, 3, 0)
+
+
+def test_predict_medium_scale(ctx):
+    """N=3000 x s=1000 reference, 150 reads of 5 kb, top 10 (oracle finishes in seconds)."""
+    ref, off, blob, roff = _world(seed=41, n_lineages=10, per_lineage=300, glen=100_000, s=1000, n_reads=150,
+                                  rlen=5000)
+    _check_predict(ctx, ref, off, blob, roff, 16, 1000, 0, 10, 0)
+
+
+def test_shared_counts_and_rank(ctx):
+    ref, off, blob, roff = _world(seed=51, n_lineages=4, per_lineage=6, glen=20_000, s=400, n_reads=5, rlen=500)
+    ctx.ref_upload(ref, off)
+    got = ctx.shared_counts(ref, off)
+    exp = oracle.shared_matrix(ref, off, ref, off)
+    assert (got == exp).all()
+    assert (np.diag(got) == np.diff(off)).all()     # docs/index.md:148-149: self-shared = s
+    col = exp[:, 3].copy()
+    gi, gs = ctx.rank_counts(col, 7)
+    order = sorted(range(col.size), key=lambda i: (-int(col[i]), i))[:7]
+    assert gi.tolist() == order and gs.tolist() == [int(col[i]) for i in order]
+
+
+def test_readset_mode(ctx):
+    from sketchy_b200.api import Sketch, Sketchy
+    ref, off, blob, roff = _world(seed=61, n_lineages=4, per_lineage=6, glen=20_000, s=400, n_reads=40, rlen=800)
+    sk = Sketchy(0)
+    rows = [Sketch(name=f"g{i}", hashes=ref[int(off[i]):int(off[i + 1])]) for i in range(off.size - 1)]
+    sk.load_reference(rows)
+    reads = [blob[int(roff[i]):int(roff[i + 1])].tobytes() for i in range(roff.size - 1)]
+    for limit in (0, 9):
+        n, gi, gs, shared = sk.predict_readset_records(reads, 5, limit)
+        en, ei, es, eall = oracle.predict_readset(ref, off, reads, 16, 400, 0, 5, limit)
+        assert n == en and gi.tolist() == ei.tolist() and gs.tolist() == es.tolist()
+        assert shared.tolist() == eall.tolist()
+    sk.close()
+
+
+def test_sharded_predict_and_merge(ctx):
+    """Two shards on one GPU (two contexts) + the merge kernel == the unsharded oracle (fake-shard test of the
+    multi-GPU path: local top-N with global indices, gather, merge by (sum desc, index asc))."""
+    import torch
+    from sketchy_b200._lib import Context
+    ref, off, blob, roff = _world(seed=71, n_lineages=5, per_lineage=8, glen=20_000, s=300, n_reads=150, rlen=1200)
+    N = off.size - 1
+    top = 10
+    ei, es, _ = oracle.predict_stream(ref, off, (blob, roff), 16, 300, 0, top)
+    n = roff.size - 1
+    parts_i, parts_s = [], []
+    cuts = [0, 7, N]  # uneven shards; the first is smaller than top -> padded entries
+    for p in range(2):
+        c = Context(0)
+        lo, hi = cuts[p], cuts[p + 1]
+        c.ref_upload(ref[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo], row_base=lo)
+        b = c.batch().add(blob, roff)
+        di = torch.zeros((n, top), dtype=torch.int32, device="cuda")
+        ds = torch.zeros((n, top), dtype=torch.int64, device="cuda")
+        c.predict_stream_device(b, 16, 300, 0, top, di.data_ptr(), ds.data_ptr(), pad=True)
+        parts_i.append(di)
+        parts_s.append(ds)
+        b.close()
+        c.close()
+    pi = torch.stack(parts_i).contiguous()
+    ps = torch.stack(parts_s).contiguous()
+    oi = torch.zeros((n, top), dtype=torch.int32, device="cuda")
+    os_ = torch.zeros((n, top), dtype=torch.int64, device="cuda")
+    ctx.merge_topn_device(pi.data_ptr(), ps.data_ptr(), 2, n, top, oi.data_ptr(), os_.data_ptr())
+    torch.cuda.synchronize()
+    gi = oi.cpu().numpy().view(np.uint32)
+    gs = os_.cpu().numpy().view(np.uint64)
+    assert (gi == ei).all() and (gs == es).all()
+
+
+def test_error_codes(ctx):
+    from sketchy_b200._lib import SkbError
+    ref = np.array([1, 2, 3, 10, 9, 11], dtype=np.uint64)
+    with pytest.raises(SkbError) as e:
+        ctx.ref_upload(ref, np.array([0, 3, 6], dtype=np.uint64))
+    assert e.value.code == -4
+    ctx.ref_upload(np.array([1, 2, 3, 9, 10, 11], dtype=np.uint64), np.array([0, 3, 6], dtype=np.uint64))
+    b = ctx.batch().add_records([b"ACGTACGTACGTACGTACGT"])
+    with pytest.raises(SkbError) as e:
+        ctx.predict_stream(b, 16, 3, 0, 3)       # top > N: the reference panics
+    assert e.value.code == -5
+    with pytest.raises(SkbError) as e:
+        ctx.predict_stream(b, 33, 3, 0, 1)
+    assert e.value.code == -7
+    gi, gs = ctx.predict_stream(b, 16, 3, 0, 2)
+    assert gi.tolist() == [[0, 1]] and gs.tolist() == [[0, 0]]
+    b.close()
