@@ -381,7 +381,7 @@ int run_hash_select(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s, uint64_t s
 }
 
 int ensure_table(skb_ctx* c, uint32_t max_keys) {
-  if (max_keys <= c->t_maxkeys) return SKB_OK;
+  if (c->t_maxkeys && max_keys <= c->t_maxkeys) return SKB_OK;
   const uint32_t mk = (uint32_t)skb_next_pow2(std::max<uint32_t>(max_keys, 1u << 16));
   const uint32_t cap = mk * 2;
   CU(c, c->t_keys.ensure(((size_t)cap + 1) * 8));
