@@ -313,7 +313,7 @@ def run_b200(args):
                                    "s=10000, --top 10" if (N, s, R) == (40000, 10000, 100000) else
                                    f"predict {R} reads vs {N} x s={s}", "refs": N, "sketch_size": s, "reads": R,
                        "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages,
-                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 2048,
+                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 4096,
                        "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass"
                              % (rows_local * s * 8 / 1e9),
                        "parallelism": f"reference rows sharded over {world} GPU(s); NCCL all-gather of local top-N"
@@ -327,6 +327,7 @@ def run_b200(args):
                          "launches": stream_n,
                          "stream_share_of_step": stream_ms / ms if ms > 0 else None},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+            "predict_stats": stats,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(out), flush=True)

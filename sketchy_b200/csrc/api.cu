@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -104,9 +105,9 @@ struct skb_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   // reference shard
-  DevBuf ref, row_off;
-  uint64_t ref_len = 0;
-  uint32_t n_rows = 0, row_base = 0, uniform_len = 0;
+  DevBuf ref, row_start, row_len, cta_row;
+  uint64_t ref_len = 0;  // hashes in the shard (without alignment padding)
+  uint32_t n_rows = 0, row_base = 0, uniform_len = 0, uniform_pitch = 0;
   uint64_t hmax = 0;
   bool has_ref = false;
   DevBuf sums[2];
@@ -118,10 +119,10 @@ struct skb_ctx {
   DevBuf sk_hashes, sk_counts;
   // predict scratch
   DevBuf q_off, qh, qread, counts, lb_sum, lb_idx, cand, cand_sorted, cand_cnt, cand_off, cand_fill, scal;
-  DevBuf t_keys, t_cnt, t_start, t_fill, t_reads, t_slot, t_bloom;
+  DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = 2048, pass_cur = 64;
+  uint32_t pass_max = SKB_MAX_PASS_READS, pass_cur = 64;
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -383,10 +384,8 @@ int run_hash_select(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s, uint64_t s
 int ensure_table(skb_ctx* c, uint32_t max_keys) {
   if (c->t_maxkeys && max_keys <= c->t_maxkeys) return SKB_OK;
   const uint32_t mk = (uint32_t)skb_next_pow2(std::max<uint32_t>(max_keys, 1u << 16));
-  const uint32_t cap = mk * 2;
-  CU(c, c->t_keys.ensure(((size_t)cap + 1) * 8));
-  CU(c, c->t_cnt.ensure(((size_t)cap + 1) * 4));
-  CU(c, c->t_start.ensure(((size_t)cap + 1) * 4));
+  const uint32_t cap = mk * 8;  // load factor <= 0.125: a lookup is almost always one 16-byte load
+  CU(c, c->t_slots.ensure(((size_t)cap + 1) * sizeof(SkbSlot)));
   CU(c, c->t_fill.ensure(((size_t)cap + 1) * 4));
   CU(c, c->t_reads.ensure((size_t)mk * 4));
   CU(c, c->t_slot.ensure((size_t)mk * 4));
@@ -398,9 +397,8 @@ int ensure_table(skb_ctx* c, uint32_t max_keys) {
 
 SkbTable table_of(skb_ctx* c) {
   SkbTable t;
-  t.keys = c->t_keys.as<uint64_t>(); t.cnt = c->t_cnt.as<uint32_t>(); t.start = c->t_start.as<uint32_t>();
-  t.fill = c->t_fill.as<uint32_t>(); t.reads = c->t_reads.as<uint32_t>(); t.slot_of = c->t_slot.as<uint32_t>();
-  t.bloom = c->t_bloom.as<uint32_t>();
+  t.slots = c->t_slots.as<SkbSlot>(); t.fill = c->t_fill.as<uint32_t>(); t.reads = c->t_reads.as<uint32_t>();
+  t.slot_of = c->t_slot.as<uint32_t>(); t.bloom = c->t_bloom.as<uint32_t>();
   t.cursor = c->scal.as<uint32_t>() + 4;
   t.cap = c->t_cap;
   uint32_t l = 0;
@@ -409,33 +407,80 @@ SkbTable table_of(skb_ctx* c) {
   return t;
 }
 
+SkbRefView ref_view(const skb_ctx* c) {
+  SkbRefView v;
+  v.ref = c->ref.as<uint64_t>(); v.row_start = c->row_start.as<uint64_t>(); v.row_len = c->row_len.as<uint32_t>();
+  v.n_rows = c->n_rows;
+  v.uniform_len = c->uniform_len; v.uniform_pitch = c->uniform_pitch;
+  return v;
+}
+
 int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const uint64_t* off, uint32_t n_rows,
                       uint32_t global_row_base) {
   if (!off && n_rows) return fail(c, SKB_ERR_INVALID_ARG, "off is null");
   const uint64_t len = n_rows ? off[n_rows] : 0;
   if (n_rows && off[0] != 0) return fail(c, SKB_ERR_INVALID_ARG, "off[0] must be 0");
-  for (uint32_t i = 0; i < n_rows; ++i)
+  for (uint32_t i = 0; i < n_rows; ++i) {
     if (off[i + 1] < off[i]) return fail(c, SKB_ERR_INVALID_ARG, "row offsets must be non-decreasing");
+    if (off[i + 1] - off[i] > 0xFFFFFFF0ull) return fail(c, SKB_ERR_INVALID_ARG, "row %u too long", i);
+  }
   if (len && !hashes) return fail(c, SKB_ERR_INVALID_ARG, "hashes is null");
   c->has_ref = false;
-  const uint64_t padded = round_up(len + 2, 2048);
+  // device layout: every row starts on an even element (16-byte aligned) so it can be bulk-copied
+  std::vector<uint64_t> start(std::max<uint32_t>(n_rows, 1));
+  std::vector<uint32_t> rlen(std::max<uint32_t>(n_rows, 1));
+  bool same = true;
+  uint64_t pos = 0;
+  for (uint32_t i = 0; i < n_rows; ++i) {
+    start[i] = pos;
+    rlen[i] = (uint32_t)(off[i + 1] - off[i]);
+    same = same && (pos == off[i]);
+    pos += round_up(rlen[i], 2);
+  }
+  const uint64_t padded = round_up(pos + 2, 2048);
   CU(c, c->ref.ensure(padded * 8));
-  CU(c, c->row_off.ensure(((size_t)n_rows + 1) * 8));
-  if (len)
-    CU(c, cudaMemcpyAsync(c->ref.p, hashes, len * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                          c->stream));
-  CU(c, cudaMemsetAsync(c->ref.as<uint64_t>() + len, 0xFF, (padded - len) * 8, c->stream));
+  CU(c, c->row_start.ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
+  CU(c, c->row_len.ensure(std::max<size_t>(4, (size_t)n_rows * 4)));
+  CU(c, cudaMemsetAsync(c->ref.p, 0xFF, padded * 8, c->stream));
   if (n_rows) {
-    CU(c, cudaMemcpyAsync(c->row_off.p, off, ((size_t)n_rows + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  } else {
-    CU(c, cudaMemsetAsync(c->row_off.p, 0, 8, c->stream));
+    CU(c, cudaMemcpyAsync(c->row_start.p, start.data(), (size_t)n_rows * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->row_len.p, rlen.data(), (size_t)n_rows * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (len) {
+    if (same) {
+      CU(c, cudaMemcpyAsync(c->ref.p, hashes, len * 8, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                            c->stream));
+    } else {
+      DevBuf tmp, doff;
+      const uint64_t* src = hashes;
+      if (!on_device) {
+        CU(c, tmp.ensure(len * 8));
+        CU(c, cudaMemcpyAsync(tmp.p, hashes, len * 8, cudaMemcpyHostToDevice, c->stream));
+        src = tmp.as<uint64_t>();
+      }
+      cudaError_t e = doff.ensure(((size_t)n_rows + 1) * 8);
+      if (e != cudaSuccess) { tmp.release(); return fail(c, SKB_ERR_OOM, "relayout: %s", cudaGetErrorString(e)); }
+      cudaMemcpyAsync(doff.p, off, ((size_t)n_rows + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+      { ProfScope ps(c, SKB_K_MISC, 1);
+        skb_launch_relayout(src, doff.as<uint64_t>(), c->ref.as<uint64_t>(), c->row_start.as<uint64_t>(), n_rows, c->stream); }
+      e = cudaStreamSynchronize(c->stream);
+      tmp.release(); doff.release();
+      if (e != cudaSuccess) return fail(c, SKB_ERR_CUDA, "relayout: %s", cudaGetErrorString(e));
+    }
+  }
+  c->n_rows = n_rows;
+  {
+    uint32_t ul = n_rows ? rlen[0] : 0;
+    for (uint32_t i = 0; i < n_rows && ul; ++i)
+      if (rlen[i] != ul) ul = 0;
+    c->uniform_len = ul;
+    c->uniform_pitch = (uint32_t)round_up(ul, 2);
   }
   CU(c, c->scal.ensure(256));
   CU(c, cudaMemsetAsync(c->scal.p, 0, 256, c->stream));
   uint32_t* d_bad = c->scal.as<uint32_t>();
   unsigned long long* d_hmax = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 8);
-  { ProfScope ps(c, SKB_K_MISC, 1);
-    skb_launch_ref_check(c->ref.as<uint64_t>(), c->row_off.as<uint64_t>(), n_rows, d_bad, d_hmax, c->stream); }
+  { ProfScope ps(c, SKB_K_MISC, 1); skb_launch_ref_check(ref_view(c), d_bad, d_hmax, c->stream); }
   if (int rc = check_launch(c, "ref_check")) return rc;
   uint32_t bad = 0;
   unsigned long long hmax = 0;
@@ -443,11 +488,23 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   CU(c, cudaMemcpyAsync(&hmax, d_hmax, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   if (bad) return fail(c, SKB_ERR_REF_NOT_SORTED, "a reference row is not strictly increasing");
-  c->ref_len = len; c->n_rows = n_rows; c->row_base = global_row_base; c->hmax = hmax;
-  uint32_t ul = n_rows ? (uint32_t)std::min<uint64_t>(off[1] - off[0], 0xFFFFFFFFull) : 0;
-  for (uint32_t i = 0; i < n_rows && ul; ++i)
-    if (off[i + 1] - off[i] != ul) ul = 0;
-  c->uniform_len = ul;
+  c->ref_len = len; c->row_base = global_row_base; c->hmax = hmax;
+  // contiguous row ranges per CTA, balanced by ring tiles (a row costs at least one unit: its rank work)
+  {
+    const uint32_t G = (uint32_t)c->num_sms, tile = skb_fused_tile();
+    std::vector<uint64_t> cum(n_rows + 1, 0);
+    for (uint32_t i = 0; i < n_rows; ++i) cum[i + 1] = cum[i] + std::max<uint64_t>(1, (rlen[i] + tile - 1) / tile);
+    std::vector<uint32_t> cta(G + 1, n_rows);
+    cta[0] = 0;
+    for (uint32_t g = 1; g < G; ++g) {
+      const uint64_t target = cum[n_rows] * g / G;
+      cta[g] = (uint32_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+      if (cta[g] < cta[g - 1]) cta[g] = cta[g - 1];
+      if (cta[g] > n_rows) cta[g] = n_rows;
+    }
+    CU(c, c->cta_row.ensure((G + 1) * 4));
+    CU(c, cudaMemcpy(c->cta_row.p, cta.data(), (G + 1) * 4, cudaMemcpyHostToDevice));
+  }
   CU(c, c->sums[0].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
   CU(c, c->sums[1].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
   CU(c, cudaMemsetAsync(c->sums[0].p, 0, std::max<size_t>(8, (size_t)n_rows * 8), c->stream));
@@ -459,11 +516,6 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   CU(c, cudaStreamSynchronize(c->stream));
   c->has_ref = true;
   return SKB_OK;
-}
-
-void fill_pad(std::vector<uint32_t>& idx, std::vector<uint64_t>& sum) {
-  std::fill(idx.begin(), idx.end(), 0xFFFFFFFFu);
-  std::fill(sum.begin(), sum.end(), 0ull);
 }
 
 int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top, int pad,
@@ -531,10 +583,10 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
     const uint32_t nkeys = (uint32_t)(q_off[r + B] - q_off[r]);
     if (int rc = ensure_table(c, nkeys)) { rc_final = rc; break; }
-    const uint32_t stride = (uint32_t)round_up(B, 8);
-    const size_t count_bytes = (size_t)c->n_rows * stride * 2;
+    const uint32_t stride = (uint32_t)round_up(B, 256);
+    const size_t ctr_bytes = (size_t)n_tracked * stride * 2;
     cudaError_t e;
-    if ((e = c->counts.ensure(count_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
+    if ((e = c->counts.ensure(ctr_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
         (e = c->lb_idx.ensure((size_t)B * 4)) != cudaSuccess || (e = c->cand_cnt.ensure((size_t)B * 4)) != cudaSuccess ||
         (e = c->cand_off.ensure(((size_t)B + 1) * 4)) != cudaSuccess ||
         (e = c->cand_fill.ensure((size_t)B * 4)) != cudaSuccess) {
@@ -542,21 +594,16 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
       break;
     }
     SkbTable t = table_of(c);
-    { ProfScope ps(c, SKB_K_TABLE, nkeys ? 3 : 0);
+    { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1);
       skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->stream); }
-    cudaMemsetAsync(c->counts.p, 0, count_bytes, c->stream);
-    SkbStreamArgs sa{};
-    sa.ref = c->ref.as<uint64_t>(); sa.ref_len = c->ref_len; sa.row_off = c->row_off.as<uint64_t>();
-    sa.n_rows = c->n_rows; sa.uniform_len = c->uniform_len; sa.table = t;
-    sa.counts = c->counts.as<uint16_t>(); sa.row_stride = stride; sa.num_ctas = c->num_sms;
-    if (nkeys && c->ref_len) { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_stream(sa, c->stream); }
+    cudaMemsetAsync(c->counts.p, 0, ctr_bytes, c->stream);
     cudaMemsetAsync(d_cand_total, 0, 4, c->stream);
     cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)B * 4, c->stream);
     cudaMemsetAsync(c->cand_fill.p, 0, (size_t)B * 4, c->stream);
+    const SkbRefView rv = ref_view(c);
     SkbRankArgs ra{};
-    ra.counts = sa.counts; ra.row_stride = stride; ra.n_rows = c->n_rows; ra.n_reads = B; ra.row_base = c->row_base;
+    ra.tracked_counts = c->counts.as<uint16_t>(); ra.row_stride = stride; ra.n_reads = B; ra.row_base = c->row_base;
     ra.sums_in = c->sums[c->sums_cur].as<unsigned long long>();
-    ra.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
     ra.tracked = c->tracked.as<uint32_t>(); ra.n_tracked = n_tracked;
     ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>();
     ra.cand = c->cand.as<SkbCand>(); ra.cand_cap = c->cand_cap; ra.cand_total = d_cand_total;
@@ -565,9 +612,18 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     ra.top = top; ra.out_idx = d_out_idx + (size_t)r * top;
     ra.out_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)r * top;
     ra.tracked_next = c->tracked_next.as<uint32_t>();
-    { ProfScope ps(c, SKB_K_RANK, 5);
-      skb_launch_rank_bounds(ra, c->stream);
-      skb_launch_rank_scan(ra, c->stream);
+    { ProfScope ps(c, SKB_K_RANK, nkeys ? 2 : 1);
+      if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, n_tracked, t, c->counts.as<uint16_t>(), stride, c->stream);
+      skb_launch_rank_bounds(ra, c->stream); }
+    SkbFusedArgs fa{};
+    fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
+    fa.n_reads = B; fa.cnt_stride = stride; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
+    { const char* dbg = getenv("SKB_DEBUG"); fa.debug = dbg ? atoi(dbg) : 0; }
+    fa.sums_in = ra.sums_in; fa.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
+    fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.cand = ra.cand; fa.cand_cap = ra.cand_cap;
+    fa.cand_total = ra.cand_total; fa.cand_cnt = ra.cand_cnt;
+    { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
+    { ProfScope ps(c, SKB_K_RANK, 3);
       skb_launch_rank_group(ra, c->stream);
       skb_launch_rank_select(ra, c->stream); }
     if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
@@ -628,11 +684,11 @@ void skb_destroy(skb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-  DevBuf* bufs[] = {&c->ref, &c->row_off, &c->sums[0], &c->sums[1], &c->tracked, &c->tracked_next, &c->g_tau, &c->g_cap,
+  DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->sums[0], &c->sums[1], &c->tracked, &c->tracked_next, &c->g_tau, &c->g_cap,
                     &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->cand_pool,
                     &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->lb_sum,
                     &c->lb_idx, &c->cand, &c->cand_sorted, &c->cand_cnt, &c->cand_off, &c->cand_fill, &c->scal,
-                    &c->t_keys, &c->t_cnt, &c->t_start, &c->t_fill, &c->t_reads, &c->t_slot, &c->t_bloom, &c->out_idx,
+                    &c->t_slots, &c->t_fill, &c->t_reads, &c->t_slot, &c->t_bloom, &c->out_idx,
                     &c->out_sum, &c->misc};
   for (DevBuf* b : bufs) b->release();
   if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -860,7 +916,7 @@ int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
-  c->pass_max = m ? std::min<uint32_t>(m, 8192) : 2048;
+  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS) : SKB_MAX_PASS_READS;
   c->pass_cur = std::min(c->pass_cur, c->pass_max);
   return SKB_OK;
 }
@@ -890,8 +946,7 @@ int skb_shared_counts(skb_ctx* c, const uint64_t* q_hashes, const uint64_t* q_of
     if (qlen) cudaMemcpyAsync(dq.p, q_hashes, qlen * 8, cudaMemcpyHostToDevice, c->stream);
     cudaMemcpyAsync(dqo.p, q_off, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream);
     { ProfScope ps(c, SKB_K_SHARED, 1);
-      skb_launch_shared(c->ref.as<uint64_t>(), c->row_off.as<uint64_t>(), c->n_rows, dq.as<uint64_t>(), dqo.as<uint64_t>(), Q,
-                        dout.as<unsigned long long>(), c->stream); }
+      skb_launch_shared(ref_view(c), dq.as<uint64_t>(), dqo.as<uint64_t>(), Q, dout.as<unsigned long long>(), c->stream); }
     rc = check_launch(c, "shared");
     if (!rc) {
       cudaMemcpyAsync(out, dout.p, pairs * 8, cudaMemcpyDeviceToHost, c->stream);

@@ -48,11 +48,23 @@ void skb_launch_compact_queries(const uint64_t* cand, const uint64_t* cand_base,
                                 cudaStream_t st);
 
 // ---- predict ---------------------------------------------------------------------------------------------
-#define SKB_BLOOM_WORDS 32768u  // 128 KB shared-memory filter (2^20 bits)
+#define SKB_BLOOM_WORDS 16384u  // 64 KB shared-memory filter (2^19 bits)
+
+// One slot of the per-pass query table (open addressing on `key`). meta bits 0-12 = cnt, the number of reads of the
+// pass that hold `key`; cnt <= 4: their pass-local read ids (12 bits each) sit inline at bits 13 + 12*i, so a lookup
+// is one 16-byte load; cnt > 4: bits 13-44 are the start of the slot's read list in `reads`.
+struct __align__(16) SkbSlot {
+  unsigned long long key;
+  unsigned long long meta;
+};
+#define SKB_SLOT_CNT(m) ((uint32_t)((m) & 0x1FFFull))
+#define SKB_SLOT_INLINE 4u
+#define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> (13 + 12 * (i))) & 0xFFFull))
+#define SKB_SLOT_START(m) ((uint32_t)(((m) >> 13) & 0xFFFFFFFFull))
+#define SKB_MAX_PASS_READS 2048u
+
 struct SkbTable {
-  uint64_t* keys;     // [cap + 1] open addressing, SKB_EMPTY_KEY = free; slot `cap` is reserved for key == EMPTY
-  uint32_t* cnt;      // [cap + 1]
-  uint32_t* start;    // [cap + 1]
+  SkbSlot* slots;     // [cap + 1]; slot `cap` is reserved for the key that equals SKB_EMPTY_KEY
   uint32_t* fill;     // [cap + 1]
   uint32_t* reads;    // [max_keys] read ids grouped by slot
   uint32_t* slot_of;  // [max_keys]
@@ -64,35 +76,57 @@ struct SkbTable {
 void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_t* qread, uint32_t n_keys,
                             uint32_t read_base, cudaStream_t st);
 
-struct SkbStreamArgs {
-  const uint64_t* ref;   // flat reference hashes, 16-byte aligned, padded to a multiple of 2
-  uint64_t ref_len;      // number of hashes
-  const uint64_t* row_off;  // [n_rows + 1]
+// Reference shard as laid out in HBM: row r = ref[row_start[r] .. row_start[r] + row_len[r]), row_start even
+// (16-byte aligned rows, the granularity of the bulk copies).
+struct SkbRefView {
+  const uint64_t* ref;
+  const uint64_t* row_start;  // [n_rows]
+  const uint32_t* row_len;    // [n_rows]
   uint32_t n_rows;
-  uint32_t uniform_len;  // != 0: every row has exactly this many hashes
-  SkbTable table;
-  uint16_t* counts;      // [n_rows][row_stride] per-pass (row, read) shared-hash counts
-  uint32_t row_stride;   // in u16 elements, multiple of 8
-  int num_ctas;
+  uint32_t uniform_len;    // != 0: every row holds exactly this many hashes ...
+  uint32_t uniform_pitch;  // ... and row r starts at r * uniform_pitch (no per-row loads needed)
 };
-void skb_launch_stream(const SkbStreamArgs& a, cudaStream_t st);
-size_t skb_stream_smem_bytes();
+
+struct SkbFusedArgs {
+  SkbRefView rv;
+  const uint32_t* cta_row;  // [num_ctas + 1] contiguous row range of every CTA (balanced by tiles)
+  int num_ctas;
+  SkbTable table;
+  uint32_t n_reads;     // reads in this pass
+  uint32_t cnt_stride;  // u16 counters per row buffer (multiple of 256, >= n_reads)
+  int skip_stream;      // the pass has no query hashes: rows are ranked without being streamed
+  int debug;            // experiments only (SKB_DEBUG env): 1 = no filter probe, 2 = probe but drop passers
+  uint32_t row_base;    // global index of local row 0
+  const unsigned long long* sums_in;  // [n_rows]
+  unsigned long long* sums_out;       // [n_rows]
+  const unsigned long long* lb_sum;   // [n_reads] lower bound of every read's top-th key
+  const uint32_t* lb_idx;             // [n_reads]
+  SkbCand* cand;                      // [cand_cap]
+  uint32_t cand_cap;
+  uint32_t* cand_total;               // [1] keeps counting past cap (= overflow)
+  uint32_t* cand_cnt;                 // [n_reads]
+};
+void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
+size_t skb_fused_smem_bytes(uint32_t cnt_stride);
+uint32_t skb_fused_tile();
+
+// per-read counts of the tracked rows only (they define the bounds): ctr[t][read], u16, row stride `stride`
+void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, uint32_t n_tracked,
+                               const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st);
 
 struct SkbRankArgs {
-  const uint16_t* counts;
+  const uint16_t* tracked_counts;  // [n_tracked][row_stride]
   uint32_t row_stride;
-  uint32_t n_rows;
   uint32_t n_reads;  // reads in this pass
   uint32_t row_base; // global index of local row 0
   const unsigned long long* sums_in;   // [n_rows]
-  unsigned long long* sums_out;        // [n_rows]
   const uint32_t* tracked;             // [n_tracked] local rows
   uint32_t n_tracked;
   unsigned long long* lb_sum;          // [n_reads]
   uint32_t* lb_idx;                    // [n_reads] (global index)
   SkbCand* cand;                       // [cand_cap]
   uint32_t cand_cap;
-  uint32_t* cand_total;                // [1] (keeps counting past cap: overflow)
+  uint32_t* cand_total;                // [1]
   uint32_t* cand_cnt;                  // [n_reads]
   uint32_t* cand_off;                  // [n_reads + 1]
   uint32_t* cand_fill;                 // [n_reads]
@@ -103,7 +137,6 @@ struct SkbRankArgs {
   uint32_t* tracked_next;              // [top] local rows of the last read's top
 };
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st);
-void skb_launch_rank_scan(const SkbRankArgs& a, cudaStream_t st);
 void skb_launch_rank_group(const SkbRankArgs& a, cudaStream_t st);   // offsets + scatter by read
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st);  // per-read top-N
 
@@ -115,10 +148,13 @@ void skb_launch_merge_topn(const uint32_t* idx_parts, const unsigned long long* 
                            uint64_t n_reads, uint32_t top, uint32_t* out_idx, unsigned long long* out_sum,
                            cudaStream_t st);
 
+// copy ragged rows into the aligned device layout
+void skb_launch_relayout(const uint64_t* src, const uint64_t* src_off, uint64_t* dst, const uint64_t* dst_start,
+                         uint32_t n_rows, cudaStream_t st);
+
 // reference validation: rows strictly increasing; writes flag != 0 on violation, and the max hash
-void skb_launch_ref_check(const uint64_t* ref, const uint64_t* row_off, uint32_t n_rows, uint32_t* bad,
-                          unsigned long long* hmax, cudaStream_t st);
+void skb_launch_ref_check(const SkbRefView& rv, uint32_t* bad, unsigned long long* hmax, cudaStream_t st);
 
 // dense shared counts: out[i*Q + j] = |ref_i ∩ q_j| (warp per pair, binary-search merge)
-void skb_launch_shared(const uint64_t* ref, const uint64_t* row_off, uint32_t n_rows, const uint64_t* q,
-                       const uint64_t* q_off, uint32_t Q, unsigned long long* out, cudaStream_t st);
+void skb_launch_shared(const SkbRefView& rv, const uint64_t* q, const uint64_t* q_off, uint32_t Q,
+                       unsigned long long* out, cudaStream_t st);

@@ -1,9 +1,19 @@
-// kernels_predict.cu — streaming predict on sm_100a:
-//   table_*      : per-pass hash set of the batch's query hashes (global table + 128 KB shared-memory filter)
-//   stream_kernel: the HBM-bound kernel. Streams the flat reference hash matrix once per pass through a
-//                  cp.async.bulk (TMA) + mbarrier shared-memory ring, probes every streamed hash, and adds the
-//                  hits into the per-pass (row, read) count matrix.
-//   rank_*       : cumulative sums over the reads of the pass + exact per-read top-N by (sum desc, index asc).
+// kernels_predict.cu — streaming predict on sm_100a.
+//
+//   table_*       : per-pass hash set of the batch's query hashes: a global open-addressing table of 16-byte
+//                   slots (L2 resident) plus a 128 KB bit filter that every CTA keeps in shared memory.
+//   fused_kernel  : the HBM-bound kernel. Persistent, one CTA per SM, each owning a contiguous range of reference
+//                   rows. 16 consumer warps each stream their share of the rows (256-hash sub-tiles, round robin)
+//                   through a PRIVATE 4-stage cp.async.bulk (TMA) + mbarrier staging ring that the warp refills
+//                   itself, probe every streamed hash against the filter, verify the few passers against the table
+//                   with loads issued a sub-tile ahead of their use, and count hits per read in shared memory; two
+//                   rank warps turn a finished row's counts into cumulative sums over the reads of the pass, test
+//                   them against the per-read bounds and emit top-N candidates. Warps only meet at row granularity
+//                   (4 rows in flight), so one warp's passers never stall the others' streams.
+//                   HBM traffic per pass = the reference matrix, once.
+//   rank_*        : bounds from the tracked rows, candidate grouping, exact per-read top-N by
+//                   (sum desc, index asc).
+//
 // Replaces `_common_hashes` x N + `sum[i] += shared` + stable sort + `[..top]`
 // (reference src/sketchy.rs:337-348, 391, 419-459). Rows are strictly increasing (checked at upload) and each
 // read's query list is distinct, so the two-pointer merge count equals the set-intersection size computed here.
@@ -15,11 +25,29 @@ __device__ __forceinline__ uint32_t table_home(uint64_t h, uint32_t log2cap) {
   return (uint32_t)((h * 0x9E3779B97F4A7C15ull) >> (64 - log2cap));
 }
 __device__ __forceinline__ uint32_t bloom_word(uint32_t lo) { return (lo >> 5) & (SKB_BLOOM_WORDS - 1u); }
-__device__ __forceinline__ uint32_t bloom_mask(uint32_t lo) { return (1u << (lo & 31u)) | (1u << ((lo >> 20) & 31u)); }
+__device__ __forceinline__ uint32_t bloom_mask(uint32_t lo) { return (1u << (lo & 31u)) | (1u << ((lo >> 19) & 31u)); }
+
+__device__ __forceinline__ SkbSlot load_slot(const SkbSlot* p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  SkbSlot s;
+  s.key = ((unsigned long long)v.y << 32) | v.x;
+  s.meta = ((unsigned long long)v.w << 32) | v.z;
+  return s;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // query table
 // ---------------------------------------------------------------------------------------------------------
+__global__ void table_clear_kernel(SkbTable t) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= t.cap) {
+    reinterpret_cast<uint4*>(t.slots)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    t.fill[i] = 0;
+  }
+  if (i < SKB_BLOOM_WORDS) t.bloom[i] = 0;
+  if (i == 0) *t.cursor = 0;
+}
+
 __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh, uint32_t n_keys) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
@@ -30,12 +58,12 @@ __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh,
   } else {
     slot = table_home(h, t.log2cap);
     for (;;) {
-      const unsigned long long prev = atomicCAS((unsigned long long*)&t.keys[slot], SKB_EMPTY_KEY, h);
+      const unsigned long long prev = atomicCAS(&t.slots[slot].key, SKB_EMPTY_KEY, (unsigned long long)h);
       if (prev == SKB_EMPTY_KEY || prev == h) break;
       slot = (slot + 1) & (t.cap - 1);
     }
   }
-  atomicAdd(&t.cnt[slot], 1u);
+  atomicAdd(&t.slots[slot].meta, 1ull);  // cnt lives in the low 13 bits; a read holds a hash at most once
   t.slot_of[i] = slot;
   const uint32_t lo = (uint32_t)h;
   atomicOr(&t.bloom[bloom_word(lo)], bloom_mask(lo));
@@ -44,8 +72,9 @@ __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh,
 __global__ void table_alloc_kernel(SkbTable t) {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > t.cap) return;
-  const uint32_t c = t.cnt[s];
-  if (c) t.start[s] = atomicAdd(t.cursor, c);
+  const unsigned long long m = t.slots[s].meta;
+  const uint32_t c = SKB_SLOT_CNT(m);
+  if (c > SKB_SLOT_INLINE) t.slots[s].meta = m | ((unsigned long long)atomicAdd(t.cursor, c) << 13);
 }
 
 __global__ void table_fill_kernel(SkbTable t, const uint32_t* __restrict__ qread, uint32_t n_keys,
@@ -53,22 +82,47 @@ __global__ void table_fill_kernel(SkbTable t, const uint32_t* __restrict__ qread
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
   const uint32_t s = t.slot_of[i];
-  const uint32_t p = t.start[s] + atomicAdd(&t.fill[s], 1u);
-  t.reads[p] = qread[i] - read_base;
+  const uint32_t rd = qread[i] - read_base;
+  // cnt (and, for long lists, the start) are final here; only the inline id bits are still being OR-ed in
+  const unsigned long long m = *reinterpret_cast<volatile unsigned long long*>(&t.slots[s].meta);
+  const uint32_t pos = atomicAdd(&t.fill[s], 1u);
+  if (SKB_SLOT_CNT(m) <= SKB_SLOT_INLINE) {
+    atomicOr(&t.slots[s].meta, (unsigned long long)rd << (13 + 12 * pos));
+  } else {
+    t.reads[SKB_SLOT_START(m) + pos] = rd;
+  }
+}
+
+// exact lookup; returns true and the slot contents when h is a query hash of this pass
+__device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbSlot& out) {
+  if (h == SKB_EMPTY_KEY) {
+    out = load_slot(&t.slots[t.cap]);
+    return SKB_SLOT_CNT(out.meta) != 0;
+  }
+  uint32_t slot = table_home(h, t.log2cap);
+  for (;;) {
+    out = load_slot(&t.slots[slot]);
+    if (out.key == h) return true;
+    if (out.key == SKB_EMPTY_KEY) return false;
+    slot = (slot + 1) & (t.cap - 1);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// stream kernel: mbarrier / bulk-copy primitives
+// mbarrier / bulk-copy primitives
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ST_TILE = 2048;  // hashes per stage (16 KB)
-constexpr int ST_STAGES = 4;
-constexpr int ST_CONSUMER_WARPS = 16;
-constexpr int ST_THREADS = (ST_CONSUMER_WARPS + 1) * 32;  // warp 0 is the bulk-copy producer
-constexpr int ST_QCAP = 64;                                // per-warp queue of filter passers
-constexpr size_t ST_SMEM_BLOOM = (size_t)SKB_BLOOM_WORDS * 4;
-constexpr size_t ST_SMEM_RING = (size_t)ST_STAGES * ST_TILE * 8;
-constexpr size_t ST_SMEM_QUEUE = (size_t)ST_CONSUMER_WARPS * ST_QCAP * 16;
-constexpr size_t ST_SMEM_TOTAL = ST_SMEM_BLOOM + ST_SMEM_RING + ST_SMEM_QUEUE;
+constexpr int FS_SUB = 512;            // hashes per sub-tile (4 KB): two chunks of 8 per lane
+constexpr int FS_STAGES = 2;           // staging buffers per consumer warp
+constexpr int FS_CONSUMER_WARPS = 16;
+constexpr int FS_RANK_WARPS = 2;       // rank warp p owns the rows of parity p
+constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
+constexpr int FS_ROWBUF = 4;           // rows in flight per CTA: counter buffers / barriers are indexed by row & 3
+constexpr int FS_QCAP = 64;            // per-warp FIFO of filter passers awaiting their table lookup (power of 2)
+constexpr int FS_NHASH = 8;            // hashes per lane per chunk (one chunk = 256 hashes)
+constexpr int FS_CHUNKS = FS_SUB / (32 * FS_NHASH);
+constexpr size_t FS_SMEM_BLOOM = (size_t)SKB_BLOOM_WORDS * 4;
+constexpr size_t FS_SMEM_RING = (size_t)FS_CONSUMER_WARPS * FS_STAGES * FS_SUB * 8;
+constexpr size_t FS_SMEM_QUEUE = (size_t)FS_CONSUMER_WARPS * FS_QCAP * 16;  // {hash, tag, pad} per entry
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -81,21 +135,38 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// row-granularity waits (rank warps, buffer hand-back): back off instead of burning issue slots
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) __nanosleep(128);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier; streamed data is marked
-// evict-first so the query table and the count matrix keep their place in L2.
+// evict-first so the query table keeps its place in L2.
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
                                           uint64_t policy) {
   asm volatile(
@@ -105,151 +176,478 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
       : "memory");
 }
 
-struct StreamShared {
-  uint32_t* bloom;
-  uint64_t* ring;
-  uint64_t* qh;    // [warps][ST_QCAP]
-  uint64_t* qpos;  // [warps][ST_QCAP]
+// two u16 counters per 32-bit word; a per-(row, read) count never exceeds 65535 (checked on the host)
+__device__ __forceinline__ void count_hit(uint32_t* cbuf, uint32_t rd) {
+  atomicAdd(cbuf + (rd >> 1), 1u << (16 * (rd & 1u)));
+}
+
+// add the slot's reads to the row's counters; returns the number of increments
+__device__ __forceinline__ uint32_t apply_hit(const SkbTable& t, const SkbSlot& s, uint32_t* cbuf) {
+  const uint32_t c = SKB_SLOT_CNT(s.meta);
+  if (c <= SKB_SLOT_INLINE) {
+    count_hit(cbuf, SKB_SLOT_ID(s.meta, 0));
+    if (c > 1) {
+      for (uint32_t j = 1; j < c; ++j) count_hit(cbuf, (uint32_t)((s.meta >> (13 + 12 * j)) & 0xFFFull));
+    }
+  } else {
+    const uint32_t st = SKB_SLOT_START(s.meta);
+    for (uint32_t j = 0; j < c; ++j) count_hit(cbuf, t.reads[st + j]);
+  }
+  return c;
+}
+
+// One lookup batch per warp is kept in flight: a lane's slot load is issued when its entry is taken from the
+// queue and the result is consumed only after the warp has probed another tile, so the L2 latency overlaps work.
+// Every lane loads (idle lanes read slot 0) so the loaded registers are written unconditionally. A lookup that
+// lands on another key's slot is put back in the queue with the next slot index instead of being chased in place.
+struct Pending {
+  uint64_t h;
+  uint32_t idx;
+  uint32_t par;  // row buffer (row & 3) the entry belongs to
+  uint4 raw;
+  bool valid;
+};
+#define SKB_Q_FRESH 0x3FFFFFFFu  // queue entry whose home slot is still to be computed (bits 30-31 = row buffer)
+
+// this warp's sub-tiles: global sub-tile numbers w, w+16, w+32, ... over the CTA's rows
+struct SubIter {
+  uint32_t row, t;    // current row, sub-tile within it
+  uint32_t len;       // hashes in the current row
+  const uint64_t* p;  // first hash of the current row
+  __device__ __forceinline__ void load_row(const SkbFusedArgs& a, uint32_t r1) {
+    if (row >= r1) { len = 0; p = a.rv.ref; return; }
+    if (a.rv.uniform_len) {
+      len = a.rv.uniform_len;
+      p = a.rv.ref + (size_t)row * a.rv.uniform_pitch;
+    } else {
+      len = a.rv.row_len[row];
+      p = a.rv.ref + a.rv.row_start[row];
+    }
+  }
+  __device__ __forceinline__ void settle(const SkbFusedArgs& a, uint32_t r1) {
+    while (row < r1) {
+      const uint32_t n = (len + FS_SUB - 1) / FS_SUB;
+      if (t < n) break;
+      t -= n;
+      ++row;
+      load_row(a, r1);
+    }
+  }
+  __device__ __forceinline__ void next(const SkbFusedArgs& a, uint32_t r1) {
+    t += FS_CONSUMER_WARPS;
+    if (a.rv.uniform_len) {  // every row has the same number of sub-tiles (>= 1): no loads, no loop of loads
+      const uint32_t n = (a.rv.uniform_len + FS_SUB - 1) / FS_SUB;
+      while (t >= n && row < r1) { t -= n; ++row; p += a.rv.uniform_pitch; }
+      return;
+    }
+    settle(a, r1);
+  }
 };
 
-__device__ __forceinline__ uint32_t row_of(const SkbStreamArgs& a, uint64_t pos) {
-  if (a.uniform_len) return (uint32_t)(pos / a.uniform_len);
-  uint32_t lo = 0, hi = a.n_rows;  // largest r with row_off[r] <= pos
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (a.row_off[mid] <= pos) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-// exact verification of the filter passers queued by one warp, and the count updates for true hits
-__device__ __forceinline__ void drain_queue(const SkbStreamArgs& a, const uint64_t* qh, const uint64_t* qpos,
-                                            uint32_t qn) {
-  __syncwarp();
-  const SkbTable& t = a.table;
-  for (uint32_t i = skb_lane(); i < qn; i += 32) {
-    const uint64_t h = qh[i];
-    uint32_t slot;
-    bool found = false;
-    if (h == SKB_EMPTY_KEY) {
-      slot = t.cap;
-      found = t.cnt[slot] != 0;
-    } else {
-      slot = table_home(h, t.log2cap);
-      for (;;) {
-        const uint64_t key = t.keys[slot];
-        if (key == h) { found = true; break; }
-        if (key == SKB_EMPTY_KEY) break;
-        slot = (slot + 1) & (t.cap - 1);
-      }
-    }
-    if (found) {
-      const uint32_t row = row_of(a, qpos[i]);
-      const uint32_t st = t.start[slot], c = t.cnt[slot];
-      uint32_t* crow = reinterpret_cast<uint32_t*>(a.counts + (size_t)row * a.row_stride);
-      for (uint32_t j = 0; j < c; ++j) {
-        const uint32_t rd = t.reads[st + j];
-        atomicAdd(crow + (rd >> 1), 1u << (16 * (rd & 1u)));  // two u16 counters per word; no carry: count <= 65535
-      }
-    }
-  }
-  __syncwarp();
-}
-
-__global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(const SkbStreamArgs a) {
+__global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[ST_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[ST_STAGES];
+  __shared__ __align__(8) uint64_t full_bar[FS_CONSUMER_WARPS][FS_STAGES];
+  __shared__ __align__(8) uint64_t row_done[FS_ROWBUF];
+  __shared__ __align__(8) uint64_t row_free[FS_ROWBUF];
+  __shared__ uint32_t row_hits[FS_ROWBUF];
 
   uint32_t* bloom = reinterpret_cast<uint32_t*>(smem_raw);
-  uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + ST_SMEM_BLOOM);
-  uint64_t* queue = reinterpret_cast<uint64_t*>(smem_raw + ST_SMEM_BLOOM + ST_SMEM_RING);
+  uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM);
+  uint64_t* queue = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
+  uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE);
+  const uint32_t cwords = a.cnt_stride >> 1;  // 32-bit words per row buffer
 
-  // tiles of this CTA: contiguous range
-  const uint64_t n_tiles = (a.ref_len + ST_TILE - 1) / ST_TILE;
-  const uint64_t t_begin = n_tiles * blockIdx.x / gridDim.x;
-  const uint64_t t_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+  const uint32_t r0 = a.cta_row[blockIdx.x], r1 = a.cta_row[blockIdx.x + 1];
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ST_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], ST_CONSUMER_WARPS);
+    for (int w = 0; w < FS_CONSUMER_WARPS; ++w)
+      for (int s = 0; s < FS_STAGES; ++s) mbar_init(&full_bar[w][s], 1);
+    for (int p = 0; p < FS_ROWBUF; ++p) {
+      mbar_init(&row_done[p], FS_CONSUMER_WARPS);
+      mbar_init(&row_free[p], 1);
+      row_hits[p] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  {  // stage the filter
+  if (!a.skip_stream) {  // stage the filter
     const uint4* src = reinterpret_cast<const uint4*>(a.table.bloom);
     uint4* dst = reinterpret_cast<uint4*>(bloom);
     for (uint32_t i = threadIdx.x; i < SKB_BLOOM_WORDS / 4; i += blockDim.x) dst[i] = src[i];
   }
+  for (uint32_t i = threadIdx.x; i < FS_ROWBUF * cwords; i += blockDim.x) cnt32[i] = 0;
   __syncthreads();
 
   const uint32_t warp = threadIdx.x >> 5, lane = skb_lane();
-  if (warp == 0) {
-    // ===== producer: one elected lane issues the bulk copies =====
-    if (lane == 0) {
-      uint64_t policy;
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      uint32_t it = 0;
-      for (uint64_t tile = t_begin; tile < t_end; ++tile, ++it) {
-        const uint32_t stage = it % ST_STAGES, phase = (it / ST_STAGES) & 1u;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        const uint64_t first = tile * ST_TILE;
-        uint64_t n = a.ref_len - first;
-        if (n > ST_TILE) n = ST_TILE;
-        const uint32_t bytes = (uint32_t)(((n + 1) & ~1ull) * 8);  // multiple of 16; the array is padded to even
-        mbar_arrive_expect_tx(&full_bar[stage], bytes);
-        bulk_load(ring + (size_t)stage * ST_TILE, a.ref + first, bytes, &full_bar[stage], policy);
+
+  if (warp < FS_CONSUMER_WARPS) {
+    // ===== consumers: private TMA staging ring, filter probe, pipelined table verification, shared counters =====
+    // Filter passers are compacted into a per-warp FIFO; lookups run as dense 32-wide batches: every lane issues
+    // one table-slot load, and the results are consumed after the next chunk has been probed, so nothing in this
+    // loop waits on a dependent load. A slot owned by another key re-queues the entry with the next slot index.
+    const uint32_t cw = warp;
+    uint64_t* my_ring = ring + (size_t)cw * FS_STAGES * FS_SUB;
+    uint4* q = reinterpret_cast<uint4*>(queue) + (size_t)cw * FS_QCAP;  // FIFO records {hash.lo, hash.hi, tag, 0}
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const SkbTable& t = a.table;
+    uint32_t qhead = 0, qn = 0;  // FIFO state (warp-uniform)
+    uint32_t outst = 0;          // unfinished entries (queued or in flight) per row buffer, 8 bits each (warp-uniform)
+    Pending pend;
+    pend.valid = false; pend.h = 0; pend.idx = 0; pend.par = 0; pend.raw = make_uint4(0, 0, 0, 0);
+    bool have_pend = false;  // warp-uniform: a lookup batch is in flight
+    uint32_t closing = 0;    // warp-uniform; bit p: the row in buffer p is fully probed, closes when outst[p] == 0
+
+    auto count_now = [&](uint64_t h, uint32_t par) {  // synchronous lookup: only when the FIFO cannot take a burst
+      SkbSlot s;
+      if (table_lookup(t, h, s)) atomicAdd(&row_hits[par], apply_hit(t, s, cnt32 + par * cwords));
+    };
+    auto try_close = [&]() {
+      const uint32_t nz = ((outst & 0xFFu) ? 1u : 0u) | ((outst & 0xFF00u) ? 2u : 0u) | ((outst & 0xFF0000u) ? 4u : 0u) |
+                          ((outst & 0xFF000000u) ? 8u : 0u);
+      const uint32_t ready = closing & ~nz;
+      if (ready) {
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (uint32_t p = 0; p < (uint32_t)FS_ROWBUF; ++p)
+            if ((ready >> p) & 1u) mbar_arrive(&row_done[p]);  // every count of that row is in shared memory
+        }
+        closing &= ~ready;
       }
+    };
+    auto finish_batch = [&]() {
+      if (have_pend) {
+        SkbSlot s;
+        s.key = ((unsigned long long)pend.raw.y << 32) | pend.raw.x;
+        s.meta = ((unsigned long long)pend.raw.w << 32) | pend.raw.z;
+        uint32_t hits = 0;
+        bool again = false;
+        if (pend.valid) {
+          uint32_t* cb = cnt32 + pend.par * cwords;
+          if (pend.h == SKB_EMPTY_KEY) {
+            if (SKB_SLOT_CNT(s.meta) != 0) hits = apply_hit(t, s, cb);
+          } else if (s.key == pend.h) {
+            hits = apply_hit(t, s, cb);
+          } else if (s.key != SKB_EMPTY_KEY) {
+            again = true;
+          }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, again);
+        if (bal) {  // slots owned by other keys: back into the FIFO with the next slot index
+          const uint32_t n = __popc(bal);
+          if (qn + n <= (uint32_t)FS_QCAP) {
+            if (again) {
+              const uint32_t at = (qhead + qn + __popc(bal & lt_mask)) & (FS_QCAP - 1);
+              q[at] = make_uint4((uint32_t)pend.h, (uint32_t)(pend.h >> 32),
+                                 ((pend.idx + 1) & (t.cap - 1)) | (pend.par << 30), 0u);
+            }
+            qn += n;
+          } else {  // no room (practically never): chase the chain here
+            if (again) {
+              uint32_t slot = pend.idx;
+              for (;;) {
+                slot = (slot + 1) & (t.cap - 1);
+                s = load_slot(&t.slots[slot]);
+                if (s.key == pend.h) { hits = apply_hit(t, s, cnt32 + pend.par * cwords); break; }
+                if (s.key == SKB_EMPTY_KEY) break;
+              }
+              again = false;
+            }
+          }
+          __syncwarp();
+        }
+        // bookkeeping per row buffer present in the batch (usually one or two)
+        const bool fin = pend.valid && !again;
+        uint32_t bufs = __reduce_or_sync(0xffffffffu, pend.valid ? (1u << pend.par) : 0u);
+        while (bufs) {
+          const uint32_t p = __ffs(bufs) - 1;
+          bufs &= bufs - 1;
+          const bool mine = pend.valid && pend.par == p;
+          outst -= __popc(__ballot_sync(0xffffffffu, fin && mine)) << (8 * p);
+          const uint32_t hsum = __reduce_add_sync(0xffffffffu, mine ? hits : 0u);
+          if (lane == 0 && hsum) atomicAdd(&row_hits[p], hsum);
+        }
+        pend.valid = false;
+        have_pend = false;
+      }
+      if (closing) try_close();
+    };
+    auto start_batch = [&]() {  // oldest (up to) 32 entries of the FIFO, one per lane
+      const uint32_t n = qn < 32u ? qn : 32u;
+      pend.valid = lane < n;
+      const uint4 e = q[(qhead + (pend.valid ? lane : 0u)) & (FS_QCAP - 1)];
+      pend.h = ((uint64_t)e.y << 32) | e.x;
+      const uint32_t tag = e.z;
+      pend.par = tag >> 30;
+      const uint32_t qidx = tag & 0x3FFFFFFFu;
+      pend.idx = !pend.valid ? 0u
+                             : (qidx != SKB_Q_FRESH ? qidx
+                                                    : (pend.h == SKB_EMPTY_KEY ? t.cap : table_home(pend.h, t.log2cap)));
+      pend.raw = __ldg(reinterpret_cast<const uint4*>(&t.slots[pend.idx]));  // every lane loads: no predicated merge
+      qhead = (qhead + n) & (FS_QCAP - 1);
+      qn -= n;
+      have_pend = true;
+      __syncwarp();  // FIFO reads done before anyone appends again
+    };
+
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    // bulk copy of the sub-tile `pre` points at into one of this warp's staging buffers (lane 0 only)
+    auto issue_copy = [&](const SubIter& si, uint32_t stage) {
+      const uint32_t first = si.t * FS_SUB;
+      uint32_t n = si.len - first;
+      if (n > (uint32_t)FS_SUB) n = FS_SUB;
+      const uint32_t bytes = ((n + 1u) & ~1u) * 8u;  // multiple of 16; rows start on even offsets
+      mbar_arrive_expect_tx(&full_bar[cw][stage], bytes);
+      bulk_load(my_ring + (size_t)stage * FS_SUB, si.p + first, bytes, &full_bar[cw][stage], policy);
+    };
+
+    SubIter it, pre;
+    it.row = a.skip_stream ? r1 : r0;
+    it.t = cw;
+    it.load_row(a, r1);
+    it.settle(a, r1);
+    pre = it;
+    for (uint32_t s = 0; s < (uint32_t)FS_STAGES; ++s) {  // prime the private ring
+      if (pre.row < r1) {
+        if (lane == 0) issue_copy(pre, s);
+        pre.next(a, r1);
+      }
+    }
+    uint32_t k = 0;  // sub-tiles consumed by this warp: stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1
+
+    for (uint32_t row = r0; row < r1; ++row) {
+      const uint32_t lr = row - r0, par = lr & (FS_ROWBUF - 1);
+      if (lr >= (uint32_t)FS_ROWBUF) {
+        while ((closing >> par) & 1u) {  // row lr-4 still open for this warp: finish its lookups now
+          finish_batch();
+          if (qn) start_batch();
+        }
+        mbar_wait_sleepy(&row_free[par], ((lr >> 2) - 1u) & 1u);  // rank warp has flushed row lr-4
+      }
+      const uint32_t fresh_tag = SKB_Q_FRESH | (par << 30);
+      const uint32_t urgent = 1u << ((lr + 2) & (FS_ROWBUF - 1));  // the buffer that is needed again in two rows
+      while (it.row == row) {  // this warp's sub-tiles of the row
+        const uint32_t stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1u;
+        mbar_wait(&full_bar[cw][stage], phase);
+        const uint4* tp = reinterpret_cast<const uint4*>(my_ring + (size_t)stage * FS_SUB);
+        const uint32_t n_sub = it.len - it.t * FS_SUB;  // >= FS_SUB for every sub-tile but a row's last
+#pragma unroll 1
+        for (uint32_t ch = 0; ch < (uint32_t)FS_CHUNKS; ++ch) {
+          uint4 v[FS_NHASH / 2];
+#pragma unroll
+          for (int r = 0; r < FS_NHASH / 2; ++r) v[r] = tp[ch * (FS_NHASH / 2) * 32 + lane + 32 * r];
+          if (ch + 1 == (uint32_t)FS_CHUNKS) {
+            // the staging buffer is fully read: refill it with this warp's next sub-tile
+            __syncwarp();
+            if (pre.row < r1) {
+              if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_copy(pre, stage);
+              }
+              pre.next(a, r1);
+            }
+            ++k;
+          }
+          const uint32_t base = ch * FS_NHASH * 32;  // first hash index of the chunk within the sub-tile
+          uint32_t pm = 0;                           // bit j: this lane's j-th hash of the chunk passed the filter
+          if ((a.debug & 3) != 1) {
+            if (n_sub >= base + FS_NHASH * 32) {
+#pragma unroll
+              for (int j = 0; j < FS_NHASH; ++j) {
+                const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
+                const uint32_t m = bloom_mask(lo);
+                pm |= ((bloom[bloom_word(lo)] & m) == m) ? (1u << j) : 0u;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < FS_NHASH; ++j) {
+                const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
+                const uint32_t idx = base + 2u * (lane + 32 * (j >> 1)) + (j & 1);
+                const uint32_t m = bloom_mask(lo);
+                pm |= (((bloom[bloom_word(lo)] & m) == m) && idx < n_sub) ? (1u << j) : 0u;
+              }
+            }
+          }
+          if ((a.debug & 3) == 2) pm = 0;
+          if (__any_sync(0xffffffffu, pm != 0u)) {  // compact this chunk's passers into the warp FIFO
+            const uint32_t c = __popc(pm);
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+              if ((int)lane >= o) incl += y;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (qn + total > (uint32_t)FS_QCAP && total <= (uint32_t)FS_QCAP) {
+              while (qn + total > (uint32_t)FS_QCAP) {  // make room (rare): run batches back to back
+                finish_batch();
+                if (qn) start_batch();
+              }
+            }
+            if (qn + total <= (uint32_t)FS_QCAP) {
+              uint32_t at = qhead + qn + incl - c;
+#pragma unroll
+              for (int j = 0; j < FS_NHASH; ++j) {
+                if (pm & (1u << j)) {
+                  q[at & (FS_QCAP - 1)] = (j & 1) ? make_uint4(v[j >> 1].z, v[j >> 1].w, fresh_tag, 0u)
+                                                  : make_uint4(v[j >> 1].x, v[j >> 1].y, fresh_tag, 0u);
+                  ++at;
+                }
+              }
+              qn += total;
+              outst += total << (8 * par);
+              __syncwarp();
+            } else {  // a burst larger than the FIFO: look the passers up in place
+#pragma unroll
+              for (int j = 0; j < FS_NHASH; ++j) {
+                if (pm & (1u << j)) {
+                  count_now((j & 1) ? (((uint64_t)v[j >> 1].w << 32) | v[j >> 1].z)
+                                    : (((uint64_t)v[j >> 1].y << 32) | v[j >> 1].x), par);
+                }
+              }
+            }
+          }
+          // lookups: a batch is consumed one chunk after it was issued; the next one starts as soon as 32 passers
+          // are queued, or earlier when a finished row is about to need its buffer back
+          if (have_pend) finish_batch();
+          if (!have_pend && (qn >= 32u || (qn && (closing & urgent)))) start_batch();
+        }
+        it.next(a, r1);
+      }
+      closing |= 1u << par;  // this warp's part of the row is probed; closes when its lookups are resolved
+      try_close();
+    }
+    while (closing) {
+      finish_batch();
+      if (qn) start_batch();
     }
     return;
   }
 
-  // ===== consumers =====
-  const uint32_t cw = warp - 1;
-  uint64_t* qh = queue + (size_t)cw * ST_QCAP * 2;
-  uint64_t* qpos = qh + ST_QCAP;
-  uint32_t qn = 0;
-  const uint32_t ct = threadIdx.x - 32;  // 0 .. 511
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  uint32_t it = 0;
-  for (uint64_t tile = t_begin; tile < t_end; ++tile, ++it) {
-    const uint32_t stage = it % ST_STAGES, phase = (it / ST_STAGES) & 1u;
-    mbar_wait(&full_bar[stage], phase);
-    const uint4* tp = reinterpret_cast<const uint4*>(ring + (size_t)stage * ST_TILE);
-    uint4 v[ST_TILE / (2 * ST_CONSUMER_WARPS * 32)];
-#pragma unroll
-    for (int r = 0; r < ST_TILE / (2 * ST_CONSUMER_WARPS * 32); ++r) v[r] = tp[ct + r * ST_CONSUMER_WARPS * 32];
+  // ===== rank warps: cumulative sums over the reads of the pass, candidate test, new running sum =====
+  const uint32_t rp = warp - FS_CONSUMER_WARPS;  // parity of the rows this warp owns
+  const uint32_t per = a.cnt_stride >> 5;        // counters per lane in the segment view (multiple of 8)
+  const uint32_t seg0 = lane * per;
+  const unsigned long long lb_min = a.lb_sum[0];  // bounds are non-decreasing along the reads
+  const unsigned long long lb_seg = seg0 < a.n_reads ? a.lb_sum[seg0] : ~0ull;
+  // candidate slots are reserved 16 at a time per lane (one global atomic per 16 candidates)
+  uint32_t slot_next = 0, slot_left = 0;
+  auto emit = [&](unsigned long long sum, uint32_t gi, uint32_t b) {
+    if (slot_left == 0) {
+      slot_next = atomicAdd(a.cand_total, 16u);
+      slot_left = 16;
+    }
+    if (slot_next < a.cand_cap) {
+      SkbCand cd;
+      cd.sum = sum; cd.idx = gi; cd.read = b;
+      a.cand[slot_next] = cd;
+    }
+    ++slot_next; --slot_left;
+    atomicAdd(&a.cand_cnt[b], 1u);
+  };
+  unsigned long long carry_next = (r0 + rp < r1) ? a.sums_in[r0 + rp] : 0ull;
+  for (uint32_t row = r0 + rp; row < r1; row += 2) {
+    const uint32_t lr = row - r0;
+    const unsigned long long carry = carry_next;
+    if (row + 2 < r1) carry_next = a.sums_in[row + 2];  // in flight while this row is processed
+    const uint32_t rb = lr & (FS_ROWBUF - 1);
+    uint32_t* cpar = cnt32 + rb * cwords;
+    mbar_wait_sleepy(&row_done[rb], (lr >> 2) & 1u);
+    const uint32_t row_total = row_hits[rb];
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);  // data is in registers: hand the slot back
-
-    const uint64_t first = tile * ST_TILE;
-    uint64_t n = a.ref_len - first;
-    if (n > ST_TILE) n = ST_TILE;
-#pragma unroll
-    for (int r = 0; r < ST_TILE / (2 * ST_CONSUMER_WARPS * 32); ++r) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const uint32_t lo = e ? v[r].z : v[r].x, hi = e ? v[r].w : v[r].y;
-        const uint32_t idx = 2u * (ct + r * ST_CONSUMER_WARPS * 32) + e;
-        const uint32_t w = bloom[bloom_word(lo)];
-        const uint32_t m = bloom_mask(lo);
-        const bool pass = ((w & m) == m) && (idx < n);
-        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-          const uint32_t np = __popc(bal);
-          if (qn + np > ST_QCAP) { drain_queue(a, qh, qpos, qn); qn = 0; }
-          if (pass) {
-            const uint32_t q = qn + __popc(bal & lt_mask);
-            qh[q] = ((uint64_t)hi << 32) | lo;
-            qpos[q] = first + idx;
-          }
-          qn += np;
+    if (lane == 0) {
+      row_hits[rb] = 0;
+      a.sums_out[row] = carry + row_total;
+    }
+    const uint32_t gi = a.row_base + row;
+    if (row_total) {
+      // sums and bounds never decrease along the reads: a row whose FINAL sum is under the FIRST bound, or a
+      // lane segment whose final sum is under the segment's first bound, cannot hold a candidate
+      if (carry + row_total >= lb_min && !(a.debug & 4)) {
+        const uint32_t* cseg = cpar + (seg0 >> 1);
+        uint32_t tot = 0;
+        for (uint32_t i = 0; i < (per >> 1); i += 4) {
+          const uint4 x = *reinterpret_cast<const uint4*>(cseg + i);
+          tot += (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) + (x.z & 0xFFFFu) + (x.z >> 16) +
+                 (x.w & 0xFFFFu) + (x.w >> 16);
         }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((int)lane >= o) incl += y;
+        }
+        if (seg0 < a.n_reads && carry + incl >= lb_seg) {
+          // Walk the segment. Between two hits the row's sum is constant while the bound only tightens, so once
+          // a read rejects the row every following read does too until the next hit: bounds are only loaded at
+          // the segment start, at hit positions, and while the row stays a candidate.
+          uint32_t run = incl - tot;
+          bool live = true;
+          for (uint32_t i = 0; i < (per >> 1); ++i) {
+            const uint32_t x = cseg[i];
+            if (x == 0u && !live) continue;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t c = half ? (x >> 16) : (x & 0xFFFFu);
+              const uint32_t b = seg0 + 2 * i + half;
+              if (c) { run += c; live = true; }
+              if (live && b < a.n_reads) {
+                const unsigned long long sv = carry + run;
+                live = false;
+                if (sv >= lb_seg) {
+                  const unsigned long long ls = a.lb_sum[b];
+                  if (sv > ls || (sv == ls && gi <= a.lb_idx[b])) {
+                    emit(sv, gi, b);
+                    live = true;
+                  }
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // clear the buffer for row lr+4 (lane-interleaved 16-byte stores: no bank conflicts)
+      uint4* z = reinterpret_cast<uint4*>(cpar);
+      for (uint32_t i = lane; i < (cwords >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    } else if (carry >= lb_min && !(a.debug & 128)) {
+      // no hit in this pass: the row's sum is `carry` for every read; it is a candidate for a prefix of the reads
+      // (first passes of a stream, when most sums tie at the bound)
+      for (uint32_t b0 = 0; b0 < a.n_reads; b0 += 32) {
+        const uint32_t b = b0 + lane;
+        bool ok = false;
+        if (b < a.n_reads) {
+          const unsigned long long ls = a.lb_sum[b];
+          ok = carry > ls || (carry == ls && gi <= a.lb_idx[b]);
+          if (ok) emit(carry, gi, b);
+        }
+        if (!__all_sync(0xffffffffu, ok)) break;
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&row_free[rb]);
   }
-  drain_queue(a, qh, qpos, qn);
+  // hand back the unused part of the last reservation as invalid records
+  for (; slot_left; --slot_left, ++slot_next) {
+    if (slot_next < a.cand_cap) {
+      SkbCand cd;
+      cd.sum = 0; cd.idx = 0xFFFFFFFFu; cd.read = 0xFFFFFFFFu;
+      a.cand[slot_next] = cd;
+    }
+  }
+}
+
+// per-read counts of the tracked rows (the rows that define the bounds); one CTA per tracked row
+__global__ void __launch_bounds__(256) tracked_counts_kernel(const SkbRefView rv, const uint32_t* __restrict__ tracked,
+                                                             const SkbTable t, uint16_t* ctr, uint32_t stride) {
+  const uint32_t row = tracked[blockIdx.x];
+  const uint64_t* src = rv.ref + rv.row_start[row];
+  const uint32_t len = rv.row_len[row];
+  uint32_t* cbuf = reinterpret_cast<uint32_t*>(ctr + (size_t)blockIdx.x * stride);
+  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+    SkbSlot s;
+    if (table_lookup(t, src[i], s)) apply_hit(t, s, cbuf);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -285,7 +683,7 @@ __global__ void __launch_bounds__(1024) rank_bounds_kernel(const SkbRankArgs a) 
   const uint32_t b1 = min(b0 + per, a.n_reads);
   for (uint32_t t = 0; t < a.n_tracked; ++t) {
     const uint32_t row = a.tracked[t];
-    const uint16_t* c = a.counts + (size_t)row * a.row_stride;
+    const uint16_t* c = a.tracked_counts + (size_t)t * a.row_stride;
     uint32_t local = 0;
     for (uint32_t b = b0; b < b1; ++b) local += c[b];
     uint32_t tot;
@@ -299,72 +697,6 @@ __global__ void __launch_bounds__(1024) rank_bounds_kernel(const SkbRankArgs a) 
         a.lb_idx[b] = gi;
       }
     }
-  }
-}
-
-// One warp per reference row: prefix sums of the row's per-read counts, candidate test against the bounds,
-// new running sum. 8 reads per lane per round (one 16-byte load).
-__global__ void __launch_bounds__(256) rank_scan_kernel(const SkbRankArgs a) {
-  const uint32_t lane = skb_lane();
-  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (uint32_t row = warp0; row < a.n_rows; row += nwarps) {
-    const unsigned long long carry = a.sums_in[row];
-    const uint32_t gi = a.row_base + row;
-    const uint16_t* c = a.counts + (size_t)row * a.row_stride;
-    uint32_t run = 0;
-    for (uint32_t r0 = 0; r0 < a.n_reads; r0 += 256) {
-      const uint32_t bl = r0 + lane * 8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (bl < a.row_stride) v = *reinterpret_cast<const uint4*>(c + bl);
-      uint32_t p[8];
-      p[0] = v.x & 0xFFFFu; p[1] = p[0] + (v.x >> 16);
-      p[2] = p[1] + (v.y & 0xFFFFu); p[3] = p[2] + (v.y >> 16);
-      p[4] = p[3] + (v.z & 0xFFFFu); p[5] = p[4] + (v.z >> 16);
-      p[6] = p[5] + (v.w & 0xFFFFu); p[7] = p[6] + (v.w >> 16);
-      uint32_t incl = p[7];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += y;
-      }
-      const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
-      const uint32_t base = run + incl - p[7];
-      // sums and bounds are non-decreasing along the reads: if the row's sum at the END of the round is below
-      // the bound at the START of the round, no read of the round can take it
-      const unsigned long long lb_first = a.lb_sum[r0];
-      if (carry + run + round_total >= lb_first) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t b = bl + e;
-          bool is_cand = false;
-          unsigned long long s = 0;
-          if (b < a.n_reads) {
-            s = carry + base + p[e];
-            const unsigned long long ls = a.lb_sum[b];
-            is_cand = s > ls || (s == ls && gi <= a.lb_idx[b]);
-          }
-          const uint32_t bal = __ballot_sync(0xffffffffu, is_cand);
-          if (bal) {
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(a.cand_total, (uint32_t)__popc(bal));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-            if (is_cand) {
-              const uint32_t slot = slot0 + __popc(bal & lt_mask);
-              if (slot < a.cand_cap) {
-                SkbCand cd;
-                cd.sum = s; cd.idx = gi; cd.read = b;
-                a.cand[slot] = cd;
-              }
-              atomicAdd(&a.cand_cnt[b], 1u);
-            }
-          }
-        }
-      }
-      run += round_total;
-    }
-    if (lane == 0) a.sums_out[row] = carry + run;
   }
 }
 
@@ -392,6 +724,7 @@ __global__ void rank_scatter_kernel(const SkbRankArgs a) {
   if (total > a.cand_cap) return;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const SkbCand c = a.cand[i];
+    if (c.read == 0xFFFFFFFFu) continue;  // unused tail of a slot reservation
     const uint32_t p = a.cand_off[c.read] + atomicAdd(&a.cand_fill[c.read], 1u);
     a.cand_sorted[p] = c;
   }
@@ -509,42 +842,51 @@ __global__ void __launch_bounds__(256) merge_topn_kernel(const uint32_t* __restr
   }
 }
 
-// rows strictly increasing? + maximum hash. One warp per row.
-__global__ void __launch_bounds__(256) ref_check_kernel(const uint64_t* __restrict__ ref,
-                                                        const uint64_t* __restrict__ row_off, uint32_t n_rows,
-                                                        uint32_t* bad, unsigned long long* hmax) {
+__global__ void __launch_bounds__(256) relayout_kernel(const uint64_t* __restrict__ src,
+                                                       const uint64_t* __restrict__ src_off, uint64_t* dst,
+                                                       const uint64_t* __restrict__ dst_start, uint32_t n_rows) {
   const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t r = warp0; r < n_rows; r += nwarps) {
-    const uint64_t lo = row_off[r], hi = row_off[r + 1];
+    const uint64_t s0 = src_off[r], n = src_off[r + 1] - s0, d0 = dst_start[r];
+    for (uint64_t i = skb_lane(); i < n; i += 32) dst[d0 + i] = src[s0 + i];
+  }
+}
+
+// rows strictly increasing? + maximum hash. One warp per row.
+__global__ void __launch_bounds__(256) ref_check_kernel(const SkbRefView rv, uint32_t* bad, unsigned long long* hmax) {
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = warp0; r < rv.n_rows; r += nwarps) {
+    const uint64_t* row = rv.ref + rv.row_start[r];
+    const uint32_t n = rv.row_len[r];
     bool ok = true;
-    for (uint64_t i = lo + skb_lane(); i + 1 < hi; i += 32) ok = ok && (ref[i] < ref[i + 1]);
+    for (uint32_t i = skb_lane(); i + 1 < n; i += 32) ok = ok && (row[i] < row[i + 1]);
     if (!ok) atomicOr(bad, 1u);
-    if (skb_lane() == 0 && hi > lo) atomicMax(hmax, (unsigned long long)ref[hi - 1]);
+    if (skb_lane() == 0 && n) atomicMax(hmax, (unsigned long long)row[n - 1]);
   }
 }
 
 // dense shared counts (reference `shared`, src/sketchy.rs:238-279): one warp per (reference row, query) pair;
 // each lane binary-searches its share of the query in the row. Inputs strictly increasing => == merge count.
-__global__ void __launch_bounds__(256) shared_kernel(const uint64_t* __restrict__ ref,
-                                                     const uint64_t* __restrict__ row_off, uint32_t n_rows,
-                                                     const uint64_t* __restrict__ q,
+__global__ void __launch_bounds__(256) shared_kernel(const SkbRefView rv, const uint64_t* __restrict__ q,
                                                      const uint64_t* __restrict__ q_off, uint32_t Q,
                                                      unsigned long long* out) {
   const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (pair >= (uint64_t)n_rows * Q) return;
+  if (pair >= (uint64_t)rv.n_rows * Q) return;
   const uint32_t i = (uint32_t)(pair / Q), j = (uint32_t)(pair % Q);
-  const uint64_t r0 = row_off[i], r1 = row_off[i + 1];
+  const uint64_t* row = rv.ref + rv.row_start[i];
+  const uint32_t rn = rv.row_len[i];
   const uint64_t q0 = q_off[j], q1 = q_off[j + 1];
   uint32_t c = 0;
   for (uint64_t x = q0 + skb_lane(); x < q1; x += 32) {
     const uint64_t h = q[x];
-    uint64_t lo = r0, hi = r1;
+    uint32_t lo = 0, hi = rn;
     while (lo < hi) {
-      const uint64_t mid = (lo + hi) >> 1;
-      if (ref[mid] < h) lo = mid + 1; else hi = mid;
+      const uint32_t mid = (lo + hi) >> 1;
+      if (row[mid] < h) lo = mid + 1; else hi = mid;
     }
-    c += (lo < r1 && ref[lo] == h) ? 1u : 0u;
+    c += (lo < rn && row[lo] == h) ? 1u : 0u;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -558,39 +900,38 @@ __global__ void __launch_bounds__(256) shared_kernel(const uint64_t* __restrict_
 // =========================================================================================================
 void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_t* qread, uint32_t n_keys,
                             uint32_t read_base, cudaStream_t st) {
-  cudaMemsetAsync(t.keys, 0xFF, ((size_t)t.cap + 1) * sizeof(uint64_t), st);
-  cudaMemsetAsync(t.cnt, 0, ((size_t)t.cap + 1) * sizeof(uint32_t), st);
-  cudaMemsetAsync(t.fill, 0, ((size_t)t.cap + 1) * sizeof(uint32_t), st);
-  cudaMemsetAsync(t.bloom, 0, (size_t)SKB_BLOOM_WORDS * sizeof(uint32_t), st);
-  cudaMemsetAsync(t.cursor, 0, sizeof(uint32_t), st);
-  if (n_keys == 0) return;
   const int th = 256;
+  const uint32_t n_clear = t.cap + 1 > SKB_BLOOM_WORDS ? t.cap + 1 : SKB_BLOOM_WORDS;
+  table_clear_kernel<<<(n_clear + th - 1) / th, th, 0, st>>>(t);
+  if (n_keys == 0) return;
   table_insert_kernel<<<(n_keys + th - 1) / th, th, 0, st>>>(t, qh, n_keys);
   table_alloc_kernel<<<(t.cap + 1 + th - 1) / th, th, 0, st>>>(t);
   table_fill_kernel<<<(n_keys + th - 1) / th, th, 0, st>>>(t, qread, n_keys, read_base);
 }
 
-size_t skb_stream_smem_bytes() { return ST_SMEM_TOTAL; }
+size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
+  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 2 * FS_ROWBUF;
+}
+uint32_t skb_fused_tile() { return FS_SUB; }
 
-void skb_launch_stream(const SkbStreamArgs& a, cudaStream_t st) {
-  if (a.ref_len == 0) return;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_TOTAL);
-    configured = true;
+void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st) {
+  if (a.rv.n_rows == 0) return;
+  const size_t smem = skb_fused_smem_bytes(a.cnt_stride);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
   }
-  stream_kernel<<<a.num_ctas, ST_THREADS, ST_SMEM_TOTAL, st>>>(a);
+  fused_kernel<<<a.num_ctas, FS_THREADS, smem, st>>>(a);
+}
+
+void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, uint32_t n_tracked, const SkbTable& t,
+                               uint16_t* ctr, uint32_t stride, cudaStream_t st) {
+  if (n_tracked == 0) return;
+  tracked_counts_kernel<<<n_tracked, 256, 0, st>>>(rv, tracked, t, ctr, stride);
 }
 
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) { rank_bounds_kernel<<<1, 1024, 0, st>>>(a); }
-
-void skb_launch_rank_scan(const SkbRankArgs& a, cudaStream_t st) {
-  const int th = 256;
-  unsigned blocks = (a.n_rows + (th / 32) - 1) / (th / 32);
-  if (blocks > 148u * 8u) blocks = 148u * 8u;
-  if (blocks == 0) return;
-  rank_scan_kernel<<<blocks, th, 0, st>>>(a);
-}
 
 void skb_launch_rank_group(const SkbRankArgs& a, cudaStream_t st) {
   rank_offsets_kernel<<<1, 1024, 0, st>>>(a);
@@ -617,19 +958,26 @@ void skb_launch_merge_topn(const uint32_t* idx_parts, const unsigned long long* 
   merge_topn_kernel<<<blocks, th, 0, st>>>(idx_parts, sum_parts, n_parts, n_reads, top, out_idx, out_sum);
 }
 
-void skb_launch_ref_check(const uint64_t* ref, const uint64_t* row_off, uint32_t n_rows, uint32_t* bad,
-                          unsigned long long* hmax, cudaStream_t st) {
+void skb_launch_relayout(const uint64_t* src, const uint64_t* src_off, uint64_t* dst, const uint64_t* dst_start,
+                         uint32_t n_rows, cudaStream_t st) {
   if (n_rows == 0) return;
   unsigned blocks = (n_rows + 7) / 8;
   if (blocks > 148u * 8u) blocks = 148u * 8u;
-  ref_check_kernel<<<blocks, 256, 0, st>>>(ref, row_off, n_rows, bad, hmax);
+  relayout_kernel<<<blocks, 256, 0, st>>>(src, src_off, dst, dst_start, n_rows);
 }
 
-void skb_launch_shared(const uint64_t* ref, const uint64_t* row_off, uint32_t n_rows, const uint64_t* q,
-                       const uint64_t* q_off, uint32_t Q, unsigned long long* out, cudaStream_t st) {
-  const uint64_t pairs = (uint64_t)n_rows * Q;
+void skb_launch_ref_check(const SkbRefView& rv, uint32_t* bad, unsigned long long* hmax, cudaStream_t st) {
+  if (rv.n_rows == 0) return;
+  unsigned blocks = (rv.n_rows + 7) / 8;
+  if (blocks > 148u * 8u) blocks = 148u * 8u;
+  ref_check_kernel<<<blocks, 256, 0, st>>>(rv, bad, hmax);
+}
+
+void skb_launch_shared(const SkbRefView& rv, const uint64_t* q, const uint64_t* q_off, uint32_t Q,
+                       unsigned long long* out, cudaStream_t st) {
+  const uint64_t pairs = (uint64_t)rv.n_rows * Q;
   if (pairs == 0) return;
   const int th = 256;
   const unsigned blocks = (unsigned)((pairs * 32 + th - 1) / th);
-  shared_kernel<<<blocks, th, 0, st>>>(ref, row_off, n_rows, q, q_off, Q, out);
+  shared_kernel<<<blocks, th, 0, st>>>(rv, q, q_off, Q, out);
 }

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Attribute ncu warp-stall samples / executed instructions of one kernel to CUDA source lines.
+
+usage: tools/prof_lines.py <report.ncu-rep> <kernel-name-substring> <source.cu> [top_n]
+Needs the library built with -lineinfo (it is) and nvdisasm / cuobjdump / ncu on PATH. ncu's SASS page and
+nvdisasm list a function's instructions in the same order, so row i of one is row i of the other.
+"""
+import csv
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+rep, kname, srcfile = sys.argv[1:4]
+top_n = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+so = os.path.join(root, "sketchy_b200", "libsketchy_b200.so")
+tmp = tempfile.mkdtemp()
+stem = os.path.splitext(os.path.basename(srcfile))[0]
+subprocess.run(["cuobjdump", "-xelf", stem, so], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.split("\n")))
+hdr = rows[1]
+data = [r for r in rows[2:] if len(r) == len(hdr)]
+
+
+def func_lines(start):
+    cur, seq = None, []
+    for l in dis[start + 1:]:
+        if l.startswith("//---------------------"):
+            break
+        m = re.search(r'//## File ".*?", line (\d+)', l)
+        if m:
+            cur = int(m.group(1))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
+            seq.append(cur)
+    return seq
+
+
+# several template instances may match the name: take the one whose instruction count equals the profiled one
+cands = [func_lines(i) for i, l in enumerate(dis) if l.startswith(".text.") and kname in l]
+seq = min(cands, key=lambda q: abs(len(q) - len(data)))
+assert len(seq) == len(data), (len(seq), len(data), [len(c) for c in cands])
+iI, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
+src = open(srcfile).read().split("\n")
+agg = {}
+for i, r in enumerate(data):
+    a = agg.setdefault(seq[i], [0, 0])
+    a[0] += int(r[iS]); a[1] += int(r[iI])
+tot = sum(a[0] for a in agg.values()); toti = sum(a[1] for a in agg.values())
+print(f"kernel {kname}: {len(seq)} SASS instrs, {toti} executed, {tot} samples")
+for ln, (s_, i_) in sorted(agg.items(), key=lambda x: -x[1][0])[:top_n]:
+    text = src[ln - 1].strip()[:95] if ln and 0 < ln <= len(src) else ""
+    print(f"{ln or 0:5d} {s_:7d} {100 * s_ / max(tot, 1):5.1f}% inst={i_:11d}  {text}")
