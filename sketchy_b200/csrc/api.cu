@@ -112,13 +112,15 @@ struct skb_ctx {
   bool has_ref = false;
   DevBuf sums[2];
   int sums_cur = 0;
-  DevBuf tracked, tracked_next;
+  DevBuf tracked[2];         // [SKB_MAX_TRACKED] local rows + (at index SKB_MAX_TRACKED) their count, double buffered
+  int tracked_cur = 0;
+  DevBuf tprefix;
   uint32_t tracked_top = 0;  // 0 = invalid
   // per-group scratch (hash/select)
   DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, cand_pool;
   DevBuf sk_hashes, sk_counts;
   // predict scratch
-  DevBuf q_off, qh, qread, counts, lb_sum, lb_idx, cand, cand_sorted, cand_cnt, cand_off, cand_fill, scal;
+  DevBuf q_off, qh, qread, counts, lb_sum, lb_idx, cand, cand_cnt, scal;
   DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
@@ -511,8 +513,8 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   c->sums_cur = 0;
   c->tracked_top = 0;
   c->pass_cur = std::min<uint32_t>(64, c->pass_max);
-  CU(c, c->tracked.ensure(SKB_MAX_TOP * 4));
-  CU(c, c->tracked_next.ensure(SKB_MAX_TOP * 4));
+  CU(c, c->tracked[0].ensure((SKB_MAX_TRACKED + 1) * 4));
+  CU(c, c->tracked[1].ensure((SKB_MAX_TRACKED + 1) * 4));
   CU(c, cudaStreamSynchronize(c->stream));
   c->has_ref = true;
   return SKB_OK;
@@ -559,22 +561,26 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   }
   if (int rc = check_launch(c, "compact")) return rc;
 
-  // ---- rows tracked for the lower bounds: the current top rows
-  const uint32_t n_tracked = std::min(top, c->n_rows);
+  // ---- rows tracked for the bounds: start from the current top rows
+  const uint32_t n_top_rows = std::min(top, c->n_rows);
   unsigned long long* sums_in = c->sums[c->sums_cur].as<unsigned long long>();
+  uint32_t* h_total = c->h_scal;
   if (c->tracked_top != top) {
-    ProfScope ps(c, SKB_K_RANK, 1);
-    skb_launch_rank_full(sums_in, c->n_rows, n_tracked, 0, nullptr, nullptr, c->tracked.as<uint32_t>(), c->stream);
+    uint32_t* tr = c->tracked[c->tracked_cur].as<uint32_t>();
+    { ProfScope ps(c, SKB_K_RANK, 1);
+      skb_launch_rank_full(sums_in, c->n_rows, n_top_rows, 0, nullptr, nullptr, tr, c->stream); }
+    h_total[4] = n_top_rows;
+    CU(c, cudaMemcpyAsync(tr + SKB_MAX_TRACKED, &h_total[4], 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     c->tracked_top = top;
   }
-  c->cand_cap = (uint32_t)std::max<uint64_t>(4u << 20, 2ull * c->n_rows);
-  CU(c, c->cand.ensure((size_t)c->cand_cap * sizeof(SkbCand)));
-  CU(c, c->cand_sorted.ensure((size_t)c->cand_cap * sizeof(SkbCand)));
+  c->cand_cap = SKB_CAND_BUCKET;
   CU(c, c->scal.ensure(256));
-  uint32_t* d_cand_total = c->scal.as<uint32_t>() + 8;
+  uint32_t* d_cand_total = c->scal.as<uint32_t>() + 8;                                                  // overflow flag
+  unsigned long long* d_cand_stat = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 64);  // statistics
+  CU(c, cudaMemsetAsync(d_cand_stat, 0, 8, c->stream));
 
   uint32_t r = 0;
-  uint32_t* h_total = c->h_scal;
   int rc_final = SKB_OK;
   while (r < R) {
     uint32_t B = std::min<uint32_t>(std::min(c->pass_cur, c->pass_max), R - r);
@@ -584,12 +590,12 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     const uint32_t nkeys = (uint32_t)(q_off[r + B] - q_off[r]);
     if (int rc = ensure_table(c, nkeys)) { rc_final = rc; break; }
     const uint32_t stride = (uint32_t)round_up(B, 256);
-    const size_t ctr_bytes = (size_t)n_tracked * stride * 2;
+    const size_t ctr_bytes = (size_t)SKB_MAX_TRACKED * stride * 2;
     cudaError_t e;
     if ((e = c->counts.ensure(ctr_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
         (e = c->lb_idx.ensure((size_t)B * 4)) != cudaSuccess || (e = c->cand_cnt.ensure((size_t)B * 4)) != cudaSuccess ||
-        (e = c->cand_off.ensure(((size_t)B + 1) * 4)) != cudaSuccess ||
-        (e = c->cand_fill.ensure((size_t)B * 4)) != cudaSuccess) {
+        (e = c->cand.ensure((size_t)B * c->cand_cap * sizeof(SkbCand))) != cudaSuccess ||
+        (e = c->tprefix.ensure((size_t)SKB_MAX_TRACKED * stride * 4)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
       break;
     }
@@ -599,21 +605,20 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     cudaMemsetAsync(c->counts.p, 0, ctr_bytes, c->stream);
     cudaMemsetAsync(d_cand_total, 0, 4, c->stream);
     cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)B * 4, c->stream);
-    cudaMemsetAsync(c->cand_fill.p, 0, (size_t)B * 4, c->stream);
     const SkbRefView rv = ref_view(c);
     SkbRankArgs ra{};
-    ra.tracked_counts = c->counts.as<uint16_t>(); ra.row_stride = stride; ra.n_reads = B; ra.row_base = c->row_base;
+    ra.tracked_counts = c->counts.as<uint16_t>(); ra.tracked_prefix = c->tprefix.as<uint32_t>();
+    ra.row_stride = stride; ra.n_reads = B; ra.row_base = c->row_base;
     ra.sums_in = c->sums[c->sums_cur].as<unsigned long long>();
-    ra.tracked = c->tracked.as<uint32_t>(); ra.n_tracked = n_tracked;
+    ra.tracked = c->tracked[c->tracked_cur].as<uint32_t>(); ra.n_tracked = ra.tracked + SKB_MAX_TRACKED;
     ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>();
     ra.cand = c->cand.as<SkbCand>(); ra.cand_cap = c->cand_cap; ra.cand_total = d_cand_total;
-    ra.cand_cnt = c->cand_cnt.as<uint32_t>(); ra.cand_off = c->cand_off.as<uint32_t>();
-    ra.cand_fill = c->cand_fill.as<uint32_t>(); ra.cand_sorted = c->cand_sorted.as<SkbCand>();
+    ra.cand_cnt = c->cand_cnt.as<uint32_t>(); ra.cand_stat = d_cand_stat;
     ra.top = top; ra.out_idx = d_out_idx + (size_t)r * top;
     ra.out_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)r * top;
-    ra.tracked_next = c->tracked_next.as<uint32_t>();
-    { ProfScope ps(c, SKB_K_RANK, nkeys ? 2 : 1);
-      if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, n_tracked, t, c->counts.as<uint16_t>(), stride, c->stream);
+    ra.tracked_next = c->tracked[c->tracked_cur ^ 1].as<uint32_t>(); ra.n_tracked_next = ra.tracked_next + SKB_MAX_TRACKED;
+    { ProfScope ps(c, SKB_K_RANK, nkeys ? 3 : 2);
+      if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, ra.n_tracked, t, c->counts.as<uint16_t>(), stride, c->stream);
       skb_launch_rank_bounds(ra, c->stream); }
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
@@ -623,9 +628,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.cand = ra.cand; fa.cand_cap = ra.cand_cap;
     fa.cand_total = ra.cand_total; fa.cand_cnt = ra.cand_cnt;
     { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
-    { ProfScope ps(c, SKB_K_RANK, 3);
-      skb_launch_rank_group(ra, c->stream);
-      skb_launch_rank_select(ra, c->stream); }
+    { ProfScope ps(c, SKB_K_RANK, 1); skb_launch_rank_select(ra, c->stream); }
     if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
     if ((e = cudaMemcpyAsync(h_total, d_cand_total, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
@@ -633,19 +636,30 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
       break;
     }
     c->st_passes += 1;
-    if (*h_total > c->cand_cap) {
-      if (B == 1) { rc_final = fail(c, SKB_ERR_INTERNAL, "candidate overflow with a single read"); break; }
-      c->pass_cur = std::max(1u, B / 2);  // too many contenders for the bound: redo with fewer reads
-      continue;
+    if (*h_total != 0) {  // some read had more contenders than a bucket holds
+      if (B > 1) {
+        c->pass_cur = std::max(1u, B / 2);  // redo with fewer reads: the bounds tighten after every pass
+        continue;
+      }
+      // a single read: its ranking is simply the top of the new sums (exact, no candidates needed)
+      ProfScope ps(c, SKB_K_RANK, 1);
+      skb_launch_rank_full(fa.sums_out, c->n_rows, n_top_rows, c->row_base, ra.out_idx, ra.out_sum, nullptr, c->stream);
+      if (n_top_rows < top) {
+        cudaMemsetAsync(ra.out_idx + n_top_rows, 0xFF, (size_t)(top - n_top_rows) * 4, c->stream);
+        cudaMemsetAsync(ra.out_sum + n_top_rows, 0, (size_t)(top - n_top_rows) * 8, c->stream);
+      }
     }
-    c->st_cands += *h_total;
+    { ProfScope ps(c, SKB_K_RANK, 1); skb_launch_tracked_update(ra, c->stream); }  // from this pass's top lists
     c->sums_cur ^= 1;
-    cudaMemcpyAsync(c->tracked.p, c->tracked_next.p, (size_t)n_tracked * 4, cudaMemcpyDeviceToDevice, c->stream);
+    c->tracked_cur ^= 1;
     r += B;
-    if (*h_total < c->cand_cap / 4) c->pass_cur = std::min(c->pass_max, std::max(B, c->pass_cur) * 2);
+    if (*h_total == 0) c->pass_cur = std::min(c->pass_max, std::max(B, c->pass_cur) * 2);
   }
   if (rc_final) return rc_final;
+  unsigned long long cands = 0;
+  CU(c, cudaMemcpyAsync(&cands, d_cand_stat, 8, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  c->st_cands = cands;
   return SKB_OK;
 }
 
@@ -684,10 +698,10 @@ void skb_destroy(skb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-  DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->sums[0], &c->sums[1], &c->tracked, &c->tracked_next, &c->g_tau, &c->g_cap,
+  DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->sums[0], &c->sums[1], &c->tracked[0], &c->tracked[1], &c->tprefix, &c->g_tau, &c->g_cap,
                     &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->cand_pool,
                     &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->lb_sum,
-                    &c->lb_idx, &c->cand, &c->cand_sorted, &c->cand_cnt, &c->cand_off, &c->cand_fill, &c->scal,
+                    &c->lb_idx, &c->cand, &c->cand_cnt, &c->scal,
                     &c->t_slots, &c->t_fill, &c->t_reads, &c->t_slot, &c->t_bloom, &c->out_idx,
                     &c->out_sum, &c->misc};
   for (DevBuf* b : bufs) b->release();

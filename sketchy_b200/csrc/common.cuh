@@ -27,11 +27,12 @@ struct SkbPackedView {
   uint32_t nseg;
 };
 
-// One candidate produced by the rank kernel: reference row `idx` has cumulative sum `sum` after read `read`.
+// One candidate produced by the rank warps: reference row `idx` has cumulative sum `sum` after the read whose
+// bucket the record sits in.
 struct __align__(16) SkbCand {
   unsigned long long sum;
   uint32_t idx;
-  uint32_t read;
+  uint32_t pad;
 };
 
 // (sum desc, idx asc) — the order of the reference's stable descending sort (src/sketchy.rs:310, 348).

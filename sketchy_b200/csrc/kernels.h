@@ -101,43 +101,47 @@ struct SkbFusedArgs {
   unsigned long long* sums_out;       // [n_rows]
   const unsigned long long* lb_sum;   // [n_reads] lower bound of every read's top-th key
   const uint32_t* lb_idx;             // [n_reads]
-  SkbCand* cand;                      // [cand_cap]
-  uint32_t cand_cap;
-  uint32_t* cand_total;               // [1] keeps counting past cap (= overflow)
-  uint32_t* cand_cnt;                 // [n_reads]
+  SkbCand* cand;                      // [n_reads][cand_cap] per-read candidate buckets
+  uint32_t cand_cap;                  // bucket capacity
+  uint32_t* cand_total;               // [1] overflow flag: some read produced more candidates than a bucket holds
+  uint32_t* cand_cnt;                 // [n_reads] candidates produced per read (may exceed cand_cap)
 };
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
 size_t skb_fused_smem_bytes(uint32_t cnt_stride);
 uint32_t skb_fused_tile();
 
 // per-read counts of the tracked rows only (they define the bounds): ctr[t][read], u16, row stride `stride`
-void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, uint32_t n_tracked,
+void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
                                const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st);
+#define SKB_CAND_BUCKET 4096u  // candidates kept per read and pass; more than that shrinks the pass
+
+#define SKB_MAX_TRACKED 192u  // rows whose exact per-read sums define the bounds
 
 struct SkbRankArgs {
-  const uint16_t* tracked_counts;  // [n_tracked][row_stride]
+  uint16_t* tracked_counts;        // [SKB_MAX_TRACKED][row_stride] per-read counts of the tracked rows
+  uint32_t* tracked_prefix;        // [SKB_MAX_TRACKED][row_stride] inclusive prefix sums of the above
   uint32_t row_stride;
   uint32_t n_reads;  // reads in this pass
   uint32_t row_base; // global index of local row 0
   const unsigned long long* sums_in;   // [n_rows]
-  const uint32_t* tracked;             // [n_tracked] local rows
-  uint32_t n_tracked;
+  const uint32_t* tracked;             // [*n_tracked] local rows
+  const uint32_t* n_tracked;           // device scalar, <= SKB_MAX_TRACKED
   unsigned long long* lb_sum;          // [n_reads]
   uint32_t* lb_idx;                    // [n_reads] (global index)
-  SkbCand* cand;                       // [cand_cap]
+  SkbCand* cand;                       // [n_reads][cand_cap] per-read candidate buckets
   uint32_t cand_cap;
-  uint32_t* cand_total;                // [1]
+  uint32_t* cand_total;                // [1] overflow flag
   uint32_t* cand_cnt;                  // [n_reads]
-  uint32_t* cand_off;                  // [n_reads + 1]
-  uint32_t* cand_fill;                 // [n_reads]
-  SkbCand* cand_sorted;                // [cand_cap]
+  unsigned long long* cand_stat;       // [1] running total of candidates (statistics only)
   uint32_t top;
   uint32_t* out_idx;                   // [n_reads * top] device
   unsigned long long* out_sum;         // [n_reads * top]
-  uint32_t* tracked_next;              // [top] local rows of the last read's top
+  uint32_t* tracked_next;              // [SKB_MAX_TRACKED] tracked rows for the next pass
+  uint32_t* n_tracked_next;            // device scalar
 };
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st);
-void skb_launch_rank_group(const SkbRankArgs& a, cudaStream_t st);   // offsets + scatter by read
+// tracked rows of the next pass = union of the top lists of 16 sampled reads of this pass (last read first)
+void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st);
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st);  // per-read top-N
 
 // top-N of a plain value array by (value desc, index asc); one CTA. idx_base is added to reported indices.

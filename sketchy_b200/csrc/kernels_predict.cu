@@ -530,20 +530,16 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   const uint32_t seg0 = lane * per;
   const unsigned long long lb_min = a.lb_sum[0];  // bounds are non-decreasing along the reads
   const unsigned long long lb_seg = seg0 < a.n_reads ? a.lb_sum[seg0] : ~0ull;
-  // candidate slots are reserved 16 at a time per lane (one global atomic per 16 candidates)
-  uint32_t slot_next = 0, slot_left = 0;
+  // candidates go straight into the read's bucket; the per-read counter doubles as the slot allocator
   auto emit = [&](unsigned long long sum, uint32_t gi, uint32_t b) {
-    if (slot_left == 0) {
-      slot_next = atomicAdd(a.cand_total, 16u);
-      slot_left = 16;
-    }
-    if (slot_next < a.cand_cap) {
+    const uint32_t slot = atomicAdd(&a.cand_cnt[b], 1u);
+    if (slot < a.cand_cap) {
       SkbCand cd;
-      cd.sum = sum; cd.idx = gi; cd.read = b;
-      a.cand[slot_next] = cd;
+      cd.sum = sum; cd.idx = gi; cd.pad = 0;
+      a.cand[(size_t)b * a.cand_cap + slot] = cd;
+    } else {
+      *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
     }
-    ++slot_next; --slot_left;
-    atomicAdd(&a.cand_cnt[b], 1u);
   };
   unsigned long long carry_next = (r0 + rp < r1) ? a.sums_in[r0 + rp] : 0ull;
   for (uint32_t row = r0 + rp; row < r1; row += 2) {
@@ -627,24 +623,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     __syncwarp();
     if (lane == 0) mbar_arrive(&row_free[rb]);
   }
-  // hand back the unused part of the last reservation as invalid records
-  for (; slot_left; --slot_left, ++slot_next) {
-    if (slot_next < a.cand_cap) {
-      SkbCand cd;
-      cd.sum = 0; cd.idx = 0xFFFFFFFFu; cd.read = 0xFFFFFFFFu;
-      a.cand[slot_next] = cd;
-    }
-  }
 }
 
 // per-read counts of the tracked rows (the rows that define the bounds); one CTA per tracked row
 __global__ void __launch_bounds__(256) tracked_counts_kernel(const SkbRefView rv, const uint32_t* __restrict__ tracked,
-                                                             const SkbTable t, uint16_t* ctr, uint32_t stride) {
-  const uint32_t row = tracked[blockIdx.x];
+                                                             const uint32_t* __restrict__ n_tracked, const SkbTable t,
+                                                             uint16_t* ctr, uint32_t stride) {
+  const uint32_t tr = blockIdx.x / 8, part = blockIdx.x % 8;  // 8 CTAs share one tracked row
+  if (tr >= *n_tracked) return;
+  const uint32_t row = tracked[tr];
   const uint64_t* src = rv.ref + rv.row_start[row];
   const uint32_t len = rv.row_len[row];
-  uint32_t* cbuf = reinterpret_cast<uint32_t*>(ctr + (size_t)blockIdx.x * stride);
-  for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+  uint32_t* cbuf = reinterpret_cast<uint32_t*>(ctr + (size_t)tr * stride);
+  for (uint32_t i = part * blockDim.x + threadIdx.x; i < len; i += 8 * blockDim.x) {
     SkbSlot s;
     if (table_lookup(t, src[i], s)) apply_hit(t, s, cbuf);
   }
@@ -674,59 +665,81 @@ __device__ __forceinline__ uint32_t cta_scan_u32(uint32_t v, uint32_t* warp_sums
   return v + off;
 }
 
-// Lower bound of every read's top-th key: the worst key among `n_tracked` fixed rows (the previous top rows).
-// Any `top` distinct rows give a valid bound because sums never decrease.
-__global__ void __launch_bounds__(1024) rank_bounds_kernel(const SkbRankArgs a) {
+// Bounds, step 1: inclusive prefix sums of every tracked row's per-read counts. One CTA per tracked row.
+__global__ void __launch_bounds__(256) tracked_prefix_kernel(const SkbRankArgs a) {
   __shared__ uint32_t warp_sums[32];
-  const uint32_t per = (a.n_reads + blockDim.x - 1) / blockDim.x;
-  const uint32_t b0 = threadIdx.x * per;
-  const uint32_t b1 = min(b0 + per, a.n_reads);
-  for (uint32_t t = 0; t < a.n_tracked; ++t) {
-    const uint32_t row = a.tracked[t];
-    const uint16_t* c = a.tracked_counts + (size_t)t * a.row_stride;
-    uint32_t local = 0;
-    for (uint32_t b = b0; b < b1; ++b) local += c[b];
-    uint32_t tot;
-    const uint32_t incl = cta_scan_u32(local, warp_sums, &tot);
-    unsigned long long s = a.sums_in[row] + (incl - local);
-    const uint32_t gi = a.row_base + row;
-    for (uint32_t b = b0; b < b1; ++b) {
-      s += c[b];
-      if (t == 0 || skb_key_better(a.lb_sum[b], a.lb_idx[b], s, gi)) {
-        a.lb_sum[b] = s;
-        a.lb_idx[b] = gi;
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(1024) rank_offsets_kernel(const SkbRankArgs a) {
-  __shared__ uint32_t warp_sums[32];
-  const bool overflow = *a.cand_total > a.cand_cap;
+  const uint32_t t = blockIdx.x;
+  if (t >= *a.n_tracked) return;
+  const uint16_t* c = a.tracked_counts + (size_t)t * a.row_stride;
+  uint32_t* p = a.tracked_prefix + (size_t)t * a.row_stride;
   const uint32_t per = (a.n_reads + blockDim.x - 1) / blockDim.x;
   const uint32_t b0 = threadIdx.x * per;
   const uint32_t b1 = min(b0 + per, a.n_reads);
   uint32_t local = 0;
-  if (!overflow)
-    for (uint32_t b = b0; b < b1; ++b) local += a.cand_cnt[b];
+  for (uint32_t b = b0; b < b1; ++b) local += c[b];
   uint32_t tot;
   const uint32_t incl = cta_scan_u32(local, warp_sums, &tot);
-  uint32_t off = incl - local;
+  uint32_t run = incl - local;
   for (uint32_t b = b0; b < b1; ++b) {
-    a.cand_off[b] = off;
-    if (!overflow) off += a.cand_cnt[b];
+    run += c[b];
+    p[b] = run;
   }
-  if (threadIdx.x == 0) a.cand_off[a.n_reads] = tot;
 }
 
-__global__ void rank_scatter_kernel(const SkbRankArgs a) {
-  const uint32_t total = *a.cand_total;
-  if (total > a.cand_cap) return;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const SkbCand c = a.cand[i];
-    if (c.read == 0xFFFFFFFFu) continue;  // unused tail of a slot reservation
-    const uint32_t p = a.cand_off[c.read] + atomicAdd(&a.cand_fill[c.read], 1u);
-    a.cand_sorted[p] = c;
+// Bounds, step 2: for every read the `top`-th best key among the tracked rows (exact sums, so a valid lower bound of
+// the read's true `top`-th key: sums never decrease and the tracked rows are distinct). One thread per read keeps the
+// best `top` keys seen so far in a small sorted list. With fewer than `top` tracked rows the bound is their worst.
+__global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.n_reads) return;
+  const uint32_t nt = *a.n_tracked;
+  const uint32_t keep = a.top < nt ? a.top : nt;
+  unsigned long long ks[SKB_MAX_TOP];
+  uint32_t ki[SKB_MAX_TOP];
+  uint32_t n = 0;
+  for (uint32_t t = 0; t < nt; ++t) {
+    const uint32_t row = a.tracked[t];
+    const unsigned long long s = a.sums_in[row] + a.tracked_prefix[(size_t)t * a.row_stride + b];
+    const uint32_t gi = a.row_base + row;
+    if (n == keep && !skb_key_better(s, gi, ks[n - 1], ki[n - 1])) continue;
+    uint32_t pos = n < keep ? n : n - 1;  // insert, dropping the worst when full
+    while (pos > 0 && skb_key_better(s, gi, ks[pos - 1], ki[pos - 1])) {
+      ks[pos] = ks[pos - 1]; ki[pos] = ki[pos - 1];
+      --pos;
+    }
+    ks[pos] = s; ki[pos] = gi;
+    if (n < keep) ++n;
+  }
+  a.lb_sum[b] = n ? ks[n - 1] : 0ull;
+  a.lb_idx[b] = n ? ki[n - 1] : 0xFFFFFFFFu;
+}
+
+// Tracked rows of the next pass: the union of the top lists of 16 evenly spaced reads of this pass, the last read's
+// list first (it alone guarantees `top` distinct rows). Rows that led at any point of the pass stay tracked, so a
+// lineage that overtakes and falls back does not loosen the bounds. One CTA.
+__global__ void __launch_bounds__(1024) tracked_update_kernel(const SkbRankArgs a) {
+  __shared__ uint32_t list[16 * SKB_MAX_TOP];
+  __shared__ uint32_t keep[16 * SKB_MAX_TOP];
+  const uint32_t n_s = 16, total = n_s * a.top;
+  for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const uint32_t j = e / a.top, tpos = e % a.top;
+    // sample j = 0 is the last read; the others are spread over the pass
+    const uint32_t b = j == 0 ? a.n_reads - 1 : (uint32_t)(((unsigned long long)j * a.n_reads) / n_s);
+    list[e] = a.out_idx[(size_t)b * a.top + tpos];
+  }
+  __syncthreads();
+  for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+    const uint32_t v = list[e];
+    bool first = v != 0xFFFFFFFFu;
+    for (uint32_t f = 0; f < e && first; ++f) first = list[f] != v;
+    keep[e] = first ? 1u : 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // order-preserving compaction (a few thousand entries at most)
+    uint32_t n = 0;
+    for (uint32_t e = 0; e < total && n < SKB_MAX_TRACKED; ++e)
+      if (keep[e]) a.tracked_next[n++] = list[e] - a.row_base;
+    *a.n_tracked_next = n;
   }
 }
 
@@ -739,29 +752,40 @@ __device__ __forceinline__ void warp_best(unsigned long long& s, uint32_t& i) {
   }
 }
 
-// One warp per read: the `top` best candidates in order. Candidate rows are distinct, so "best key strictly
-// worse than the previous pick" enumerates them without marking. Missing entries are (sum 0, idx UINT32_MAX).
-__global__ void __launch_bounds__(256) rank_select_kernel(const SkbRankArgs a) {
-  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One warp per read: the `top` best candidates of the read's bucket, in order. Candidate rows are distinct, so
+// "best key strictly worse than the previous pick" enumerates them without marking. The first RS_CACHE records of
+// the bucket are staged in shared memory once; missing entries are (sum 0, idx UINT32_MAX).
+constexpr int RS_WARPS = 8;
+constexpr int RS_CACHE = 512;
+__global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRankArgs a) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  const uint32_t wid = threadIdx.x >> 5, lane = skb_lane();
+  const uint32_t b = blockIdx.x * RS_WARPS + wid;
   if (b >= a.n_reads) return;
-  const uint32_t lane = skb_lane();
-  const uint32_t lo = a.cand_off[b], hi = a.cand_off[b + 1];
+  uint4* cache = reinterpret_cast<uint4*>(rs_smem) + (size_t)wid * RS_CACHE;
+  const uint32_t produced = a.cand_cnt[b];
+  const uint32_t n = produced < a.cand_cap ? produced : a.cand_cap;
+  const uint4* list = reinterpret_cast<const uint4*>(a.cand + (size_t)b * a.cand_cap);
+  const uint32_t nc = n < (uint32_t)RS_CACHE ? n : (uint32_t)RS_CACHE;
+  for (uint32_t i = lane; i < nc; i += 32) cache[i] = list[i];
+  if (lane == 0 && a.cand_stat) atomicAdd(a.cand_stat, (unsigned long long)produced);
+  __syncwarp();
   unsigned long long last_s = 0;
   uint32_t last_i = 0;
   for (uint32_t t = 0; t < a.top; ++t) {
     unsigned long long bs = 0;
     uint32_t bi = 0xFFFFFFFFu;
-    for (uint32_t i = lo + lane; i < hi; i += 32) {
-      const SkbCand c = a.cand_sorted[i];
-      if ((t == 0 || skb_key_better(last_s, last_i, c.sum, c.idx)) && skb_key_better(c.sum, c.idx, bs, bi)) {
-        bs = c.sum; bi = c.idx;
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint4 c = i < nc ? cache[i] : list[i];
+      const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
+      if ((t == 0 || skb_key_better(last_s, last_i, cs, c.z)) && skb_key_better(cs, c.z, bs, bi)) {
+        bs = cs; bi = c.z;
       }
     }
     warp_best(bs, bi);
     if (lane == 0) {
       a.out_idx[(size_t)b * a.top + t] = bi;
       a.out_sum[(size_t)b * a.top + t] = bs;
-      if (b == a.n_reads - 1 && a.tracked_next && bi != 0xFFFFFFFFu) a.tracked_next[t] = bi - a.row_base;
     }
     last_s = bs; last_i = bi;
     if (bi == 0xFFFFFFFFu) {  // exhausted: pad the rest
@@ -925,23 +949,27 @@ void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st) {
   fused_kernel<<<a.num_ctas, FS_THREADS, smem, st>>>(a);
 }
 
-void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, uint32_t n_tracked, const SkbTable& t,
-                               uint16_t* ctr, uint32_t stride, cudaStream_t st) {
-  if (n_tracked == 0) return;
-  tracked_counts_kernel<<<n_tracked, 256, 0, st>>>(rv, tracked, t, ctr, stride);
+void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
+                               const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st) {
+  tracked_counts_kernel<<<SKB_MAX_TRACKED * 8, 256, 0, st>>>(rv, tracked, n_tracked, t, ctr, stride);
 }
 
-void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) { rank_bounds_kernel<<<1, 1024, 0, st>>>(a); }
-
-void skb_launch_rank_group(const SkbRankArgs& a, cudaStream_t st) {
-  rank_offsets_kernel<<<1, 1024, 0, st>>>(a);
-  rank_scatter_kernel<<<148 * 4, 256, 0, st>>>(a);
+void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) {
+  tracked_prefix_kernel<<<SKB_MAX_TRACKED, 256, 0, st>>>(a);
+  rank_bounds_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
 }
+
+void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st) { tracked_update_kernel<<<1, 1024, 0, st>>>(a); }
 
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st) {
-  const int th = 256;
-  const unsigned blocks = (unsigned)(((uint64_t)a.n_reads * 32 + th - 1) / th);
-  rank_select_kernel<<<blocks, th, 0, st>>>(a);
+  const size_t smem = (size_t)RS_WARPS * RS_CACHE * 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(rank_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  const unsigned blocks = (a.n_reads + RS_WARPS - 1) / RS_WARPS;
+  rank_select_kernel<<<blocks, RS_WARPS * 32, smem, st>>>(a);
 }
 
 void skb_launch_rank_full(const unsigned long long* vals, uint32_t n, uint32_t top, uint32_t idx_base,

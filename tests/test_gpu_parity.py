@@ -171,6 +171,21 @@ def test_predict_medium_scale(ctx):
     _check_predict(ctx, ref, off, blob, roff, 16, 1000, 0, 10, 0)
 
 
+def test_predict_more_contenders_than_a_bucket(ctx):
+    """4500 references beat the tracked row at once: the per-read candidate bucket (4096) overflows, the pass is
+    halved down to single reads and those are ranked exactly from the new sums."""
+    ga = synth.random_genome(20_000, 901)
+    gb = synth.random_genome(20_000, 902)
+    sk, _, _ = oracle.sketch_groups([ga.tobytes(), gb.tobytes()], [0, 1], 2, 16, 300, 0)
+    rows = [sk[0][0]] + [sk[1][0]] * 4500
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    blob, roff, _ = synth.sample_reads([gb], 24, 1500, 77, sub=0.0, ins=0.0, dele=0.0)
+    for top in (1, 3):
+        _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, top, 8)
+
+
 def test_shared_counts_and_rank(ctx):
     ref, off, blob, roff = _world(seed=51, n_lineages=4, per_lineage=6, glen=20_000, s=400, n_reads=5, rlen=500)
     ctx.ref_upload(ref, off)
