@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--cpu-sample", type=int, default=12, help="reads in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--verify", action="store_true", help="N>1: check the merged ranking against one GPU holding all rows")
     return p.parse_args()
 
 
@@ -156,8 +157,8 @@ def run_b200(args):
     assert all(r.size == s for r in base_rows)
     base_t = torch.from_numpy(np.stack(base_rows).astype(np.int64))
     assert int(base_t.min()) >= 0
-    lo = (N * rank // world) // st.ROW_BLOCK * st.ROW_BLOCK
-    hi = N if rank == world - 1 else (N * (rank + 1) // world) // st.ROW_BLOCK * st.ROW_BLOCK
+    from sketchy_b200.dist import shard_rows
+    lo, hi = shard_rows(N, rank, world, st.ROW_BLOCK)
     ref = st.expand_reference_block(base_t.to(device), lo, hi - lo, 0.02, 4000, device)
     off = np.arange(hi - lo + 1, dtype=np.uint64) * np.uint64(s)
     ctx.ref_upload_device(ref.data_ptr(), off, row_base=lo)
@@ -221,6 +222,25 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sync_all()
+    if world > 1 and args.verify:
+        # parity gate of the sharded path: the merged ranking of the first reads == one GPU holding every row
+        n_v = min(4096, R)
+        ok = torch.ones(1, device=device)
+        if rank == 0:
+            full = st.expand_reference_block(base_t.to(device), 0, N, 0.02, 4000, device)
+            c2 = Context(local)
+            c2.ref_upload_device(full.data_ptr(), np.arange(N + 1, dtype=np.uint64) * np.uint64(s), row_base=0)
+            del full
+            vb = c2.batch().add(blob[:n_v * args.read_len], roff[:n_v + 1])
+            vi, vs = c2.predict_stream(vb, K, s, SEED, top)
+            vb.close(); c2.close()
+            mi = m_idx[:n_v].cpu().numpy().view(np.uint32)
+            ms = m_sum[:n_v].cpu().numpy().view(np.uint64)
+            good = bool((mi == vi).all() and (ms == vs).all())
+            log(f"[rank 0] sharded ({world} GPUs) vs unsharded on {n_v} reads: {'ok' if good else 'MISMATCH'}")
+            ok[0] = 1.0 if good else 0.0
+        dist.broadcast(ok, 0)
+        assert ok.item() == 1.0, "sharded predict differs from unsharded"
     ctx.prof_reset()
     ctx.prof_enable(True)
     launches0 = ctx.launch_count
@@ -313,7 +333,7 @@ def run_b200(args):
                                    "s=10000, --top 10" if (N, s, R) == (40000, 10000, 100000) else
                                    f"predict {R} reads vs {N} x s={s}", "refs": N, "sketch_size": s, "reads": R,
                        "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages,
-                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 4096,
+                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 1792,
                        "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass"
                              % (rows_local * s * 8 / 1e9),
                        "parallelism": f"reference rows sharded over {world} GPU(s); NCCL all-gather of local top-N"

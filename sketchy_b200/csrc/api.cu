@@ -120,7 +120,7 @@ struct skb_ctx {
   DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, cand_pool;
   DevBuf sk_hashes, sk_counts;
   // predict scratch
-  DevBuf q_off, qh, qread, counts, lb_sum, lb_idx, cand, cand_cnt, scal;
+  DevBuf q_off, qh, qread, counts, lb_sum, lb_rel, lb_idx, cand, cand_cnt, ivl, scal;
   DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
@@ -512,7 +512,7 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   CU(c, cudaMemsetAsync(c->sums[0].p, 0, std::max<size_t>(8, (size_t)n_rows * 8), c->stream));
   c->sums_cur = 0;
   c->tracked_top = 0;
-  c->pass_cur = std::min<uint32_t>(64, c->pass_max);
+  c->pass_cur = std::min<uint32_t>(128, c->pass_max);
   CU(c, c->tracked[0].ensure((SKB_MAX_TRACKED + 1) * 4));
   CU(c, c->tracked[1].ensure((SKB_MAX_TRACKED + 1) * 4));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -574,7 +574,6 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     CU(c, cudaStreamSynchronize(c->stream));
     c->tracked_top = top;
   }
-  c->cand_cap = SKB_CAND_BUCKET;
   CU(c, c->scal.ensure(256));
   uint32_t* d_cand_total = c->scal.as<uint32_t>() + 8;                                                  // overflow flag
   unsigned long long* d_cand_stat = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 64);  // statistics
@@ -589,11 +588,17 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
     const uint32_t nkeys = (uint32_t)(q_off[r + B] - q_off[r]);
     if (int rc = ensure_table(c, nkeys)) { rc_final = rc; break; }
+    // per-read candidate buckets share one fixed budget: small passes (loose bounds right after a reset) get buckets
+    // as large as the shard itself, full passes still hold thousands of contenders per read
+    uint64_t budget = SKB_CAND_BUDGET;
+    if (const char* eb = getenv("SKB_CAND_BUDGET")) budget = std::max<uint64_t>(64, strtoull(eb, nullptr, 10));  // tests only
+    c->cand_cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(c->n_rows, 64), budget / B));
     const uint32_t stride = (uint32_t)round_up(B, 256);
     const size_t ctr_bytes = (size_t)SKB_MAX_TRACKED * stride * 2;
     cudaError_t e;
     if ((e = c->counts.ensure(ctr_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
         (e = c->lb_idx.ensure((size_t)B * 4)) != cudaSuccess || (e = c->cand_cnt.ensure((size_t)B * 4)) != cudaSuccess ||
+        (e = c->lb_rel.ensure((size_t)B * 4)) != cudaSuccess || (e = c->ivl.ensure((size_t)SKB_IVL_CAP * sizeof(SkbInterval))) != cudaSuccess ||
         (e = c->cand.ensure((size_t)B * c->cand_cap * sizeof(SkbCand))) != cudaSuccess ||
         (e = c->tprefix.ensure((size_t)SKB_MAX_TRACKED * stride * 4)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
@@ -603,7 +608,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1);
       skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->stream); }
     cudaMemsetAsync(c->counts.p, 0, ctr_bytes, c->stream);
-    cudaMemsetAsync(d_cand_total, 0, 4, c->stream);
+    cudaMemsetAsync(d_cand_total, 0, 8, c->stream);  // bucket-overflow flag + interval slot counter
     cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)B * 4, c->stream);
     const SkbRefView rv = ref_view(c);
     SkbRankArgs ra{};
@@ -611,13 +616,14 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     ra.row_stride = stride; ra.n_reads = B; ra.row_base = c->row_base;
     ra.sums_in = c->sums[c->sums_cur].as<unsigned long long>();
     ra.tracked = c->tracked[c->tracked_cur].as<uint32_t>(); ra.n_tracked = ra.tracked + SKB_MAX_TRACKED;
-    ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>();
+    ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>(); ra.lb_rel = c->lb_rel.as<uint32_t>();
+    ra.ivl = c->ivl.as<SkbInterval>(); ra.ivl_cap = SKB_IVL_CAP; ra.ivl_total = d_cand_total + 1;
     ra.cand = c->cand.as<SkbCand>(); ra.cand_cap = c->cand_cap; ra.cand_total = d_cand_total;
     ra.cand_cnt = c->cand_cnt.as<uint32_t>(); ra.cand_stat = d_cand_stat;
     ra.top = top; ra.out_idx = d_out_idx + (size_t)r * top;
     ra.out_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)r * top;
     ra.tracked_next = c->tracked[c->tracked_cur ^ 1].as<uint32_t>(); ra.n_tracked_next = ra.tracked_next + SKB_MAX_TRACKED;
-    { ProfScope ps(c, SKB_K_RANK, nkeys ? 3 : 2);
+    { ProfScope ps(c, SKB_K_RANK, nkeys ? 4 : 3);
       if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, ra.n_tracked, t, c->counts.as<uint16_t>(), stride, c->stream);
       skb_launch_rank_bounds(ra, c->stream); }
     SkbFusedArgs fa{};
@@ -625,18 +631,18 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     fa.n_reads = B; fa.cnt_stride = stride; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
     { const char* dbg = getenv("SKB_DEBUG"); fa.debug = dbg ? atoi(dbg) : 0; }
     fa.sums_in = ra.sums_in; fa.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
-    fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.cand = ra.cand; fa.cand_cap = ra.cand_cap;
-    fa.cand_total = ra.cand_total; fa.cand_cnt = ra.cand_cnt;
+    fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.lb_rel = ra.lb_rel;
+    fa.ivl = c->ivl.as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_cand_total + 1;
     { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
-    { ProfScope ps(c, SKB_K_RANK, 1); skb_launch_rank_select(ra, c->stream); }
+    { ProfScope ps(c, SKB_K_RANK, 2); skb_launch_rank_expand(ra, c->stream); skb_launch_rank_select(ra, c->stream); }
     if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
-    if ((e = cudaMemcpyAsync(h_total, d_cand_total, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+    if ((e = cudaMemcpyAsync(h_total, d_cand_total, 8, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e));
       break;
     }
     c->st_passes += 1;
-    if (*h_total != 0) {  // some read had more contenders than a bucket holds
+    if (h_total[0] != 0 || h_total[1] > SKB_IVL_CAP) {  // more contenders than a bucket / the interval list holds
       if (B > 1) {
         c->pass_cur = std::max(1u, B / 2);  // redo with fewer reads: the bounds tighten after every pass
         continue;
@@ -653,7 +659,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     c->sums_cur ^= 1;
     c->tracked_cur ^= 1;
     r += B;
-    if (*h_total == 0) c->pass_cur = std::min(c->pass_max, std::max(B, c->pass_cur) * 2);
+    if (h_total[0] == 0 && h_total[1] <= SKB_IVL_CAP) c->pass_cur = std::min(c->pass_max, std::max(B, c->pass_cur) * 2);
   }
   if (rc_final) return rc_final;
   unsigned long long cands = 0;
@@ -701,7 +707,7 @@ void skb_destroy(skb_ctx* c) {
   DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->sums[0], &c->sums[1], &c->tracked[0], &c->tracked[1], &c->tprefix, &c->g_tau, &c->g_cap,
                     &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->cand_pool,
                     &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->lb_sum,
-                    &c->lb_idx, &c->cand, &c->cand_cnt, &c->scal,
+                    &c->lb_idx, &c->lb_rel, &c->ivl, &c->cand, &c->cand_cnt, &c->scal,
                     &c->t_slots, &c->t_fill, &c->t_reads, &c->t_slot, &c->t_bloom, &c->out_idx,
                     &c->out_sum, &c->misc};
   for (DevBuf* b : bufs) b->release();
@@ -905,7 +911,7 @@ int skb_sums_reset(skb_ctx* c) {
   if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
   CU(c, cudaMemsetAsync(c->sums[c->sums_cur].p, 0, std::max<size_t>(8, (size_t)c->n_rows * 8), c->stream));
   c->tracked_top = 0;
-  c->pass_cur = std::min<uint32_t>(64, c->pass_max);
+  c->pass_cur = std::min<uint32_t>(128, c->pass_max);
   return SKB_OK;
 }
 

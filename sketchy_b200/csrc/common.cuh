@@ -35,6 +35,14 @@ struct __align__(16) SkbCand {
   uint32_t pad;
 };
 
+// Run-length form the rank warps produce: row `idx` has cumulative sum `sum` and is a top-N candidate for every read
+// in [b0, b1) of the pass (span = b0 | b1 << 16).
+struct __align__(16) SkbInterval {
+  unsigned long long sum;
+  uint32_t idx;
+  uint32_t span;
+};
+
 // (sum desc, idx asc) — the order of the reference's stable descending sort (src/sketchy.rs:310, 348).
 __host__ __device__ __forceinline__ bool skb_key_better(unsigned long long sa, uint32_t ia, unsigned long long sb,
                                                         uint32_t ib) {

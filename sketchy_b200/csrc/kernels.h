@@ -61,7 +61,7 @@ struct __align__(16) SkbSlot {
 #define SKB_SLOT_INLINE 4u
 #define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> (13 + 12 * (i))) & 0xFFFull))
 #define SKB_SLOT_START(m) ((uint32_t)(((m) >> 13) & 0xFFFFFFFFull))
-#define SKB_MAX_PASS_READS 2048u
+#define SKB_MAX_PASS_READS 1792u  // bounded by shared memory: 4 row buffers + staged bounds = 10 B per read
 
 struct SkbTable {
   SkbSlot* slots;     // [cap + 1]; slot `cap` is reserved for the key that equals SKB_EMPTY_KEY
@@ -100,20 +100,21 @@ struct SkbFusedArgs {
   const unsigned long long* sums_in;  // [n_rows]
   unsigned long long* sums_out;       // [n_rows]
   const unsigned long long* lb_sum;   // [n_reads] lower bound of every read's top-th key
+  const uint32_t* lb_rel;             // [n_reads] lb_sum[b] - lb_sum[0] (staged in shared memory by the kernel)
   const uint32_t* lb_idx;             // [n_reads]
-  SkbCand* cand;                      // [n_reads][cand_cap] per-read candidate buckets
-  uint32_t cand_cap;                  // bucket capacity
-  uint32_t* cand_total;               // [1] overflow flag: some read produced more candidates than a bucket holds
-  uint32_t* cand_cnt;                 // [n_reads] candidates produced per read (may exceed cand_cap)
+  SkbInterval* ivl;                   // [ivl_cap] candidate intervals produced by the rank warps
+  uint32_t ivl_cap;
+  uint32_t* ivl_total;                // [1] slots reserved (16 at a time); > ivl_cap = overflow
 };
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
 size_t skb_fused_smem_bytes(uint32_t cnt_stride);
+#define SKB_IVL_CAP (4u << 20)  // candidate intervals per pass; more than that shrinks the pass
 uint32_t skb_fused_tile();
 
 // per-read counts of the tracked rows only (they define the bounds): ctr[t][read], u16, row stride `stride`
 void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
                                const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st);
-#define SKB_CAND_BUCKET 4096u  // candidates kept per read and pass; more than that shrinks the pass
+#define SKB_CAND_BUDGET (24u << 20)  // candidate records per pass over all reads (384 MB); bucket = budget / reads
 
 #define SKB_MAX_TRACKED 192u  // rows whose exact per-read sums define the bounds
 
@@ -127,7 +128,11 @@ struct SkbRankArgs {
   const uint32_t* tracked;             // [*n_tracked] local rows
   const uint32_t* n_tracked;           // device scalar, <= SKB_MAX_TRACKED
   unsigned long long* lb_sum;          // [n_reads]
+  uint32_t* lb_rel;                    // [n_reads] lb_sum[b] - lb_sum[0]
   uint32_t* lb_idx;                    // [n_reads] (global index)
+  const SkbInterval* ivl;              // candidate intervals of the pass
+  uint32_t ivl_cap;
+  const uint32_t* ivl_total;
   SkbCand* cand;                       // [n_reads][cand_cap] per-read candidate buckets
   uint32_t cand_cap;
   uint32_t* cand_total;                // [1] overflow flag
@@ -142,6 +147,7 @@ struct SkbRankArgs {
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st);
 // tracked rows of the next pass = union of the top lists of 16 sampled reads of this pass (last read first)
 void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st);
+void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st);  // intervals -> per-read candidate buckets
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st);  // per-read top-N
 
 // top-N of a plain value array by (value desc, index asc); one CTA. idx_base is added to reported indices.

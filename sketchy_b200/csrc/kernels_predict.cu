@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   uint64_t* queue = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
   uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE);
   const uint32_t cwords = a.cnt_stride >> 1;  // 32-bit words per row buffer
+  uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride] bound growth since read 0, saturating
 
   const uint32_t r0 = a.cta_row[blockIdx.x], r1 = a.cta_row[blockIdx.x + 1];
 
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     for (uint32_t i = threadIdx.x; i < SKB_BLOOM_WORDS / 4; i += blockDim.x) dst[i] = src[i];
   }
   for (uint32_t i = threadIdx.x; i < FS_ROWBUF * cwords; i += blockDim.x) cnt32[i] = 0;
+  for (uint32_t i = threadIdx.x; i < a.n_reads; i += blockDim.x) lbrel[i] = (uint16_t)min(a.lb_rel[i], 0xFFFFu);
   __syncthreads();
 
   const uint32_t warp = threadIdx.x >> 5, lane = skb_lane();
@@ -529,17 +531,28 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   const uint32_t per = a.cnt_stride >> 5;        // counters per lane in the segment view (multiple of 8)
   const uint32_t seg0 = lane * per;
   const unsigned long long lb_min = a.lb_sum[0];  // bounds are non-decreasing along the reads
-  const unsigned long long lb_seg = seg0 < a.n_reads ? a.lb_sum[seg0] : ~0ull;
-  // candidates go straight into the read's bucket; the per-read counter doubles as the slot allocator
-  auto emit = [&](unsigned long long sum, uint32_t gi, uint32_t b) {
-    const uint32_t slot = atomicAdd(&a.cand_cnt[b], 1u);
-    if (slot < a.cand_cap) {
-      SkbCand cd;
-      cd.sum = sum; cd.idx = gi; cd.pad = 0;
-      a.cand[(size_t)b * a.cand_cap + slot] = cd;
-    } else {
-      *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
+  const unsigned long long lb_seg = seg0 < a.n_reads ? lb_min + lbrel[seg0] : ~0ull;
+  // is (sum sv, row gi) at least as good as the bound of read b?  (index only matters on the rare exact tie)
+  auto is_cand = [&](unsigned long long sv, uint32_t gi, uint32_t b) -> bool {
+    const uint32_t rel = lbrel[b];
+    const unsigned long long ls = rel != 0xFFFFu ? lb_min + rel : a.lb_sum[b];  // saturated: read the exact bound
+    return sv > ls || (sv == ls && gi <= a.lb_idx[b]);
+  };
+  // Candidates leave the kernel as intervals "row gi holds sum sv and meets the bound for reads [b0, b1)": a
+  // contending row produces one record per hit instead of one per read, and slots are reserved 16 at a time per lane
+  // so the rank warp never waits on an atomic per candidate.
+  uint32_t slot_next = 0, slot_left = 0;
+  auto emit = [&](unsigned long long sv, uint32_t gi, uint32_t b0, uint32_t b1) {
+    if (slot_left == 0) {
+      slot_next = atomicAdd(a.ivl_total, 16u);
+      slot_left = 16;
     }
+    if (slot_next < a.ivl_cap) {
+      SkbInterval iv;
+      iv.sum = sv; iv.idx = gi; iv.span = b0 | (b1 << 16);
+      a.ivl[slot_next] = iv;
+    }
+    ++slot_next; --slot_left;
   };
   unsigned long long carry_next = (r0 + rp < r1) ? a.sums_in[r0 + rp] : 0ull;
   for (uint32_t row = r0 + rp; row < r1; row += 2) {
@@ -574,32 +587,38 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
           if ((int)lane >= o) incl += y;
         }
         if (seg0 < a.n_reads && carry + incl >= lb_seg) {
-          // Walk the segment. Between two hits the row's sum is constant while the bound only tightens, so once
-          // a read rejects the row every following read does too until the next hit: bounds are only loaded at
-          // the segment start, at hit positions, and while the row stays a candidate.
+          // Walk the segment. Between two hits the row's sum is constant while the bound only tightens, so an
+          // interval opens at a hit (or at the segment start) and closes at the next hit or when the bound overtakes.
+          const uint32_t seg_end = min(seg0 + per, a.n_reads);
           uint32_t run = incl - tot;
-          bool live = true;
+          bool open = false, first = true;
+          uint32_t ob = 0;
+          unsigned long long os = 0;
           for (uint32_t i = 0; i < (per >> 1); ++i) {
             const uint32_t x = cseg[i];
-            if (x == 0u && !live) continue;
+            if (x == 0u && !open && !first) continue;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const uint32_t c = half ? (x >> 16) : (x & 0xFFFFu);
               const uint32_t b = seg0 + 2 * i + half;
-              if (c) { run += c; live = true; }
-              if (live && b < a.n_reads) {
-                const unsigned long long sv = carry + run;
-                live = false;
-                if (sv >= lb_seg) {
-                  const unsigned long long ls = a.lb_sum[b];
-                  if (sv > ls || (sv == ls && gi <= a.lb_idx[b])) {
-                    emit(sv, gi, b);
-                    live = true;
-                  }
+              if (b < seg_end) {
+                bool check = open || first;
+                first = false;
+                if (c) {
+                  if (open) { emit(os, gi, ob, b); open = false; }
+                  run += c;
+                  check = true;
+                }
+                if (check) {
+                  const unsigned long long sv = carry + run;
+                  const bool cand = sv >= lb_seg && is_cand(sv, gi, b);
+                  if (cand && !open) { open = true; ob = b; os = sv; }
+                  if (!cand && open) { emit(os, gi, ob, b); open = false; }
                 }
               }
             }
           }
+          if (open) emit(os, gi, ob, seg_end);
         }
         __syncwarp();
       }
@@ -607,21 +626,29 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
       uint4* z = reinterpret_cast<uint4*>(cpar);
       for (uint32_t i = lane; i < (cwords >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
     } else if (carry >= lb_min && !(a.debug & 128)) {
-      // no hit in this pass: the row's sum is `carry` for every read; it is a candidate for a prefix of the reads
-      // (first passes of a stream, when most sums tie at the bound)
+      // no hit in this pass: the row's sum is `carry` for every read, so it meets the bound for a prefix [0, e) of
+      // the reads (first passes of a stream, when most sums tie at the bound)
+      uint32_t e = 0;
       for (uint32_t b0 = 0; b0 < a.n_reads; b0 += 32) {
         const uint32_t b = b0 + lane;
-        bool ok = false;
-        if (b < a.n_reads) {
-          const unsigned long long ls = a.lb_sum[b];
-          ok = carry > ls || (carry == ls && gi <= a.lb_idx[b]);
-          if (ok) emit(carry, gi, b);
-        }
-        if (!__all_sync(0xffffffffu, ok)) break;
+        const bool ok = b < a.n_reads && is_cand(carry, gi, b);
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        if (bal != 0xffffffffu) { e = b0 + (uint32_t)__ffs(~bal) - 1; break; }
+        e = b0 + 32;
       }
+      if (e > a.n_reads) e = a.n_reads;
+      if (lane == 0 && e) emit(carry, gi, 0, e);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&row_free[rb]);
+  }
+  // hand back the unused part of the last reservation as empty intervals
+  for (; slot_left; --slot_left, ++slot_next) {
+    if (slot_next < a.ivl_cap) {
+      SkbInterval iv;
+      iv.sum = 0; iv.idx = 0xFFFFFFFFu; iv.span = 0;
+      a.ivl[slot_next] = iv;
+    }
   }
 }
 
@@ -712,6 +739,32 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
   }
   a.lb_sum[b] = n ? ks[n - 1] : 0ull;
   a.lb_idx[b] = n ? ki[n - 1] : 0xFFFFFFFFu;
+}
+
+__global__ void lb_rel_kernel(const SkbRankArgs a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < a.n_reads) a.lb_rel[b] = (uint32_t)(a.lb_sum[b] - a.lb_sum[0]);  // in-pass growth always fits 32 bits
+}
+
+// intervals -> per-read candidate buckets. One warp per interval; the per-read counter is the slot allocator.
+__global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
+  const uint32_t total = min(*a.ivl_total, a.ivl_cap);
+  const uint32_t lane = skb_lane();
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += nwarps) {
+    const SkbInterval iv = a.ivl[w];
+    const uint32_t b0 = iv.span & 0xFFFFu, b1 = iv.span >> 16;
+    for (uint32_t b = b0 + lane; b < b1; b += 32) {
+      const uint32_t slot = atomicAdd(&a.cand_cnt[b], 1u);
+      if (slot < a.cand_cap) {
+        SkbCand cd;
+        cd.sum = iv.sum; cd.idx = iv.idx; cd.pad = 0;
+        a.cand[(size_t)b * a.cand_cap + slot] = cd;
+      } else {
+        *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
+      }
+    }
+  }
 }
 
 // Tracked rows of the next pass: the union of the top lists of 16 evenly spaced reads of this pass, the last read's
@@ -934,7 +987,7 @@ void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_
 }
 
 size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 2 * FS_ROWBUF;
+  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 2 * FS_ROWBUF + (size_t)cnt_stride * 2;
 }
 uint32_t skb_fused_tile() { return FS_SUB; }
 
@@ -957,7 +1010,10 @@ void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, co
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) {
   tracked_prefix_kernel<<<SKB_MAX_TRACKED, 256, 0, st>>>(a);
   rank_bounds_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
+  lb_rel_kernel<<<(a.n_reads + 255) / 256, 256, 0, st>>>(a);
 }
+
+void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st) { expand_kernel<<<148 * 8, 256, 0, st>>>(a); }
 
 void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st) { tracked_update_kernel<<<1, 1024, 0, st>>>(a); }
 

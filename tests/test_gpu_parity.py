@@ -171,9 +171,10 @@ def test_predict_medium_scale(ctx):
     _check_predict(ctx, ref, off, blob, roff, 16, 1000, 0, 10, 0)
 
 
-def test_predict_more_contenders_than_a_bucket(ctx):
-    """4500 references beat the tracked row at once: the per-read candidate bucket (4096) overflows, the pass is
-    halved down to single reads and those are ranked exactly from the new sums."""
+def test_predict_more_contenders_than_a_bucket(ctx, monkeypatch):
+    """4500 references beat the tracked row at once while the candidate budget is forced tiny: buckets overflow, the
+    pass is halved down to single reads and those are ranked exactly from the new sums."""
+    monkeypatch.setenv("SKB_CAND_BUDGET", "4096")
     ga = synth.random_genome(20_000, 901)
     gb = synth.random_genome(20_000, 902)
     sk, _, _ = oracle.sketch_groups([ga.tobytes(), gb.tobytes()], [0, 1], 2, 16, 300, 0)
