@@ -124,7 +124,7 @@ struct skb_ctx {
   DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = SKB_MAX_PASS_READS, pass_cur = 64;
+  uint32_t pass_max = 2560, pass_cur = 64;  // default reads per pass (<= SKB_MAX_PASS_READS_NARROW)
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -583,6 +583,11 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   int rc_final = SKB_OK;
   while (r < R) {
     uint32_t B = std::min<uint32_t>(std::min(c->pass_cur, c->pass_max), R - r);
+    // u8 counters need every read of the pass to keep <= 255 query hashes; otherwise u16 counters and fewer reads
+    bool narrow = true;
+    for (uint32_t i = r; i < r + B; ++i)
+      if (qn[i] > 255u) { narrow = false; break; }
+    if (!narrow) B = std::min<uint32_t>(B, SKB_MAX_PASS_READS);
     // keep the pass's key count inside the filter's design load (and the table)
     const uint64_t key_budget = 1u << 17;
     while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
@@ -593,7 +598,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     uint64_t budget = SKB_CAND_BUDGET;
     if (const char* eb = getenv("SKB_CAND_BUDGET")) budget = std::max<uint64_t>(64, strtoull(eb, nullptr, 10));  // tests only
     c->cand_cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(c->n_rows, 64), budget / B));
-    const uint32_t stride = (uint32_t)round_up(B, 256);
+    const uint32_t stride = (uint32_t)round_up(B, narrow ? 512 : 256);
     const size_t ctr_bytes = (size_t)SKB_MAX_TRACKED * stride * 2;
     cudaError_t e;
     if ((e = c->counts.ensure(ctr_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
@@ -628,7 +633,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
       skb_launch_rank_bounds(ra, c->stream); }
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
-    fa.n_reads = B; fa.cnt_stride = stride; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
+    fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
     { const char* dbg = getenv("SKB_DEBUG"); fa.debug = dbg ? atoi(dbg) : 0; }
     fa.sums_in = ra.sums_in; fa.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
     fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.lb_rel = ra.lb_rel;
@@ -936,7 +941,7 @@ int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
-  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS) : SKB_MAX_PASS_READS;
+  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS_NARROW) : 2560;
   c->pass_cur = std::min(c->pass_cur, c->pass_max);
   return SKB_OK;
 }

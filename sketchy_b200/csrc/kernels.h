@@ -61,7 +61,8 @@ struct __align__(16) SkbSlot {
 #define SKB_SLOT_INLINE 4u
 #define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> (13 + 12 * (i))) & 0xFFFull))
 #define SKB_SLOT_START(m) ((uint32_t)(((m) >> 13) & 0xFFFFFFFFull))
-#define SKB_MAX_PASS_READS 1792u  // bounded by shared memory: 4 row buffers + staged bounds = 10 B per read
+#define SKB_MAX_PASS_READS 1792u         // u16 counters: 4 row buffers + staged bounds = 10 B of shared memory per read
+#define SKB_MAX_PASS_READS_NARROW 3072u  // u8 counters (reads with <= 255 query hashes): 6 B per read
 
 struct SkbTable {
   SkbSlot* slots;     // [cap + 1]; slot `cap` is reserved for the key that equals SKB_EMPTY_KEY
@@ -93,7 +94,8 @@ struct SkbFusedArgs {
   int num_ctas;
   SkbTable table;
   uint32_t n_reads;     // reads in this pass
-  uint32_t cnt_stride;  // u16 counters per row buffer (multiple of 256, >= n_reads)
+  uint32_t cnt_stride;  // counters per row buffer (multiple of 512, >= n_reads)
+  int narrow;           // counters are u8 (every read of the pass keeps <= 255 query hashes) instead of u16
   int skip_stream;      // the pass has no query hashes: rows are ranked without being streamed
   int debug;            // experiments only (SKB_DEBUG env): 1 = no filter probe, 2 = probe but drop passers
   uint32_t row_base;    // global index of local row 0
@@ -108,6 +110,7 @@ struct SkbFusedArgs {
 };
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
 size_t skb_fused_smem_bytes(uint32_t cnt_stride);
+size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride);
 #define SKB_IVL_CAP (4u << 20)  // candidate intervals per pass; more than that shrinks the pass
 uint32_t skb_fused_tile();
 

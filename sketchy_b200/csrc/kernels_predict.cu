@@ -177,21 +177,24 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 }
 
 // two u16 counters per 32-bit word; a per-(row, read) count never exceeds 65535 (checked on the host)
+template <int CPW>
 __device__ __forceinline__ void count_hit(uint32_t* cbuf, uint32_t rd) {
-  atomicAdd(cbuf + (rd >> 1), 1u << (16 * (rd & 1u)));
+  if (CPW == 2) atomicAdd(cbuf + (rd >> 1), 1u << (16 * (rd & 1u)));
+  else atomicAdd(cbuf + (rd >> 2), 1u << (8 * (rd & 3u)));  // u8 counters: the host guarantees counts <= 255
 }
 
 // add the slot's reads to the row's counters; returns the number of increments
+template <int CPW>
 __device__ __forceinline__ uint32_t apply_hit(const SkbTable& t, const SkbSlot& s, uint32_t* cbuf) {
   const uint32_t c = SKB_SLOT_CNT(s.meta);
   if (c <= SKB_SLOT_INLINE) {
-    count_hit(cbuf, SKB_SLOT_ID(s.meta, 0));
+    count_hit<CPW>(cbuf, SKB_SLOT_ID(s.meta, 0));
     if (c > 1) {
-      for (uint32_t j = 1; j < c; ++j) count_hit(cbuf, (uint32_t)((s.meta >> (13 + 12 * j)) & 0xFFFull));
+      for (uint32_t j = 1; j < c; ++j) count_hit<CPW>(cbuf, (uint32_t)((s.meta >> (13 + 12 * j)) & 0xFFFull));
     }
   } else {
     const uint32_t st = SKB_SLOT_START(s.meta);
-    for (uint32_t j = 0; j < c; ++j) count_hit(cbuf, t.reads[st + j]);
+    for (uint32_t j = 0; j < c; ++j) count_hit<CPW>(cbuf, t.reads[st + j]);
   }
   return c;
 }
@@ -244,6 +247,9 @@ struct SubIter {
   }
 };
 
+// CPW = counters per 32-bit word of a row buffer: 2 (u16, any pass) or 4 (u8, when no read of the pass keeps more than
+// 255 query hashes; more reads fit a pass).
+template <int CPW>
 __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[FS_CONSUMER_WARPS][FS_STAGES];
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM);
   uint64_t* queue = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
   uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE);
-  const uint32_t cwords = a.cnt_stride >> 1;  // 32-bit words per row buffer
+  const uint32_t cwords = a.cnt_stride / CPW;  // 32-bit words per row buffer
   uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride] bound growth since read 0, saturating
 
   const uint32_t r0 = a.cta_row[blockIdx.x], r1 = a.cta_row[blockIdx.x + 1];
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
 
     auto count_now = [&](uint64_t h, uint32_t par) {  // synchronous lookup: only when the FIFO cannot take a burst
       SkbSlot s;
-      if (table_lookup(t, h, s)) atomicAdd(&row_hits[par], apply_hit(t, s, cnt32 + par * cwords));
+      if (table_lookup(t, h, s)) atomicAdd(&row_hits[par], apply_hit<CPW>(t, s, cnt32 + par * cwords));
     };
     auto try_close = [&]() {
       const uint32_t nz = ((outst & 0xFFu) ? 1u : 0u) | ((outst & 0xFF00u) ? 2u : 0u) | ((outst & 0xFF0000u) ? 4u : 0u) |
@@ -326,9 +332,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
         if (pend.valid) {
           uint32_t* cb = cnt32 + pend.par * cwords;
           if (pend.h == SKB_EMPTY_KEY) {
-            if (SKB_SLOT_CNT(s.meta) != 0) hits = apply_hit(t, s, cb);
+            if (SKB_SLOT_CNT(s.meta) != 0) hits = apply_hit<CPW>(t, s, cb);
           } else if (s.key == pend.h) {
-            hits = apply_hit(t, s, cb);
+            hits = apply_hit<CPW>(t, s, cb);
           } else if (s.key != SKB_EMPTY_KEY) {
             again = true;
           }
@@ -349,7 +355,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
               for (;;) {
                 slot = (slot + 1) & (t.cap - 1);
                 s = load_slot(&t.slots[slot]);
-                if (s.key == pend.h) { hits = apply_hit(t, s, cnt32 + pend.par * cwords); break; }
+                if (s.key == pend.h) { hits = apply_hit<CPW>(t, s, cnt32 + pend.par * cwords); break; }
                 if (s.key == SKB_EMPTY_KEY) break;
               }
               again = false;
@@ -573,12 +579,22 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
       // sums and bounds never decrease along the reads: a row whose FINAL sum is under the FIRST bound, or a
       // lane segment whose final sum is under the segment's first bound, cannot hold a candidate
       if (carry + row_total >= lb_min && !(a.debug & 4)) {
-        const uint32_t* cseg = cpar + (seg0 >> 1);
+        const uint32_t* cseg = cpar + seg0 / CPW;
+        const uint32_t segw = per / CPW;  // words in this lane's segment (multiple of 4)
         uint32_t tot = 0;
-        for (uint32_t i = 0; i < (per >> 1); i += 4) {
+        for (uint32_t i = 0; i < segw; i += 4) {
           const uint4 x = *reinterpret_cast<const uint4*>(cseg + i);
-          tot += (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) + (x.z & 0xFFFFu) + (x.z >> 16) +
-                 (x.w & 0xFFFFu) + (x.w >> 16);
+          if (CPW == 2) {
+            tot += (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) + (x.z & 0xFFFFu) + (x.z >> 16) +
+                   (x.w & 0xFFFFu) + (x.w >> 16);
+          } else {  // four u8 counters per word: sum the byte lanes with a masked add
+            const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t pair = (w4[q] & 0x00FF00FFu) + ((w4[q] >> 8) & 0x00FF00FFu);
+              tot += (pair & 0xFFFFu) + (pair >> 16);
+            }
+          }
         }
         uint32_t incl = tot;
 #pragma unroll
@@ -594,13 +610,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
           bool open = false, first = true;
           uint32_t ob = 0;
           unsigned long long os = 0;
-          for (uint32_t i = 0; i < (per >> 1); ++i) {
+          for (uint32_t i = 0; i < segw; ++i) {
             const uint32_t x = cseg[i];
             if (x == 0u && !open && !first) continue;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint32_t c = half ? (x >> 16) : (x & 0xFFFFu);
-              const uint32_t b = seg0 + 2 * i + half;
+            for (int half = 0; half < CPW; ++half) {
+              const uint32_t c = CPW == 2 ? (half ? (x >> 16) : (x & 0xFFFFu)) : ((x >> (8 * half)) & 0xFFu);
+              const uint32_t b = seg0 + CPW * i + half;
               if (b < seg_end) {
                 bool check = open || first;
                 first = false;
@@ -664,7 +680,7 @@ __global__ void __launch_bounds__(256) tracked_counts_kernel(const SkbRefView rv
   uint32_t* cbuf = reinterpret_cast<uint32_t*>(ctr + (size_t)tr * stride);
   for (uint32_t i = part * blockDim.x + threadIdx.x; i < len; i += 8 * blockDim.x) {
     SkbSlot s;
-    if (table_lookup(t, src[i], s)) apply_hit(t, s, cbuf);
+    if (table_lookup(t, src[i], s)) apply_hit<2>(t, s, cbuf);
   }
 }
 
@@ -989,17 +1005,22 @@ void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_
 size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
   return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 2 * FS_ROWBUF + (size_t)cnt_stride * 2;
 }
+size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
+  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 1 * FS_ROWBUF + (size_t)cnt_stride * 2;
+}
 uint32_t skb_fused_tile() { return FS_SUB; }
 
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st) {
   if (a.rv.n_rows == 0) return;
-  const size_t smem = skb_fused_smem_bytes(a.cnt_stride);
+  const size_t smem = a.narrow ? skb_fused_smem_bytes_narrow(a.cnt_stride) : skb_fused_smem_bytes(a.cnt_stride);
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
-  fused_kernel<<<a.num_ctas, FS_THREADS, smem, st>>>(a);
+  if (a.narrow) fused_kernel<4><<<a.num_ctas, FS_THREADS, smem, st>>>(a);
+  else fused_kernel<2><<<a.num_ctas, FS_THREADS, smem, st>>>(a);
 }
 
 void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
