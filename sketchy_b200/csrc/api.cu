@@ -65,12 +65,71 @@ struct PackLut {
 };
 const PackLut kPackLut;
 
+// Two input bytes at a time: lut2[b0 | b1 << 8] = code0 | code1 << 2 when both bytes are ACGT/acgt/Uu, 0xFF otherwise
+// (the rare chunk with anything else takes the byte-wise path).
+struct PackLut2 {
+  uint8_t t[65536];
+  PackLut2() {
+    for (int b0 = 0; b0 < 256; ++b0)
+      for (int b1 = 0; b1 < 256; ++b1) {
+        const uint8_t c0 = kPackLut.t[b0], c1 = kPackLut.t[b1];
+        t[b0 | (b1 << 8)] = (c0 < 4 && c1 < 4) ? (uint8_t)(c0 | (c1 << 2)) : 0xFF;
+      }
+  }
+};
+const PackLut2 kPackLut2;
+
 // Pack one record at base position P (multiple of 32); everything up to Pnext (multiple of 32) not covered by a
 // valid base is marked invalid. The words touched belong to this record alone.
 void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uint32_t* codes, uint32_t* nmask) {
   uint64_t pos = P;
+  uint64_t i = 0;
+  // fast path: 32 clean bases -> two code words and one all-valid mask word (pos stays a multiple of 32)
+  while (i + 32 <= len) {
+    uint32_t w[2];
+    bool clean = true;
+    for (int h = 0; h < 2 && clean; ++h) {
+      uint32_t cw = 0;
+      const uint8_t* p = s + i + 16 * h;
+      for (int j = 0; j < 8; ++j) {
+        const uint8_t v = kPackLut2.t[p[2 * j] | ((uint32_t)p[2 * j + 1] << 8)];
+        if (v == 0xFF) { clean = false; break; }
+        cw |= (uint32_t)v << (4 * j);
+      }
+      w[h] = cw;
+    }
+    if (!clean) break;
+    codes[pos >> 4] = w[0];
+    codes[(pos >> 4) + 1] = w[1];
+    nmask[pos >> 5] = 0;
+    pos += 32;
+    i += 32;
+  }
   uint32_t cw = 0, mw = 0;
-  for (uint64_t i = 0; i < len; ++i) {
+  for (; i < len; ++i) {
+    // resume the fast path whenever we are block-aligned again and the next 32 bytes are clean
+    if ((pos & 31) == 0 && i + 32 <= len) {
+      uint32_t w[2];
+      bool clean = true;
+      for (int h = 0; h < 2 && clean; ++h) {
+        uint32_t c2 = 0;
+        const uint8_t* p = s + i + 16 * h;
+        for (int j = 0; j < 8; ++j) {
+          const uint8_t v = kPackLut2.t[p[2 * j] | ((uint32_t)p[2 * j + 1] << 8)];
+          if (v == 0xFF) { clean = false; break; }
+          c2 |= (uint32_t)v << (4 * j);
+        }
+        w[h] = c2;
+      }
+      if (clean) {
+        codes[pos >> 4] = w[0];
+        codes[(pos >> 4) + 1] = w[1];
+        nmask[pos >> 5] = 0;
+        pos += 32;
+        i += 31;  // the loop adds one
+        continue;
+      }
+    }
     const uint32_t v = kPackLut.t[s[i]];
     if (v == 5) continue;
     if (v < 4) cw |= v << (2 * (pos & 15));
