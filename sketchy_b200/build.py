@@ -27,6 +27,10 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(SO)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps += [os.path.join(HERE, "host", f) for f in ("main.cpp", "msh.cpp", "msh.hpp", "fastx.hpp", "capnp_lite.hpp")]
+    cli = os.path.join(HERE, "bin", "sketchy")
+    if not os.path.exists(cli):
+        return True
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -53,7 +57,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO, *objs, "-lcudart"]
     subprocess.check_call(cmd)
+    build_host()
     return SO
+
+
+HOST = os.path.join(HERE, "host")
+CLI = os.path.join(HERE, "bin", "sketchy")
+
+
+def build_host() -> str:
+    """The `sketchy` CLI host (C++): same sub-commands / flags / rows as the reference binary, over the C ABI."""
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", os.path.join(HOST, "main.cpp"), os.path.join(HOST, "msh.cpp"), "-o", CLI,
+           "-L" + HERE, "-lsketchy_b200", "-lz", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
+    subprocess.check_call(cmd)
+    return CLI
 
 
 if __name__ == "__main__":

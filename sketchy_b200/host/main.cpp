@@ -1,0 +1,437 @@
+// main.cpp — `sketchy` command line host over libsketchy_b200.so: the same sub-commands, flags, defaults, stdout rows
+// and error texts as the reference CLI (src/cli.rs:23-133, src/main.rs:17-68, src/sketchy.rs), with the hot path on the
+// GPU through the C ABI. `info` and the hidden `msh-*` helpers need no GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/sketchy_b200.h"
+#include "fastx.hpp"
+#include "msh.hpp"
+
+namespace {
+
+struct Args {
+  std::string cmd;
+  std::map<std::string, std::vector<std::string>> opt;
+  bool has(const std::string& k) const { return opt.count(k) != 0; }
+  std::string one(const std::string& k, const std::string& dflt = "") const {
+    auto it = opt.find(k);
+    return it == opt.end() || it->second.empty() ? dflt : it->second[0];
+  }
+};
+
+const std::map<std::string, std::string> kShort = {
+    {"-i", "input"}, {"-o", "output"}, {"-s", "sketch-size|stream"}, {"-k", "kmer-size"}, {"-c", "scale|consensus"},
+    {"-e", "seed"}, {"-p", "params"}, {"-r", "reference"}, {"-g", "genotypes"}, {"-q", "query"}, {"-t", "top"},
+    {"-l", "limit"}, {"-H", "header"}};
+
+Args parse(int argc, char** argv) {
+  Args a;
+  if (argc < 2) throw std::runtime_error("usage: sketchy <sketch|info|check|shared|predict> [options]");
+  a.cmd = argv[1];
+  std::string cur;
+  for (int i = 2; i < argc; ++i) {
+    std::string t = argv[i];
+    if (t.size() >= 2 && t[0] == '-' && !(t.size() > 1 && (isdigit((unsigned char)t[1]) || t[1] == '.'))) {
+      std::string name;
+      if (t.rfind("--", 0) == 0) {
+        name = t.substr(2);
+      } else {
+        auto it = kShort.find(t);
+        if (it == kShort.end()) throw std::runtime_error("unknown option " + t);
+        name = it->second;
+        const size_t bar = name.find('|');
+        if (bar != std::string::npos) {  // -s / -c mean different things per sub-command (src/cli.rs:33, 124; :39, 127)
+          name = a.cmd == "predict" ? name.substr(bar + 1) : name.substr(0, bar);
+        }
+      }
+      cur = name;
+      a.opt[cur];
+    } else {
+      if (cur.empty()) throw std::runtime_error("unexpected argument " + t);
+      a.opt[cur].push_back(t);
+    }
+  }
+  return a;
+}
+
+std::string basename_of(const std::string& p) {
+  const size_t s = p.find_last_of('/');
+  return s == std::string::npos ? p : p.substr(s + 1);
+}
+std::string ext_of(const std::string& p) {
+  const std::string b = basename_of(p);
+  const size_t d = b.find_last_of('.');
+  return d == std::string::npos ? "" : b.substr(d + 1);
+}
+
+void require_msh(const std::string& path) {
+  const std::string e = ext_of(path);
+  if (e == "fsh") throw std::runtime_error("Finch (.fsh) scaled sketches are not supported by the B200 build (DESIGN.md §7)");
+  if (e != "msh") throw std::runtime_error("reference sketch file must have Mash (.msh) or Finch (.fsh) extension");
+}
+
+struct Ctx {
+  skb_ctx* c = nullptr;
+  Ctx() {
+    const char* dev = getenv("SKETCHY_B200_DEVICE");
+    const int rc = skb_create(dev ? atoi(dev) : 0, &c);
+    if (rc != SKB_OK) throw std::runtime_error("no B200 (sm_100) device: the B200 build has no CPU fallback");
+  }
+  ~Ctx() { if (c) skb_destroy(c); }
+  void check(int rc) const { if (rc != SKB_OK) throw std::runtime_error(skb_last_error(c)); }
+};
+
+struct Blob {
+  std::vector<uint8_t> bytes;
+  std::vector<uint64_t> off{0};
+  std::vector<uint32_t> grp;
+  void add(const std::string& s, uint32_t g) {
+    bytes.insert(bytes.end(), s.begin(), s.end());
+    off.push_back(bytes.size());
+    grp.push_back(g);
+  }
+  void clear() { bytes.clear(); off.assign(1, 0); grp.clear(); }
+  size_t n() const { return grp.size(); }
+};
+
+// ---- genotype table (src/sketchy.rs:538-571): TSV with header; header minus the first column; name -> columns
+struct Genotypes {
+  std::string header;
+  std::vector<std::vector<std::string>> rows;
+  std::unordered_map<std::string, std::vector<std::string>> map;
+};
+std::vector<std::string> split_tab(const std::string& l) {
+  std::vector<std::string> f;
+  size_t s = 0;
+  for (;;) {
+    const size_t e = l.find('\t', s);
+    f.push_back(l.substr(s, e == std::string::npos ? std::string::npos : e - s));
+    if (e == std::string::npos) break;
+    s = e + 1;
+  }
+  return f;
+}
+Genotypes read_genotypes(const std::string& path) {
+  FILE* fp = fopen(path.c_str(), "r");
+  if (!fp) throw std::runtime_error("failed to open genotype file or record with CSV");
+  Genotypes g;
+  std::string line;
+  char buf[1 << 16];
+  bool first = true;
+  std::string acc;
+  while (fgets(buf, sizeof buf, fp)) {
+    acc += buf;
+    if (acc.empty() || acc.back() != '\n') continue;
+    while (!acc.empty() && (acc.back() == '\n' || acc.back() == '\r')) acc.pop_back();
+    if (!acc.empty()) {
+      std::vector<std::string> f = split_tab(acc);
+      if (first) {
+        for (size_t i = 1; i < f.size(); ++i) g.header += (i > 1 ? "\t" : "") + f[i];
+        first = false;
+      } else {
+        g.map[f[0]] = std::vector<std::string>(f.begin() + 1, f.end());  // duplicate names: last wins
+        g.rows.push_back(std::move(f));
+      }
+    }
+    acc.clear();
+  }
+  if (!acc.empty()) {
+    std::vector<std::string> f = split_tab(acc);
+    if (!first) { g.map[f[0]] = std::vector<std::string>(f.begin() + 1, f.end()); g.rows.push_back(std::move(f)); }
+  }
+  fclose(fp);
+  return g;
+}
+
+std::string join_tab(const std::vector<std::string>& v) {
+  std::string s;
+  for (size_t i = 0; i < v.size(); ++i) s += (i ? "\t" : "") + v[i];
+  return s;
+}
+
+// src/sketchy.rs:358-413; consensus ties go to the value met first in rank order (the reference's HashMap order is
+// nondeterministic there — DESIGN.md §2)
+void print_results(const msh::File& ref, const Genotypes& g, uint64_t read, const uint32_t* idx, const uint64_t* sum,
+                   uint32_t top, bool consensus) {
+  if (consensus) {
+    std::vector<const std::vector<std::string>*> gs;
+    for (uint32_t t = 0; t < top; ++t) gs.push_back(&g.map.at(ref.sketches[idx[t]].name));
+    std::string out = std::to_string(read) + "\t-\t-\t";
+    const size_t nf = gs.empty() ? 0 : gs[0]->size();
+    for (size_t j = 0; j < nf; ++j) {
+      std::string best;
+      size_t best_n = 0;
+      for (uint32_t t = 0; t < top; ++t) {
+        size_t c = 0;
+        for (uint32_t u = 0; u < top; ++u) c += (*gs[u])[j] == (*gs[t])[j];
+        if (c > best_n) { best_n = c; best = (*gs[t])[j]; }
+      }
+      out += (j ? "\t" : "") + best;
+    }
+    puts(out.c_str());
+  } else {
+    for (uint32_t t = 0; t < top; ++t) {
+      const std::string& name = ref.sketches[idx[t]].name;
+      printf("%llu\t%s\t%llu\t%s\n", (unsigned long long)read, name.c_str(), (unsigned long long)sum[t],
+             join_tab(g.map.at(name)).c_str());
+    }
+  }
+}
+
+void upload_reference(const Ctx& c, const msh::File& ref) {
+  std::vector<uint64_t> flat, off{0};
+  for (const auto& s : ref.sketches) {
+    flat.insert(flat.end(), s.hashes.begin(), s.hashes.end());
+    off.push_back(flat.size());
+  }
+  c.check(skb_ref_upload(c.c, flat.data(), off.data(), (uint32_t)ref.sketches.size(), 0));
+}
+
+// ---- sub-commands -----------------------------------------------------------------------------------------------
+int cmd_sketch(const Args& a) {
+  if (!a.has("output")) throw std::runtime_error("error: The following required arguments were not provided: --output <output>");
+  const std::string out = a.one("output");
+  require_msh(out);
+  const uint32_t s = (uint32_t)std::stoul(a.one("sketch-size", "1000"));
+  const uint32_t k = (uint32_t)std::stoul(a.one("kmer-size", "16"));
+  const uint64_t seed = std::stoull(a.one("seed", "0"));
+  const double scale = std::stod(a.one("scale", "0.001"));
+  if (!(scale >= 0.0 && scale <= 1.0)) throw std::runtime_error("Scale parameter must be between 0 and 1");
+  std::vector<std::string> files;
+  if (a.has("input")) files = a.opt.at("input");
+  else for (std::string l; std::getline(std::cin, l);) if (!l.empty()) files.push_back(l);  // src/sketchy.rs:137-146
+  FILE* fp = fopen(out.c_str(), "wb");  // created before sketching, like the reference (:153)
+  if (!fp) throw std::runtime_error("failed to open file");
+  fclose(fp);
+  Ctx c;
+  skb_batch* b = nullptr;
+  c.check(skb_batch_create(c.c, &b));
+  msh::File f;
+  f.kmer_size = k; f.sketch_size = s; f.hash_seed = seed;
+  Blob blob;
+  for (size_t g = 0; g < files.size(); ++g) {
+    fastx::Reader rd(files[g]);
+    fastx::Record r;
+    while (rd.next(r)) blob.add(r.seq, (uint32_t)g);
+    msh::Sketch sk;
+    sk.name = basename_of(files[g]);
+    f.sketches.push_back(sk);
+    if (blob.bytes.size() > (1ull << 30) || g + 1 == files.size()) {
+      if (blob.n()) c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), blob.grp.data(), blob.n(), 0));
+      blob.clear();
+    }
+  }
+  const uint32_t G = (uint32_t)files.size();
+  const uint32_t have = skb_batch_num_groups(b);  // trailing empty files have no group yet
+  std::vector<uint64_t> hs((size_t)G * s), bases(G, 0), kmers(G, 0);
+  std::vector<uint32_t> cnt((size_t)G * s), n(G, 0);
+  if (have) c.check(skb_sketch(c.c, b, k, s, seed, hs.data(), cnt.data(), n.data(), bases.data(), kmers.data()));
+  for (uint32_t g = 0; g < G; ++g) {
+    auto& sk = f.sketches[g];
+    sk.seq_length = bases[g]; sk.num_valid_kmers = kmers[g];
+    sk.hashes.assign(hs.begin() + (size_t)g * s, hs.begin() + (size_t)g * s + n[g]);
+    sk.counts.assign(cnt.begin() + (size_t)g * s, cnt.begin() + (size_t)g * s + n[g]);
+  }
+  skb_batch_destroy(b);
+  msh::write_file(out, f);
+  return 0;
+}
+
+int cmd_info(const Args& a) {
+  const std::string in = a.one("input");
+  require_msh(in);
+  const msh::File f = msh::read_file(in);
+  if (f.sketches.empty()) throw std::runtime_error("sketch file holds no sketches");
+  if (a.has("params")) {
+    // the reference derives sketch_size from the first sketch's length (src/sketchy.rs:520-527, :195)
+    printf("type=mash sketch_size=%zu kmer_size=%u seed=%llu\n", f.sketches[0].hashes.size(), f.kmer_size,
+           (unsigned long long)f.hash_seed);
+  } else {
+    for (const auto& s : f.sketches) {
+      // finch::statistics::cardinality [RECALLED]: (len - 1) / (max_hash / usize::MAX) in f32
+      unsigned long long card = 0;
+      if (!s.hashes.empty()) {
+        const float frac = (float)s.hashes.back() / (float)UINT64_MAX;
+        card = (unsigned long long)((float)(s.hashes.size() - 1) / frac);
+      }
+      printf("%s %llu %llu\n", s.name.c_str(), (unsigned long long)s.seq_length, card);
+    }
+  }
+  return 0;
+}
+
+int cmd_check(const Args& a) {
+  const msh::File f = msh::read_file(a.one("reference"));
+  const Genotypes g = read_genotypes(a.one("genotypes"));
+  // the reference builds an InvalidIdentifier error for mismatching names but discards it (src/sketchy.rs:219-228):
+  // only the sizes are enforced
+  if (f.sketches.size() != g.rows.size()) throw std::runtime_error("reference sketch and genotype table must have the same length");
+  puts("ok");
+  return 0;
+}
+
+int cmd_shared(const Args& a) {
+  require_msh(a.one("reference"));
+  require_msh(a.one("query"));
+  const msh::File ref = msh::read_file(a.one("reference")), qry = msh::read_file(a.one("query"));
+  if (ref.kmer_size != qry.kmer_size)
+    throw std::runtime_error("reference (" + ref.sketches[0].name + ") k-mer size (" + std::to_string(ref.kmer_size) +
+                             ") does not match query (" + qry.sketches[0].name + ") k-mer size (" + std::to_string(qry.kmer_size) + ")");
+  Ctx c;
+  upload_reference(c, ref);
+  std::vector<uint64_t> flat, off{0};
+  for (const auto& s : qry.sketches) { flat.insert(flat.end(), s.hashes.begin(), s.hashes.end()); off.push_back(flat.size()); }
+  const uint32_t N = (uint32_t)ref.sketches.size(), Q = (uint32_t)qry.sketches.size();
+  std::vector<uint64_t> out((size_t)N * Q);
+  c.check(skb_shared_counts(c.c, flat.data(), off.data(), Q, out.data()));
+  for (uint32_t i = 0; i < N; ++i)
+    for (uint32_t j = 0; j < Q; ++j)
+      printf("%s %s %llu\n", ref.sketches[i].name.c_str(), qry.sketches[j].name.c_str(), (unsigned long long)out[(size_t)i * Q + j]);
+  return 0;
+}
+
+int cmd_predict(const Args& a) {
+  const uint32_t top = (uint32_t)std::stoul(a.one("top", "1"));
+  const uint64_t limit = std::stoull(a.one("limit", "0"));
+  const bool stream = a.has("stream"), consensus = a.has("consensus"), header = a.has("header");
+  if (consensus && top % 2 != 1) throw std::runtime_error("--top must be an odd number when using --consensus");
+  require_msh(a.one("reference"));
+  const msh::File ref = msh::read_file(a.one("reference"));
+  if (ref.sketches.empty()) throw std::runtime_error("reference sketch file holds no sketches");
+  const uint32_t k = ref.kmer_size;
+  const uint32_t s_query = (uint32_t)std::max<size_t>(1, ref.sketches[0].hashes.size());  // src/sketchy.rs:82, 522
+  const uint64_t seed = ref.hash_seed;
+  fastx::Reader rd(a.has("input") ? a.one("input") : std::string("-"));
+  const Genotypes g = read_genotypes(a.one("genotypes"));
+  for (const auto& s : ref.sketches)
+    if (!g.map.count(s.name)) throw std::runtime_error("reference sketch identifier " + s.name + " has no genotype row");
+  if (header) printf("reads\tsketch_id\tshared_hashes\t%s\n", g.header.c_str());
+  if (top > ref.sketches.size()) throw std::runtime_error("--top exceeds the number of reference sketches");
+  Ctx c;
+  upload_reference(c, ref);
+  skb_batch* b = nullptr;
+  c.check(skb_batch_create(c.c, &b));
+  fastx::Record r;
+  Blob blob;
+  if (stream) {  // src/sketchy.rs:317-356
+    uint64_t read = 1;
+    bool more = true;
+    std::vector<uint32_t> idx;
+    std::vector<uint64_t> sum;
+    while (more) {
+      blob.clear();
+      while (blob.n() < 65536 && (more = rd.next(r))) {
+        blob.add(r.seq, 0);
+        if (limit && read + blob.n() - 1 == limit) { more = false; break; }
+      }
+      if (!blob.n()) break;
+      c.check(skb_batch_clear(b));
+      c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), nullptr, blob.n(), 0));
+      idx.resize(blob.n() * top); sum.resize(blob.n() * top);
+      c.check(skb_predict_stream(c.c, b, k, s_query, seed, top, 0, idx.data(), sum.data()));
+      for (size_t i = 0; i < blob.n(); ++i, ++read) print_results(ref, g, read, &idx[i * top], &sum[i * top], top, consensus);
+    }
+  } else {  // src/sketchy.rs:281-315: one sketcher for all reads
+    uint64_t read = 0;
+    c.check(skb_batch_clear(b));
+    bool any = false;
+    for (;;) {
+      blob.clear();
+      bool stop = false;
+      while (blob.bytes.size() < (256u << 20)) {
+        if (!rd.next(r)) { stop = true; break; }
+        blob.add(r.seq, 0);
+        read += 1;
+        if (read == limit) { stop = true; break; }
+      }
+      if (blob.n()) { c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), blob.grp.data(), blob.n(), 0)); any = true; }
+      if (stop) break;
+    }
+    std::vector<uint64_t> q(s_query);
+    uint32_t qn = 0;
+    uint64_t bases = 0, kmers = 0;
+    if (any) c.check(skb_sketch(c.c, b, k, s_query, seed, q.data(), nullptr, &qn, &bases, &kmers));
+    const uint64_t qoff[2] = {0, qn};
+    const uint32_t N = (uint32_t)ref.sketches.size();
+    std::vector<uint64_t> counts(N);
+    c.check(skb_shared_counts(c.c, q.data(), qoff, 1, counts.data()));
+    std::vector<uint32_t> idx(top);
+    std::vector<uint64_t> sum(top);
+    c.check(skb_rank_counts(c.c, counts.data(), N, top, idx.data(), sum.data()));
+    print_results(ref, g, read, idx.data(), sum.data(), top, consensus);
+  }
+  skb_batch_destroy(b);
+  return 0;
+}
+
+// hidden helpers for the CPU tests of the .msh codec (no GPU needed): text <-> msh
+//   line 1: k seed sketch_size n ; per sketch: "name<TAB>comment<TAB>seq_length<TAB>num_valid_kmers", a line of hashes,
+//   a line of counts
+int cmd_msh_from_text(const std::string& in, const std::string& out) {
+  std::ifstream is(in);
+  if (!is) throw std::runtime_error("failed to open file");
+  msh::File f;
+  size_t n = 0;
+  std::string line;
+  std::getline(is, line);
+  { std::istringstream h(line); h >> f.kmer_size >> f.hash_seed >> f.sketch_size >> n; }
+  for (size_t i = 0; i < n; ++i) {
+    msh::Sketch s;
+    std::getline(is, line);
+    const std::vector<std::string> fl = split_tab(line);
+    if (fl.size() < 4) throw std::runtime_error("bad sketch line");
+    s.name = fl[0]; s.comment = fl[1]; s.seq_length = std::stoull(fl[2]); s.num_valid_kmers = std::stoull(fl[3]);
+    std::getline(is, line);
+    { std::istringstream hs(line); for (uint64_t v; hs >> v;) s.hashes.push_back(v); }
+    std::getline(is, line);
+    { std::istringstream cs(line); for (uint32_t v; cs >> v;) s.counts.push_back(v); }
+    f.sketches.push_back(std::move(s));
+  }
+  msh::write_file(out, f);
+  return 0;
+}
+
+int cmd_msh_to_text(const std::string& in) {
+  const msh::File f = msh::read_file(in);
+  printf("%u %llu %u %zu\n", f.kmer_size, (unsigned long long)f.hash_seed, f.sketch_size, f.sketches.size());
+  for (const auto& s : f.sketches) {
+    printf("%s\t%s\t%llu\t%llu\n", s.name.c_str(), s.comment.c_str(), (unsigned long long)s.seq_length,
+           (unsigned long long)s.num_valid_kmers);
+    for (size_t i = 0; i < s.hashes.size(); ++i) printf(i ? " %llu" : "%llu", (unsigned long long)s.hashes[i]);
+    printf("\n");
+    for (size_t i = 0; i < s.counts.size(); ++i) printf(i ? " %u" : "%u", s.counts[i]);
+    printf("\n");
+  }
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    if (argc == 4 && std::string(argv[1]) == "msh-from-text") return cmd_msh_from_text(argv[2], argv[3]);
+    if (argc == 3 && std::string(argv[1]) == "msh-to-text") return cmd_msh_to_text(argv[2]);
+    const Args a = parse(argc, argv);
+    if (a.cmd == "sketch") return cmd_sketch(a);
+    if (a.cmd == "info") return cmd_info(a);
+    if (a.cmd == "check") return cmd_check(a);
+    if (a.cmd == "shared") return cmd_shared(a);
+    if (a.cmd == "predict") return cmd_predict(a);
+    throw std::runtime_error("unknown sub-command " + a.cmd);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "Error: %s\n", e.what());
+    return 1;
+  }
+}
