@@ -267,3 +267,87 @@ def test_error_codes(ctx):
     gi, gs = ctx.predict_stream(b, 16, 3, 0, 2)
     assert gi.tolist() == [[0, 1]] and gs.tolist() == [[0, 0]]
     b.close()
+
+
+def test_predict_large_scale_against_independent_gpu_path(ctx):
+    """Scale the oracle cannot reach in seconds (6,000 x s=2,000 reference, 3,000 reads of 5 kb): the streaming
+    path (fused kernel, bounds, candidates) must equal the result assembled from the independent dense path
+    (per-read sketches -> skb_shared_counts binary-search kernel -> cumulative sums -> numpy ranking)."""
+    base = [synth.random_genome(200_000, 7000 + l) for l in range(12)]
+    b = ctx.batch().add_records([g.tobytes() for g in base])
+    sk, _, _ = ctx.sketch(b, 16, 2000, 0)
+    b.close()
+    rng = np.random.default_rng(5)
+    rows = []
+    for g in range(6000):
+        row = sk[g % 12][0].copy()
+        pos = rng.choice(row.size, size=40, replace=False)
+        row[pos] = rng.integers(0, int(row.max()), size=40, dtype=np.uint64)
+        row = np.unique(row)
+        rows.append(row)
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    blob, roff, _ = synth.sample_reads(base, 3000, 5000, 99)
+    ctx.ref_upload(ref, off)
+    ctx.set_pass_reads(0)
+    rb = ctx.batch().add(blob, roff)
+    gi, gs = ctx.predict_stream(rb, 16, 2000, 0, 10)
+    final = ctx.sums_download()
+    rb.close()
+    # independent path: one sketch per read, dense counts, cumulative sums, stable ranking on the host
+    qb = ctx.batch().add(blob, roff)
+    qs, _, _ = ctx.sketch(qb, 16, 2000, 0)
+    qb.close()
+    qoff = np.zeros(len(qs) + 1, dtype=np.uint64)
+    qoff[1:] = np.cumsum([h.size for h, _ in qs])
+    counts = ctx.shared_counts(np.concatenate([h for h, _ in qs]), qoff)   # [N, R]
+    cum = np.cumsum(counts, axis=1)
+    assert (cum[:, -1] == final).all()
+    idx = np.arange(cum.shape[0])
+    for r in list(range(0, 64)) + list(range(64, 3000, 97)) + [2999]:
+        order = np.lexsort((idx, -cum[:, r].astype(np.int64)))[:10]
+        assert gi[r].tolist() == order.tolist(), r
+        assert gs[r].tolist() == cum[order, r].tolist(), r
+
+
+def test_limits_and_edge_cases(ctx):
+    from sketchy_b200._lib import SkbError
+    g = synth.random_genome(3000, 1)
+    sk, _, _ = oracle.sketch_groups([g.tobytes()] , [0], 1, 16, 50, 0)
+    rows = [sk[0][0]] * 200
+    off = np.arange(201, dtype=np.uint64) * np.uint64(50)
+    ctx.ref_upload(np.concatenate(rows), off)
+    ctx.set_pass_reads(0)
+    # empty batch and reads without any k-mer
+    b = ctx.batch()
+    gi, gs = ctx.predict_stream(b, 16, 50, 0, 3)
+    assert gi.shape == (0, 3)
+    with pytest.raises(SkbError) as e:      # a staged batch is immutable until cleared
+        b.add_records([b"ACGT"])
+    assert e.value.code == -10
+    b.clear()
+    b.add_records([b"", b"ACGT", b"NNNNNNNNNNNNNNNNNNNNNNNN"])
+    gi, gs = ctx.predict_stream(b, 16, 50, 0, 3)
+    assert gi.tolist() == [[0, 1, 2]] * 3 and gs.tolist() == [[0, 0, 0]] * 3
+    b.close()
+    # top at the supported maximum, equal sums everywhere -> index order
+    b = ctx.batch().add_records([g[:500].tobytes()])
+    gi, gs = ctx.predict_stream(b, 16, 50, 0, 128)
+    assert gi[0].tolist() == list(range(128)) and len(set(gs[0].tolist())) == 1
+    with pytest.raises(SkbError) as e:
+        ctx.predict_stream(b, 16, 50, 0, 129)
+    assert e.value.code == -1
+    b.close()
+    # unsorted query sketch is rejected (the merge of src/sketchy.rs:419-459 is only a set intersection on sorted input)
+    with pytest.raises(SkbError) as e:
+        ctx.shared_counts(np.array([5, 3, 9], dtype=np.uint64), np.array([0, 3], dtype=np.uint64))
+    assert e.value.code == -4
+    # sketch: k = 32 and k = 1 against the oracle
+    for k in (32, 1, 2):
+        bb = ctx.batch().add_records([g.tobytes()])
+        got, gbases, gk = ctx.sketch(bb, k, 40, 7)
+        exp, eb, ek = oracle.sketch_groups([g.tobytes()], [0], 1, k, 40, 7)
+        assert got[0][0].tolist() == exp[0][0].tolist() and got[0][1].tolist() == exp[0][1].tolist()
+        assert int(gk[0]) == int(ek[0])
+        bb.close()

@@ -53,6 +53,7 @@ for i, r in enumerate(data):
     a[0] += int(r[iS]); a[1] += int(r[iI])
 tot = sum(a[0] for a in agg.values()); toti = sum(a[1] for a in agg.values())
 print(f"kernel {kname}: {len(seq)} SASS instrs, {toti} executed, {tot} samples")
-for ln, (s_, i_) in sorted(agg.items(), key=lambda x: -x[1][0])[:top_n]:
+key_i = 1 if os.environ.get("BY_INST") else 0
+for ln, (s_, i_) in sorted(agg.items(), key=lambda x: -x[1][key_i])[:top_n]:
     text = src[ln - 1].strip()[:95] if ln and 0 < ln <= len(src) else ""
     print(f"{ln or 0:5d} {s_:7d} {100 * s_ / max(tot, 1):5.1f}% inst={i_:11d}  {text}")
