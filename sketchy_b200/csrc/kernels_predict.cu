@@ -148,10 +148,6 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// row-granularity waits (rank warps, buffer hand-back): back off instead of burning issue slots
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try(bar, parity)) __nanosleep(128);
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -165,6 +161,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
+// row-granularity waits (rank warps, buffer hand-back): same hardware-suspended wait; a nanosleep poll loop here cost
+// 15 % of the kernel's issued instructions
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier; streamed data is marked
 // evict-first so the query table keeps its place in L2.
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
@@ -183,9 +182,9 @@ __device__ __forceinline__ void count_hit(uint32_t* cbuf, uint32_t rd) {
   else atomicAdd(cbuf + (rd >> 2), 1u << (8 * (rd & 3u)));  // u8 counters: the host guarantees counts <= 255
 }
 
-// add the slot's reads to the row's counters; returns the number of increments
+// add the slot's reads to the row's counters
 template <int CPW>
-__device__ __forceinline__ uint32_t apply_hit(const SkbTable& t, const SkbSlot& s, uint32_t* cbuf) {
+__device__ __forceinline__ void apply_hit(const SkbTable& t, const SkbSlot& s, uint32_t* cbuf) {
   const uint32_t c = SKB_SLOT_CNT(s.meta);
   if (c <= SKB_SLOT_INLINE) {
     count_hit<CPW>(cbuf, SKB_SLOT_ID(s.meta, 0));
@@ -196,7 +195,6 @@ __device__ __forceinline__ uint32_t apply_hit(const SkbTable& t, const SkbSlot& 
     const uint32_t st = SKB_SLOT_START(s.meta);
     for (uint32_t j = 0; j < c; ++j) count_hit<CPW>(cbuf, t.reads[st + j]);
   }
-  return c;
 }
 
 // One lookup batch per warp is kept in flight: a lane's slot load is issued when its entry is taken from the
@@ -255,7 +253,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   __shared__ __align__(8) uint64_t full_bar[FS_CONSUMER_WARPS][FS_STAGES];
   __shared__ __align__(8) uint64_t row_done[FS_ROWBUF];
   __shared__ __align__(8) uint64_t row_free[FS_ROWBUF];
-  __shared__ uint32_t row_hits[FS_ROWBUF];
 
   uint32_t* bloom = reinterpret_cast<uint32_t*>(smem_raw);
   uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM);
@@ -272,7 +269,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     for (int p = 0; p < FS_ROWBUF; ++p) {
       mbar_init(&row_done[p], FS_CONSUMER_WARPS);
       mbar_init(&row_free[p], 1);
-      row_hits[p] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -306,7 +302,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
 
     auto count_now = [&](uint64_t h, uint32_t par) {  // synchronous lookup: only when the FIFO cannot take a burst
       SkbSlot s;
-      if (table_lookup(t, h, s)) atomicAdd(&row_hits[par], apply_hit<CPW>(t, s, cnt32 + par * cwords));
+      if (table_lookup(t, h, s)) apply_hit<CPW>(t, s, cnt32 + par * cwords);
     };
     auto try_close = [&]() {
       const uint32_t nz = ((outst & 0xFFu) ? 1u : 0u) | ((outst & 0xFF00u) ? 2u : 0u) | ((outst & 0xFF0000u) ? 4u : 0u) |
@@ -327,14 +323,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
         SkbSlot s;
         s.key = ((unsigned long long)pend.raw.y << 32) | pend.raw.x;
         s.meta = ((unsigned long long)pend.raw.w << 32) | pend.raw.z;
-        uint32_t hits = 0;
         bool again = false;
         if (pend.valid) {
           uint32_t* cb = cnt32 + pend.par * cwords;
           if (pend.h == SKB_EMPTY_KEY) {
-            if (SKB_SLOT_CNT(s.meta) != 0) hits = apply_hit<CPW>(t, s, cb);
+            if (SKB_SLOT_CNT(s.meta) != 0) apply_hit<CPW>(t, s, cb);
           } else if (s.key == pend.h) {
-            hits = apply_hit<CPW>(t, s, cb);
+            apply_hit<CPW>(t, s, cb);
           } else if (s.key != SKB_EMPTY_KEY) {
             again = true;
           }
@@ -355,7 +350,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
               for (;;) {
                 slot = (slot + 1) & (t.cap - 1);
                 s = load_slot(&t.slots[slot]);
-                if (s.key == pend.h) { hits = apply_hit<CPW>(t, s, cnt32 + pend.par * cwords); break; }
+                if (s.key == pend.h) { apply_hit<CPW>(t, s, cnt32 + pend.par * cwords); break; }
                 if (s.key == SKB_EMPTY_KEY) break;
               }
               again = false;
@@ -363,17 +358,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
           }
           __syncwarp();
         }
-        // bookkeeping per row buffer present in the batch (usually one or two)
-        const bool fin = pend.valid && !again;
-        uint32_t bufs = __reduce_or_sync(0xffffffffu, pend.valid ? (1u << pend.par) : 0u);
-        while (bufs) {
-          const uint32_t p = __ffs(bufs) - 1;
-          bufs &= bufs - 1;
-          const bool mine = pend.valid && pend.par == p;
-          outst -= __popc(__ballot_sync(0xffffffffu, fin && mine)) << (8 * p);
-          const uint32_t hsum = __reduce_add_sync(0xffffffffu, mine ? hits : 0u);
-          if (lane == 0 && hsum) atomicAdd(&row_hits[p], hsum);
-        }
+        // resolved entries per row buffer: one packed warp reduction (a field gets at most 32, the fields are 8 bits)
+        outst -= __reduce_add_sync(0xffffffffu, (pend.valid && !again) ? (1u << (8 * pend.par)) : 0u);
         pend.valid = false;
         have_pend = false;
       }
@@ -568,34 +554,31 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     const uint32_t rb = lr & (FS_ROWBUF - 1);
     uint32_t* cpar = cnt32 + rb * cwords;
     mbar_wait_sleepy(&row_done[rb], (lr >> 2) & 1u);
-    const uint32_t row_total = row_hits[rb];
-    __syncwarp();
-    if (lane == 0) {
-      row_hits[rb] = 0;
-      a.sums_out[row] = carry + row_total;
+    // per-lane segment totals of the row's counters; their sum is the row's total for the pass
+    const uint32_t* cseg = cpar + seg0 / CPW;
+    const uint32_t segw = per / CPW;  // words in this lane's segment (multiple of 4)
+    uint32_t tot = 0;
+    for (uint32_t i = 0; i < segw; i += 4) {
+      const uint4 x = *reinterpret_cast<const uint4*>(cseg + i);
+      if (CPW == 2) {
+        tot += (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) + (x.z & 0xFFFFu) + (x.z >> 16) +
+               (x.w & 0xFFFFu) + (x.w >> 16);
+      } else {  // four u8 counters per word: sum the byte lanes with a masked add
+        const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t pair = (w4[q] & 0x00FF00FFu) + ((w4[q] >> 8) & 0x00FF00FFu);
+          tot += (pair & 0xFFFFu) + (pair >> 16);
+        }
+      }
     }
+    const uint32_t row_total = __reduce_add_sync(0xffffffffu, tot);
+    if (lane == 0) a.sums_out[row] = carry + row_total;
     const uint32_t gi = a.row_base + row;
     if (row_total) {
       // sums and bounds never decrease along the reads: a row whose FINAL sum is under the FIRST bound, or a
       // lane segment whose final sum is under the segment's first bound, cannot hold a candidate
       if (carry + row_total >= lb_min && !(a.debug & 4)) {
-        const uint32_t* cseg = cpar + seg0 / CPW;
-        const uint32_t segw = per / CPW;  // words in this lane's segment (multiple of 4)
-        uint32_t tot = 0;
-        for (uint32_t i = 0; i < segw; i += 4) {
-          const uint4 x = *reinterpret_cast<const uint4*>(cseg + i);
-          if (CPW == 2) {
-            tot += (x.x & 0xFFFFu) + (x.x >> 16) + (x.y & 0xFFFFu) + (x.y >> 16) + (x.z & 0xFFFFu) + (x.z >> 16) +
-                   (x.w & 0xFFFFu) + (x.w >> 16);
-          } else {  // four u8 counters per word: sum the byte lanes with a masked add
-            const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t pair = (w4[q] & 0x00FF00FFu) + ((w4[q] >> 8) & 0x00FF00FFu);
-              tot += (pair & 0xFFFFu) + (pair >> 16);
-            }
-          }
-        }
         uint32_t incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
