@@ -74,8 +74,10 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
 uint32_t skb_batch_num_groups(const skb_batch* b);
 uint64_t skb_batch_num_records(const skb_batch* b);
 uint64_t skb_batch_num_bases(const skb_batch* b); /* sum of raw record lengths (finch total_bases) */
-/* Copy the packed batch to the device now (async H2D + wait). Calls that consume a batch stage it on demand;
- * staging ahead lets a caller keep inputs resident in HBM. */
+/* Copy the packed batch to the device now (H2D on the context's copy stream + wait). Calls that consume a batch
+ * stage it on demand; staging ahead lets a caller keep inputs resident in HBM. skb_batch_add / skb_batch_stage of
+ * one batch may run on another host thread while the context works on a different batch (double buffering: the
+ * copy overlaps the kernels). */
 int skb_batch_stage(skb_batch* b);
 
 /* ---- sketch (replaces `_sketch_files`, src/sketchy.rs:465-494: create_sketcher :473, process :477, to_vec :480,

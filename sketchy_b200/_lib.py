@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsketchy_b200.so")
+SO_PATH = os.environ.get("SKB_LIB") or os.path.join(_HERE, "libsketchy_b200.so")  # SKB_LIB: another build of the same library (kernel A/B runs)
 
 ERRORS = {0: "SKB_OK", -1: "SKB_ERR_INVALID_ARG", -2: "SKB_ERR_CUDA", -3: "SKB_ERR_NO_DEVICE",
           -4: "SKB_ERR_REF_NOT_SORTED", -5: "SKB_ERR_TOP_GT_N", -6: "SKB_ERR_NO_REFERENCE",

@@ -15,6 +15,9 @@
 // ---------------------------------------------------------------------------------------------------------
 // small utilities
 // ---------------------------------------------------------------------------------------------------------
+// AVX2 block packer (pack_avx2.cpp); internal, exported only so that the CPU test-suite can call it directly
+extern "C" uint64_t skb_pack_blocks_avx2(const uint8_t* s, uint64_t nbytes, uint32_t* codes, uint32_t* nmask);
+
 namespace {
 
 struct DevBuf {
@@ -79,56 +82,49 @@ struct PackLut2 {
 };
 const PackLut2 kPackLut2;
 
-// Pack one record at base position P (multiple of 32); everything up to Pnext (multiple of 32) not covered by a
-// valid base is marked invalid. The words touched belong to this record alone.
-void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uint32_t* codes, uint32_t* nmask) {
-  uint64_t pos = P;
+// Whole 32-byte blocks without a removed byte: two code words and one mask word each. Returns the bytes consumed (a
+// multiple of 32); stops at the first block it cannot take. AVX2 version in pack_avx2.cpp, chosen at load time.
+
+uint64_t pack_blocks_scalar(const uint8_t* s, uint64_t nbytes, uint32_t* codes, uint32_t* nmask) {
   uint64_t i = 0;
-  // fast path: 32 clean bases -> two code words and one all-valid mask word (pos stays a multiple of 32)
-  while (i + 32 <= len) {
+  for (; i + 32 <= nbytes; i += 32) {  // only blocks of 32 clean bases (anything else goes byte by byte)
     uint32_t w[2];
-    bool clean = true;
-    for (int h = 0; h < 2 && clean; ++h) {
+    for (int h = 0; h < 2; ++h) {
       uint32_t cw = 0;
       const uint8_t* p = s + i + 16 * h;
       for (int j = 0; j < 8; ++j) {
         const uint8_t v = kPackLut2.t[p[2 * j] | ((uint32_t)p[2 * j + 1] << 8)];
-        if (v == 0xFF) { clean = false; break; }
+        if (v == 0xFF) return i;
         cw |= (uint32_t)v << (4 * j);
       }
       w[h] = cw;
     }
-    if (!clean) break;
-    codes[pos >> 4] = w[0];
-    codes[(pos >> 4) + 1] = w[1];
-    nmask[pos >> 5] = 0;
-    pos += 32;
-    i += 32;
+    codes[i >> 4] = w[0];
+    codes[(i >> 4) + 1] = w[1];
+    nmask[i >> 5] = 0;
   }
+  return i;
+}
+
+typedef uint64_t (*pack_blocks_fn)(const uint8_t*, uint64_t, uint32_t*, uint32_t*);
+pack_blocks_fn choose_pack_blocks() {
+  if (const char* e = getenv("SKB_NO_AVX2")) { if (e[0] == '1') return pack_blocks_scalar; }
+  return __builtin_cpu_supports("avx2") ? skb_pack_blocks_avx2 : pack_blocks_scalar;
+}
+const pack_blocks_fn kPackBlocks = choose_pack_blocks();
+
+// Pack one record at base position P (multiple of 32); everything up to Pnext (multiple of 32) not covered by a
+// valid base is marked invalid. The words touched belong to this record alone.
+void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uint32_t* codes, uint32_t* nmask) {
+  uint64_t pos = P;
   uint32_t cw = 0, mw = 0;
-  for (; i < len; ++i) {
-    // resume the fast path whenever we are block-aligned again and the next 32 bytes are clean
+  for (uint64_t i = 0; i < len; ++i) {
+    // block path whenever the output is block-aligned (cw/mw are empty then) and 32 bytes are left
     if ((pos & 31) == 0 && i + 32 <= len) {
-      uint32_t w[2];
-      bool clean = true;
-      for (int h = 0; h < 2 && clean; ++h) {
-        uint32_t c2 = 0;
-        const uint8_t* p = s + i + 16 * h;
-        for (int j = 0; j < 8; ++j) {
-          const uint8_t v = kPackLut2.t[p[2 * j] | ((uint32_t)p[2 * j + 1] << 8)];
-          if (v == 0xFF) { clean = false; break; }
-          c2 |= (uint32_t)v << (4 * j);
-        }
-        w[h] = c2;
-      }
-      if (clean) {
-        codes[pos >> 4] = w[0];
-        codes[(pos >> 4) + 1] = w[1];
-        nmask[pos >> 5] = 0;
-        pos += 32;
-        i += 31;  // the loop adds one
-        continue;
-      }
+      const uint64_t n = kPackBlocks(s + i, len - i, codes + (pos >> 4), nmask + (pos >> 5));
+      pos += n;
+      i += n;
+      if (i >= len) break;
     }
     const uint32_t v = kPackLut.t[s[i]];
     if (v == 5) continue;
@@ -162,6 +158,7 @@ struct skb_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // batch staging (H2D): lets skb_batch_stage overlap a predict running on `stream`
   std::string err;
   // reference shard
   DevBuf ref, row_start, row_len, cta_row;
@@ -290,14 +287,14 @@ int stage_batch(skb_batch* b) {
   CU(c, b->d_seg_group.ensure(std::max<size_t>(4, sg.size() * 4)));
   CU(c, b->d_seg_chunk0.ensure(std::max<size_t>(4, sc.size() * 4)));
   CU(c, b->d_seg_n.ensure(std::max<size_t>(4, sn.size())));
-  CU(c, cudaMemcpyAsync(b->d_codes.p, b->codes.p, ncode * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(b->d_nmask.p, b->nmask.p, nmask * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(b->d_codes.p, b->codes.p, ncode * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(c, cudaMemcpyAsync(b->d_nmask.p, b->nmask.p, nmask * 4, cudaMemcpyHostToDevice, c->copy_stream));
   if (!sg.empty()) {
-    CU(c, cudaMemcpyAsync(b->d_seg_group.p, sg.data(), sg.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(b->d_seg_chunk0.p, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(b->d_seg_n.p, sn.data(), sn.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(b->d_seg_group.p, sg.data(), sg.size() * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(b->d_seg_chunk0.p, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(b->d_seg_n.p, sn.data(), sn.size(), cudaMemcpyHostToDevice, c->copy_stream));
   }
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaStreamSynchronize(c->copy_stream));
   b->staged = true;
   return SKB_OK;
 }
@@ -755,7 +752,8 @@ int skb_create(int device, skb_ctx** out) {
   skb_ctx* c = new skb_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SKB_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SKB_ERR_CUDA; }
   if (cudaHostAlloc((void**)&c->h_scal, 64, cudaHostAllocDefault) != cudaSuccess) {
     cudaStreamDestroy(c->stream); delete c; return SKB_ERR_OOM;
   }
@@ -777,6 +775,7 @@ void skb_destroy(skb_ctx* c) {
   for (DevBuf* b : bufs) b->release();
   if (c->h_scal) cudaFreeHost(c->h_scal);
   cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
@@ -817,6 +816,7 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
                   uint32_t nthreads) {
   if (!b) return SKB_ERR_INVALID_ARG;
   skb_ctx* c = b->ctx;
+  cudaSetDevice(c->device);  // the pinned staging buffers belong to this context's device (callers may use any thread)
   if (b->staged) return fail(c, SKB_ERR_STATE, "batch already staged; clear it before adding");
   if (n == 0) return SKB_OK;
   if (!offsets || (!blob && offsets[n] != offsets[0])) return fail(c, SKB_ERR_INVALID_ARG, "null blob/offsets");

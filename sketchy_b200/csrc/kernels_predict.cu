@@ -114,9 +114,13 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 constexpr int FS_SUB = 512;            // hashes per sub-tile (4 KB): two chunks of 8 per lane
 constexpr int FS_STAGES = 2;           // staging buffers per consumer warp
 constexpr int FS_CONSUMER_WARPS = 16;
-constexpr int FS_RANK_WARPS = 2;       // rank warp p owns the rows of parity p
+constexpr int FS_RANK_WARPS = 2;             // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
 constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
-constexpr int FS_ROWBUF = 4;           // rows in flight per CTA: counter buffers / barriers are indexed by row & 3
+constexpr int FS_ROWBUF = 4;           // rows in flight per CTA: counter buffers / barriers are indexed by row % 4
+                                       // (6 or 8 buffers were measured: 1 % faster at best, and fewer reads fit a pass)
+// a rank warp may only wait on a row buffer whose previous row it flushed itself (consumer warps can close rows out of
+// order, so the barrier parity of a buffer is only unambiguous to the warp that saw its previous phase)
+static_assert(FS_ROWBUF % FS_RANK_WARPS == 0 && FS_ROWBUF <= 8, "FS_RANK_WARPS must divide FS_ROWBUF");
 constexpr int FS_QCAP = 64;            // per-warp FIFO of filter passers awaiting their table lookup (power of 2)
 constexpr int FS_NHASH = 8;            // hashes per lane per chunk (one chunk = 256 hashes)
 constexpr int FS_CHUNKS = FS_SUB / (32 * FS_NHASH);
@@ -161,9 +165,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
       : "memory");
 }
-// row-granularity waits (rank warps, buffer hand-back): same hardware-suspended wait; a nanosleep poll loop here cost
-// 15 % of the kernel's issued instructions
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+// buffer hand-back (a consumer warp waits for the rank warp to flush row lr-4): same loop, kept apart so that profiles
+// tell the two waits apart
+__device__ __forceinline__ void mbar_wait_free(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITF_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONEF_%=;\n\t"
+      "bra WAITF_%=;\n\t"
+      "DONEF_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(1000000u)
+      : "memory");
+}
+// rank warps wait a whole row (microseconds) and have two rows of slack: poll with a real sleep in between, a
+// try_wait loop alone re-issues every few cycles and takes issue slots from the consumer warps
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try(bar, parity)) __nanosleep(500);
+}
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier; streamed data is marked
 // evict-first so the query table keeps its place in L2.
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
@@ -208,21 +229,24 @@ struct Pending {
   uint4 raw;
   bool valid;
 };
-#define SKB_Q_FRESH 0x3FFFFFFFu  // queue entry whose home slot is still to be computed (bits 30-31 = row buffer)
+#define SKB_Q_FRESH 0x1FFFFFFFu  // queue entry whose home slot is still to be computed (bits 29-31 = row buffer)
 
-// this warp's sub-tiles: global sub-tile numbers w, w+16, w+32, ... over the CTA's rows
+// this warp's sub-tiles: global sub-tile numbers w, w+16, w+32, ... over the CTA's rows (a shared claim counter was
+// tried instead: the waits on row buffers stayed and the claim's round trip cost 7 %)
 struct SubIter {
-  uint32_t row, t;    // current row, sub-tile within it
+  uint32_t row, t;    // current row (CTA-local number), sub-tile within it
   uint32_t len;       // hashes in the current row
   const uint64_t* p;  // first hash of the current row
+  uint32_t c0, G;     // local row lr is row c0 + lr * G of the shard
   __device__ __forceinline__ void load_row(const SkbFusedArgs& a, uint32_t r1) {
     if (row >= r1) { len = 0; p = a.rv.ref; return; }
+    const uint32_t g = c0 + row * G;
     if (a.rv.uniform_len) {
       len = a.rv.uniform_len;
-      p = a.rv.ref + (size_t)row * a.rv.uniform_pitch;
+      p = a.rv.ref + (size_t)g * a.rv.uniform_pitch;
     } else {
-      len = a.rv.row_len[row];
-      p = a.rv.ref + a.rv.row_start[row];
+      len = a.rv.row_len[g];
+      p = a.rv.ref + a.rv.row_start[g];
     }
   }
   __device__ __forceinline__ void settle(const SkbFusedArgs& a, uint32_t r1) {
@@ -238,7 +262,8 @@ struct SubIter {
     t += FS_CONSUMER_WARPS;
     if (a.rv.uniform_len) {  // every row has the same number of sub-tiles (>= 1): no loads, no loop of loads
       const uint32_t n = (a.rv.uniform_len + FS_SUB - 1) / FS_SUB;
-      while (t >= n && row < r1) { t -= n; ++row; p += a.rv.uniform_pitch; }
+      const size_t step = (size_t)a.rv.uniform_pitch * G;
+      while (t >= n && row < r1) { t -= n; ++row; p += step; }
       return;
     }
     settle(a, r1);
@@ -261,7 +286,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   const uint32_t cwords = a.cnt_stride / CPW;  // 32-bit words per row buffer
   uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride] bound growth since read 0, saturating
 
-  const uint32_t r0 = a.cta_row[blockIdx.x], r1 = a.cta_row[blockIdx.x + 1];
+  // Every CTA owns a contiguous range of rows (balanced by sub-tiles on the host). Dealing the rows round-robin was
+  // tried to spread the rows that contend for a pass's reads: the average CTA took as long, the slowest 10-70 % longer.
+  // r0/r1 and every `row` below are CTA-local numbers; grow() is the row of the shard.
+  const uint32_t c0 = a.cta_row[blockIdx.x], G = 1;
+  const uint32_t r0 = 0, r1 = a.cta_row[blockIdx.x + 1] - c0;
+  auto grow = [&](uint32_t lr) -> uint32_t { return c0 + lr * G; };
 
   if (threadIdx.x == 0) {
     for (int w = 0; w < FS_CONSUMER_WARPS; ++w)
@@ -294,7 +324,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     const uint32_t lt_mask = (1u << lane) - 1u;
     const SkbTable& t = a.table;
     uint32_t qhead = 0, qn = 0;  // FIFO state (warp-uniform)
-    uint32_t outst = 0;          // unfinished entries (queued or in flight) per row buffer, 8 bits each (warp-uniform)
+    uint64_t outst = 0;          // unfinished entries (queued or in flight) per row buffer, 8 bits each (warp-uniform)
     Pending pend;
     pend.valid = false; pend.h = 0; pend.idx = 0; pend.par = 0; pend.raw = make_uint4(0, 0, 0, 0);
     bool have_pend = false;  // warp-uniform: a lookup batch is in flight
@@ -305,8 +335,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
       if (table_lookup(t, h, s)) apply_hit<CPW>(t, s, cnt32 + par * cwords);
     };
     auto try_close = [&]() {
-      const uint32_t nz = ((outst & 0xFFu) ? 1u : 0u) | ((outst & 0xFF00u) ? 2u : 0u) | ((outst & 0xFF0000u) ? 4u : 0u) |
-                          ((outst & 0xFF000000u) ? 8u : 0u);
+      uint32_t nz = 0;
+#pragma unroll
+      for (int p = 0; p < FS_ROWBUF; ++p) nz |= ((outst >> (8 * p)) & 0xFFull) ? (1u << p) : 0u;
       const uint32_t ready = closing & ~nz;
       if (ready) {
         __syncwarp();
@@ -341,7 +372,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
             if (again) {
               const uint32_t at = (qhead + qn + __popc(bal & lt_mask)) & (FS_QCAP - 1);
               q[at] = make_uint4((uint32_t)pend.h, (uint32_t)(pend.h >> 32),
-                                 ((pend.idx + 1) & (t.cap - 1)) | (pend.par << 30), 0u);
+                                 ((pend.idx + 1) & (t.cap - 1)) | (pend.par << 29), 0u);
             }
             qn += n;
           } else {  // no room (practically never): chase the chain here
@@ -359,7 +390,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
           __syncwarp();
         }
         // resolved entries per row buffer: one packed warp reduction (a field gets at most 32, the fields are 8 bits)
-        outst -= __reduce_add_sync(0xffffffffu, (pend.valid && !again) ? (1u << (8 * pend.par)) : 0u);
+        {
+          const bool fin = pend.valid && !again;
+          outst -= __reduce_add_sync(0xffffffffu, (fin && pend.par < 4u) ? (1u << (8 * pend.par)) : 0u);
+          if (FS_ROWBUF > 4)
+            outst -= (uint64_t)__reduce_add_sync(0xffffffffu, (fin && pend.par >= 4u) ? (1u << (8 * (pend.par - 4u))) : 0u) << 32;
+        }
         pend.valid = false;
         have_pend = false;
       }
@@ -371,8 +407,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
       const uint4 e = q[(qhead + (pend.valid ? lane : 0u)) & (FS_QCAP - 1)];
       pend.h = ((uint64_t)e.y << 32) | e.x;
       const uint32_t tag = e.z;
-      pend.par = tag >> 30;
-      const uint32_t qidx = tag & 0x3FFFFFFFu;
+      pend.par = tag >> 29;
+      const uint32_t qidx = tag & 0x1FFFFFFFu;
       pend.idx = !pend.valid ? 0u
                              : (qidx != SKB_Q_FRESH ? qidx
                                                     : (pend.h == SKB_EMPTY_KEY ? t.cap : table_home(pend.h, t.log2cap)));
@@ -396,6 +432,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     };
 
     SubIter it, pre;
+    it.c0 = c0; it.G = G;
     it.row = a.skip_stream ? r1 : r0;
     it.t = cw;
     it.load_row(a, r1);
@@ -410,16 +447,18 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     uint32_t k = 0;  // sub-tiles consumed by this warp: stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1
 
     for (uint32_t row = r0; row < r1; ++row) {
-      const uint32_t lr = row - r0, par = lr & (FS_ROWBUF - 1);
+      const uint32_t lr = row - r0, par = lr % FS_ROWBUF;
       if (lr >= (uint32_t)FS_ROWBUF) {
         while ((closing >> par) & 1u) {  // row lr-4 still open for this warp: finish its lookups now
           finish_batch();
           if (qn) start_batch();
         }
-        mbar_wait_sleepy(&row_free[par], ((lr >> 2) - 1u) & 1u);  // rank warp has flushed row lr-4
+        mbar_wait_free(&row_free[par], ((lr / FS_ROWBUF) - 1u) & 1u);  // rank warp has flushed row lr-4
       }
-      const uint32_t fresh_tag = SKB_Q_FRESH | (par << 30);
-      const uint32_t urgent = 1u << ((lr + 2) & (FS_ROWBUF - 1));  // the buffer that is needed again in two rows
+      const uint32_t fresh_tag = SKB_Q_FRESH | (par << 29);
+      // leftovers of the previous row are looked up as soon as this row starts: the row closes a whole row earlier than
+      // with "two rows back", and the warps no longer wait for the rank warp to hand the buffer back
+      const uint32_t urgent = 1u << ((lr + FS_ROWBUF - 1) % FS_ROWBUF);
       while (it.row == row) {  // this warp's sub-tiles of the row
         const uint32_t stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1u;
         mbar_wait(&full_bar[cw][stage], phase);
@@ -463,15 +502,28 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
             }
           }
           if ((a.debug & 3) == 2) pm = 0;
-          if (__any_sync(0xffffffffu, pm != 0u)) {  // compact this chunk's passers into the warp FIFO
+          const uint32_t anyb = __ballot_sync(0xffffffffu, pm != 0u);
+          if (anyb) {  // compact this chunk's passers into the warp FIFO
+            // exclusive prefix of the per-lane passer counts from ballots of the count's bit planes (no shuffle chain);
+            // a lane with four or more passers in one chunk is rare and takes the scan
             const uint32_t c = __popc(pm);
-            uint32_t incl = c;
+            uint32_t excl, total;
+            const uint32_t bh = __ballot_sync(0xffffffffu, c >= 4u);
+            if (bh == 0u) {
+              const uint32_t b0 = __ballot_sync(0xffffffffu, (c & 1u) != 0u);
+              const uint32_t b1 = __ballot_sync(0xffffffffu, (c & 2u) != 0u);
+              excl = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
+              total = __popc(b0) + 2u * __popc(b1);
+            } else {
+              uint32_t incl = c;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-              if ((int)lane >= o) incl += y;
+              for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += y;
+              }
+              total = __shfl_sync(0xffffffffu, incl, 31);
+              excl = incl - c;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             if (qn + total > (uint32_t)FS_QCAP && total <= (uint32_t)FS_QCAP) {
               while (qn + total > (uint32_t)FS_QCAP) {  // make room (rare): run batches back to back
                 finish_batch();
@@ -479,17 +531,23 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
               }
             }
             if (qn + total <= (uint32_t)FS_QCAP) {
-              uint32_t at = qhead + qn + incl - c;
+              // a passer stores its 8-byte hash (an aligned register pair); the tags of the `total` new records are
+              // written by the first lanes
+              const uint32_t tail = (qhead + qn) & (FS_QCAP - 1);
+              uint2* qe = reinterpret_cast<uint2*>(q);  // record i = qe[2 * i] (hash), qe[2 * i + 1] (tag, pad)
+              uint32_t at = tail + excl;
 #pragma unroll
               for (int j = 0; j < FS_NHASH; ++j) {
                 if (pm & (1u << j)) {
-                  q[at & (FS_QCAP - 1)] = (j & 1) ? make_uint4(v[j >> 1].z, v[j >> 1].w, fresh_tag, 0u)
-                                                  : make_uint4(v[j >> 1].x, v[j >> 1].y, fresh_tag, 0u);
+                  qe[2u * (at & (FS_QCAP - 1))] =
+                      (j & 1) ? make_uint2(v[j >> 1].z, v[j >> 1].w) : make_uint2(v[j >> 1].x, v[j >> 1].y);
                   ++at;
                 }
               }
+              if (lane < total) qe[2u * ((tail + lane) & (FS_QCAP - 1)) + 1] = make_uint2(fresh_tag, 0u);
+              if (total > 32u && lane + 32u < total) qe[2u * ((tail + lane + 32u) & (FS_QCAP - 1)) + 1] = make_uint2(fresh_tag, 0u);
               qn += total;
-              outst += total << (8 * par);
+              outst += (uint64_t)total << (8 * par);
               __syncwarp();
             } else {  // a burst larger than the FIFO: look the passers up in place
 #pragma unroll
@@ -519,21 +577,40 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   }
 
   // ===== rank warps: cumulative sums over the reads of the pass, candidate test, new running sum =====
-  const uint32_t rp = warp - FS_CONSUMER_WARPS;  // parity of the rows this warp owns
+  const uint32_t rp = warp - FS_CONSUMER_WARPS;  // residue of the rows this warp owns
   const uint32_t per = a.cnt_stride >> 5;        // counters per lane in the segment view (multiple of 8)
   const uint32_t seg0 = lane * per;
   const unsigned long long lb_min = a.lb_sum[0];  // bounds are non-decreasing along the reads
   const unsigned long long lb_seg = seg0 < a.n_reads ? lb_min + lbrel[seg0] : ~0ull;
-  // is (sum sv, row gi) at least as good as the bound of read b?  (index only matters on the rare exact tie)
+  // On an exact tie with the bound the row index decides. The bound's row rarely changes inside a lane's segment, so
+  // the lane keeps the smallest and largest bound index of its segment and reads the per-read index from global
+  // memory only when the row lies between the two (a global load per tied read made single walks take 40 us).
+  uint32_t li_min = 0xFFFFFFFFu, li_max = 0;
+  for (uint32_t b = seg0; b < min(seg0 + per, a.n_reads); ++b) {
+    const uint32_t li = a.lb_idx[b];
+    li_min = min(li_min, li);
+    li_max = max(li_max, li);
+  }
+  // is (sum sv, row gi) at least as good as the bound of read b?  (index only matters on the exact tie)
   auto is_cand = [&](unsigned long long sv, uint32_t gi, uint32_t b) -> bool {
     const uint32_t rel = lbrel[b];
     const unsigned long long ls = rel != 0xFFFFu ? lb_min + rel : a.lb_sum[b];  // saturated: read the exact bound
-    return sv > ls || (sv == ls && gi <= a.lb_idx[b]);
+    if (sv != ls) return sv > ls;
+    if (gi <= li_min) return true;
+    if (gi > li_max) return false;
+    return gi <= a.lb_idx[b];
   };
   // Candidates leave the kernel as intervals "row gi holds sum sv and meets the bound for reads [b0, b1)": a
   // contending row produces one record per hit instead of one per read, and slots are reserved 16 at a time per lane
   // so the rank warp never waits on an atomic per candidate.
-  uint32_t slot_next = 0, slot_left = 0;
+  // (the first block of every lane comes from one reservation per warp: ten thousand lanes hitting the one counter at
+  // kernel start took tens of microseconds to drain)
+  uint32_t slot_next = 0, slot_left = 16;
+  {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.ivl_total, 512u);
+    slot_next = __shfl_sync(0xffffffffu, base, 0) + 16u * lane;
+  }
   auto emit = [&](unsigned long long sv, uint32_t gi, uint32_t b0, uint32_t b1) {
     if (slot_left == 0) {
       slot_next = atomicAdd(a.ivl_total, 16u);
@@ -546,14 +623,14 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     }
     ++slot_next; --slot_left;
   };
-  unsigned long long carry_next = (r0 + rp < r1) ? a.sums_in[r0 + rp] : 0ull;
-  for (uint32_t row = r0 + rp; row < r1; row += 2) {
+  unsigned long long carry_next = (r0 + rp < r1) ? a.sums_in[grow(r0 + rp)] : 0ull;
+  for (uint32_t row = r0 + rp; row < r1; row += FS_RANK_WARPS) {
     const uint32_t lr = row - r0;
     const unsigned long long carry = carry_next;
-    if (row + 2 < r1) carry_next = a.sums_in[row + 2];  // in flight while this row is processed
-    const uint32_t rb = lr & (FS_ROWBUF - 1);
+    if (row + FS_RANK_WARPS < r1) carry_next = a.sums_in[grow(row + FS_RANK_WARPS)];  // in flight while this row is processed
+    const uint32_t rb = lr % FS_ROWBUF;
     uint32_t* cpar = cnt32 + rb * cwords;
-    mbar_wait_sleepy(&row_done[rb], (lr >> 2) & 1u);
+    mbar_wait_sleepy(&row_done[rb], (lr / FS_ROWBUF) & 1u);
     // per-lane segment totals of the row's counters; their sum is the row's total for the pass
     const uint32_t* cseg = cpar + seg0 / CPW;
     const uint32_t segw = per / CPW;  // words in this lane's segment (multiple of 4)
@@ -573,8 +650,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
       }
     }
     const uint32_t row_total = __reduce_add_sync(0xffffffffu, tot);
-    if (lane == 0) a.sums_out[row] = carry + row_total;
-    const uint32_t gi = a.row_base + row;
+    if (lane == 0) a.sums_out[grow(row)] = carry + row_total;
+    const uint32_t gi = a.row_base + grow(row);
     if (row_total) {
       // sums and bounds never decrease along the reads: a row whose FINAL sum is under the FIRST bound, or a
       // lane segment whose final sum is under the segment's first bound, cannot hold a candidate
@@ -822,13 +899,53 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRan
   for (uint32_t i = lane; i < nc; i += 32) cache[i] = list[i];
   if (lane == 0 && a.cand_stat) atomicAdd(a.cand_stat, (unsigned long long)produced);
   __syncwarp();
+  // A bucket larger than the cache (loose bounds: a few reads per pass) is first cut down to the records that can still
+  // be in the top: the top-th best of the 32 per-lane maxima is a lower bound of the top-th best record, and the
+  // records at least that good are compacted into the cache. Two coalesced passes instead of `top` of them.
+  uint32_t m = n;       // records the selection rounds look at
+  bool cached = n <= (uint32_t)RS_CACHE;
+  if (!cached && a.top <= 32u) {  // (the 32 lane maxima bound the top-th best only for top <= 32)
+    unsigned long long ls = 0;
+    uint32_t li = 0xFFFFFFFFu;
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint4 c = list[i];
+      const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
+      if (skb_key_better(cs, c.z, ls, li)) { ls = cs; li = c.z; }
+    }
+    unsigned long long ts = 0;  // threshold key = the top-th best lane maximum (n > RS_CACHE >= 32: every lane has one)
+    uint32_t ti = 0xFFFFFFFFu;
+    for (uint32_t t = 0; t < a.top; ++t) {
+      unsigned long long bs = ls;
+      uint32_t bi = li;
+      warp_best(bs, bi);
+      ts = bs; ti = bi;
+      if (ls == bs && li == bi) { ls = 0; li = 0xFFFFFFFFu; }  // the winner's lane steps aside
+    }
+    uint32_t kept = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      uint4 c = make_uint4(0, 0, 0, 0);
+      bool keep = false;
+      if (i < n) {
+        c = list[i];
+        const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
+        keep = !skb_key_better(ts, ti, cs, c.z);  // at least as good as the threshold
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      const uint32_t at = kept + __popc(bal & ((1u << lane) - 1u));
+      if (keep && at < (uint32_t)RS_CACHE) cache[at] = c;
+      kept += __popc(bal);
+    }
+    __syncwarp();
+    if (kept <= (uint32_t)RS_CACHE) { cached = true; m = kept; }  // else (never seen): rounds over the whole bucket
+  }
   unsigned long long last_s = 0;
   uint32_t last_i = 0;
   for (uint32_t t = 0; t < a.top; ++t) {
     unsigned long long bs = 0;
     uint32_t bi = 0xFFFFFFFFu;
-    for (uint32_t i = lane; i < n; i += 32) {
-      const uint4 c = i < nc ? cache[i] : list[i];
+    for (uint32_t i = lane; i < m; i += 32) {
+      const uint4 c = cached ? cache[i] : list[i];
       const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
       if ((t == 0 || skb_key_better(last_s, last_i, cs, c.z)) && skb_key_better(cs, c.z, bs, bi)) {
         bs = cs; bi = c.z;

@@ -58,3 +58,45 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
                 assert "liboracle" not in txt, f
+
+
+def test_avx2_block_packer_matches_the_bytewise_rule():
+    """Host-side packer fast path (pack_avx2.cpp): codes/mask per 32-byte block must follow the same rule as the
+    byte-wise packer (needletail normalize(false): ACGT/acgt/Uu -> 0..3, other kept bytes invalid with code 0), and a
+    block holding a removed byte (blank, tab, CR, LF) must be left alone."""
+    import ctypes as C
+    import numpy as np
+    if "avx2" not in open("/proc/cpuinfo").read():
+        pytest.skip("no AVX2 on this host")
+    from sketchy_b200 import _lib, build
+    build.build()
+    lib = C.CDLL(_lib.SO_PATH)
+    fn = lib.skb_pack_blocks_avx2
+    fn.restype = C.c_uint64
+    fn.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"ACGTacgtUuNnRYKM-.*xX@\x00\xff\xc1\xe1", dtype=np.uint8)
+    p = np.array([20] * 4 + [6] * 4 + [2, 2] + [1] * (alphabet.size - 10), dtype=np.float64)
+    s = rng.choice(alphabet, size=32 * 200 + 17, p=p / p.sum()).astype(np.uint8)
+    codes = np.zeros(2 * 201, dtype=np.uint32)
+    mask = np.zeros(201, dtype=np.uint32)
+    n = fn(s.ctypes.data, s.size, codes.ctypes.data, mask.ctypes.data)
+    assert n == 32 * 200
+    code_of = {ord("A"): 0, ord("a"): 0, ord("C"): 1, ord("c"): 1, ord("G"): 2, ord("g"): 2,
+               ord("T"): 3, ord("t"): 3, ord("U"): 3, ord("u"): 3}
+    for blk in range(200):
+        e_codes = [0, 0]
+        e_mask = 0
+        for j in range(32):
+            b = int(s[32 * blk + j])
+            if b in code_of:
+                e_codes[j // 16] |= code_of[b] << (2 * (j % 16))
+            else:
+                e_mask |= 1 << j
+        assert int(codes[2 * blk]) == e_codes[0] and int(codes[2 * blk + 1]) == e_codes[1], blk
+        assert int(mask[blk]) == e_mask, blk
+    # stops in front of the first block with a removed byte
+    for ws in b" \t\r\n":
+        t = s.copy()
+        t[32 * 7 + 5] = ws
+        assert fn(t.ctypes.data, t.size, codes.ctypes.data, mask.ctypes.data) == 32 * 7
