@@ -277,9 +277,13 @@ def run_b200(args):
 
         # a streaming caller feeds reads in chunks: chunk i+1 is normalised + 2-bit packed into pinned memory by the
         # library's host threads while the GPU works on chunk i (two batches, double buffered)
-        CH = 47_500
-        first = min(R, 5_000)  # a short first chunk: its packing is the only one the GPU has to wait for
-        chunks = [(0, first)] + [(lo, min(lo + CH, R)) for lo in range(first, R, CH)]
+        # chunk sizes grow (5k, 15k, then 40k reads): packing + copying chunk i+1 always fits inside the GPU time of chunk i
+        sizes, lo = [5_000, 15_000], 0
+        chunks = []
+        while lo < R:
+            n = sizes[len(chunks)] if len(chunks) < len(sizes) else 40_000
+            chunks.append((lo, min(lo + n, R)))
+            lo = chunks[-1][1]
         pack_s = [0.0]
         hbs = [hb, ctx.batch()]
 
@@ -335,7 +339,7 @@ def run_b200(args):
         h2d = packed // 4 + packed // 8 + (packed // 1024 + R) * 9
         e2e = {"value": R / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(R * top * 12), "ms_per_step": dt * 1e3,
-               "includes": "host normalise+2-bit pack into pinned memory (5k reads, then chunks of 47.5k, packed and copied "
+               "includes": "host normalise+2-bit pack into pinned memory (chunks of 5k, 15k, then 40k reads, packed and copied "
                            "to the device while the GPU works on the previous chunk), all kernels, D2H of top-N",
                "host_threads": os.cpu_count(), "host_pack_ms_per_step": pack_s[0] / n_e2e * 1e3}
         # the e2e result must equal the resident result

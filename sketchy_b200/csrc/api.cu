@@ -635,6 +635,16 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   unsigned long long* d_cand_stat = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 64);  // statistics
   CU(c, cudaMemsetAsync(d_cand_stat, 0, 8, c->stream));
 
+  // Passes are enqueued back to back and checked on the host only every few passes: a pass whose candidates overflow
+  // records itself in `abort` on the device, the passes enqueued behind it do nothing, and the host rolls back to it.
+  struct PassRec { uint32_t r, B; int sums_cur, tracked_cur; };
+  std::vector<PassRec> recs;
+  uint32_t* d_abort = c->scal.as<uint32_t>() + 24;
+  CU(c, cudaMemsetAsync(d_abort, 0, 8, c->stream));
+  CU(c, cudaMemsetAsync(d_cand_total, 0, 8, c->stream));  // bucket-overflow flag + interval slot counter (the verdict kernel clears them after every pass)
+  const uint32_t kBatch = 8;
+  bool force_sync = false;  // after a rollback: one pass at a time until the pass size is back at its maximum
+  uint32_t seq = 0;
   uint32_t r = 0;
   int rc_final = SKB_OK;
   while (r < R) {
@@ -669,7 +679,6 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1);
       skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->stream); }
     cudaMemsetAsync(c->counts.p, 0, ctr_bytes, c->stream);
-    cudaMemsetAsync(d_cand_total, 0, 8, c->stream);  // bucket-overflow flag + interval slot counter
     cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)B * 4, c->stream);
     const SkbRefView rv = ref_view(c);
     SkbRankArgs ra{};
@@ -684,6 +693,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     ra.top = top; ra.out_idx = d_out_idx + (size_t)r * top;
     ra.out_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)r * top;
     ra.tracked_next = c->tracked[c->tracked_cur ^ 1].as<uint32_t>(); ra.n_tracked_next = ra.tracked_next + SKB_MAX_TRACKED;
+    ra.abort = d_abort; ra.seq = seq;
     { ProfScope ps(c, SKB_K_RANK, nkeys ? 4 : 3);
       if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, ra.n_tracked, t, c->counts.as<uint16_t>(), stride, c->stream);
       skb_launch_rank_bounds(ra, c->stream); }
@@ -693,34 +703,57 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     { const char* dbg = getenv("SKB_DEBUG"); fa.debug = dbg ? atoi(dbg) : 0; }
     fa.sums_in = ra.sums_in; fa.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
     fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.lb_rel = ra.lb_rel;
-    fa.ivl = c->ivl.as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_cand_total + 1;
+    fa.ivl = c->ivl.as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_cand_total + 1; fa.abort = d_abort;
     { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
-    { ProfScope ps(c, SKB_K_RANK, 2); skb_launch_rank_expand(ra, c->stream); skb_launch_rank_select(ra, c->stream); }
+    { ProfScope ps(c, SKB_K_RANK, 4);
+      skb_launch_rank_expand(ra, c->stream); skb_launch_rank_select(ra, c->stream);
+      skb_launch_pass_verdict(ra, c->stream);
+      skb_launch_tracked_update(ra, c->stream); }  // from this pass's top lists (skipped on the device after an overflow)
     if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
-    if ((e = cudaMemcpyAsync(h_total, d_cand_total, 8, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+    recs.push_back({r, B, c->sums_cur, c->tracked_cur});
+    c->st_passes += 1;
+    c->sums_cur ^= 1;
+    c->tracked_cur ^= 1;
+    r += B;
+    ++seq;
+    const bool batchable = !force_sync && B > 1 && c->pass_cur >= c->pass_max;
+    if (batchable && recs.size() < kBatch && r < R) continue;
+    // ---- checkpoint: did any pass since the last one overflow?
+    if ((e = cudaMemcpyAsync(h_total, d_abort, 8, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e));
       break;
     }
-    c->st_passes += 1;
-    if (h_total[0] != 0 || h_total[1] > SKB_IVL_CAP) {  // more contenders than a bucket / the interval list holds
-      if (B > 1) {
-        c->pass_cur = std::max(1u, B / 2);  // redo with fewer reads: the bounds tighten after every pass
+    if (h_total[0] != 0) {  // more contenders than a bucket / the interval list holds, in the pass numbered h_total[1]
+      const PassRec& pr = recs[recs.size() - (seq - h_total[1])];
+      c->st_passes -= (seq - h_total[1]) - 1;  // the passes behind the failed one did not run
+      cudaMemsetAsync(d_abort, 0, 8, c->stream);
+      if (pr.B > 1) {
+        // redo from that pass with fewer reads: the bounds tighten after every pass
+        r = pr.r; c->sums_cur = pr.sums_cur; c->tracked_cur = pr.tracked_cur;
+        c->pass_cur = std::max(1u, pr.B / 2);
+        force_sync = true;
+        recs.clear();
         continue;
       }
-      // a single read: its ranking is simply the top of the new sums (exact, no candidates needed)
-      ProfScope ps(c, SKB_K_RANK, 1);
-      skb_launch_rank_full(fa.sums_out, c->n_rows, n_top_rows, c->row_base, ra.out_idx, ra.out_sum, nullptr, c->stream);
+      // a single read (always the newest pass: single-read passes are checked one by one): its ranking is simply
+      // the top of the new sums (exact, no candidates needed)
+      ProfScope ps(c, SKB_K_RANK, 2);
+      unsigned long long* sums_new = c->sums[c->sums_cur].as<unsigned long long>();
+      uint32_t* o_idx = d_out_idx + (size_t)pr.r * top;
+      unsigned long long* o_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)pr.r * top;
+      skb_launch_rank_full(sums_new, c->n_rows, n_top_rows, c->row_base, o_idx, o_sum, nullptr, c->stream);
       if (n_top_rows < top) {
-        cudaMemsetAsync(ra.out_idx + n_top_rows, 0xFF, (size_t)(top - n_top_rows) * 4, c->stream);
-        cudaMemsetAsync(ra.out_sum + n_top_rows, 0, (size_t)(top - n_top_rows) * 8, c->stream);
+        cudaMemsetAsync(o_idx + n_top_rows, 0xFF, (size_t)(top - n_top_rows) * 4, c->stream);
+        cudaMemsetAsync(o_sum + n_top_rows, 0, (size_t)(top - n_top_rows) * 8, c->stream);
       }
+      skb_launch_tracked_update(ra, c->stream);  // the guard is clear again
+    } else {
+      const uint32_t lastB = recs.back().B;
+      c->pass_cur = std::min(c->pass_max, std::max(lastB, c->pass_cur) * 2);
+      if (c->pass_cur >= c->pass_max) force_sync = false;
     }
-    { ProfScope ps(c, SKB_K_RANK, 1); skb_launch_tracked_update(ra, c->stream); }  // from this pass's top lists
-    c->sums_cur ^= 1;
-    c->tracked_cur ^= 1;
-    r += B;
-    if (h_total[0] == 0 && h_total[1] <= SKB_IVL_CAP) c->pass_cur = std::min(c->pass_max, std::max(B, c->pass_cur) * 2);
+    recs.clear();
   }
   if (rc_final) return rc_final;
   unsigned long long cands = 0;

@@ -107,6 +107,7 @@ struct SkbFusedArgs {
   SkbInterval* ivl;                   // [ivl_cap] candidate intervals produced by the rank warps
   uint32_t ivl_cap;
   uint32_t* ivl_total;                // [1] slots reserved (16 at a time); > ivl_cap = overflow
+  const uint32_t* abort;              // [2] {set once an earlier pass of the batch overflowed, its sequence number}: skip
 };
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
 size_t skb_fused_smem_bytes(uint32_t cnt_stride);
@@ -146,12 +147,17 @@ struct SkbRankArgs {
   unsigned long long* out_sum;         // [n_reads * top]
   uint32_t* tracked_next;              // [SKB_MAX_TRACKED] tracked rows for the next pass
   uint32_t* n_tracked_next;            // device scalar
+  uint32_t* abort;                     // [2] see SkbFusedArgs::abort
+  uint32_t seq;                        // sequence number of this pass within the call
 };
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st);
 // tracked rows of the next pass = union of the top lists of 16 sampled reads of this pass (last read first)
 void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st);
 void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st);  // intervals -> per-read candidate buckets
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st);  // per-read top-N
+// after a pass: record the first pass whose candidates overflowed (abort[0] = 1, abort[1] = seq) and clear the pass's
+// overflow counters; passes enqueued behind a failed one leave the running sums and the tracked rows untouched
+void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st);
 
 // top-N of a plain value array by (value desc, index asc); one CTA. idx_base is added to reported indices.
 void skb_launch_rank_full(const unsigned long long* vals, uint32_t n, uint32_t top, uint32_t idx_base,

@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   __shared__ __align__(8) uint64_t row_done[FS_ROWBUF];
   __shared__ __align__(8) uint64_t row_free[FS_ROWBUF];
 
+  if (*a.abort) return;  // an earlier pass of this batch has to be redone: leave sums and candidates alone
+
   uint32_t* bloom = reinterpret_cast<uint32_t*>(smem_raw);
   uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM);
   uint64_t* queue = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
@@ -846,7 +848,17 @@ __global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
 // Tracked rows of the next pass: the union of the top lists of 16 evenly spaced reads of this pass, the last read's
 // list first (it alone guarantees `top` distinct rows). Rows that led at any point of the pass stay tracked, so a
 // lineage that overtakes and falls back does not loosen the bounds. One CTA.
+__global__ void pass_verdict_kernel(const SkbRankArgs a) {
+  if (a.abort[0] == 0u && (*a.cand_total != 0u || *a.ivl_total > a.ivl_cap)) {
+    a.abort[1] = a.seq;
+    a.abort[0] = 1u;
+  }
+  *a.cand_total = 0u;
+  *const_cast<uint32_t*>(a.ivl_total) = 0u;
+}
+
 __global__ void __launch_bounds__(1024) tracked_update_kernel(const SkbRankArgs a) {
+  if (a.abort[0]) return;  // this pass (or one before it) is redone: keep the tracked rows it started from
   __shared__ uint32_t list[16 * SKB_MAX_TOP];
   __shared__ uint32_t keep[16 * SKB_MAX_TOP];
   const uint32_t n_s = 16, total = n_s * a.top;
@@ -1137,6 +1149,8 @@ void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) {
 void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st) { expand_kernel<<<148 * 8, 256, 0, st>>>(a); }
 
 void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st) { tracked_update_kernel<<<1, 1024, 0, st>>>(a); }
+
+void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st) { pass_verdict_kernel<<<1, 1, 0, st>>>(a); }
 
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)RS_WARPS * RS_CACHE * 16;
