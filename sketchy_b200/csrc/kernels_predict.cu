@@ -24,8 +24,16 @@ namespace {
 __device__ __forceinline__ uint32_t table_home(uint64_t h, uint32_t log2cap) {
   return (uint32_t)((h * 0x9E3779B97F4A7C15ull) >> (64 - log2cap));
 }
-__device__ __forceinline__ uint32_t bloom_word(uint32_t lo) { return (lo >> 5) & (SKB_BLOOM_WORDS - 1u); }
-__device__ __forceinline__ uint32_t bloom_mask(uint32_t lo) { return (1u << (lo & 31u)) | (1u << ((lo >> 19) & 31u)); }
+// Filter geometry, chosen for the probe's instruction count: the word's BYTE offset is lo & 0xFFFC (one LOP), the two
+// bit positions are the low ten bits of hi, which wrap-mode shifts consume without masking (hashes under the reference
+// maximum still have uniform bits 32-41 unless the maximum is below 2^42, i.e. never for real sketches).
+__device__ __forceinline__ uint32_t bloom_word(uint32_t lo) { return (lo >> 2) & (SKB_BLOOM_WORDS - 1u); }
+__device__ __forceinline__ uint32_t bloom_mask(uint32_t hi) { return (1u << (hi & 31u)) | (1u << ((hi >> 5) & 31u)); }
+// 1 when both bits of the key (lo, hi) are set in its filter word
+__device__ __forceinline__ uint32_t bloom_probe(const uint32_t* bloom, uint32_t lo, uint32_t hi) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bloom) + (lo & (4u * SKB_BLOOM_WORDS - 4u)));
+  return (w >> (hi & 31u)) & (w >> ((hi >> 5) & 31u)) & 1u;
+}
 
 __device__ __forceinline__ SkbSlot load_slot(const SkbSlot* p) {
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
@@ -66,7 +74,7 @@ __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh,
   atomicAdd(&t.slots[slot].meta, 1ull);  // cnt lives in the low 13 bits; a read holds a hash at most once
   t.slot_of[i] = slot;
   const uint32_t lo = (uint32_t)h;
-  atomicOr(&t.bloom[bloom_word(lo)], bloom_mask(lo));
+  atomicOr(&t.bloom[bloom_word(lo)], bloom_mask((uint32_t)(h >> 32)));
 }
 
 __global__ void table_alloc_kernel(SkbTable t) {
@@ -490,16 +498,16 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
 #pragma unroll
               for (int j = 0; j < FS_NHASH; ++j) {
                 const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
-                const uint32_t m = bloom_mask(lo);
-                pm |= ((bloom[bloom_word(lo)] & m) == m) ? (1u << j) : 0u;
+                const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
+                pm += bloom_probe(bloom, lo, hi) << j;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < FS_NHASH; ++j) {
                 const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
                 const uint32_t idx = base + 2u * (lane + 32 * (j >> 1)) + (j & 1);
-                const uint32_t m = bloom_mask(lo);
-                pm |= (((bloom[bloom_word(lo)] & m) == m) && idx < n_sub) ? (1u << j) : 0u;
+                const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
+                pm += (idx < n_sub ? bloom_probe(bloom, lo, hi) : 0u) << j;
               }
             }
           }
