@@ -394,7 +394,7 @@ def run_b200(args):
                                    "s=10000, --top 10" if (N, s, R) == (40000, 10000, 100000) else
                                    f"predict {R} reads vs {N} x s={s}", "refs": N, "sketch_size": s, "reads": R,
                        "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages,
-                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 2560,
+                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 3072,
                        "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass"
                              % (rows_local * s * 8 / 1e9),
                        "parallelism": f"reference rows sharded over {world} GPU(s); NCCL all-gather of local top-N"

@@ -180,7 +180,7 @@ struct skb_ctx {
   DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = 2560, pass_cur = 64;  // default reads per pass (<= SKB_MAX_PASS_READS_NARROW)
+  uint32_t pass_max = 3072, pass_cur = 64;  // default reads per pass (<= SKB_MAX_PASS_READS_NARROW)
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -1033,7 +1033,7 @@ int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
-  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS_NARROW) : 2560;
+  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS_NARROW) : 3072;
   c->pass_cur = std::min(c->pass_cur, c->pass_max);
   return SKB_OK;
 }

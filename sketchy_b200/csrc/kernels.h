@@ -61,7 +61,7 @@ struct __align__(16) SkbSlot {
 #define SKB_SLOT_INLINE 4u
 #define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> (13 + 12 * (i))) & 0xFFFull))
 #define SKB_SLOT_START(m) ((uint32_t)(((m) >> 13) & 0xFFFFFFFFull))
-#define SKB_MAX_PASS_READS 1792u         // u16 counters: 4 row buffers + staged bounds = 10 B of shared memory per read
+#define SKB_MAX_PASS_READS 2048u         // u16 counters: 4 row buffers + staged bounds = 10 B of shared memory per read
 #define SKB_MAX_PASS_READS_NARROW 3072u  // u8 counters (reads with <= 255 query hashes): 6 B per read
 
 struct SkbTable {

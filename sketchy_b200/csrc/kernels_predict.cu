@@ -24,15 +24,26 @@ namespace {
 __device__ __forceinline__ uint32_t table_home(uint64_t h, uint32_t log2cap) {
   return (uint32_t)((h * 0x9E3779B97F4A7C15ull) >> (64 - log2cap));
 }
-// Filter geometry, chosen for the probe's instruction count: the word's BYTE offset is lo & 0xFFFC (one LOP), the two
-// bit positions are the low ten bits of hi, which wrap-mode shifts consume without masking (hashes under the reference
-// maximum still have uniform bits 32-41 unless the maximum is below 2^42, i.e. never for real sketches).
+// Filter geometry, chosen for the probe's instruction count: the word's BYTE offset is lo & 0xFFFC (one LOP); the bit
+// positions are 5-bit fields of lo above the word index (bits 16-30) and the low bits of hi, which wrap-mode shifts
+// consume without masking. All of these bits are uniform for any reference maximum >= 2^37.
+#ifndef SKB_BLOOM_K
+#define SKB_BLOOM_K 3
+#endif
 __device__ __forceinline__ uint32_t bloom_word(uint32_t lo) { return (lo >> 2) & (SKB_BLOOM_WORDS - 1u); }
-__device__ __forceinline__ uint32_t bloom_mask(uint32_t hi) { return (1u << (hi & 31u)) | (1u << ((hi >> 5) & 31u)); }
-// 1 when both bits of the key (lo, hi) are set in its filter word
+__device__ __forceinline__ uint32_t bloom_mask(uint32_t lo, uint32_t hi) {
+  uint32_t m = (1u << (hi & 31u)) | (1u << ((lo >> 16) & 31u));
+  if (SKB_BLOOM_K >= 3) m |= 1u << ((lo >> 21) & 31u);
+  if (SKB_BLOOM_K >= 4) m |= 1u << ((lo >> 26) & 31u);
+  return m;
+}
+// 1 when every bit of the key (lo, hi) is set in its filter word
 __device__ __forceinline__ uint32_t bloom_probe(const uint32_t* bloom, uint32_t lo, uint32_t hi) {
   const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bloom) + (lo & (4u * SKB_BLOOM_WORDS - 4u)));
-  return (w >> (hi & 31u)) & (w >> ((hi >> 5) & 31u)) & 1u;
+  uint32_t r = (w >> (hi & 31u)) & (w >> ((lo >> 16) & 31u));
+  if (SKB_BLOOM_K >= 3) r &= w >> ((lo >> 21) & 31u);
+  if (SKB_BLOOM_K >= 4) r &= w >> ((lo >> 26) & 31u);
+  return r & 1u;
 }
 
 __device__ __forceinline__ SkbSlot load_slot(const SkbSlot* p) {
@@ -74,7 +85,7 @@ __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh,
   atomicAdd(&t.slots[slot].meta, 1ull);  // cnt lives in the low 13 bits; a read holds a hash at most once
   t.slot_of[i] = slot;
   const uint32_t lo = (uint32_t)h;
-  atomicOr(&t.bloom[bloom_word(lo)], bloom_mask((uint32_t)(h >> 32)));
+  atomicOr(&t.bloom[bloom_word(lo)], bloom_mask(lo, (uint32_t)(h >> 32)));
 }
 
 __global__ void table_alloc_kernel(SkbTable t) {
@@ -134,7 +145,7 @@ constexpr int FS_NHASH = 8;            // hashes per lane per chunk (one chunk =
 constexpr int FS_CHUNKS = FS_SUB / (32 * FS_NHASH);
 constexpr size_t FS_SMEM_BLOOM = (size_t)SKB_BLOOM_WORDS * 4;
 constexpr size_t FS_SMEM_RING = (size_t)FS_CONSUMER_WARPS * FS_STAGES * FS_SUB * 8;
-constexpr size_t FS_SMEM_QUEUE = (size_t)FS_CONSUMER_WARPS * FS_QCAP * 16;  // {hash, tag, pad} per entry
+constexpr size_t FS_SMEM_QUEUE = (size_t)FS_CONSUMER_WARPS * FS_QCAP * 12;  // 8-byte hash + 4-byte tag per entry (two arrays)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -330,7 +341,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     // loop waits on a dependent load. A slot owned by another key re-queues the entry with the next slot index.
     const uint32_t cw = warp;
     uint64_t* my_ring = ring + (size_t)cw * FS_STAGES * FS_SUB;
-    uint4* q = reinterpret_cast<uint4*>(queue) + (size_t)cw * FS_QCAP;  // FIFO records {hash.lo, hash.hi, tag, 0}
+    // FIFO records: hash in qh[], tag (slot index or SKB_Q_FRESH, row buffer in the top bits) in qt[]
+    uint2* qh = reinterpret_cast<uint2*>(queue) + (size_t)cw * FS_QCAP;
+    uint32_t* qt = reinterpret_cast<uint32_t*>(queue + (size_t)FS_CONSUMER_WARPS * FS_QCAP) + (size_t)cw * FS_QCAP;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const SkbTable& t = a.table;
     uint32_t qhead = 0, qn = 0;  // FIFO state (warp-uniform)
@@ -381,8 +394,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
           if (qn + n <= (uint32_t)FS_QCAP) {
             if (again) {
               const uint32_t at = (qhead + qn + __popc(bal & lt_mask)) & (FS_QCAP - 1);
-              q[at] = make_uint4((uint32_t)pend.h, (uint32_t)(pend.h >> 32),
-                                 ((pend.idx + 1) & (t.cap - 1)) | (pend.par << 29), 0u);
+              qh[at] = make_uint2((uint32_t)pend.h, (uint32_t)(pend.h >> 32));
+              qt[at] = ((pend.idx + 1) & (t.cap - 1)) | (pend.par << 29);
             }
             qn += n;
           } else {  // no room (practically never): chase the chain here
@@ -414,9 +427,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     auto start_batch = [&]() {  // oldest (up to) 32 entries of the FIFO, one per lane
       const uint32_t n = qn < 32u ? qn : 32u;
       pend.valid = lane < n;
-      const uint4 e = q[(qhead + (pend.valid ? lane : 0u)) & (FS_QCAP - 1)];
+      const uint32_t qpos = (qhead + (pend.valid ? lane : 0u)) & (FS_QCAP - 1);
+      const uint2 e = qh[qpos];
       pend.h = ((uint64_t)e.y << 32) | e.x;
-      const uint32_t tag = e.z;
+      const uint32_t tag = qt[qpos];
       pend.par = tag >> 29;
       const uint32_t qidx = tag & 0x1FFFFFFFu;
       pend.idx = !pend.valid ? 0u
@@ -544,18 +558,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
               // a passer stores its 8-byte hash (an aligned register pair); the tags of the `total` new records are
               // written by the first lanes
               const uint32_t tail = (qhead + qn) & (FS_QCAP - 1);
-              uint2* qe = reinterpret_cast<uint2*>(q);  // record i = qe[2 * i] (hash), qe[2 * i + 1] (tag, pad)
               uint32_t at = tail + excl;
 #pragma unroll
               for (int j = 0; j < FS_NHASH; ++j) {
                 if (pm & (1u << j)) {
-                  qe[2u * (at & (FS_QCAP - 1))] =
+                  qh[at & (FS_QCAP - 1)] =
                       (j & 1) ? make_uint2(v[j >> 1].z, v[j >> 1].w) : make_uint2(v[j >> 1].x, v[j >> 1].y);
                   ++at;
                 }
               }
-              if (lane < total) qe[2u * ((tail + lane) & (FS_QCAP - 1)) + 1] = make_uint2(fresh_tag, 0u);
-              if (total > 32u && lane + 32u < total) qe[2u * ((tail + lane + 32u) & (FS_QCAP - 1)) + 1] = make_uint2(fresh_tag, 0u);
+              if (lane < total) qt[(tail + lane) & (FS_QCAP - 1)] = fresh_tag;
+              if (total > 32u && lane + 32u < total) qt[(tail + lane + 32u) & (FS_QCAP - 1)] = fresh_tag;
               qn += total;
               outst += (uint64_t)total << (8 * par);
               __syncwarp();
