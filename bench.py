@@ -278,38 +278,37 @@ def run_b200(args):
         # a streaming caller feeds reads in chunks: chunk i+1 is normalised + 2-bit packed into pinned memory by the
         # library's host threads while the GPU works on chunk i (two batches, double buffered)
         # chunk sizes grow (5k, 15k, then 40k reads): packing + copying chunk i+1 always fits inside the GPU time of chunk i
-        sizes, lo = [5_000, 15_000], 0
+        sizes, c_lo = [5_000, 15_000], 0
         chunks = []
-        while lo < R:
-            n = sizes[len(chunks)] if len(chunks) < len(sizes) else 40_000
-            chunks.append((lo, min(lo + n, R)))
-            lo = chunks[-1][1]
+        while c_lo < R:
+            n_c = sizes[len(chunks)] if len(chunks) < len(sizes) else 40_000
+            chunks.append((c_lo, min(c_lo + n_c, R)))
+            c_lo = chunks[-1][1]
         pack_s = [0.0]
         hbs = [hb, ctx.batch()]
 
-        def pack(j, lo, hi):
+        def pack(j, p_lo, p_hi):
             t0 = time.perf_counter()
             hbs[j].clear()
-            hbs[j].add(blob[lo * args.read_len:hi * args.read_len], roff[lo:hi + 1] - roff[lo])
+            hbs[j].add(blob[p_lo * args.read_len:p_hi * args.read_len], roff[p_lo:p_hi + 1] - roff[p_lo])
             pack_s[0] += time.perf_counter() - t0
             hbs[j].stage()   # H2D on the copy stream, overlapping the kernels of the previous chunk
 
         def step_e2e():
             ctx.sums_reset()
             pack(0, *chunks[0])
-            for ci, (lo, hi) in enumerate(chunks):
+            for ci, (q_lo, q_hi) in enumerate(chunks):
                 th = None
                 if ci + 1 < len(chunks):
                     th = threading.Thread(target=pack, args=((ci + 1) & 1, *chunks[ci + 1]))
                     th.start()
                 b = hbs[ci & 1]
                 if world > 1:
-                    n = hi - lo
-                    ctx.predict_stream_device(b, K, s, SEED, top, d_idx[lo:hi].data_ptr(), d_sum[lo:hi].data_ptr(), pad=True)
+                    ctx.predict_stream_device(b, K, s, SEED, top, d_idx[q_lo:q_hi].data_ptr(), d_sum[q_lo:q_hi].data_ptr(), pad=True)
                 else:
                     gi, gs = ctx.predict_stream(b, K, s, SEED, top)   # H2D + kernels + D2H of the top-N
-                    oi[lo:hi] = gi
-                    os_[lo:hi] = gs
+                    oi[q_lo:q_hi] = gi
+                    os_[q_lo:q_hi] = gs
                 if th is not None:
                     th.join()
             if world > 1:
@@ -335,7 +334,7 @@ def run_b200(args):
             t = torch.tensor([dt], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        packed = sum(-(-((hi - lo) * (args.read_len + 1)) // 32) * 32 for lo, hi in chunks)
+        packed = sum(-(-((b1 - b0) * (args.read_len + 1)) // 32) * 32 for b0, b1 in chunks)
         h2d = packed // 4 + packed // 8 + (packed // 1024 + R) * 9
         e2e = {"value": R / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(R * top * 12), "ms_per_step": dt * 1e3,

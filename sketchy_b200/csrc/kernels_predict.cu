@@ -136,7 +136,7 @@ constexpr int FS_CONSUMER_WARPS = 16;
 constexpr int FS_RANK_WARPS = 2;             // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
 constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
 constexpr int FS_ROWBUF = 4;           // rows in flight per CTA: counter buffers / barriers are indexed by row % 4
-                                       // (6 or 8 buffers were measured: 1 % faster at best, and fewer reads fit a pass)
+                                       // (6 buffers: 2.5 % faster per pass at 2560 reads, but 3072 reads no longer fit)
 // a rank warp may only wait on a row buffer whose previous row it flushed itself (consumer warps can close rows out of
 // order, so the barrier parity of a buffer is only unambiguous to the warp that saw its previous phase)
 static_assert(FS_ROWBUF % FS_RANK_WARPS == 0 && FS_ROWBUF <= 8, "FS_RANK_WARPS must divide FS_ROWBUF");

@@ -16,7 +16,7 @@ ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Met
 agg = collections.OrderedDict()
 mine_total = 0.0
 for r in rows[hi + 2:]:
-    if len(r) <= iv or "unnamed" not in r[ik]:
+    if len(r) <= iv or "unnamed" not in r[ik] or "at::" in r[ik] or "at_cuda_detail" in r[ik]:
         continue  # torch data-generation kernels of the untimed set-up are not ours
     v = float(r[iv].replace(",", ""))
     v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[iu], 1.0)
