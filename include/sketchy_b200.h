@@ -159,6 +159,9 @@ uint64_t skb_launch_count(const skb_ctx* ctx); /* kernels launched by this conte
 /* Bytes of reference hashes the last predict call streamed per pass, and the number of passes it made. */
 int skb_last_predict_stats(const skb_ctx* ctx, uint64_t* ref_bytes_per_pass, uint64_t* passes,
                            uint64_t* query_hashes, uint64_t* candidates);
+/* Query hashes of the last predict call that occur in at least one reference row of the shard according to the
+ * membership prefilter (the others never entered a pass's table). Equals query_hashes when the prefilter is off. */
+uint64_t skb_last_predict_member_hashes(const skb_ctx* ctx);
 
 /* ---- debug / parity hooks (used only by tests) --------------------------------------------------------------- */
 

@@ -53,6 +53,7 @@ SYMBOLS = [
     ("skb_prof_get", _i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(_u64)]),
     ("skb_launch_count", _u64, [_vp]),
     ("skb_last_predict_stats", _i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    ("skb_last_predict_member_hashes", _u64, [_vp]),
     ("skb_batch_packed_len", _u64, [_vp]),
     ("skb_batch_record_start", _i, [_vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     ("skb_debug_kmer_hashes", _i, [_vp, _vp, _u32, _u64, _vp, _vp]),
@@ -230,7 +231,7 @@ class Context:
         a, b, c_, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.check(self.lib.skb_last_predict_stats(self.h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
         return {"ref_bytes_per_pass": int(a.value), "passes": int(b.value), "query_hashes": int(c_.value),
-                "candidates": int(d.value)}
+                "candidates": int(d.value), "member_hashes": int(self.lib.skb_last_predict_member_hashes(self.h))}
 
     # -- debug
     def debug_kmer_hashes(self, batch: "Batch", k: int, seed: int = 0):

@@ -161,7 +161,8 @@ struct skb_ctx {
   cudaStream_t copy_stream = nullptr;  // batch staging (H2D): lets skb_batch_stage overlap a predict running on `stream`
   std::string err;
   // reference shard
-  DevBuf ref, row_start, row_len, cta_row;
+  DevBuf ref, row_start, row_len, cta_row, memb;
+  uint32_t memb_log2 = 0;  // 0 = no membership prefilter
   uint64_t ref_len = 0;  // hashes in the shard (without alignment padding)
   uint32_t n_rows = 0, row_base = 0, uniform_len = 0, uniform_pitch = 0;
   uint64_t hmax = 0;
@@ -188,7 +189,7 @@ struct skb_ctx {
   double prof_ms[SKB_K_COUNT] = {0};
   uint64_t prof_n[SKB_K_COUNT] = {0};
   uint64_t launches = 0;
-  uint64_t st_ref_bytes = 0, st_passes = 0, st_qhashes = 0, st_cands = 0;
+  uint64_t st_ref_bytes = 0, st_passes = 0, st_qhashes = 0, st_cands = 0, st_members = 0;
   uint32_t* h_scal = nullptr;  // pinned, 64 bytes
 };
 
@@ -459,6 +460,9 @@ SkbTable table_of(skb_ctx* c) {
   t.slot_of = c->t_slot.as<uint32_t>(); t.bloom = c->t_bloom.as<uint32_t>();
   t.cursor = c->scal.as<uint32_t>() + 4;
   t.cap = c->t_cap;
+  t.memb = c->memb_log2 ? c->memb.as<uint32_t>() : nullptr;
+  t.memb_log2 = c->memb_log2;
+  t.memb_kept = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 72);
   uint32_t l = 0;
   while ((1u << l) < t.cap) ++l;
   t.log2cap = l;
@@ -547,6 +551,20 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   CU(c, cudaStreamSynchronize(c->stream));
   if (bad) return fail(c, SKB_ERR_REF_NOT_SORTED, "a reference row is not strictly increasing");
   c->ref_len = len; c->row_base = global_row_base; c->hmax = hmax;
+  // membership filter of the shard: 8 bits per stored hash, 128 KB .. 2 GB (SKB_NO_PREFILTER=1 turns it off: experiments)
+  {
+    const char* off = getenv("SKB_NO_PREFILTER");
+    c->memb_log2 = 0;
+    if (!(off && off[0] == '1') && len > 0) {
+      uint32_t l2 = 15;
+      while (l2 < 29 && (32ull << l2) < len * 8ull) ++l2;
+      CU(c, c->memb.ensure((size_t)4 << l2));
+      CU(c, cudaMemsetAsync(c->memb.p, 0, (size_t)4 << l2, c->stream));
+      { ProfScope ps(c, SKB_K_MISC, 1); skb_launch_memb_build(ref_view(c), c->memb.as<uint32_t>(), l2, c->stream); }
+      if (int rc = check_launch(c, "memb_build")) return rc;
+      c->memb_log2 = l2;
+    }
+  }
   // contiguous row ranges per CTA, balanced by ring tiles (a row costs at least one unit: its rank work)
   {
     const uint32_t G = (uint32_t)c->num_sms, tile = skb_fused_tile();
@@ -633,7 +651,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   CU(c, c->scal.ensure(256));
   uint32_t* d_cand_total = c->scal.as<uint32_t>() + 8;                                                  // overflow flag
   unsigned long long* d_cand_stat = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 64);  // statistics
-  CU(c, cudaMemsetAsync(d_cand_stat, 0, 8, c->stream));
+  CU(c, cudaMemsetAsync(d_cand_stat, 0, 16, c->stream));  // candidates, member keys
 
   // Passes are enqueued back to back and checked on the host only every few passes: a pass whose candidates overflow
   // records itself in `abort` on the device, the passes enqueued behind it do nothing, and the host rolls back to it.
@@ -756,10 +774,11 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     recs.clear();
   }
   if (rc_final) return rc_final;
-  unsigned long long cands = 0;
-  CU(c, cudaMemcpyAsync(&cands, d_cand_stat, 8, cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long cands[2] = {0, 0};
+  CU(c, cudaMemcpyAsync(cands, d_cand_stat, 16, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  c->st_cands = cands;
+  c->st_cands = cands[0];
+  c->st_members = cands[1];
   return SKB_OK;
 }
 
@@ -799,7 +818,7 @@ void skb_destroy(skb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-  DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->sums[0], &c->sums[1], &c->tracked[0], &c->tracked[1], &c->tprefix, &c->g_tau, &c->g_cap,
+  DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->memb, &c->sums[0], &c->sums[1], &c->tracked[0], &c->tracked[1], &c->tprefix, &c->g_tau, &c->g_cap,
                     &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->cand_pool,
                     &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->lb_sum,
                     &c->lb_idx, &c->lb_rel, &c->ivl, &c->cand, &c->cand_cnt, &c->scal,
@@ -1140,6 +1159,11 @@ int skb_last_predict_stats(const skb_ctx* c, uint64_t* ref_bytes_per_pass, uint6
   if (query_hashes) *query_hashes = c->st_qhashes;
   if (candidates) *candidates = c->st_cands;
   return SKB_OK;
+}
+
+uint64_t skb_last_predict_member_hashes(const skb_ctx* c) {
+  if (!c) return 0;
+  return c->memb_log2 ? c->st_members : c->st_qhashes;
 }
 
 // ---- debug ------------------------------------------------------------------------------------------------

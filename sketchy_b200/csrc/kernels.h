@@ -73,7 +73,14 @@ struct SkbTable {
   uint32_t* cursor;   // [1]
   uint32_t cap;       // power of two
   uint32_t log2cap;
+  // membership filter of the whole reference shard (built once per upload): a query hash that is in no reference row
+  // (sequencing errors make most read k-mers novel) is left out of the table and of the shared-memory filter
+  const uint32_t* memb;   // [1 << memb_log2] words, null = no prefilter
+  uint32_t memb_log2;
+  unsigned long long* memb_kept;  // [1] statistics: keys that passed, or null
 };
+// three bits of one word per reference hash
+void skb_launch_memb_build(const struct SkbRefView& rv, uint32_t* memb, uint32_t memb_log2, cudaStream_t st);
 void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_t* qread, uint32_t n_keys,
                             uint32_t read_base, cudaStream_t st);
 

@@ -55,6 +55,33 @@ __device__ __forceinline__ SkbSlot load_slot(const SkbSlot* p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// reference membership filter (query-side prefilter)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void memb_pos(uint64_t h, uint32_t log2w, uint32_t& word, uint32_t& mask) {
+  const uint64_t x = h * 0xD6E8FEB86659FD93ull;
+  word = (uint32_t)(x >> (64 - log2w));
+  mask = (1u << (x & 31u)) | (1u << ((x >> 5) & 31u)) | (1u << ((x >> 10) & 31u));
+}
+__device__ __forceinline__ bool memb_test(const SkbTable& t, uint64_t h) {
+  uint32_t word, mask;
+  memb_pos(h, t.memb_log2, word, mask);
+  return (__ldg(t.memb + word) & mask) == mask;
+}
+__global__ void __launch_bounds__(256) memb_build_kernel(const SkbRefView rv, uint32_t* memb, uint32_t log2w) {
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t r = warp0; r < rv.n_rows; r += nwarps) {
+    const uint64_t* row = rv.ref + rv.row_start[r];
+    const uint32_t n = rv.row_len[r];
+    for (uint32_t i = skb_lane(); i < n; i += 32) {
+      uint32_t word, mask;
+      memb_pos(row[i], log2w, word, mask);
+      if ((memb[word] & mask) != mask) atomicOr(memb + word, mask);  // near-identical rows: most bits are set already
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // query table
 // ---------------------------------------------------------------------------------------------------------
 __global__ void table_clear_kernel(SkbTable t) {
@@ -71,6 +98,11 @@ __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh,
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
   const uint64_t h = qh[i];
+  if (t.memb && !memb_test(t, h)) {  // in no reference row: it can never be hit
+    t.slot_of[i] = 0xFFFFFFFFu;
+    return;
+  }
+  if (t.memb_kept) atomicAdd(t.memb_kept, 1ull);
   uint32_t slot;
   if (h == SKB_EMPTY_KEY) {
     slot = t.cap;
@@ -101,6 +133,7 @@ __global__ void table_fill_kernel(SkbTable t, const uint32_t* __restrict__ qread
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
   const uint32_t s = t.slot_of[i];
+  if (s == 0xFFFFFFFFu) return;  // dropped by the membership prefilter
   const uint32_t rd = qread[i] - read_base;
   // cnt (and, for long lists, the start) are final here; only the inline id bits are still being OR-ed in
   const unsigned long long m = *reinterpret_cast<volatile unsigned long long*>(&t.slots[s].meta);
@@ -1133,6 +1166,13 @@ void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_
   table_insert_kernel<<<(n_keys + th - 1) / th, th, 0, st>>>(t, qh, n_keys);
   table_alloc_kernel<<<(t.cap + 1 + th - 1) / th, th, 0, st>>>(t);
   table_fill_kernel<<<(n_keys + th - 1) / th, th, 0, st>>>(t, qread, n_keys, read_base);
+}
+
+void skb_launch_memb_build(const SkbRefView& rv, uint32_t* memb, uint32_t memb_log2, cudaStream_t st) {
+  if (rv.n_rows == 0) return;
+  unsigned blocks = (rv.n_rows + 7) / 8;
+  if (blocks > 148u * 8u) blocks = 148u * 8u;
+  memb_build_kernel<<<blocks, 256, 0, st>>>(rv, memb, memb_log2);
 }
 
 size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
