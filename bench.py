@@ -277,11 +277,12 @@ def run_b200(args):
 
         # a streaming caller feeds reads in chunks: chunk i+1 is normalised + 2-bit packed into pinned memory by the
         # library's host threads while the GPU works on chunk i (two batches, double buffered)
-        # chunk sizes grow (5k, 15k, then 40k reads): packing + copying chunk i+1 always fits inside the GPU time of chunk i
-        sizes, c_lo = [5_000, 15_000], 0
+        # chunk sizes grow so that packing + copying chunk i+1 always fits inside the GPU time of chunk i, and they are
+        # multiples of the library's pass sizes (ramp 128..2048 = 3968 reads, then 4096 per pass): no partial passes
+        sizes, c_lo = [3_968, 4 * 4_096], 0
         chunks = []
         while c_lo < R:
-            n_c = sizes[len(chunks)] if len(chunks) < len(sizes) else 40_000
+            n_c = sizes[len(chunks)] if len(chunks) < len(sizes) else 10 * 4_096
             chunks.append((c_lo, min(c_lo + n_c, R)))
             c_lo = chunks[-1][1]
         pack_s = [0.0]
@@ -338,7 +339,7 @@ def run_b200(args):
         h2d = packed // 4 + packed // 8 + (packed // 1024 + R) * 9
         e2e = {"value": R / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(R * top * 12), "ms_per_step": dt * 1e3,
-               "includes": "host normalise+2-bit pack into pinned memory (chunks of 5k, 15k, then 40k reads, packed and copied "
+               "includes": "host normalise+2-bit pack into pinned memory (chunks of 3968, 16384, then 40960 reads, packed and copied "
                            "to the device while the GPU works on the previous chunk), all kernels, D2H of top-N",
                "host_threads": os.cpu_count(), "host_pack_ms_per_step": pack_s[0] / n_e2e * 1e3}
         # the e2e result must equal the resident result
@@ -393,7 +394,7 @@ def run_b200(args):
                                    "s=10000, --top 10" if (N, s, R) == (40000, 10000, 100000) else
                                    f"predict {R} reads vs {N} x s={s}", "refs": N, "sketch_size": s, "reads": R,
                        "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages,
-                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 3072,
+                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 4096,
                        "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass"
                              % (rows_local * s * 8 / 1e9),
                        "parallelism": f"reference rows sharded over {world} GPU(s); NCCL all-gather of local top-N"

@@ -181,7 +181,7 @@ struct skb_ctx {
   DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = 3072, pass_cur = 64;  // default reads per pass (<= SKB_MAX_PASS_READS_NARROW)
+  uint32_t pass_max = 4096, pass_cur = 64;  // default reads per pass (<= SKB_MAX_PASS_READS_NARROW)
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -658,7 +658,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   struct PassRec { uint32_t r, B; int sums_cur, tracked_cur; };
   std::vector<PassRec> recs;
   uint32_t* d_abort = c->scal.as<uint32_t>() + 24;
-  CU(c, cudaMemsetAsync(d_abort, 0, 8, c->stream));
+  CU(c, cudaMemsetAsync(d_abort, 0, 16, c->stream));
   CU(c, cudaMemsetAsync(d_cand_total, 0, 8, c->stream));  // bucket-overflow flag + interval slot counter (the verdict kernel clears them after every pass)
   const uint32_t kBatch = 8;
   bool force_sync = false;  // after a rollback: one pass at a time until the pass size is back at its maximum
@@ -737,15 +737,18 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     const bool batchable = !force_sync && B > 1 && c->pass_cur >= c->pass_max;
     if (batchable && recs.size() < kBatch && r < R) continue;
     // ---- checkpoint: did any pass since the last one overflow?
-    if ((e = cudaMemcpyAsync(h_total, d_abort, 8, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+    if ((e = cudaMemcpyAsync(h_total, d_abort, 16, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e));
       break;
     }
     if (h_total[0] != 0) {  // more contenders than a bucket / the interval list holds, in the pass numbered h_total[1]
       const PassRec& pr = recs[recs.size() - (seq - h_total[1])];
+      if (getenv("SKB_TRACE_PASSES"))
+        fprintf(stderr, "[skb] pass at read %u with %u reads overflowed (bucket flag %u, intervals %u of %u): redo with %u\n", pr.r, pr.B,
+                h_total[2], h_total[3], (unsigned)SKB_IVL_CAP, std::max(1u, pr.B / 2));
       c->st_passes -= (seq - h_total[1]) - 1;  // the passes behind the failed one did not run
-      cudaMemsetAsync(d_abort, 0, 8, c->stream);
+      cudaMemsetAsync(d_abort, 0, 16, c->stream);
       if (pr.B > 1) {
         // redo from that pass with fewer reads: the bounds tighten after every pass
         r = pr.r; c->sums_cur = pr.sums_cur; c->tracked_cur = pr.tracked_cur;
@@ -767,8 +770,13 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
       }
       skb_launch_tracked_update(ra, c->stream);  // the guard is clear again
     } else {
+      // grow the pass only when the fullest bucket of the last pass leaves headroom: twice the reads means half the
+      // bucket, and the tracked rows are staler towards the end of a longer pass (assume twice the contenders)
       const uint32_t lastB = recs.back().B;
-      c->pass_cur = std::min(c->pass_max, std::max(lastB, c->pass_cur) * 2);
+      const uint64_t grown = std::min<uint64_t>(c->pass_max, (uint64_t)std::max(lastB, c->pass_cur) * 2);
+      const uint64_t cap_grown = std::min<uint64_t>(std::max<uint32_t>(c->n_rows, 64), budget / std::max<uint64_t>(grown, 1));
+      if (2ull * h_total[2] <= cap_grown || cap_grown >= c->n_rows) c->pass_cur = (uint32_t)grown;
+      else c->pass_cur = std::max(lastB, c->pass_cur);
       if (c->pass_cur >= c->pass_max) force_sync = false;
     }
     recs.clear();
@@ -1052,7 +1060,7 @@ int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
-  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS_NARROW) : 3072;
+  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS_NARROW) : 4096;
   c->pass_cur = std::min(c->pass_cur, c->pass_max);
   return SKB_OK;
 }

@@ -61,8 +61,8 @@ struct __align__(16) SkbSlot {
 #define SKB_SLOT_INLINE 4u
 #define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> (13 + 12 * (i))) & 0xFFFull))
 #define SKB_SLOT_START(m) ((uint32_t)(((m) >> 13) & 0xFFFFFFFFull))
-#define SKB_MAX_PASS_READS 2048u         // u16 counters: 4 row buffers + staged bounds = 10 B of shared memory per read
-#define SKB_MAX_PASS_READS_NARROW 3072u  // u8 counters (reads with <= 255 query hashes): 6 B per read
+#define SKB_MAX_PASS_READS 2560u         // u16 counters: 4 row buffers + bounds at every 4th read = 8.5 B of shared memory per read
+#define SKB_MAX_PASS_READS_NARROW 4096u  // u8 counters (reads with <= 255 query hashes): 4.5 B per read; 12-bit read ids in a slot
 
 struct SkbTable {
   SkbSlot* slots;     // [cap + 1]; slot `cap` is reserved for the key that equals SKB_EMPTY_KEY

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   uint64_t* queue = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
   uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE);
   const uint32_t cwords = a.cnt_stride / CPW;  // 32-bit words per row buffer
-  uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride] bound growth since read 0, saturating
+  uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride / 4] bound growth since read 0 at every 4th read, saturating
 
   // Every CTA owns a contiguous range of rows (balanced by sub-tiles on the host). Dealing the rows round-robin was
   // tried to spread the rows that contend for a pass's reads: the average CTA took as long, the slowest 10-70 % longer.
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     for (uint32_t i = threadIdx.x; i < SKB_BLOOM_WORDS / 4; i += blockDim.x) dst[i] = src[i];
   }
   for (uint32_t i = threadIdx.x; i < FS_ROWBUF * cwords; i += blockDim.x) cnt32[i] = 0;
-  for (uint32_t i = threadIdx.x; i < a.n_reads; i += blockDim.x) lbrel[i] = (uint16_t)min(a.lb_rel[i], 0xFFFFu);
+  for (uint32_t i = threadIdx.x; 4u * i < a.n_reads; i += blockDim.x) lbrel[i] = (uint16_t)min(a.lb_rel[4u * i], 0xFFFFu);
   __syncthreads();
 
   const uint32_t warp = threadIdx.x >> 5, lane = skb_lane();
@@ -637,24 +637,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   const uint32_t per = a.cnt_stride >> 5;        // counters per lane in the segment view (multiple of 8)
   const uint32_t seg0 = lane * per;
   const unsigned long long lb_min = a.lb_sum[0];  // bounds are non-decreasing along the reads
-  const unsigned long long lb_seg = seg0 < a.n_reads ? lb_min + lbrel[seg0] : ~0ull;
-  // On an exact tie with the bound the row index decides. The bound's row rarely changes inside a lane's segment, so
-  // the lane keeps the smallest and largest bound index of its segment and reads the per-read index from global
-  // memory only when the row lies between the two (a global load per tied read made single walks take 40 us).
-  uint32_t li_min = 0xFFFFFFFFu, li_max = 0;
-  for (uint32_t b = seg0; b < min(seg0 + per, a.n_reads); ++b) {
-    const uint32_t li = a.lb_idx[b];
-    li_min = min(li_min, li);
-    li_max = max(li_max, li);
-  }
-  // is (sum sv, row gi) at least as good as the bound of read b?  (index only matters on the exact tie)
-  auto is_cand = [&](unsigned long long sv, uint32_t gi, uint32_t b) -> bool {
-    const uint32_t rel = lbrel[b];
-    const unsigned long long ls = rel != 0xFFFFu ? lb_min + rel : a.lb_sum[b];  // saturated: read the exact bound
-    if (sv != ls) return sv > ls;
-    if (gi <= li_min) return true;
-    if (gi > li_max) return false;
-    return gi <= a.lb_idx[b];
+  // The bounds are staged at every 4th read only (0.5 B of shared memory per read): read b is tested against the bound
+  // of read b & ~3, which is lower or equal, so the test can only add candidates; the per-read selection is exact over
+  // whatever it is given. On a tie with the bound the row index decides: here a row passes when its index does not
+  // exceed the LARGEST bound index of the reads the caller looks at (`li_cap`), again a superset and free of global
+  // loads (a load per tied read made single walks take 40 us).
+  const unsigned long long lb_seg = seg0 < a.n_reads ? lb_min + lbrel[seg0 >> 2] : ~0ull;
+  uint32_t li_seg = 0;  // largest bound index in this lane's segment / in the whole pass
+  for (uint32_t b = seg0; b < min(seg0 + per, a.n_reads); ++b) li_seg = max(li_seg, a.lb_idx[b]);
+  const uint32_t li_all = __reduce_max_sync(0xffffffffu, li_seg);
+  auto is_cand = [&](unsigned long long sv, uint32_t gi, uint32_t b, uint32_t li_cap) -> bool {
+    const uint32_t rel = lbrel[b >> 2];
+    const unsigned long long ls = rel != 0xFFFFu ? lb_min + rel : a.lb_sum[b & ~3u];  // saturated: read the bound
+    return sv > ls || (sv == ls && gi <= li_cap);
   };
   // Candidates leave the kernel as intervals "row gi holds sum sv and meets the bound for reads [b0, b1)": a
   // contending row produces one record per hit instead of one per read, and slots are reserved 16 at a time per lane
@@ -743,7 +738,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
                 }
                 if (check) {
                   const unsigned long long sv = carry + run;
-                  const bool cand = sv >= lb_seg && is_cand(sv, gi, b);
+                  const bool cand = sv >= lb_seg && is_cand(sv, gi, b, li_seg);
                   if (cand && !open) { open = true; ob = b; os = sv; }
                   if (!cand && open) { emit(os, gi, ob, b); open = false; }
                 }
@@ -763,7 +758,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
       uint32_t e = 0;
       for (uint32_t b0 = 0; b0 < a.n_reads; b0 += 32) {
         const uint32_t b = b0 + lane;
-        const bool ok = b < a.n_reads && is_cand(carry, gi, b);
+        const bool ok = b < a.n_reads && is_cand(carry, gi, b, li_all);
         const uint32_t bal = __ballot_sync(0xffffffffu, ok);
         if (bal != 0xffffffffu) { e = b0 + (uint32_t)__ffs(~bal) - 1; break; }
         e = b0 + 32;
@@ -902,10 +897,22 @@ __global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
 // Tracked rows of the next pass: the union of the top lists of 16 evenly spaced reads of this pass, the last read's
 // list first (it alone guarantees `top` distinct rows). Rows that led at any point of the pass stay tracked, so a
 // lineage that overtakes and falls back does not loosen the bounds. One CTA.
-__global__ void pass_verdict_kernel(const SkbRankArgs a) {
-  if (a.abort[0] == 0u && (*a.cand_total != 0u || *a.ivl_total > a.ivl_cap)) {
-    a.abort[1] = a.seq;
-    a.abort[0] = 1u;
+__global__ void __launch_bounds__(256) pass_verdict_kernel(const SkbRankArgs a) {
+  __shared__ uint32_t wmax[8];
+  uint32_t m = 0;  // fullest candidate bucket of the pass: the host grows the next pass only when there is headroom
+  for (uint32_t b = threadIdx.x; b < a.n_reads; b += blockDim.x) m = max(m, a.cand_cnt[b]);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31u) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < 8; ++w) m = max(m, wmax[w]);
+  if (a.abort[0] == 0u) {
+    a.abort[2] = m;
+    a.abort[3] = *a.ivl_total;
+    if (*a.cand_total != 0u || *a.ivl_total > a.ivl_cap) {
+      a.abort[1] = a.seq;
+      a.abort[0] = 1u;
+    }
   }
   *a.cand_total = 0u;
   *const_cast<uint32_t*>(a.ivl_total) = 0u;
@@ -1176,10 +1183,10 @@ void skb_launch_memb_build(const SkbRefView& rv, uint32_t* memb, uint32_t memb_l
 }
 
 size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 2 * FS_ROWBUF + (size_t)cnt_stride * 2;
+  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 2 * FS_ROWBUF + (size_t)cnt_stride / 2;
 }
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 1 * FS_ROWBUF + (size_t)cnt_stride * 2;
+  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 1 * FS_ROWBUF + (size_t)cnt_stride / 2;
 }
 uint32_t skb_fused_tile() { return FS_SUB; }
 
@@ -1211,7 +1218,7 @@ void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st) { expand_kern
 
 void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st) { tracked_update_kernel<<<1, 1024, 0, st>>>(a); }
 
-void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st) { pass_verdict_kernel<<<1, 1, 0, st>>>(a); }
+void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st) { pass_verdict_kernel<<<1, 256, 0, st>>>(a); }
 
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)RS_WARPS * RS_CACHE * 16;
