@@ -351,3 +351,36 @@ def test_limits_and_edge_cases(ctx):
         assert got[0][0].tolist() == exp[0][0].tolist() and got[0][1].tolist() == exp[0][1].tolist()
         assert int(gk[0]) == int(ek[0])
         bb.close()
+
+
+def test_membership_prefilter_does_not_change_results(monkeypatch):
+    """The reference-membership prefilter only drops query hashes that occur in no reference row: the ranking, the
+    sums and the final state must equal a context that was uploaded with the prefilter switched off."""
+    import sketchy_b200 as skb
+    base = [synth.random_genome(60_000, 400 + l) for l in range(6)]
+    sk, _, _ = oracle.sketch_groups([g.tobytes() for g in base], list(range(6)), 6, 16, 800, 0)
+    rng = np.random.default_rng(11)
+    rows = []
+    for g in range(900):
+        row = sk[g % 6][0].copy()
+        pos = rng.choice(row.size, size=25, replace=False)
+        row[pos] = rng.integers(0, int(row.max()), size=25, dtype=np.uint64)
+        rows.append(np.unique(row))
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    blob, roff, _ = synth.sample_reads(base, 700, 3000, 5)
+    out = []
+    for off_flag in ("0", "1"):
+        monkeypatch.setenv("SKB_NO_PREFILTER", off_flag)
+        c = skb.Context(0)
+        c.ref_upload(ref, off)
+        b = c.batch().add(blob, roff)
+        gi, gs = c.predict_stream(b, 16, 800, 0, 10)
+        st = c.last_predict_stats()
+        out.append((gi.copy(), gs.copy(), c.sums_download().copy(), st))
+        b.close()
+        c.close()
+    assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all() and (out[0][2] == out[1][2]).all()
+    assert out[1][3]["member_hashes"] == out[1][3]["query_hashes"]          # prefilter off: every key is kept
+    assert 0 < out[0][3]["member_hashes"] < out[0][3]["query_hashes"]       # reads carry errors: novel k-mers are dropped
