@@ -166,7 +166,10 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 constexpr int FS_SUB = 512;            // hashes per sub-tile (4 KB): two chunks of 8 per lane
 constexpr int FS_STAGES = 2;           // staging buffers per consumer warp
 constexpr int FS_CONSUMER_WARPS = 16;
-constexpr int FS_RANK_WARPS = 2;             // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
+#ifndef SKB_X_RANKW
+#define SKB_X_RANKW 2
+#endif
+constexpr int FS_RANK_WARPS = SKB_X_RANKW;    // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
 constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
 constexpr int FS_ROWBUF = 4;           // rows in flight per CTA: counter buffers / barriers are indexed by row % 4
                                        // (6 buffers: 2.5 % faster per pass at 2560 reads, but 3072 reads no longer fit)
