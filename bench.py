@@ -278,8 +278,12 @@ def run_b200(args):
         # a streaming caller feeds reads in chunks: chunk i+1 is normalised + 2-bit packed into pinned memory by the
         # library's host threads while the GPU works on chunk i (two batches, double buffered)
         # chunk sizes grow so that packing + copying chunk i+1 always fits inside the GPU time of chunk i, and they are
-        # multiples of the library's pass sizes (ramp 128..2048 = 3968 reads, then 4096 per pass): no partial passes
-        sizes, c_lo = [3_968, 4 * 4_096], 0
+        # multiples of the library's pass sizes (ramp, then 4096 per pass): no partial passes
+        b0 = 128   # the library's first pass size after a reset (largest pass whose buckets hold the whole shard) ...
+        while b0 * 2 <= (24 << 20) // max(hi - lo, 64) and b0 * 2 <= 4096:
+            b0 *= 2
+        ramp = sum(b0 << i for i in range(8) if (b0 << i) < 4096)   # ... and the reads of the passes that ramp up to 4096
+        sizes, c_lo = [ramp if ramp else 4_096, 4 * 4_096], 0
         chunks = []
         while c_lo < R:
             n_c = sizes[len(chunks)] if len(chunks) < len(sizes) else 10 * 4_096
@@ -339,7 +343,7 @@ def run_b200(args):
         h2d = packed // 4 + packed // 8 + (packed // 1024 + R) * 9
         e2e = {"value": R / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(R * top * 12), "ms_per_step": dt * 1e3,
-               "includes": "host normalise+2-bit pack into pinned memory (chunks of 3968, 16384, then 40960 reads, packed and copied "
+               "includes": "host normalise+2-bit pack into pinned memory (a first chunk covering the ramp passes, 16384, then chunks of 40960 reads, packed and copied "
                            "to the device while the GPU works on the previous chunk), all kernels, D2H of top-N",
                "host_threads": os.cpu_count(), "host_pack_ms_per_step": pack_s[0] / n_e2e * 1e3}
         # the e2e result must equal the resident result

@@ -454,6 +454,18 @@ int ensure_table(skb_ctx* c, uint32_t max_keys) {
   return SKB_OK;
 }
 
+// Reads in the first pass after an upload / a reset of the sums. Nothing is known about the ranking yet, so the
+// bounds are loose and a read may have every row as a candidate: start with the largest pass whose per-read bucket
+// still holds the whole shard (it cannot overflow), then grow (see the headroom rule in predict_device).
+uint32_t first_pass_reads(const skb_ctx* c) {
+  uint64_t budget = SKB_CAND_BUDGET;
+  if (const char* eb = getenv("SKB_CAND_BUDGET")) budget = std::max<uint64_t>(64, strtoull(eb, nullptr, 10));  // tests only
+  const uint64_t fit = budget / std::max<uint32_t>(c->n_rows, 64);
+  uint32_t b = 128;
+  while ((uint64_t)b * 2 <= fit && b * 2 <= c->pass_max) b *= 2;
+  return std::min<uint32_t>(b, c->pass_max);
+}
+
 SkbTable table_of(skb_ctx* c) {
   SkbTable t;
   t.slots = c->t_slots.as<SkbSlot>(); t.fill = c->t_fill.as<uint32_t>(); t.reads = c->t_reads.as<uint32_t>();
@@ -586,7 +598,7 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   CU(c, cudaMemsetAsync(c->sums[0].p, 0, std::max<size_t>(8, (size_t)n_rows * 8), c->stream));
   c->sums_cur = 0;
   c->tracked_top = 0;
-  c->pass_cur = std::min<uint32_t>(128, c->pass_max);
+  c->pass_cur = first_pass_reads(c);
   CU(c, c->tracked[0].ensure((SKB_MAX_TRACKED + 1) * 4));
   CU(c, c->tracked[1].ensure((SKB_MAX_TRACKED + 1) * 4));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -775,7 +787,8 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
       const uint32_t lastB = recs.back().B;
       const uint64_t grown = std::min<uint64_t>(c->pass_max, (uint64_t)std::max(lastB, c->pass_cur) * 2);
       const uint64_t cap_grown = std::min<uint64_t>(std::max<uint32_t>(c->n_rows, 64), budget / std::max<uint64_t>(grown, 1));
-      if (2ull * h_total[2] <= cap_grown || cap_grown >= c->n_rows) c->pass_cur = (uint32_t)grown;
+      // (a short last pass of a call says little about a full one: it never grows the pass)
+      if (lastB >= c->pass_cur && (2ull * h_total[2] <= cap_grown || cap_grown >= c->n_rows)) c->pass_cur = (uint32_t)grown;
       else c->pass_cur = std::max(lastB, c->pass_cur);
       if (c->pass_cur >= c->pass_max) force_sync = false;
     }
@@ -1035,7 +1048,7 @@ int skb_sums_reset(skb_ctx* c) {
   if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
   CU(c, cudaMemsetAsync(c->sums[c->sums_cur].p, 0, std::max<size_t>(8, (size_t)c->n_rows * 8), c->stream));
   c->tracked_top = 0;
-  c->pass_cur = std::min<uint32_t>(128, c->pass_max);
+  c->pass_cur = first_pass_reads(c);
   return SKB_OK;
 }
 
