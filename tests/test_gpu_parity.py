@@ -384,3 +384,24 @@ def test_membership_prefilter_does_not_change_results(monkeypatch):
     assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all() and (out[0][2] == out[1][2]).all()
     assert out[1][3]["member_hashes"] == out[1][3]["query_hashes"]          # prefilter off: every key is kept
     assert 0 < out[0][3]["member_hashes"] < out[0][3]["query_hashes"]       # reads carry errors: novel k-mers are dropped
+
+
+def test_overflow_inside_a_batch_of_passes_rolls_back(ctx, monkeypatch):
+    """Steady state (passes enqueued eight at a time, checked on the host afterwards): the stream switches from lineage A
+    to lineage B, whose 3,000 identical rows overtake the tracked rows at the same read and overflow every bucket. The
+    device marks the failing pass, the passes queued behind it do nothing, the host rolls back to it, halves the pass
+    down to single reads and ranks those from the sums. Results must still equal the oracle's."""
+    monkeypatch.setenv("SKB_CAND_BUDGET", str(16 * 512))
+    ga = [synth.random_genome(20_000, 910 + i) for i in range(3)]
+    gb = synth.random_genome(20_000, 920)
+    sk, _, _ = oracle.sketch_groups([g.tobytes() for g in ga] + [gb.tobytes()], [0, 1, 2, 3], 4, 16, 300, 0)
+    rows = [sk[i % 3][0] for i in range(30)] + [sk[3][0]] * 3000
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    blob_a, roff_a, _ = synth.sample_reads(ga, 200, 1200, 5, sub=0.0, ins=0.0, dele=0.0)
+    blob_b, roff_b, _ = synth.sample_reads([gb], 260, 1200, 6, sub=0.0, ins=0.0, dele=0.0)
+    blob = np.concatenate([blob_a, blob_b])
+    roff = np.concatenate([roff_a, roff_b[1:] + roff_a[-1]])
+    _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, 3, 16)
+    assert ctx.last_predict_stats()["passes"] > (460 + 15) // 16     # some passes were redone smaller
