@@ -384,7 +384,8 @@ def run_b200(args):
         peak, how = measured_peak_gbs()
         rows_local = hi - lo
         passes = stats["passes"]
-        keys_per_pass = stats["query_hashes"] / max(passes, 1)
+        # query hashes that actually enter a pass (the membership prefilter drops the ones no reference row holds)
+        keys_per_pass = stats.get("member_hashes", stats["query_hashes"]) / max(passes, 1)
         bytes_per_launch = rows_local * s * 8 + keys_per_pass * 8
         avg_ms = stream_ms / max(stream_n, 1)
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
