@@ -263,6 +263,11 @@ def run_b200(args):
     prof = {k: ctx.prof_get(k) for k in ("hash", "select", "table", "stream", "rank", "merge")}
     ctx.prof_enable(False)
     stats = ctx.last_predict_stats()
+    # checksum of the whole job's answer (every read's top-N rows and sums): equal across builds, pass sizes and GPU
+    # counts when the results are identical, so kernel variants and shardings can be compared at full size
+    import zlib
+    r_idx, r_sum = (m_idx, m_sum) if world > 1 else (d_idx, d_sum)
+    result_crc = zlib.crc32(r_sum.cpu().numpy().tobytes(), zlib.crc32(r_idx.cpu().numpy().tobytes()))
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -407,13 +412,14 @@ def run_b200(args):
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "stream_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "fused_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": f"of {how}",
                          "traffic": None, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                          "launches": stream_n,
                          "stream_share_of_step": stream_ms / ms if ms > 0 else None},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "predict_stats": stats,
+            "result_crc32": f"{result_crc:08x}",
             "cpu_baseline": cpu_baseline,
             "sketch": sketch_info,
         }

@@ -181,7 +181,7 @@ struct skb_ctx {
   DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = 4096, pass_cur = 64;  // default reads per pass (<= SKB_MAX_PASS_READS_NARROW)
+  uint32_t pass_max = skb_fused_max_reads(1), pass_cur = 64;  // default reads per pass: what the kernel's shared memory holds
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -683,7 +683,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     bool narrow = true;
     for (uint32_t i = r; i < r + B; ++i)
       if (qn[i] > 255u) { narrow = false; break; }
-    if (!narrow) B = std::min<uint32_t>(B, SKB_MAX_PASS_READS);
+    if (!narrow) B = std::min<uint32_t>(B, skb_fused_max_reads(0));
     // keep the pass's key count inside the filter's design load (and the table)
     const uint64_t key_budget = 1u << 17;
     while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
@@ -1073,7 +1073,7 @@ int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
-  c->pass_max = m ? std::min<uint32_t>(m, SKB_MAX_PASS_READS_NARROW) : 4096;
+  c->pass_max = m ? std::min<uint32_t>(m, skb_fused_max_reads(1)) : skb_fused_max_reads(1);
   c->pass_cur = std::min(c->pass_cur, c->pass_max);
   return SKB_OK;
 }

@@ -61,8 +61,9 @@ struct __align__(16) SkbSlot {
 #define SKB_SLOT_INLINE 4u
 #define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> (13 + 12 * (i))) & 0xFFFull))
 #define SKB_SLOT_START(m) ((uint32_t)(((m) >> 13) & 0xFFFFFFFFull))
-#define SKB_MAX_PASS_READS 2560u         // u16 counters: 4 row buffers + bounds at every 4th read = 8.5 B of shared memory per read
-#define SKB_MAX_PASS_READS_NARROW 4096u  // u8 counters (reads with <= 255 query hashes): 4.5 B per read; 12-bit read ids in a slot
+// Reads per pass are bounded by the fused kernel's shared memory: skb_fused_max_reads(narrow) (kernels_predict.cu).
+// Default build: 2560 with u16 counters (4 row buffers + bounds at every 4th read = 8.5 B per read), 4096 with u8
+// counters (reads with <= 255 query hashes: 4.5 B per read; also the range of the 12-bit read ids in a slot).
 
 struct SkbTable {
   SkbSlot* slots;     // [cap + 1]; slot `cap` is reserved for the key that equals SKB_EMPTY_KEY
@@ -121,6 +122,7 @@ size_t skb_fused_smem_bytes(uint32_t cnt_stride);
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride);
 #define SKB_IVL_CAP (4u << 20)  // candidate intervals per pass; more than that shrinks the pass
 uint32_t skb_fused_tile();
+uint32_t skb_fused_max_reads(int narrow);
 
 // per-read counts of the tracked rows only (they define the bounds): ctr[t][read], u16, row stride `stride`
 void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,

@@ -163,16 +163,27 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 // ---------------------------------------------------------------------------------------------------------
 // mbarrier / bulk-copy primitives
 // ---------------------------------------------------------------------------------------------------------
-constexpr int FS_SUB = 512;            // hashes per sub-tile (4 KB): two chunks of 8 per lane
-constexpr int FS_STAGES = 2;           // staging buffers per consumer warp
-constexpr int FS_CONSUMER_WARPS = 16;
+#ifndef SKB_X_SUB
+#define SKB_X_SUB 512
+#endif
+#ifndef SKB_X_STAGES
+#define SKB_X_STAGES 2
+#endif
+#ifndef SKB_X_CW
+#define SKB_X_CW 16
+#endif
+constexpr int FS_SUB = SKB_X_SUB;      // hashes per sub-tile (4 KB): two chunks of 8 per lane
+constexpr int FS_STAGES = SKB_X_STAGES;  // staging buffers per consumer warp
+constexpr int FS_CONSUMER_WARPS = SKB_X_CW;
 #ifndef SKB_X_RANKW
 #define SKB_X_RANKW 2
 #endif
 constexpr int FS_RANK_WARPS = SKB_X_RANKW;    // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
 constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
-constexpr int FS_ROWBUF = 4;           // rows in flight per CTA: counter buffers / barriers are indexed by row % 4
-                                       // (6 buffers: 2.5 % faster per pass at 2560 reads, but 3072 reads no longer fit)
+#ifndef SKB_X_ROWBUF
+#define SKB_X_ROWBUF 4
+#endif
+constexpr int FS_ROWBUF = SKB_X_ROWBUF;  // rows in flight per CTA: counter buffers / barriers are indexed by row % FS_ROWBUF
 // a rank warp may only wait on a row buffer whose previous row it flushed itself (consumer warps can close rows out of
 // order, so the barrier parity of a buffer is only unambiguous to the warp that saw its previous phase)
 static_assert(FS_ROWBUF % FS_RANK_WARPS == 0 && FS_ROWBUF <= 8, "FS_RANK_WARPS must divide FS_ROWBUF");
@@ -1192,6 +1203,18 @@ size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
   return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 1 * FS_ROWBUF + (size_t)cnt_stride / 2;
 }
 uint32_t skb_fused_tile() { return FS_SUB; }
+// Largest pass the kernel's shared memory holds: 227 KB per CTA minus the static barriers, the filter, the staging
+// rings and the FIFOs leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each) plus the bounds staged at
+// every 4th read (0.5 B per read). Pass-local read ids are 12 bits in a table slot, so 4096 is the cap either way.
+uint32_t skb_fused_max_reads(int narrow) {
+  const size_t fixed = FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + 1024;  // 1 KB: static barriers + slack
+  const size_t budget = 232448;                                             // opt-in maximum per CTA on sm_100
+  if (fixed >= budget) return 0;
+  const size_t per2 = (narrow ? 2 * FS_ROWBUF : 4 * FS_ROWBUF) + 1;         // bytes per read, times two
+  const uint32_t gran = narrow ? 512u : 256u;                               // cnt_stride granularity (api.cu)
+  uint32_t b = (uint32_t)std::min<size_t>(4096, 2 * (budget - fixed) / per2);
+  return b / gran * gran;
+}
 
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st) {
   if (a.rv.n_rows == 0) return;
