@@ -155,8 +155,17 @@ class Context:
         return int(self.lib.skb_ref_rows(self.h))
 
     # -- predict
-    def predict_stream(self, batch: "Batch", k: int, s_query: int, seed: int, top: int, pad: bool = False):
+    def predict_stream(self, batch: "Batch", k: int, s_query: int, seed: int, top: int, pad: bool = False, out=None):
+        """`out` = (idx uint32 [R, top], sum uint64 [R, top]) caller-owned C-contiguous host arrays to fill in place
+        (page-locked ones make the device-to-host copy a plain DMA); fresh arrays otherwise."""
         R = batch.num_groups
+        if out is not None:
+            oi, os_ = out
+            if not (oi.dtype == np.uint32 and os_.dtype == np.uint64 and oi.shape == (R, top) and os_.shape == (R, top)
+                    and oi.flags.c_contiguous and os_.flags.c_contiguous):
+                raise ValueError("out must be C-contiguous (uint32 [R, top], uint64 [R, top])")
+            self.check(self.lib.skb_predict_stream(self.h, batch.h, k, s_query, seed, top, int(pad), _ptr(oi), _ptr(os_)))
+            return oi, os_
         oi = np.zeros((max(R, 1), top), dtype=np.uint32)
         os_ = np.zeros((max(R, 1), top), dtype=np.uint64)
         self.check(self.lib.skb_predict_stream(self.h, batch.h, k, s_query, seed, top, int(pad), _ptr(oi), _ptr(os_)))

@@ -75,7 +75,7 @@ def build_host() -> str:
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
     cxx = shutil.which("g++") or "g++"
     cmd = [cxx, "-O2", "-std=c++17", "-Wall", os.path.join(HOST, "main.cpp"), os.path.join(HOST, "msh.cpp"), "-o", CLI,
-           "-L" + HERE, "-lsketchy_b200", "-lz", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
+           "-L" + HERE, "-lsketchy_b200", "-lz", "-ldl", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
     subprocess.check_call(cmd)
     return CLI
 

@@ -178,6 +178,9 @@ constexpr int FS_CONSUMER_WARPS = SKB_X_CW;
 #ifndef SKB_X_RANKW
 #define SKB_X_RANKW 2
 #endif
+#ifndef SKB_X_RANK2
+#define SKB_X_RANK2 0  // 1: rank_bounds fetches eight tracked sums at a time; rank_select cuts every bucket down first
+#endif
 constexpr int FS_RANK_WARPS = SKB_X_RANKW;    // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
 constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
 #ifndef SKB_X_ROWBUF
@@ -865,11 +868,8 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
   unsigned long long ks[SKB_MAX_TOP];
   uint32_t ki[SKB_MAX_TOP];
   uint32_t n = 0;
-  for (uint32_t t = 0; t < nt; ++t) {
-    const uint32_t row = a.tracked[t];
-    const unsigned long long s = a.sums_in[row] + a.tracked_prefix[(size_t)t * a.row_stride + b];
-    const uint32_t gi = a.row_base + row;
-    if (n == keep && !skb_key_better(s, gi, ks[n - 1], ki[n - 1])) continue;
+  auto offer = [&](unsigned long long s, uint32_t gi) {
+    if (n == keep && !skb_key_better(s, gi, ks[n - 1], ki[n - 1])) return;
     uint32_t pos = n < keep ? n : n - 1;  // insert, dropping the worst when full
     while (pos > 0 && skb_key_better(s, gi, ks[pos - 1], ki[pos - 1])) {
       ks[pos] = ks[pos - 1]; ki[pos] = ki[pos - 1];
@@ -877,7 +877,28 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
     }
     ks[pos] = s; ki[pos] = gi;
     if (n < keep) ++n;
+  };
+#if SKB_X_RANK2
+  // the tracked rows' sums are fetched eight at a time (row id -> running sum is a dependent load: one at a time the
+  // loop is a chain of ~400 L2 round trips per read); the offers keep their order, so the bound is the same
+  for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
+    uint32_t rw[8];
+    unsigned long long sv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rw[j] = t0 + j < nt ? a.tracked[t0 + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sv[j] = t0 + j < nt ? a.sums_in[rw[j]] + a.tracked_prefix[(size_t)(t0 + j) * a.row_stride + b] : 0ull;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (t0 + j < nt) offer(sv[j], a.row_base + rw[j]);
   }
+#else
+  for (uint32_t t = 0; t < nt; ++t) {
+    const uint32_t row = a.tracked[t];
+    offer(a.sums_in[row] + a.tracked_prefix[(size_t)t * a.row_stride + b], a.row_base + row);
+  }
+#endif
   a.lb_sum[b] = n ? ks[n - 1] : 0ull;
   a.lb_idx[b] = n ? ki[n - 1] : 0xFFFFFFFFu;
 }
@@ -892,6 +913,41 @@ __global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
   const uint32_t total = min(*a.ivl_total, a.ivl_cap);
   const uint32_t lane = skb_lane();
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+#if SKB_X_RANK2
+  // A warp takes 32 intervals at a time. Most intervals span a handful of reads (a row contends between two of its
+  // hits): those are expanded one per lane, 32 slot allocations in flight per warp instead of one interval's; the
+  // long ones (more than 16 reads) are expanded by the whole warp as before. The order of a bucket's records changes,
+  // the records do not, and the selection does not depend on their order.
+  auto put = [&](unsigned long long sum, uint32_t idx, uint32_t b) {
+    const uint32_t slot = atomicAdd(&a.cand_cnt[b], 1u);
+    if (slot < a.cand_cap) {
+      SkbCand cd;
+      cd.sum = sum; cd.idx = idx; cd.pad = 0;
+      a.cand[(size_t)b * a.cand_cap + slot] = cd;
+    } else {
+      *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
+    }
+  };
+  for (uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; w0 < total; w0 += nwarps * 32u) {
+    SkbInterval iv;
+    iv.sum = 0; iv.idx = 0xFFFFFFFFu; iv.span = 0;
+    if (w0 + lane < total) iv = a.ivl[w0 + lane];
+    const uint32_t b0 = iv.span & 0xFFFFu, b1 = iv.span >> 16;
+    const bool is_long = b1 > b0 + 16u;
+    uint32_t longs = __ballot_sync(0xffffffffu, is_long);
+    while (longs) {
+      const int src = __ffs(longs) - 1;
+      longs &= longs - 1u;
+      const unsigned long long ssum = __shfl_sync(0xffffffffu, iv.sum, src);
+      const uint32_t sidx = __shfl_sync(0xffffffffu, iv.idx, src);
+      const uint32_t sspan = __shfl_sync(0xffffffffu, iv.span, src);
+      for (uint32_t b = (sspan & 0xFFFFu) + lane; b < (sspan >> 16); b += 32) put(ssum, sidx, b);
+    }
+    if (!is_long)
+      for (uint32_t b = b0; b < b1; ++b) put(iv.sum, iv.idx, b);
+  }
+  return;
+#endif
   for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += nwarps) {
     const SkbInterval iv = a.ivl[w];
     const uint32_t b0 = iv.span & 0xFFFFu, b1 = iv.span >> 16;
@@ -971,7 +1027,7 @@ __device__ __forceinline__ void warp_best(unsigned long long& s, uint32_t& i) {
 // One warp per read: the `top` best candidates of the read's bucket, in order. Candidate rows are distinct, so
 // "best key strictly worse than the previous pick" enumerates them without marking. The first RS_CACHE records of
 // the bucket are staged in shared memory once; missing entries are (sum 0, idx UINT32_MAX).
-constexpr int RS_WARPS = 8;
+constexpr int RS_WARPS = SKB_X_RANK2 ? 4 : 8;  // 4 warps x 8 KB: seven CTAs per SM, a 4096-read pass is one wave
 constexpr int RS_CACHE = 512;
 __global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRankArgs a) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -991,11 +1047,14 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRan
   // records at least that good are compacted into the cache. Two coalesced passes instead of `top` of them.
   uint32_t m = n;       // records the selection rounds look at
   bool cached = n <= (uint32_t)RS_CACHE;
-  if (!cached && a.top <= 32u) {  // (the 32 lane maxima bound the top-th best only for top <= 32)
+  // (SKB_X_RANK2: a cached bucket of more than 64 records is cut down the same way, in place: `top` rounds over a
+  // dozen survivors instead of over hundreds of records)
+  const bool in_place = SKB_X_RANK2 && cached && n > 64u;
+  if ((!cached || in_place) && a.top <= 32u) {  // (the 32 lane maxima bound the top-th best only for top <= 32)
     unsigned long long ls = 0;
     uint32_t li = 0xFFFFFFFFu;
     for (uint32_t i = lane; i < n; i += 32) {
-      const uint4 c = list[i];
+      const uint4 c = in_place ? cache[i] : list[i];
       const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
       if (skb_key_better(cs, c.z, ls, li)) { ls = cs; li = c.z; }
     }
@@ -1014,12 +1073,13 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRan
       uint4 c = make_uint4(0, 0, 0, 0);
       bool keep = false;
       if (i < n) {
-        c = list[i];
+        c = in_place ? cache[i] : list[i];
         const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
         keep = !skb_key_better(ts, ti, cs, c.z);  // at least as good as the threshold
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, keep);
       const uint32_t at = kept + __popc(bal & ((1u << lane) - 1u));
+      __syncwarp();  // in place: a survivor lands at or before its own position, after every lane has read this block
       if (keep && at < (uint32_t)RS_CACHE) cache[at] = c;
       kept += __popc(bal);
     }

@@ -1,11 +1,24 @@
-// fastx.hpp — FASTA/FASTQ (+gzip) record reader for the host side (replaces needletail's parse_fastx_file /
-// parse_fastx_stdin at reference src/sketchy.rs:89-92, 474). Records keep their RAW sequence slice: for multi-line FASTA
-// the interior line breaks are part of it (needletail `raw_seq`; the library strips whitespace while packing, and
-// finch counts total_bases on the raw slice — SURVEY.md Appendix F-3). bz2/xz are not supported in this image.
+// fastx.hpp — FASTA/FASTQ record reader for the host side, plain or gzip / bzip2 / xz compressed (replaces
+// needletail's parse_fastx_file / parse_fastx_stdin at reference src/sketchy.rs:89-92, 474; the reference CLI documents
+// "Fast{a,q}.{gz,xz,bz}, stdin if not present", src/cli.rs:26,96). Records keep their RAW sequence slice: for
+// multi-line FASTA the interior line breaks are part of it (needletail `raw_seq`; the library strips whitespace while
+// packing, and finch counts total_bases on the raw slice — SURVEY.md Appendix F-3).
+//
+// The compression is sniffed from the first bytes, as needletail does (not from the file name), for files and stdin
+// alike. gzip goes through zlib's inflate (headers are in the image). This image has no bzlib.h / lzma.h, only the
+// runtime libraries, so libbz2.so.1.0 and liblzma.so.5 are loaded with dlopen on first use and driven through their
+// stable C ABI declared below; a box without them gets a clear error for such a file instead of a link failure.
 #pragma once
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <cerrno>
 #include <cstdint>
+#include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -17,21 +30,253 @@ struct Record {
   std::string seq;  // raw slice, interior newlines kept, trailing line ending dropped
 };
 
+inline std::runtime_error open_error() {
+  return std::runtime_error("failed to open Fastx file or record with Needletail");
+}
+
+// ---- compressed byte sources -------------------------------------------------------------------------------------
+class RawInput {  // buffered reads from a file descriptor
+ public:
+  explicit RawInput(int fd, bool own) : fd_(fd), own_(own), buf_(1 << 20) {}
+  ~RawInput() { if (own_ && fd_ >= 0) ::close(fd_); }
+  RawInput(const RawInput&) = delete;
+  // makes at least one byte available unless the input is exhausted; returns the bytes available
+  size_t ensure() {
+    if (pos_ < end_) return end_ - pos_;
+    if (eof_) return 0;
+    pos_ = end_ = 0;
+    for (;;) {
+      const ssize_t n = ::read(fd_, buf_.data(), buf_.size());
+      if (n < 0) { if (errno == EINTR) continue; throw open_error(); }
+      if (n == 0) eof_ = true;
+      end_ = (size_t)n;
+      break;
+    }
+    return end_;
+  }
+  // the first n bytes of the input without consuming them (called before anything is consumed; fewer at EOF)
+  size_t peek(uint8_t* out, size_t n) {
+    while (end_ - pos_ < n && !eof_) {
+      const ssize_t r = ::read(fd_, buf_.data() + end_, buf_.size() - end_);
+      if (r < 0) { if (errno == EINTR) continue; throw open_error(); }
+      if (r == 0) { eof_ = true; break; }
+      end_ += (size_t)r;
+    }
+    const size_t m = std::min(n, end_ - pos_);
+    std::memcpy(out, buf_.data() + pos_, m);
+    return m;
+  }
+  const uint8_t* data() const { return buf_.data() + pos_; }
+  void consume(size_t n) { pos_ += n; }
+
+ private:
+  int fd_;
+  bool own_, eof_ = false;
+  std::vector<uint8_t> buf_;
+  size_t pos_ = 0, end_ = 0;
+};
+
+class Decoder {
+ public:
+  virtual ~Decoder() {}
+  virtual size_t read(uint8_t* out, size_t cap) = 0;  // 0 = end of data
+};
+
+class PlainDecoder : public Decoder {
+ public:
+  explicit PlainDecoder(RawInput& in) : in_(in) {}
+  size_t read(uint8_t* out, size_t cap) override {
+    const size_t n = std::min(cap, in_.ensure());
+    std::memcpy(out, in_.data(), n);
+    in_.consume(n);
+    return n;
+  }
+
+ private:
+  RawInput& in_;
+};
+
+class GzDecoder : public Decoder {  // multi-member gzip, like gzread / flate2's MultiGzDecoder
+ public:
+  explicit GzDecoder(RawInput& in) : in_(in) {
+    std::memset(&z_, 0, sizeof z_);
+    if (inflateInit2(&z_, 16 + MAX_WBITS) != Z_OK) throw open_error();
+  }
+  ~GzDecoder() override { inflateEnd(&z_); }
+  size_t read(uint8_t* out, size_t cap) override {
+    z_.next_out = out;
+    z_.avail_out = (uInt)cap;
+    while (z_.avail_out == cap) {
+      const size_t have = in_.ensure();
+      if (have == 0) {
+        if (!member_done_) throw open_error();  // truncated stream
+        break;
+      }
+      if (member_done_) {  // another member follows
+        if (inflateReset(&z_) != Z_OK) throw open_error();
+        member_done_ = false;
+      }
+      z_.next_in = const_cast<Bytef*>(in_.data());
+      z_.avail_in = (uInt)have;
+      const int rc = inflate(&z_, Z_NO_FLUSH);
+      in_.consume(have - z_.avail_in);
+      if (rc == Z_STREAM_END) member_done_ = true;
+      else if (rc != Z_OK && rc != Z_BUF_ERROR) throw open_error();
+    }
+    return cap - z_.avail_out;
+  }
+
+ private:
+  RawInput& in_;
+  z_stream z_;
+  bool member_done_ = false;
+};
+
+// libbz2's public stream ABI (bzlib.h, unchanged since 1.0)
+struct BzStream {
+  char* next_in; unsigned int avail_in; unsigned int total_in_lo32; unsigned int total_in_hi32;
+  char* next_out; unsigned int avail_out; unsigned int total_out_lo32; unsigned int total_out_hi32;
+  void* state;
+  void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+};
+
+class Bz2Decoder : public Decoder {
+ public:
+  explicit Bz2Decoder(RawInput& in) : in_(in) {
+    lib_ = dlopen("libbz2.so.1.0", RTLD_NOW);
+    if (!lib_) lib_ = dlopen("libbz2.so.1", RTLD_NOW);
+    if (!lib_) throw std::runtime_error("bzip2 input needs libbz2.so.1.0, which is not on this machine");
+    init_ = (int (*)(BzStream*, int, int))dlsym(lib_, "BZ2_bzDecompressInit");
+    run_ = (int (*)(BzStream*))dlsym(lib_, "BZ2_bzDecompress");
+    end_ = (int (*)(BzStream*))dlsym(lib_, "BZ2_bzDecompressEnd");
+    if (!init_ || !run_ || !end_) throw std::runtime_error("libbz2 lacks the BZ2_bzDecompress entry points");
+    std::memset(&s_, 0, sizeof s_);
+    if (init_(&s_, 0, 0) != 0) throw open_error();
+    live_ = true;
+  }
+  ~Bz2Decoder() override {
+    if (live_) end_(&s_);
+    if (lib_) dlclose(lib_);
+  }
+  size_t read(uint8_t* out, size_t cap) override {
+    s_.next_out = reinterpret_cast<char*>(out);
+    s_.avail_out = (unsigned)cap;
+    while (s_.avail_out == cap) {
+      const size_t have = in_.ensure();
+      if (have == 0) {
+        if (live_) throw open_error();  // truncated stream
+        break;
+      }
+      if (!live_) {  // concatenated streams (bzip2 -c a b, pbzip2)
+        std::memset(&s_, 0, sizeof s_);
+        if (init_(&s_, 0, 0) != 0) throw open_error();
+        s_.next_out = reinterpret_cast<char*>(out);
+        s_.avail_out = (unsigned)cap;
+        live_ = true;
+      }
+      s_.next_in = const_cast<char*>(reinterpret_cast<const char*>(in_.data()));
+      s_.avail_in = (unsigned)have;
+      const int rc = run_(&s_);
+      in_.consume(have - s_.avail_in);
+      if (rc == 4) {  // BZ_STREAM_END
+        const size_t got = cap - s_.avail_out;
+        end_(&s_);
+        live_ = false;
+        if (got) return got;
+        s_.avail_out = (unsigned)cap;  // nothing produced yet: look for a following stream
+      } else if (rc != 0) {
+        throw open_error();
+      }
+    }
+    return cap - s_.avail_out;
+  }
+
+ private:
+  RawInput& in_;
+  void* lib_ = nullptr;
+  int (*init_)(BzStream*, int, int) = nullptr;
+  int (*run_)(BzStream*) = nullptr;
+  int (*end_)(BzStream*) = nullptr;
+  BzStream s_;
+  bool live_ = false;
+};
+
+// liblzma's public stream ABI (lzma/base.h, liblzma.so.5)
+struct LzmaStream {
+  const uint8_t* next_in; size_t avail_in; uint64_t total_in;
+  uint8_t* next_out; size_t avail_out; uint64_t total_out;
+  const void* allocator; void* internal;
+  void* reserved_ptr1; void* reserved_ptr2; void* reserved_ptr3; void* reserved_ptr4;
+  uint64_t reserved_int1; uint64_t reserved_int2; size_t reserved_int3; size_t reserved_int4;
+  int reserved_enum1; int reserved_enum2;
+};
+
+class XzDecoder : public Decoder {
+ public:
+  explicit XzDecoder(RawInput& in) : in_(in) {
+    lib_ = dlopen("liblzma.so.5", RTLD_NOW);
+    if (!lib_) throw std::runtime_error("xz input needs liblzma.so.5, which is not on this machine");
+    auto init = (int (*)(LzmaStream*, uint64_t, uint32_t))dlsym(lib_, "lzma_stream_decoder");
+    run_ = (int (*)(LzmaStream*, int))dlsym(lib_, "lzma_code");
+    end_ = (void (*)(LzmaStream*))dlsym(lib_, "lzma_end");
+    if (!init || !run_ || !end_) throw std::runtime_error("liblzma lacks the stream decoder entry points");
+    std::memset(&s_, 0, sizeof s_);  // LZMA_STREAM_INIT
+    if (init(&s_, UINT64_MAX, 0x08u /* LZMA_CONCATENATED */) != 0) throw open_error();
+    live_ = true;
+  }
+  ~XzDecoder() override {
+    if (live_) end_(&s_);
+    if (lib_) dlclose(lib_);
+  }
+  size_t read(uint8_t* out, size_t cap) override {
+    if (done_) return 0;
+    s_.next_out = out;
+    s_.avail_out = cap;
+    while (s_.avail_out == cap) {
+      const size_t have = in_.ensure();
+      s_.next_in = in_.data();
+      s_.avail_in = have;
+      const int rc = run_(&s_, have == 0 ? 3 /* LZMA_FINISH */ : 0 /* LZMA_RUN */);
+      in_.consume(have - s_.avail_in);
+      if (rc == 1) { done_ = true; break; }  // LZMA_STREAM_END
+      if (rc != 0) throw open_error();       // includes LZMA_BUF_ERROR on a truncated file
+    }
+    return cap - s_.avail_out;
+  }
+
+ private:
+  RawInput& in_;
+  void* lib_ = nullptr;
+  int (*run_)(LzmaStream*, int) = nullptr;
+  void (*end_)(LzmaStream*) = nullptr;
+  LzmaStream s_;
+  bool live_ = false, done_ = false;
+};
+
+// ---- records -----------------------------------------------------------------------------------------------------
 class Reader {
  public:
   explicit Reader(const std::string& path) {
-    gz_ = path == "-" ? gzdopen(0, "rb") : gzopen(path.c_str(), "rb");
-    if (!gz_) throw std::runtime_error("failed to open Fastx file or record with Needletail");
-    gzbuffer(gz_, 1 << 20);
+    int fd = 0;
+    if (path != "-") {
+      fd = ::open(path.c_str(), O_RDONLY);
+      if (fd < 0) throw open_error();
+    }
+    in_.reset(new RawInput(fd, path != "-"));
+    uint8_t magic[6] = {0, 0, 0, 0, 0, 0};
+    const size_t got = in_->peek(magic, 6);
+    if (got >= 2 && magic[0] == 0x1F && magic[1] == 0x8B) dec_.reset(new GzDecoder(*in_));
+    else if (got >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') dec_.reset(new Bz2Decoder(*in_));
+    else if (got >= 6 && std::memcmp(magic, "\xFD" "7zXZ\0", 6) == 0) dec_.reset(new XzDecoder(*in_));
+    else dec_.reset(new PlainDecoder(*in_));
     fill();
     while (pos_ < buf_.size() && (buf_[pos_] == '\n' || buf_[pos_] == '\r')) ++pos_;
     if (pos_ < buf_.size()) {
       if (buf_[pos_] == '>') fasta_ = true;
       else if (buf_[pos_] == '@') fasta_ = false;
-      else throw std::runtime_error("failed to open Fastx file or record with Needletail");
+      else throw open_error();
     }
   }
-  ~Reader() { if (gz_) gzclose(gz_); }
   Reader(const Reader&) = delete;
 
   bool next(Record& r) {
@@ -41,7 +286,7 @@ class Reader {
     r.id = line.substr(1);
     r.seq.clear();
     if (fasta_) {
-      if (line[0] != '>') throw std::runtime_error("failed to open Fastx file or record with Needletail");
+      if (line[0] != '>') throw open_error();
       bool first = true;
       while (peek() != -1 && peek() != '>') {
         getline(line);
@@ -51,11 +296,10 @@ class Reader {
       }
       while (!r.seq.empty() && (r.seq.back() == '\n' || r.seq.back() == '\r')) r.seq.pop_back();
     } else {
-      if (line[0] != '@') throw std::runtime_error("failed to open Fastx file or record with Needletail");
-      if (!getline(r.seq)) throw std::runtime_error("failed to open Fastx file or record with Needletail");
+      if (line[0] != '@') throw open_error();
+      if (!getline(r.seq)) throw open_error();
       std::string plus, qual;
-      if (!getline(plus) || plus.empty() || plus[0] != '+' || !getline(qual))
-        throw std::runtime_error("failed to open Fastx file or record with Needletail");
+      if (!getline(plus) || plus.empty() || plus[0] != '+' || !getline(qual)) throw open_error();
     }
     return true;
   }
@@ -66,9 +310,8 @@ class Reader {
     if (pos_ > 0) { buf_.erase(buf_.begin(), buf_.begin() + pos_); pos_ = 0; }
     const size_t old = buf_.size();
     buf_.resize(old + (1 << 20));
-    const int n = gzread(gz_, buf_.data() + old, 1 << 20);
-    if (n < 0) throw std::runtime_error("failed to open Fastx file or record with Needletail");
-    buf_.resize(old + (size_t)n);
+    const size_t n = dec_->read(reinterpret_cast<uint8_t*>(buf_.data()) + old, 1 << 20);
+    buf_.resize(old + n);
     if (n == 0) eof_ = true;
   }
   int peek() {
@@ -91,7 +334,8 @@ class Reader {
     if (!out.empty() && out.back() == '\r') out.pop_back();
     return true;
   }
-  gzFile gz_ = nullptr;
+  std::unique_ptr<RawInput> in_;
+  std::unique_ptr<Decoder> dec_;
   std::vector<char> buf_;
   size_t pos_ = 0;
   bool eof_ = false, fasta_ = true;

@@ -1,0 +1,107 @@
+"""Host FASTA/FASTQ reader (sketchy_b200/host/fastx.hpp): plain, gzip (multi-member), bzip2 (concatenated streams) and
+xz (concatenated) inputs, from a path and from stdin, must yield the same records; truncated compressed files fail with
+the reference's error text. CPU only: a small C++ harness over the header prints id, raw length and a checksum per
+record. The reference CLI accepts Fast{a,q}.{gz,xz,bz} (src/cli.rs:26,96; needletail sniffs the first bytes)."""
+import bz2
+import gzip
+import lzma
+import os
+import random
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = r'''
+#include "fastx.hpp"
+#include <cstdio>
+int main(int argc, char** argv) {
+  try {
+    fastx::Reader rd(argc > 1 ? argv[1] : "-");
+    fastx::Record r;
+    while (rd.next(r)) {
+      unsigned long long h = 1469598103934665603ull;
+      for (unsigned char c : r.seq) { h ^= c; h *= 1099511628211ull; }
+      std::printf("%s\t%zu\t%llu\n", r.id.c_str(), r.seq.size(), h);
+    }
+  } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+  return 0;
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    d = tmp_path_factory.mktemp("fastx")
+    src = d / "h.cpp"
+    src.write_text(HARNESS)
+    exe = d / "h"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "sketchy_b200", "host"), str(src), "-o",
+                           str(exe), "-lz", "-ldl"])
+    return str(exe)
+
+
+def _fasta(rng, n):
+    out = []
+    for i in range(n):
+        seq = "".join(rng.choice("ACGTN") for _ in range(rng.randint(0, 400)))
+        w = rng.choice([60, 70, 10_000])
+        eol = rng.choice(["\n", "\r\n"])
+        out.append(f">contig_{i} some description{eol}" + eol.join(seq[j:j + w] for j in range(0, len(seq), w)) + eol)
+    return "".join(out).encode()
+
+
+def _fastq(rng, n):
+    out = []
+    for i in range(n):
+        seq = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 3000)))
+        out.append(f"@read_{i} ch=5\n{seq}\n+\n{'I' * len(seq)}\n")
+    return "".join(out).encode()
+
+
+def _run(exe, path=None, data=None):
+    p = subprocess.run([exe] + ([path] if path else []), input=data, capture_output=True)
+    return p.returncode, p.stdout, p.stderr.decode()
+
+
+@pytest.mark.parametrize("kind", ["fasta", "fastq"])
+def test_compressed_inputs_yield_the_same_records(harness, tmp_path, kind):
+    rng = random.Random(11)
+    raw = _fasta(rng, 300) if kind == "fasta" else _fastq(rng, 900)   # > 1 MiB of FASTQ: several buffer refills
+    half = raw.rfind(b"\n>" if kind == "fasta" else b"\n@read", 0, len(raw) // 2) + 1
+    forms = {
+        "plain": raw,
+        "gz": gzip.compress(raw),
+        "gz2": gzip.compress(raw[:half]) + gzip.compress(raw[half:]),        # multi-member (bgzip, cat a.gz b.gz)
+        "bz2": bz2.compress(raw),
+        "bz2x2": bz2.compress(raw[:half]) + bz2.compress(raw[half:]),         # concatenated streams (pbzip2)
+        "xz": lzma.compress(raw, format=lzma.FORMAT_XZ),
+        "xzx2": lzma.compress(raw[:half], format=lzma.FORMAT_XZ) + lzma.compress(raw[half:], format=lzma.FORMAT_XZ),
+    }
+    rc, want, err = _run(harness, data=raw)
+    assert rc == 0 and want.count(b"\n") == (300 if kind == "fasta" else 900), err
+    for name, blob in forms.items():
+        path = tmp_path / f"x.{name}"            # the name says nothing: the content is sniffed
+        path.write_bytes(blob)
+        rc, got, err = _run(harness, path=str(path))
+        assert rc == 0 and got == want, (name, err)
+        rc, got, err = _run(harness, data=blob)   # stdin
+        assert rc == 0 and got == want, (name, "stdin", err)
+
+
+def test_truncated_and_garbage_inputs_fail_like_the_reference(harness, tmp_path):
+    rng = random.Random(12)
+    raw = _fastq(rng, 200)
+    for name, blob in {"gz": gzip.compress(raw), "bz2": bz2.compress(raw), "xz": lzma.compress(raw)}.items():
+        path = tmp_path / f"t.{name}"
+        path.write_bytes(blob[:len(blob) // 2])
+        rc, _, err = _run(harness, path=str(path))
+        assert rc == 1 and "failed to open Fastx file or record with Needletail" in err, name
+    (tmp_path / "g.txt").write_bytes(b"hello\nworld\n")
+    rc, _, err = _run(harness, path=str(tmp_path / "g.txt"))
+    assert rc == 1 and "failed to open Fastx file" in err
+    rc, _, err = _run(harness, path=str(tmp_path / "missing.fa"))
+    assert rc == 1 and "failed to open Fastx file" in err
+    (tmp_path / "empty.fa").write_bytes(b"")
+    rc, out, _ = _run(harness, path=str(tmp_path / "empty.fa"))
+    assert rc == 0 and out == b""

@@ -311,6 +311,51 @@ def test_predict_large_scale_against_independent_gpu_path(ctx):
         assert gs[r].tolist() == cum[order, r].tolist(), r
 
 
+def test_predict_full_size_passes_against_independent_gpu_path(ctx):
+    """Passes of the maximum size (4096 reads: u8 counters, every 12-bit pass-local read id in use, three passes with
+    a ragged last one). 10,000 short reads vs 2,000 x s=500: the candidate buckets hold the whole shard, so the very
+    first pass is a full one. Checked against the dense path like the test above."""
+    base = [synth.random_genome(60_000, 7100 + l) for l in range(8)]
+    b = ctx.batch().add_records([g.tobytes() for g in base])
+    sk, _, _ = ctx.sketch(b, 16, 500, 0)
+    b.close()
+    rng = np.random.default_rng(6)
+    rows = []
+    for g in range(2000):
+        row = sk[g % 8][0].copy()
+        pos = rng.choice(row.size, size=10, replace=False)
+        row[pos] = rng.integers(0, int(row.max()), size=10, dtype=np.uint64)
+        rows.append(np.unique(row))
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    n_reads = 10_000
+    blob, roff, _ = synth.sample_reads(base, n_reads, 600, 98)
+    ctx.ref_upload(ref, off)
+    ctx.set_pass_reads(0)
+    rb = ctx.batch().add(blob, roff)
+    gi, gs = ctx.predict_stream(rb, 16, 500, 0, 10)
+    final = ctx.sums_download()
+    stats = ctx.last_predict_stats()
+    rb.close()
+    assert stats["passes"] == 3, stats   # 4096 + 4096 + 1808
+    qb = ctx.batch().add(blob, roff)
+    qs, _, _ = ctx.sketch(qb, 16, 500, 0)
+    qb.close()
+    qoff = np.zeros(len(qs) + 1, dtype=np.uint64)
+    qoff[1:] = np.cumsum([h.size for h, _ in qs])
+    counts = ctx.shared_counts(np.concatenate([h for h, _ in qs]), qoff)   # [N, R]
+    cum = np.cumsum(counts, axis=1)
+    assert (cum[:, -1] == final).all()
+    idx = np.arange(cum.shape[0])
+    picks = sorted(set(list(range(0, 32)) + list(range(4064, 4128)) + list(range(8160, 8224)) +
+                       list(range(32, n_reads, 61)) + [n_reads - 1]))
+    for r in picks:
+        order = np.lexsort((idx, -cum[:, r].astype(np.int64)))[:10]
+        assert gi[r].tolist() == order.tolist(), r
+        assert gs[r].tolist() == cum[order, r].tolist(), r
+
+
 def test_limits_and_edge_cases(ctx):
     from sketchy_b200._lib import SkbError
     g = synth.random_genome(3000, 1)
