@@ -685,7 +685,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
       if (qn[i] > 255u) { narrow = false; break; }
     if (!narrow) B = std::min<uint32_t>(B, skb_fused_max_reads(0));
     // keep the pass's key count inside the filter's design load (and the table)
-    const uint64_t key_budget = 1u << 17;
+    const uint64_t key_budget = 32ull * skb_fused_max_reads(1);  // 2^17 for 4096-read passes
     while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
     const uint32_t nkeys = (uint32_t)(q_off[r + B] - q_off[r]);
     if (int rc = ensure_table(c, nkeys)) { rc_final = rc; break; }

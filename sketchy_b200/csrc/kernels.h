@@ -50,17 +50,25 @@ void skb_launch_compact_queries(const uint64_t* cand, const uint64_t* cand_base,
 // ---- predict ---------------------------------------------------------------------------------------------
 #define SKB_BLOOM_WORDS 16384u  // 64 KB shared-memory filter (2^19 bits)
 
-// One slot of the per-pass query table (open addressing on `key`). meta bits 0-12 = cnt, the number of reads of the
-// pass that hold `key`; cnt <= 4: their pass-local read ids (12 bits each) sit inline at bits 13 + 12*i, so a lookup
-// is one 16-byte load; cnt > 4: bits 13-44 are the start of the slot's read list in `reads`.
+// One slot of the per-pass query table (open addressing on `key`). A pass holds up to 2^SKB_SLOT_ID_BITS reads.
+// meta: the low SKB_SLOT_CNT_BITS bits = cnt, the number of reads of the pass that hold `key` (0 .. 2^ID_BITS);
+// cnt <= SKB_SLOT_INLINE: their pass-local read ids sit inline above cnt, so a lookup is one 16-byte load;
+// more: the 32 bits above cnt are the start of the slot's read list in `reads`.
+// Default: 12-bit ids (4096 reads per pass), 13-bit cnt, 4 inline ids. SKB_X_IDBITS=13: 8192 reads, 14-bit cnt, 3 inline.
+#ifndef SKB_X_IDBITS
+#define SKB_X_IDBITS 12
+#endif
+#define SKB_SLOT_ID_BITS SKB_X_IDBITS
+#define SKB_SLOT_CNT_BITS (SKB_X_IDBITS + 1)
 struct __align__(16) SkbSlot {
   unsigned long long key;
   unsigned long long meta;
 };
-#define SKB_SLOT_CNT(m) ((uint32_t)((m) & 0x1FFFull))
-#define SKB_SLOT_INLINE 4u
-#define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> (13 + 12 * (i))) & 0xFFFull))
-#define SKB_SLOT_START(m) ((uint32_t)(((m) >> 13) & 0xFFFFFFFFull))
+#define SKB_SLOT_CNT(m) ((uint32_t)((m) & ((1ull << SKB_SLOT_CNT_BITS) - 1ull)))
+#define SKB_SLOT_INLINE ((uint32_t)((64 - SKB_SLOT_CNT_BITS) / SKB_SLOT_ID_BITS))
+#define SKB_SLOT_ID_SHIFT(i) (SKB_SLOT_CNT_BITS + SKB_SLOT_ID_BITS * (i))
+#define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> SKB_SLOT_ID_SHIFT(i)) & ((1ull << SKB_SLOT_ID_BITS) - 1ull)))
+#define SKB_SLOT_START(m) ((uint32_t)(((m) >> SKB_SLOT_CNT_BITS) & 0xFFFFFFFFull))
 // Reads per pass are bounded by the fused kernel's shared memory: skb_fused_max_reads(narrow) (kernels_predict.cu).
 // Default build: 2560 with u16 counters (4 row buffers + bounds at every 4th read = 8.5 B per read), 4096 with u8
 // counters (reads with <= 255 query hashes: 4.5 B per read; also the range of the 12-bit read ids in a slot).
@@ -120,14 +128,14 @@ struct SkbFusedArgs {
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
 size_t skb_fused_smem_bytes(uint32_t cnt_stride);
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride);
-#define SKB_IVL_CAP (4u << 20)  // candidate intervals per pass; more than that shrinks the pass
+#define SKB_IVL_CAP ((4u << 20) << (SKB_X_IDBITS - 12))  // candidate intervals per pass (4 M per 4096 reads); more than that shrinks the pass
 uint32_t skb_fused_tile();
 uint32_t skb_fused_max_reads(int narrow);
 
 // per-read counts of the tracked rows only (they define the bounds): ctr[t][read], u16, row stride `stride`
 void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
                                const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st);
-#define SKB_CAND_BUDGET (24u << 20)  // candidate records per pass over all reads (384 MB); bucket = budget / reads
+#define SKB_CAND_BUDGET ((24u << 20) << (SKB_X_IDBITS - 12))  // candidate records per pass over all reads (384 MB per 4096 reads); bucket = budget / reads
 
 #define SKB_MAX_TRACKED 192u  // rows whose exact per-read sums define the bounds
 

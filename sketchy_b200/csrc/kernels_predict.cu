@@ -125,7 +125,7 @@ __global__ void table_alloc_kernel(SkbTable t) {
   if (s > t.cap) return;
   const unsigned long long m = t.slots[s].meta;
   const uint32_t c = SKB_SLOT_CNT(m);
-  if (c > SKB_SLOT_INLINE) t.slots[s].meta = m | ((unsigned long long)atomicAdd(t.cursor, c) << 13);
+  if (c > SKB_SLOT_INLINE) t.slots[s].meta = m | ((unsigned long long)atomicAdd(t.cursor, c) << SKB_SLOT_CNT_BITS);
 }
 
 __global__ void table_fill_kernel(SkbTable t, const uint32_t* __restrict__ qread, uint32_t n_keys,
@@ -139,7 +139,7 @@ __global__ void table_fill_kernel(SkbTable t, const uint32_t* __restrict__ qread
   const unsigned long long m = *reinterpret_cast<volatile unsigned long long*>(&t.slots[s].meta);
   const uint32_t pos = atomicAdd(&t.fill[s], 1u);
   if (SKB_SLOT_CNT(m) <= SKB_SLOT_INLINE) {
-    atomicOr(&t.slots[s].meta, (unsigned long long)rd << (13 + 12 * pos));
+    atomicOr(&t.slots[s].meta, (unsigned long long)rd << SKB_SLOT_ID_SHIFT(pos));
   } else {
     t.reads[SKB_SLOT_START(m) + pos] = rd;
   }
@@ -178,9 +178,6 @@ constexpr int FS_CONSUMER_WARPS = SKB_X_CW;
 #ifndef SKB_X_RANKW
 #define SKB_X_RANKW 2
 #endif
-#ifndef SKB_X_RANK2
-#define SKB_X_RANK2 0  // 1: rank_bounds fetches eight tracked sums at a time; rank_select cuts every bucket down first
-#endif
 constexpr int FS_RANK_WARPS = SKB_X_RANKW;    // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
 constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
 #ifndef SKB_X_ROWBUF
@@ -190,7 +187,11 @@ constexpr int FS_ROWBUF = SKB_X_ROWBUF;  // rows in flight per CTA: counter buff
 // a rank warp may only wait on a row buffer whose previous row it flushed itself (consumer warps can close rows out of
 // order, so the barrier parity of a buffer is only unambiguous to the warp that saw its previous phase)
 static_assert(FS_ROWBUF % FS_RANK_WARPS == 0 && FS_ROWBUF <= 8, "FS_RANK_WARPS must divide FS_ROWBUF");
-constexpr int FS_QCAP = 64;            // per-warp FIFO of filter passers awaiting their table lookup (power of 2)
+#ifndef SKB_X_QCAP
+#define SKB_X_QCAP 64
+#endif
+constexpr int FS_QCAP = SKB_X_QCAP;    // per-warp FIFO of filter passers awaiting their table lookup (power of 2, <= 128)
+static_assert((FS_QCAP & (FS_QCAP - 1)) == 0 && FS_QCAP >= 64 && FS_QCAP + 32 < 256, "FIFO size: power of two; outstanding counts are 8 bits");
 constexpr int FS_NHASH = 8;            // hashes per lane per chunk (one chunk = 256 hashes)
 constexpr int FS_CHUNKS = FS_SUB / (32 * FS_NHASH);
 constexpr size_t FS_SMEM_BLOOM = (size_t)SKB_BLOOM_WORDS * 4;
@@ -279,7 +280,7 @@ __device__ __forceinline__ void apply_hit(const SkbTable& t, const SkbSlot& s, u
   if (c <= SKB_SLOT_INLINE) {
     count_hit<CPW>(cbuf, SKB_SLOT_ID(s.meta, 0));
     if (c > 1) {
-      for (uint32_t j = 1; j < c; ++j) count_hit<CPW>(cbuf, (uint32_t)((s.meta >> (13 + 12 * j)) & 0xFFFull));
+      for (uint32_t j = 1; j < c; ++j) count_hit<CPW>(cbuf, SKB_SLOT_ID(s.meta, j));
     }
   } else {
     const uint32_t st = SKB_SLOT_START(s.meta);
@@ -619,6 +620,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
               }
               if (lane < total) qt[(tail + lane) & (FS_QCAP - 1)] = fresh_tag;
               if (total > 32u && lane + 32u < total) qt[(tail + lane + 32u) & (FS_QCAP - 1)] = fresh_tag;
+              if (FS_QCAP > 64)
+                for (uint32_t o = lane + 64u; o < total; o += 32u) qt[(tail + o) & (FS_QCAP - 1)] = fresh_tag;
               qn += total;
               outst += (uint64_t)total << (8 * par);
               __syncwarp();
@@ -878,27 +881,10 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
     ks[pos] = s; ki[pos] = gi;
     if (n < keep) ++n;
   };
-#if SKB_X_RANK2
-  // the tracked rows' sums are fetched eight at a time (row id -> running sum is a dependent load: one at a time the
-  // loop is a chain of ~400 L2 round trips per read); the offers keep their order, so the bound is the same
-  for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
-    uint32_t rw[8];
-    unsigned long long sv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rw[j] = t0 + j < nt ? a.tracked[t0 + j] : 0u;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      sv[j] = t0 + j < nt ? a.sums_in[rw[j]] + a.tracked_prefix[(size_t)(t0 + j) * a.row_stride + b] : 0ull;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (t0 + j < nt) offer(sv[j], a.row_base + rw[j]);
-  }
-#else
   for (uint32_t t = 0; t < nt; ++t) {
     const uint32_t row = a.tracked[t];
     offer(a.sums_in[row] + a.tracked_prefix[(size_t)t * a.row_stride + b], a.row_base + row);
   }
-#endif
   a.lb_sum[b] = n ? ks[n - 1] : 0ull;
   a.lb_idx[b] = n ? ki[n - 1] : 0xFFFFFFFFu;
 }
@@ -913,41 +899,6 @@ __global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
   const uint32_t total = min(*a.ivl_total, a.ivl_cap);
   const uint32_t lane = skb_lane();
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-#if SKB_X_RANK2
-  // A warp takes 32 intervals at a time. Most intervals span a handful of reads (a row contends between two of its
-  // hits): those are expanded one per lane, 32 slot allocations in flight per warp instead of one interval's; the
-  // long ones (more than 16 reads) are expanded by the whole warp as before. The order of a bucket's records changes,
-  // the records do not, and the selection does not depend on their order.
-  auto put = [&](unsigned long long sum, uint32_t idx, uint32_t b) {
-    const uint32_t slot = atomicAdd(&a.cand_cnt[b], 1u);
-    if (slot < a.cand_cap) {
-      SkbCand cd;
-      cd.sum = sum; cd.idx = idx; cd.pad = 0;
-      a.cand[(size_t)b * a.cand_cap + slot] = cd;
-    } else {
-      *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
-    }
-  };
-  for (uint32_t w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; w0 < total; w0 += nwarps * 32u) {
-    SkbInterval iv;
-    iv.sum = 0; iv.idx = 0xFFFFFFFFu; iv.span = 0;
-    if (w0 + lane < total) iv = a.ivl[w0 + lane];
-    const uint32_t b0 = iv.span & 0xFFFFu, b1 = iv.span >> 16;
-    const bool is_long = b1 > b0 + 16u;
-    uint32_t longs = __ballot_sync(0xffffffffu, is_long);
-    while (longs) {
-      const int src = __ffs(longs) - 1;
-      longs &= longs - 1u;
-      const unsigned long long ssum = __shfl_sync(0xffffffffu, iv.sum, src);
-      const uint32_t sidx = __shfl_sync(0xffffffffu, iv.idx, src);
-      const uint32_t sspan = __shfl_sync(0xffffffffu, iv.span, src);
-      for (uint32_t b = (sspan & 0xFFFFu) + lane; b < (sspan >> 16); b += 32) put(ssum, sidx, b);
-    }
-    if (!is_long)
-      for (uint32_t b = b0; b < b1; ++b) put(iv.sum, iv.idx, b);
-  }
-  return;
-#endif
   for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += nwarps) {
     const SkbInterval iv = a.ivl[w];
     const uint32_t b0 = iv.span & 0xFFFFu, b1 = iv.span >> 16;
@@ -1027,7 +978,7 @@ __device__ __forceinline__ void warp_best(unsigned long long& s, uint32_t& i) {
 // One warp per read: the `top` best candidates of the read's bucket, in order. Candidate rows are distinct, so
 // "best key strictly worse than the previous pick" enumerates them without marking. The first RS_CACHE records of
 // the bucket are staged in shared memory once; missing entries are (sum 0, idx UINT32_MAX).
-constexpr int RS_WARPS = SKB_X_RANK2 ? 4 : 8;  // 4 warps x 8 KB: seven CTAs per SM, a 4096-read pass is one wave
+constexpr int RS_WARPS = 8;
 constexpr int RS_CACHE = 512;
 __global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRankArgs a) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
@@ -1047,14 +998,11 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRan
   // records at least that good are compacted into the cache. Two coalesced passes instead of `top` of them.
   uint32_t m = n;       // records the selection rounds look at
   bool cached = n <= (uint32_t)RS_CACHE;
-  // (SKB_X_RANK2: a cached bucket of more than 64 records is cut down the same way, in place: `top` rounds over a
-  // dozen survivors instead of over hundreds of records)
-  const bool in_place = SKB_X_RANK2 && cached && n > 64u;
-  if ((!cached || in_place) && a.top <= 32u) {  // (the 32 lane maxima bound the top-th best only for top <= 32)
+  if (!cached && a.top <= 32u) {  // (the 32 lane maxima bound the top-th best only for top <= 32)
     unsigned long long ls = 0;
     uint32_t li = 0xFFFFFFFFu;
     for (uint32_t i = lane; i < n; i += 32) {
-      const uint4 c = in_place ? cache[i] : list[i];
+      const uint4 c = list[i];
       const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
       if (skb_key_better(cs, c.z, ls, li)) { ls = cs; li = c.z; }
     }
@@ -1073,13 +1021,12 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rank_select_kernel(const SkbRan
       uint4 c = make_uint4(0, 0, 0, 0);
       bool keep = false;
       if (i < n) {
-        c = in_place ? cache[i] : list[i];
+        c = list[i];
         const unsigned long long cs = ((unsigned long long)c.y << 32) | c.x;
         keep = !skb_key_better(ts, ti, cs, c.z);  // at least as good as the threshold
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, keep);
       const uint32_t at = kept + __popc(bal & ((1u << lane) - 1u));
-      __syncwarp();  // in place: a survivor lands at or before its own position, after every lane has read this block
       if (keep && at < (uint32_t)RS_CACHE) cache[at] = c;
       kept += __popc(bal);
     }
@@ -1265,14 +1212,14 @@ size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
 uint32_t skb_fused_tile() { return FS_SUB; }
 // Largest pass the kernel's shared memory holds: 227 KB per CTA minus the static barriers, the filter, the staging
 // rings and the FIFOs leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each) plus the bounds staged at
-// every 4th read (0.5 B per read). Pass-local read ids are 12 bits in a table slot, so 4096 is the cap either way.
+// every 4th read (0.5 B per read). Pass-local read ids are SKB_SLOT_ID_BITS wide in a table slot: that caps it either way.
 uint32_t skb_fused_max_reads(int narrow) {
   const size_t fixed = FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + 1024;  // 1 KB: static barriers + slack
   const size_t budget = 232448;                                             // opt-in maximum per CTA on sm_100
   if (fixed >= budget) return 0;
   const size_t per2 = (narrow ? 2 * FS_ROWBUF : 4 * FS_ROWBUF) + 1;         // bytes per read, times two
   const uint32_t gran = narrow ? 512u : 256u;                               // cnt_stride granularity (api.cu)
-  uint32_t b = (uint32_t)std::min<size_t>(4096, 2 * (budget - fixed) / per2);
+  uint32_t b = (uint32_t)std::min<size_t>(1u << SKB_SLOT_ID_BITS, 2 * (budget - fixed) / per2);
   return b / gran * gran;
 }
 
