@@ -10,6 +10,21 @@
 
 #define SKB_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a launcher remembers, per device, the largest size it
+// has opted in to, so a process that drives several GPUs (one context each) configures every one of them.
+struct SkbSmemOptIn {
+  size_t bytes[64] = {};
+  // true when `smem` bytes still have to be opted in to on the current device (and records it)
+  bool needs(size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& have = bytes[dev & 63];
+    if (smem <= have) return false;
+    have = smem;
+    return true;
+  }
+};
+
 // ---- packed sequence layout -----------------------------------------------------------------------------
 // codes: 2 bit/base, 16 bases per u32, base p lives in word p/16 at bits 2*(p%16)   (A=0 C=1 G=2 T=3)
 // nmask: 1 bit/base, 32 bases per u32, bit p%32 set = base p is NOT one of ACGT (or is padding / a separator)

@@ -1226,11 +1226,10 @@ uint32_t skb_fused_max_reads(int narrow) {
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st) {
   if (a.rv.n_rows == 0) return;
   const size_t smem = a.narrow ? skb_fused_smem_bytes_narrow(a.cnt_stride) : skb_fused_smem_bytes(a.cnt_stride);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static SkbSmemOptIn opt_in;
+  if (opt_in.needs(smem)) {
     cudaFuncSetAttribute(fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
   }
   if (a.narrow) fused_kernel<4><<<a.num_ctas, FS_THREADS, smem, st>>>(a);
   else fused_kernel<2><<<a.num_ctas, FS_THREADS, smem, st>>>(a);
@@ -1255,11 +1254,8 @@ void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st) { pass_verdi
 
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)RS_WARPS * RS_CACHE * 16;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(rank_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static SkbSmemOptIn opt_in;
+  if (opt_in.needs(smem)) cudaFuncSetAttribute(rank_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned blocks = (a.n_reads + RS_WARPS - 1) / RS_WARPS;
   rank_select_kernel<<<blocks, RS_WARPS * 32, smem, st>>>(a);
 }

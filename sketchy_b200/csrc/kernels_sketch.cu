@@ -317,11 +317,9 @@ void skb_launch_hash(const SkbHashArgs& a, cudaStream_t st) {
 void skb_launch_select(const SkbSelectArgs& a, cudaStream_t st) {
   if (a.n_groups == 0) return;
   const size_t smem = (size_t)a.smem_elems * sizeof(uint64_t);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static SkbSmemOptIn opt_in;
+  if (smem > 48 * 1024 && opt_in.needs(smem))
     cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   select_kernel<<<a.n_groups, a.threads, smem, st>>>(a);
 }
 
