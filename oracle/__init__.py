@@ -58,6 +58,8 @@ def lib() -> C.CDLL:
                                          C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
         L.orc_predict_stream.restype = C.c_int64
+        L.orc_predict_stream_mt.argtypes = L.orc_predict_stream.argtypes + [C.c_uint32]
+        L.orc_predict_stream_mt.restype = C.c_int64
         L.orc_predict_readset.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
                                           C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
@@ -163,8 +165,10 @@ def sketch_groups(records, groups, ngroups: int, k: int, s: int, seed: int = 0, 
 
 
 def predict_stream(ref: np.ndarray, ref_off: np.ndarray, reads, k: int, s_query: int, seed: int, top: int,
-                   limit: int = 0, sums: np.ndarray | None = None):
-    """reference `_sum_of_shared_hashes`. Returns (idx[nproc, top], sum[nproc, top], sums[N])."""
+                   limit: int = 0, sums: np.ndarray | None = None, nthreads: int = 1):
+    """reference `_sum_of_shared_hashes`. Returns (idx[nproc, top], sum[nproc, top], sums[N]).
+    nthreads > 1 spreads every read's N merges over host threads: same results, but not how the reference runs (its
+    predict loop is single-threaded); bench.py reports that number only as a labelled extra."""
     ref = np.ascontiguousarray(ref, dtype=np.uint64)
     ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
     N = ref_off.size - 1
@@ -173,8 +177,12 @@ def predict_stream(ref: np.ndarray, ref_off: np.ndarray, reads, k: int, s_query:
     sums = np.zeros(N, dtype=np.uint64) if sums is None else np.ascontiguousarray(sums, dtype=np.uint64).copy()
     oi = np.zeros((max(n, 1), top), dtype=np.uint32)
     os_ = np.zeros((max(n, 1), top), dtype=np.uint64)
-    done = lib().orc_predict_stream(_p(ref), _p(ref_off), N, _p(blob), _p(off), n, k, s_query, seed, top, limit,
-                                    _p(sums), _p(oi), _p(os_))
+    if nthreads > 1:
+        done = lib().orc_predict_stream_mt(_p(ref), _p(ref_off), N, _p(blob), _p(off), n, k, s_query, seed, top,
+                                           limit, _p(sums), _p(oi), _p(os_), nthreads)
+    else:
+        done = lib().orc_predict_stream(_p(ref), _p(ref_off), N, _p(blob), _p(off), n, k, s_query, seed, top, limit,
+                                        _p(sums), _p(oi), _p(os_))
     if done < 0:
         raise ValueError("top > number of reference sketches (reference panics, src/sketchy.rs:391)")
     return oi[:done], os_[:done], sums

@@ -355,6 +355,42 @@ int64_t orc_predict_stream(const uint64_t* ref, const uint64_t* ref_off, uint32_
   return static_cast<int64_t>(done);
 }
 
+// The same loop with the N merges of every read spread over `nthreads` host threads (contiguous row ranges). NOT what
+// the reference does — its predict loop is single-threaded (src/sketchy.rs:328-355) — and only used by bench.py to
+// report, next to the faithful single-thread number, what all host cores could do on this path. Results are identical.
+int64_t orc_predict_stream_mt(const uint64_t* ref, const uint64_t* ref_off, uint32_t N, const uint8_t* blob,
+                              const uint64_t* read_off, uint64_t nreads, uint32_t k, uint32_t s_query,
+                              uint64_t seed, uint32_t top, uint64_t limit, uint64_t* sums, uint32_t* out_idx,
+                              uint64_t* out_sum, uint32_t nthreads) {
+  if (top > N) return -1;
+  if (nthreads < 1) nthreads = 1;
+  std::vector<uint64_t> sum(sums, sums + N);
+  std::vector<uint64_t> qh;
+  std::vector<uint32_t> qc;
+  uint64_t read = 1, done = 0;
+  for (uint64_t r = 0; r < nreads; ++r) {
+    MashSketcher sk(s_query, k, seed);
+    sk.process(blob + read_off[r], read_off[r + 1] - read_off[r], read_off[r + 1] - read_off[r]);
+    sk.to_vec(qh, qc);
+    auto part = [&](uint32_t t) {
+      const uint32_t lo = static_cast<uint32_t>(static_cast<uint64_t>(N) * t / nthreads);
+      const uint32_t hi = static_cast<uint32_t>(static_cast<uint64_t>(N) * (t + 1) / nthreads);
+      for (uint32_t i = lo; i < hi; ++i)
+        sum[i] += common_hashes(ref + ref_off[i], ref_off[i + 1] - ref_off[i], qh.data(), qh.size(), 0.);
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < nthreads; ++t) pool.emplace_back(part, t);
+    part(0);
+    for (auto& th : pool) th.join();
+    rank_top(sum, top, out_idx + r * top, out_sum + r * top);
+    ++done;
+    read += 1;
+    if (read == limit + 1) break;
+  }
+  std::copy(sum.begin(), sum.end(), sums);
+  return static_cast<int64_t>(done);
+}
+
 // reference src/sketchy.rs:281-315 `_shared_hashes` (read-set predict): ONE sketcher over all reads
 // (limit check at :297), one to_vec (:302), shared vs every reference (:305-309), stable sort (:310).
 // Returns the number of reads consumed (the `read` printed at :312). out_idx/out_sum are [top];

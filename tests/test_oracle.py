@@ -152,6 +152,10 @@ def test_predict_stream_matches_pyspec_and_ties():
     assert (idx3 == idx[7:]).all() and (sm3 == sm[7:]).all() and (s3 == sums).all()
     with pytest.raises(ValueError):
         oracle.predict_stream(ref, off, reads, 16, 64, 0, len(rows) + 1)
+    # the all-cores variant bench.py reports as a labelled extra gives the same answer
+    for nt in (2, 5, 64):
+        idx4, sm4, s4 = oracle.predict_stream(ref, off, reads, 16, 64, 0, 5, nthreads=nt)
+        assert (idx4 == idx).all() and (sm4 == sm).all() and (s4 == sums).all()
 
 
 def test_predict_readset_and_shared_matrix():
