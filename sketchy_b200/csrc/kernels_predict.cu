@@ -237,7 +237,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // buffer hand-back (a consumer warp waits for the rank warp to flush row lr-4): same loop, kept apart so that profiles
 // tell the two waits apart
+#ifndef SKB_X_FREE_SLEEP
+#define SKB_X_FREE_SLEEP 0  // > 0: poll with a nanosleep of that many ns instead (experiment: the try_wait loop re-issues)
+#endif
+#ifndef SKB_X_RANK_SLEEP
+#define SKB_X_RANK_SLEEP 500
+#endif
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity);
 __device__ __forceinline__ void mbar_wait_free(uint64_t* bar, uint32_t parity) {
+  if (SKB_X_FREE_SLEEP > 0) {
+    while (!mbar_try(bar, parity)) __nanosleep(SKB_X_FREE_SLEEP);
+    return;
+  }
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -253,7 +264,7 @@ __device__ __forceinline__ void mbar_wait_free(uint64_t* bar, uint32_t parity) {
 // rank warps wait a whole row (microseconds) and have two rows of slack: poll with a real sleep in between, a
 // try_wait loop alone re-issues every few cycles and takes issue slots from the consumer warps
 __device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try(bar, parity)) __nanosleep(500);
+  while (!mbar_try(bar, parity)) __nanosleep(SKB_X_RANK_SLEEP);
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier; streamed data is marked
 // evict-first so the query table keeps its place in L2.
@@ -871,8 +882,11 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
   unsigned long long ks[SKB_MAX_TOP];
   uint32_t ki[SKB_MAX_TOP];
   uint32_t n = 0;
-  auto offer = [&](unsigned long long s, uint32_t gi) {
-    if (n == keep && !skb_key_better(s, gi, ks[n - 1], ki[n - 1])) return;
+  for (uint32_t t = 0; t < nt; ++t) {
+    const uint32_t row = a.tracked[t];
+    const unsigned long long s = a.sums_in[row] + a.tracked_prefix[(size_t)t * a.row_stride + b];
+    const uint32_t gi = a.row_base + row;
+    if (n == keep && !skb_key_better(s, gi, ks[n - 1], ki[n - 1])) continue;
     uint32_t pos = n < keep ? n : n - 1;  // insert, dropping the worst when full
     while (pos > 0 && skb_key_better(s, gi, ks[pos - 1], ki[pos - 1])) {
       ks[pos] = ks[pos - 1]; ki[pos] = ki[pos - 1];
@@ -880,10 +894,6 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
     }
     ks[pos] = s; ki[pos] = gi;
     if (n < keep) ++n;
-  };
-  for (uint32_t t = 0; t < nt; ++t) {
-    const uint32_t row = a.tracked[t];
-    offer(a.sums_in[row] + a.tracked_prefix[(size_t)t * a.row_stride + b], a.row_base + row);
   }
   a.lb_sum[b] = n ? ks[n - 1] : 0ull;
   a.lb_idx[b] = n ? ki[n - 1] : 0xFFFFFFFFu;
