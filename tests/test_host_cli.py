@@ -1,6 +1,9 @@
 """Host-side tests of the `sketchy` CLI shell: .msh codec (CPU, cross-checked against an independent Python codec,
 including a multi-segment file with far / double-far pointers), genotype/info/check behaviour, and (GPU) the full
 sketch -> shared -> predict pipeline against the oracle with the reference's row formats."""
+import bz2
+import gzip
+import lzma
 import os
 import random
 import subprocess
@@ -144,6 +147,12 @@ def test_cli_sketch_shared_predict_match_oracle(tmp_path):
             exp_lines.append(f"{r + 1}\t{n}\t{int(es[r, t])}\t" + "\t".join(gm[n]))
     got = run("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "3", "-s", "-H").stdout.splitlines()
     assert got == exp_lines
+    # compressed reads (src/cli.rs:96 "Fast{a,q}.{gz,xz,bz}"): the content is sniffed, the rows are the same
+    for ext, comp in (("gz", gzip.compress), ("bz2", bz2.compress), ("xz", lzma.compress)):
+        fz = tmp_path / f"reads.fq.{ext}"
+        fz.write_bytes(comp(fq.read_bytes()))
+        gz_rows = run("predict", "-i", str(fz), "-r", str(ref), "-g", str(geno), "-t", "3", "-s", "-H").stdout.splitlines()
+        assert gz_rows == exp_lines, ext
     lim = run("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "3", "-s", "-l", "5").stdout.splitlines()
     assert lim == exp_lines[1:1 + 15]
     n, ri, rs, _ = oracle.predict_readset(np.concatenate(rows), off, reads, k, s_, seed, 3)
