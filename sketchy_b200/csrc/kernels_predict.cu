@@ -243,7 +243,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef SKB_X_RANK_SLEEP
 #define SKB_X_RANK_SLEEP 500
 #endif
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity);
 __device__ __forceinline__ void mbar_wait_free(uint64_t* bar, uint32_t parity) {
   if (SKB_X_FREE_SLEEP > 0) {
     while (!mbar_try(bar, parity)) __nanosleep(SKB_X_FREE_SLEEP);

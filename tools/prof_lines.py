@@ -32,9 +32,9 @@ def func_lines(start):
     for l in dis[start + 1:]:
         if l.startswith("//---------------------"):
             break
-        m = re.search(r'//## File ".*?", line (\d+)', l)
+        m = re.search(r'//## File "(.*?)", line (\d+)', l)
         if m:
-            cur = int(m.group(1))
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
             seq.append(cur)
@@ -46,7 +46,21 @@ cands = [func_lines(i) for i, l in enumerate(dis) if l.startswith(".text.") and 
 seq = min(cands, key=lambda q: abs(len(q) - len(data)))
 assert len(seq) == len(data), (len(seq), len(data), [len(c) for c in cands])
 iI, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
-src = open(srcfile).read().split("\n")
+srcs = {}
+
+
+def text_of(key):
+    """source text of (file name, line); the kernel inlines code from the headers next to it"""
+    if not key:
+        return ""
+    fn, ln = key
+    if fn not in srcs:
+        path = os.path.join(os.path.dirname(os.path.abspath(srcfile)), fn)
+        srcs[fn] = open(path).read().split("\n") if os.path.exists(path) else []
+    lines = srcs[fn]
+    return lines[ln - 1].strip()[:95] if 0 < ln <= len(lines) else ""
+
+
 agg = {}
 for i, r in enumerate(data):
     a = agg.setdefault(seq[i], [0, 0])
@@ -54,6 +68,13 @@ for i, r in enumerate(data):
 tot = sum(a[0] for a in agg.values()); toti = sum(a[1] for a in agg.values())
 print(f"kernel {kname}: {len(seq)} SASS instrs, {toti} executed, {tot} samples")
 key_i = 1 if os.environ.get("BY_INST") else 0
-for ln, (s_, i_) in sorted(agg.items(), key=lambda x: -x[1][key_i])[:top_n]:
-    text = src[ln - 1].strip()[:95] if ln and 0 < ln <= len(src) else ""
-    print(f"{ln or 0:5d} {s_:7d} {100 * s_ / max(tot, 1):5.1f}% inst={i_:11d}  {text}")
+if os.environ.get("DUMP_TSV"):  # machine-readable: file, line, samples, executed instructions (tools/inst_budget.py)
+    with open(os.environ["DUMP_TSV"], "w") as f:
+        for key, (s_, i_) in agg.items():
+            fn, ln = key if key else ("", 0)
+            f.write(f"{fn}\t{ln}\t{s_}\t{i_}\n")
+main = os.path.basename(srcfile)
+for key, (s_, i_) in sorted(agg.items(), key=lambda x: -x[1][key_i])[:top_n]:
+    fn, ln = key if key else ("", 0)
+    where = f"{ln:5d}" if fn == main else f"{fn}:{ln}"
+    print(f"{where:>5s} {s_:7d} {100 * s_ / max(tot, 1):5.1f}% inst={i_:11d}  {text_of(key)}")
