@@ -11,6 +11,7 @@
 #pragma once
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <poll.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -68,6 +69,13 @@ class RawInput {  // buffered reads from a file descriptor
   }
   const uint8_t* data() const { return buf_.data() + pos_; }
   void consume(size_t n) { pos_ += n; }
+  // true when a read would block right now: nothing buffered, not at the end, and the descriptor has nothing to give
+  // (a live pipe whose writer is pausing; a regular file is always readable)
+  bool would_block() const {
+    if (pos_ < end_ || eof_) return false;
+    struct pollfd pfd = {fd_, POLLIN, 0};
+    return ::poll(&pfd, 1, 0) == 0;
+  }
 
  private:
   int fd_;
@@ -278,6 +286,11 @@ class Reader {
     }
   }
   Reader(const Reader&) = delete;
+
+  // true when every byte received so far has been handed out as records and more input has not arrived yet: a caller
+  // that batches records (the streaming predict loop) should work on what it has instead of waiting for a full batch.
+  // The reference prints a row as soon as a read arrives (src/sketchy.rs:328-355).
+  bool input_idle() const { return pos_ >= buf_.size() && !eof_ && in_->would_block(); }
 
   bool next(Record& r) {
     std::string line;

@@ -335,6 +335,7 @@ int cmd_predict(const Args& a) {
       while (blob.n() < 65536 && (more = rd.next(r))) {
         blob.add(r.seq, 0);
         if (limit && read + blob.n() - 1 == limit) { more = false; break; }
+        if (rd.input_idle()) break;  // a live stream that is pausing: predict what has arrived instead of waiting for 65536 reads
       }
       if (!blob.n()) break;
       c.check(skb_batch_clear(b));
@@ -342,6 +343,7 @@ int cmd_predict(const Args& a) {
       idx.resize(blob.n() * top); sum.resize(blob.n() * top);
       c.check(skb_predict_stream(c.c, b, k, s_query, seed, top, 0, idx.data(), sum.data()));
       for (size_t i = 0; i < blob.n(); ++i, ++read) print_results(ref, g, read, &idx[i * top], &sum[i * top], top, consensus);
+      fflush(stdout);  // the reference's println! reaches a pipe line by line: a consumer of the live stream sees each chunk at once
     }
   } else {  // src/sketchy.rs:281-315: one sketcher for all reads
     uint64_t read = 0;

@@ -22,7 +22,9 @@ int main(int argc, char** argv) {
     while (rd.next(r)) {
       unsigned long long h = 1469598103934665603ull;
       for (unsigned char c : r.seq) { h ^= c; h *= 1099511628211ull; }
-      std::printf("%s\t%zu\t%llu\n", r.id.c_str(), r.seq.size(), h);
+      if (argc > 2) std::printf("%s\tidle=%d\n", r.id.c_str(), rd.input_idle() ? 1 : 0);   // live-stream probe
+      else std::printf("%s\t%zu\t%llu\n", r.id.c_str(), r.seq.size(), h);
+      std::fflush(stdout);
     }
   } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
   return 0;
@@ -105,3 +107,25 @@ def test_truncated_and_garbage_inputs_fail_like_the_reference(harness, tmp_path)
     (tmp_path / "empty.fa").write_bytes(b"")
     rc, out, _ = _run(harness, path=str(tmp_path / "empty.fa"))
     assert rc == 0 and out == b""
+
+
+def test_live_stream_reports_idle_between_bursts(harness, tmp_path):
+    """A pausing writer on stdin (a sequencer): after the last record of a burst the reader says the input is idle, so
+    the streaming predict loop works on what has arrived instead of waiting for a full batch (the reference prints a
+    row per read as it arrives, src/sketchy.rs:328-355). A regular file is never idle."""
+    import time
+    p = subprocess.Popen([harness, "-", "idle"], stdin=subprocess.PIPE, stdout=subprocess.PIPE)
+    p.stdin.write(b"@a\nACGT\n+\nIIII\n@b\nACGTA\n+\nIIIII\n")
+    p.stdin.flush()
+    first = [p.stdout.readline(), p.stdout.readline()]
+    time.sleep(0.2)
+    p.stdin.write(b"@c\nAC\n+\nII\n")
+    p.stdin.close()
+    rest = p.stdout.read().splitlines()
+    assert p.wait() == 0
+    assert first == [b"a\tidle=0\n", b"b\tidle=1\n"]
+    assert rest == [b"c\tidle=0"]            # the writer hung up: end of input, not a pause
+    f = tmp_path / "r.fq"
+    f.write_bytes(b"@a\nACGT\n+\nIIII\n@b\nACGTA\n+\nIIIII\n")
+    out = subprocess.run([harness, str(f), "idle"], capture_output=True).stdout.splitlines()
+    assert out == [b"a\tidle=0", b"b\tidle=0"]
