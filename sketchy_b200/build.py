@@ -27,7 +27,7 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(SO)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
-    deps += [os.path.join(HERE, "host", f) for f in ("main.cpp", "msh.cpp", "msh.hpp", "fastx.hpp", "capnp_lite.hpp")]
+    deps += [os.path.join(HERE, "host", f) for f in ("main.cpp", "msh.cpp", "msh.hpp", "fastx.hpp", "ingest.hpp", "capnp_lite.hpp")]
     cli = os.path.join(HERE, "bin", "sketchy")
     if not os.path.exists(cli):
         return True
@@ -75,7 +75,7 @@ def build_host() -> str:
     os.makedirs(os.path.dirname(CLI), exist_ok=True)
     cxx = shutil.which("g++") or "g++"
     cmd = [cxx, "-O2", "-std=c++17", "-Wall", os.path.join(HOST, "main.cpp"), os.path.join(HOST, "msh.cpp"), "-o", CLI,
-           "-L" + HERE, "-lsketchy_b200", "-lz", "-ldl", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
+           "-L" + HERE, "-lsketchy_b200", "-lz", "-ldl", "-pthread", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
     subprocess.check_call(cmd)
     return CLI
 

@@ -278,8 +278,8 @@ class Reader {
     else if (got >= 6 && std::memcmp(magic, "\xFD" "7zXZ\0", 6) == 0) dec_.reset(new XzDecoder(*in_));
     else dec_.reset(new PlainDecoder(*in_));
     fill();
-    while (pos_ < buf_.size() && (buf_[pos_] == '\n' || buf_[pos_] == '\r')) ++pos_;
-    if (pos_ < buf_.size()) {
+    while (pos_ < len_ && (buf_[pos_] == '\n' || buf_[pos_] == '\r')) ++pos_;
+    if (pos_ < len_) {
       if (buf_[pos_] == '>') fasta_ = true;
       else if (buf_[pos_] == '@') fasta_ = false;
       else throw open_error();
@@ -290,7 +290,7 @@ class Reader {
   // true when every byte received so far has been handed out as records and more input has not arrived yet: a caller
   // that batches records (the streaming predict loop) should work on what it has instead of waiting for a full batch.
   // The reference prints a row as soon as a read arrives (src/sketchy.rs:328-355).
-  bool input_idle() const { return pos_ >= buf_.size() && !eof_ && in_->would_block(); }
+  bool input_idle() const { return pos_ >= len_ && !eof_ && in_->would_block(); }
 
   bool next(Record& r) {
     std::string line;
@@ -301,10 +301,9 @@ class Reader {
     if (fasta_) {
       if (line[0] != '>') throw open_error();
       bool first = true;
-      while (peek() != -1 && peek() != '>') {
-        getline(line);
+      while (peek() != -1 && peek() != '>') {  // sequence lines go straight into the record, joined by '\n'
         if (!first) r.seq.push_back('\n');
-        r.seq += line;
+        append_line(r.seq);
         first = false;
       }
       while (!r.seq.empty() && (r.seq.back() == '\n' || r.seq.back() == '\r')) r.seq.pop_back();
@@ -318,39 +317,53 @@ class Reader {
   }
 
  private:
+  static constexpr size_t kChunk = 1 << 20;
+  // decoded bytes not yet handed out: buf_[pos_, len_)
   void fill() {
     if (eof_) return;
-    if (pos_ > 0) { buf_.erase(buf_.begin(), buf_.begin() + pos_); pos_ = 0; }
-    const size_t old = buf_.size();
-    buf_.resize(old + (1 << 20));
-    const size_t n = dec_->read(reinterpret_cast<uint8_t*>(buf_.data()) + old, 1 << 20);
-    buf_.resize(old + n);
+    if (pos_ > 0) {
+      std::memmove(buf_.data(), buf_.data() + pos_, len_ - pos_);
+      len_ -= pos_;
+      pos_ = 0;
+    }
+    if (buf_.size() < len_ + kChunk) buf_.resize(len_ + kChunk);
+    const size_t n = dec_->read(reinterpret_cast<uint8_t*>(buf_.data()) + len_, kChunk);
+    len_ += n;
     if (n == 0) eof_ = true;
   }
   int peek() {
-    if (pos_ >= buf_.size()) { fill(); if (pos_ >= buf_.size()) return -1; }
+    if (pos_ >= len_) { fill(); if (pos_ >= len_) return -1; }
     return (unsigned char)buf_[pos_];
   }
-  bool getline(std::string& out) {
-    out.clear();
+  // appends the next line, without its terminator, to `out`; false at the end of the input
+  bool append_line(std::string& out) {
     if (peek() == -1) return false;
     for (;;) {
-      size_t e = pos_;
-      while (e < buf_.size() && buf_[e] != '\n') ++e;
-      out.append(buf_.begin() + pos_, buf_.begin() + e);
-      if (e < buf_.size()) { pos_ = e + 1; break; }
-      pos_ = e;
+      const char* p = buf_.data() + pos_;
+      const size_t avail = len_ - pos_;
+      const char* nl = static_cast<const char*>(std::memchr(p, '\n', avail));
+      if (nl) {
+        out.append(p, (size_t)(nl - p));
+        pos_ += (size_t)(nl - p) + 1;
+        break;
+      }
+      out.append(p, avail);
+      pos_ = len_;
       if (eof_) break;
       fill();
-      if (pos_ >= buf_.size()) break;
+      if (pos_ >= len_) break;
     }
     if (!out.empty() && out.back() == '\r') out.pop_back();
     return true;
   }
+  bool getline(std::string& out) {
+    out.clear();
+    return append_line(out);
+  }
   std::unique_ptr<RawInput> in_;
   std::unique_ptr<Decoder> dec_;
   std::vector<char> buf_;
-  size_t pos_ = 0;
+  size_t pos_ = 0, len_ = 0;
   bool eof_ = false, fasta_ = true;
 };
 

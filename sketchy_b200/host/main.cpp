@@ -17,6 +17,7 @@
 
 #include "../../include/sketchy_b200.h"
 #include "fastx.hpp"
+#include "ingest.hpp"
 #include "msh.hpp"
 
 namespace {
@@ -93,18 +94,7 @@ struct Ctx {
   void check(int rc) const { if (rc != SKB_OK) throw std::runtime_error(skb_last_error(c)); }
 };
 
-struct Blob {
-  std::vector<uint8_t> bytes;
-  std::vector<uint64_t> off{0};
-  std::vector<uint32_t> grp;
-  void add(const std::string& s, uint32_t g) {
-    bytes.insert(bytes.end(), s.begin(), s.end());
-    off.push_back(bytes.size());
-    grp.push_back(g);
-  }
-  void clear() { bytes.clear(); off.assign(1, 0); grp.clear(); }
-  size_t n() const { return grp.size(); }
-};
+using ingest::Blob;
 
 // ---- genotype table (src/sketchy.rs:538-571): TSV with header; header minus the first column; name -> columns
 struct Genotypes {
@@ -220,18 +210,18 @@ int cmd_sketch(const Args& a) {
   c.check(skb_batch_create(c.c, &b));
   msh::File f;
   f.kmer_size = k; f.sketch_size = s; f.hash_seed = seed;
-  Blob blob;
-  for (size_t g = 0; g < files.size(); ++g) {
-    fastx::Reader rd(files[g]);
-    fastx::Record r;
-    while (rd.next(r)) blob.add(r.seq, (uint32_t)g);
+  for (const std::string& p : files) {
     msh::Sketch sk;
-    sk.name = basename_of(files[g]);
+    sk.name = basename_of(p);
     f.sketches.push_back(sk);
-    if (blob.bytes.size() > (1ull << 30) || g + 1 == files.size()) {
-      if (blob.n()) c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), blob.grp.data(), blob.n(), 0));
-      blob.clear();
-    }
+  }
+  // windows of files (<= 1 GB on disk each) are read, decompressed and split into records on all host threads, then
+  // packed in file order: the reference runs its files on a rayon pool (src/sketchy.rs:470-472)
+  for (size_t g0 = 0; g0 < files.size();) {
+    const size_t g1 = ingest::window_end(files, g0, 1ull << 30);
+    const Blob blob = ingest::read_files(files, g0, g1);
+    if (blob.n()) c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), blob.grp.data(), blob.n(), 0));
+    g0 = g1;
   }
   const uint32_t G = (uint32_t)files.size();
   const uint32_t have = skb_batch_num_groups(b);  // trailing empty files have no group yet

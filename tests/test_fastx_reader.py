@@ -61,6 +61,35 @@ def _fastq(rng, n):
     return "".join(out).encode()
 
 
+def _fnv(b: bytes) -> int:
+    h = 1469598103934665603
+    for c in b:
+        h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _expected(raw: bytes, kind: str) -> bytes:
+    """Independent parse: id = header line minus its marker; FASTA sequence = its lines (CR stripped) joined by LF (the
+    raw slice needletail hands on); FASTQ sequence = line 2 of the record."""
+    lines = [l[:-1] if l.endswith(b"\r") else l for l in raw.split(b"\n")]
+    out = []
+    if kind == "fasta":
+        rid, seq = None, []
+        for l in lines + [b">"]:
+            if l.startswith(b">"):
+                if rid is not None:
+                    body = b"\n".join(seq).rstrip(b"\n")
+                    out.append(b"%s\t%d\t%d\n" % (rid, len(body), _fnv(body)))
+                rid, seq = l[1:], []
+            elif rid is not None:
+                seq.append(l)
+    else:
+        rec = [l for l in lines if l != b""]
+        for i in range(0, len(rec), 4):
+            out.append(b"%s\t%d\t%d\n" % (rec[i][1:], len(rec[i + 1]), _fnv(rec[i + 1])))
+    return b"".join(out)
+
+
 def _run(exe, path=None, data=None):
     p = subprocess.run([exe] + ([path] if path else []), input=data, capture_output=True)
     return p.returncode, p.stdout, p.stderr.decode()
@@ -82,6 +111,7 @@ def test_compressed_inputs_yield_the_same_records(harness, tmp_path, kind):
     }
     rc, want, err = _run(harness, data=raw)
     assert rc == 0 and want.count(b"\n") == (300 if kind == "fasta" else 900), err
+    assert want == _expected(raw, kind)
     for name, blob in forms.items():
         path = tmp_path / f"x.{name}"            # the name says nothing: the content is sniffed
         path.write_bytes(blob)
@@ -129,3 +159,66 @@ def test_live_stream_reports_idle_between_bursts(harness, tmp_path):
     f.write_bytes(b"@a\nACGT\n+\nIIII\n@b\nACGTA\n+\nIIIII\n")
     out = subprocess.run([harness, str(f), "idle"], capture_output=True).stdout.splitlines()
     assert out == [b"a\tidle=0", b"b\tidle=0"]
+
+
+INGEST_HARNESS = r'''
+#include "ingest.hpp"
+#include <cstdio>
+#include <cstdlib>
+// usage: h <threads> <window-budget-bytes> file...   -> one line per window: g0 g1 records bytes fnv(bytes) fnv(off) fnv(grp)
+static unsigned long long fnv(const void* p, size_t n) {
+  unsigned long long h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= ((const unsigned char*)p)[i]; h *= 1099511628211ull; }
+  return h;
+}
+int main(int argc, char** argv) {
+  try {
+    const unsigned T = (unsigned)atoi(argv[1]);
+    const unsigned long long budget = strtoull(argv[2], nullptr, 10);
+    std::vector<std::string> files(argv + 3, argv + argc);
+    for (size_t g0 = 0; g0 < files.size();) {
+      const size_t g1 = ingest::window_end(files, g0, budget);
+      const ingest::Blob b = ingest::read_files(files, g0, g1, T);
+      std::printf("%zu %zu %zu %zu %llu %llu %llu\n", g0, g1, b.n(), b.bytes.size(), fnv(b.bytes.data(), b.bytes.size()),
+                  fnv(b.off.data(), b.off.size() * 8), fnv(b.grp.data(), b.grp.size() * 4));
+      g0 = g1;
+    }
+  } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+  return 0;
+}
+'''
+
+
+def test_parallel_file_reader_equals_the_sequential_one(tmp_path):
+    """`sketchy sketch` reads its files on all host threads (the reference uses a rayon pool, src/sketchy.rs:470-472):
+    the record batch must not depend on the thread count, windows must respect the budget, and the first unreadable
+    file decides the error."""
+    src = tmp_path / "i.cpp"
+    src.write_text(INGEST_HARNESS)
+    exe = str(tmp_path / "i")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "sketchy_b200", "host"), str(src),
+                           "-o", exe, "-lz", "-ldl"])
+    rng = random.Random(21)
+    comps = [lambda b: b, gzip.compress, bz2.compress, lambda b: lzma.compress(b, format=lzma.FORMAT_XZ)]
+    files = []
+    for g in range(14):
+        raw = b"" if g == 5 else _fasta(rng, rng.randint(1, 6))
+        p = tmp_path / f"g{g}.fa"
+        p.write_bytes(comps[g % 4](raw) if raw else raw)
+        files.append(str(p))
+    outs = {}
+    for t in (1, 3, 16):
+        p = subprocess.run([exe, str(t), str(1 << 30)] + files, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        outs[t] = p.stdout
+    assert outs[1] == outs[3] == outs[16] and outs[1].split()[:2] == ["0", "14"]
+    # a tiny budget: one window per file, still every file exactly once and in order
+    p = subprocess.run([exe, "4", "1"] + files, capture_output=True, text=True)
+    wins = [l.split() for l in p.stdout.splitlines()]
+    assert [(int(w[0]), int(w[1])) for w in wins] == [(g, g + 1) for g in range(14)]
+    assert sum(int(w[2]) for w in wins) == int(outs[1].split()[2])
+    # unreadable files: the reference's error text
+    (tmp_path / "bad.fa").write_bytes(b"not a sequence file\n")
+    p = subprocess.run([exe, "8", str(1 << 30)] + files[:3] + [str(tmp_path / "bad.fa")] + files[3:] + [str(tmp_path / "nope.fa")],
+                       capture_output=True, text=True)
+    assert p.returncode == 1 and "failed to open Fastx file or record with Needletail" in p.stderr
