@@ -1,6 +1,7 @@
 """Host-side tests of the `sketchy` CLI shell: .msh codec (CPU, cross-checked against an independent Python codec,
-including a multi-segment file with far / double-far pointers), genotype/info/check behaviour, and (GPU) the full
-sketch -> shared -> predict pipeline against the oracle with the reference's row formats."""
+including a multi-segment file with far / double-far pointers), genotype/info/check behaviour, the host logic of
+`sketch` / `predict` against a recording stand-in of the library (CPU: what is handed to the ABI, in which order), and
+(GPU) the full sketch -> shared -> predict pipeline against the oracle with the reference's row formats."""
 import bz2
 import gzip
 import lzma
@@ -164,3 +165,118 @@ def test_cli_sketch_shared_predict_match_oracle(tmp_path):
     ref2 = tmp_path / "ref2.msh"
     run("sketch", "-o", str(ref2), "-s", str(s_), "-k", str(k), "-e", str(seed), stdin="\n".join(p for p, _ in paths) + "\n")
     assert capnp_py.decode_msh(ref2.read_bytes()) == dec
+
+
+# ---- host logic of the GPU sub-commands against a recording stand-in of the library (no GPU) ---------------------------
+def _fnv(b: bytes) -> int:
+    h = 1469598103934665603
+    for c in b:
+        h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.fixture(scope="module")
+def mock_cli(tmp_path_factory):
+    """The CLI host linked against tests/mock_abi.cpp, which records every ABI call instead of computing."""
+    d = tmp_path_factory.mktemp("mockcli")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", os.path.join(root, "tests", "mock_abi.cpp"), "-o",
+                           str(d / "libsketchy_b200.so")])
+    host = os.path.join(root, "sketchy_b200", "host")
+    exe = str(d / "sketchy")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", os.path.join(host, "main.cpp"), os.path.join(host, "msh.cpp"),
+                           "-o", exe, "-L" + str(d), "-lsketchy_b200", "-lz", "-ldl", "-Wl,-rpath," + str(d)])
+
+    def run_mock(*args, stdin=None):
+        log = d / "calls.log"
+        if log.exists():
+            log.unlink()
+        p = subprocess.run([exe, *args], input=stdin, capture_output=True, env=dict(os.environ, MOCK_ABI_LOG=str(log)))
+        return p, (log.read_text().splitlines() if log.exists() else [])
+    run_mock.exe = exe
+    return run_mock
+
+
+def test_sketch_host_hands_every_record_to_the_library_in_file_order(mock_cli, tmp_path):
+    """`sketch`: files are read on several threads, but the library must see one record per FASTA record, raw slices
+    (interior line breaks kept), grouped by file index in file order — for files named on the command line and for a
+    file list on stdin (src/sketchy.rs:137-146, 465-494); empty files keep their place in the output."""
+    rng = random.Random(5)
+    files, expect = [], []
+    for g in range(9):
+        recs = [] if g == 4 else ["".join(rng.choice("ACGTN") for _ in range(rng.randint(1, 300))) for _ in range(rng.randint(1, 3))]
+        body, raw = "", []
+        for i, s in enumerate(recs):
+            lines = [s[j:j + 60] for j in range(0, len(s), 60)]
+            body += f">c{i}\n" + "\n".join(lines) + "\n"
+            raw.append("\n".join(lines).encode())
+        p = tmp_path / f"f{g}.fa"
+        data = body.encode()
+        p.write_bytes(gzip.compress(data) if g % 3 == 1 else (bz2.compress(data) if g % 3 == 2 and data else data))
+        files.append(str(p))
+        expect += [f"  rec group={g} len={len(r)} fnv={_fnv(r)}" for r in raw]
+    out = tmp_path / "o.msh"
+    for via_stdin in (False, True):
+        if via_stdin:
+            p, log = mock_cli("sketch", "-o", str(out), "-s", "50", "-k", "21", "-e", "9", stdin=("\n".join(files) + "\n").encode())
+        else:
+            p, log = mock_cli("sketch", "-i", *files, "-o", str(out), "-s", "50", "-k", "21", "-e", "9")
+        assert p.returncode == 0, p.stderr
+        assert [l for l in log if l.startswith("  rec")] == expect
+        assert [l for l in log if l.startswith("batch_add")] == [f"batch_add n={len(expect)} groups=given"]
+        assert log[-1] == f"sketch k=21 s=50 seed=9 groups=9 records={len(expect)}"
+        dec = capnp_py.decode_msh(out.read_bytes())
+        assert [s["name"] for s in dec["sketches"]] == [f"f{g}.fa" for g in range(9)]
+        assert dec["k"] == 21 and dec["seed"] == 9
+
+
+def test_predict_host_batches_reads_and_follows_a_live_stream(mock_cli, tmp_path):
+    """streaming `predict`: every read is its own group (one sketcher per read, src/sketchy.rs:331), `-l` stops feeding
+    reads (:350-353), rows are numbered from 1; when a live stdin pauses, the reads that have arrived are predicted at
+    once instead of waiting for a full batch. Read-set mode puts all reads in group 0 (:291)."""
+    import time
+    ref = tmp_path / "ref.msh"
+    rng = random.Random(6)
+    f = _file(rng, n=3, s=8)
+    for s in f["sketches"]:
+        while len(s["hashes"]) < 2:               # a usable reference: s_query comes from sketch #0
+            s["hashes"] = sorted(rng.sample(range(1, 2**63), 4)); s["counts"] = [1] * 4
+    (tmp_path / "ref.txt").write_text(_to_text(f))
+    run("msh-from-text", str(tmp_path / "ref.txt"), str(ref))
+    geno = tmp_path / "g.tsv"
+    geno.write_text("id\tst\n" + "".join(f"{s['name']}\tST{i}\n" for i, s in enumerate(f["sketches"])))
+    reads = ["".join(rng.choice("ACGT") for _ in range(rng.randint(20, 200))) for _ in range(5)]
+    fq = tmp_path / "r.fq"
+    fq.write_text("".join(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads)))
+    names = [s["name"] for s in f["sketches"]]
+    s_query = len(f["sketches"][0]["hashes"])
+    p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "2", "-s", "-H")
+    assert p.returncode == 0, p.stderr
+    assert [l for l in log if l.startswith(("batch_add", "predict"))] == [
+        "batch_add n=5 groups=null", f"predict_stream k={f['k']} s_query={s_query} seed={f['seed']} top=2 pad=0 reads=5"]
+    assert [l for l in log if l.startswith("  rec")] == [f"  rec group={i} len={len(r)} fnv={_fnv(r.encode())}" for i, r in enumerate(reads)]
+    rows = p.stdout.decode().splitlines()
+    assert rows[0] == "reads\tsketch_id\tshared_hashes\tst"
+    assert rows[1:] == [f"{r + 1}\t{names[t]}\t7\tST{t}" for r in range(5) for t in range(2)]
+    p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "1", "-s", "-l", "3")
+    assert [l for l in log if l.startswith("batch_add")] == ["batch_add n=3 groups=null"] and len(p.stdout.splitlines()) == 3
+    # read-set mode: one sketcher for all reads, then shared counts and one ranking
+    p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "2")
+    assert [l for l in log if l.startswith("  rec")] == [f"  rec group=0 len={len(r)} fnv={_fnv(r.encode())}" for r in reads]
+    assert [l.split()[0] for l in log if not l.startswith(("  rec", "create", "batch_clear"))] == [
+        "ref_upload", "batch_add", "sketch", "shared_counts", "rank_counts"]
+    assert p.stdout.decode().splitlines() == [f"5\t{names[t]}\t3\tST{t}" for t in range(2)]
+    # live stream: two bursts -> two predict calls, rows of the first burst arrive before the second is written
+    log_path = str(tmp_path / "live.log")   # (the fixture's runner waits for exit; this one is driven by hand)
+    pr = subprocess.Popen([mock_cli.exe, "predict", "-r", str(ref), "-g", str(geno), "-t", "1", "-s"], stdin=subprocess.PIPE,
+                          stdout=subprocess.PIPE, env=dict(os.environ, MOCK_ABI_LOG=log_path))
+    burst1 = "".join(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads[:2])).encode()
+    pr.stdin.write(burst1); pr.stdin.flush()
+    first = [pr.stdout.readline(), pr.stdout.readline()]          # would block forever without the idle check + flush
+    time.sleep(0.1)
+    pr.stdin.write(f"@r2\n{reads[2]}\n+\n{'I' * len(reads[2])}\n".encode()); pr.stdin.close()
+    rest = pr.stdout.read().decode().splitlines()
+    assert pr.wait() == 0
+    assert [l.decode().split("\t")[0] for l in first] == ["1", "2"] and [l.split("\t")[0] for l in rest] == ["3"]
+    calls = [l for l in open(log_path).read().splitlines() if l.startswith("batch_add")]
+    assert calls == ["batch_add n=2 groups=null", "batch_add n=1 groups=null"]
