@@ -2,7 +2,7 @@
 
 Same method names, argument meaning and error behaviour as the reference so parity tests read like tests of the
 reference itself; the compute goes through libsketchy_b200.so (no CPU path here). File formats (.msh, FASTA/FASTQ,
-genotype TSV) live in ``sketchy_b200.io``.
+genotype TSV) are handled by the C++ host (``sketchy_b200/host``: the `sketchy` CLI).
 """
 from __future__ import annotations
 
