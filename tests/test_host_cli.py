@@ -260,6 +260,11 @@ def test_predict_host_batches_reads_and_follows_a_live_stream(mock_cli, tmp_path
     assert rows[1:] == [f"{r + 1}\t{names[t]}\t7\tST{t}" for r in range(5) for t in range(2)]
     p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "1", "-s", "-l", "3")
     assert [l for l in log if l.startswith("batch_add")] == ["batch_add n=3 groups=null"] and len(p.stdout.splitlines()) == 3
+    # consensus row over the top 3 (src/sketchy.rs:363-389); the stand-in ranks rows 0,1,2 -> a three-way tie -> first in rank order
+    p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "3", "-s", "-c")
+    assert p.stdout.decode().splitlines() == [f"{r + 1}\t-\t-\tST0" for r in range(5)]
+    p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "2", "-s", "-c")
+    assert p.returncode == 1 and b"--top must be an odd number when using --consensus" in p.stderr
     # read-set mode: one sketcher for all reads, then shared counts and one ranking
     p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "2")
     assert [l for l in log if l.startswith("  rec")] == [f"  rec group=0 len={len(r)} fnv={_fnv(r.encode())}" for r in reads]
