@@ -730,7 +730,6 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
     fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
-    { const char* dbg = getenv("SKB_DEBUG"); fa.debug = dbg ? atoi(dbg) : 0; }
     fa.sums_in = ra.sums_in; fa.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
     fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.lb_rel = ra.lb_rel;
     fa.ivl = c->ivl.as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_cand_total + 1; fa.abort = d_abort;

@@ -113,7 +113,6 @@ struct SkbFusedArgs {
   uint32_t cnt_stride;  // counters per row buffer (multiple of 512, >= n_reads)
   int narrow;           // counters are u8 (every read of the pass keeps <= 255 query hashes) instead of u16
   int skip_stream;      // the pass has no query hashes: rows are ranked without being streamed
-  int debug;            // experiments only (SKB_DEBUG env): 1 = no filter probe, 2 = probe but drop passers
   uint32_t row_base;    // global index of local row 0
   const unsigned long long* sums_in;  // [n_rows]
   unsigned long long* sums_out;       // [n_rows]

@@ -21,29 +21,35 @@
 
 namespace {
 
+// Home slot of a key: the low word is already MurmurHash3 output, one 32-bit multiply spreads it further (the choice
+// affects probe lengths only, never results).
 __device__ __forceinline__ uint32_t table_home(uint64_t h, uint32_t log2cap) {
-  return (uint32_t)((h * 0x9E3779B97F4A7C15ull) >> (64 - log2cap));
+  return ((uint32_t)h * 0x9E3779B1u) >> (32 - log2cap);
 }
-// Filter geometry, chosen for the probe's instruction count: the word's BYTE offset is lo & 0xFFFC (one LOP); the bit
-// positions are 5-bit fields of lo above the word index (bits 16-30) and the low bits of hi, which wrap-mode shifts
-// consume without masking. All of these bits are uniform for any reference maximum >= 2^37.
+// Filter geometry, chosen for the probe's instruction count: the word's BYTE offset is lo & 0xFFFC (one LOP); a key
+// sets SKB_BLOOM_K bits of its word at positions 31 - f, f = 5-bit fields of the hash (low bits of hi, bits 16-20 and
+// 21-25 of lo). Shifting the word LEFT by f (wrap-mode shifts take f mod 32 without masking) brings the bit to position
+// 31, so the conjunction of the shifted words has the verdict in its top bit and one funnel shift appends it to the
+// chunk's passer mask. All of these hash bits are uniform for any reference maximum >= 2^37.
 #ifndef SKB_BLOOM_K
 #define SKB_BLOOM_K 3
 #endif
 __device__ __forceinline__ uint32_t bloom_word(uint32_t lo) { return (lo >> 2) & (SKB_BLOOM_WORDS - 1u); }
 __device__ __forceinline__ uint32_t bloom_mask(uint32_t lo, uint32_t hi) {
-  uint32_t m = (1u << (hi & 31u)) | (1u << ((lo >> 16) & 31u));
-  if (SKB_BLOOM_K >= 3) m |= 1u << ((lo >> 21) & 31u);
-  if (SKB_BLOOM_K >= 4) m |= 1u << ((lo >> 26) & 31u);
+  uint32_t m = 0x80000000u >> (hi & 31u);
+  if (SKB_BLOOM_K >= 2) m |= 0x80000000u >> ((lo >> 16) & 31u);
+  if (SKB_BLOOM_K >= 3) m |= 0x80000000u >> ((lo >> 21) & 31u);
+  if (SKB_BLOOM_K >= 4) m |= 0x80000000u >> ((lo >> 26) & 31u);
   return m;
 }
-// 1 when every bit of the key (lo, hi) is set in its filter word
+// top bit set when every bit of the key (lo, hi) is set in its filter word (the lower bits are garbage)
 __device__ __forceinline__ uint32_t bloom_probe(const uint32_t* bloom, uint32_t lo, uint32_t hi) {
   const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(bloom) + (lo & (4u * SKB_BLOOM_WORDS - 4u)));
-  uint32_t r = (w >> (hi & 31u)) & (w >> ((lo >> 16) & 31u));
-  if (SKB_BLOOM_K >= 3) r &= w >> ((lo >> 21) & 31u);
-  if (SKB_BLOOM_K >= 4) r &= w >> ((lo >> 26) & 31u);
-  return r & 1u;
+  uint32_t r = w << (hi & 31u);
+  if (SKB_BLOOM_K >= 2) r &= w << ((lo >> 16) & 31u);
+  if (SKB_BLOOM_K >= 3) r &= w << ((lo >> 21) & 31u);
+  if (SKB_BLOOM_K >= 4) r &= w << ((lo >> 26) & 31u);
+  return r;
 }
 
 __device__ __forceinline__ SkbSlot load_slot(const SkbSlot* p) {
@@ -172,56 +178,33 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 #ifndef SKB_X_CW
 #define SKB_X_CW 16
 #endif
-constexpr int FS_SUB = SKB_X_SUB;      // hashes per sub-tile (4 KB): two chunks of 8 per lane
-constexpr int FS_STAGES = SKB_X_STAGES;  // staging buffers per consumer warp
-constexpr int FS_CONSUMER_WARPS = SKB_X_CW;
-#ifndef SKB_X_RANKW
-#define SKB_X_RANKW 2
-#endif
-constexpr int FS_RANK_WARPS = SKB_X_RANKW;    // rank warp p owns the rows with (row - r0) % FS_RANK_WARPS == p
-constexpr int FS_THREADS = (FS_CONSUMER_WARPS + FS_RANK_WARPS) * 32;
 #ifndef SKB_X_ROWBUF
-#define SKB_X_ROWBUF 4
+#define SKB_X_ROWBUF 6
 #endif
-constexpr int FS_ROWBUF = SKB_X_ROWBUF;  // rows in flight per CTA: counter buffers / barriers are indexed by row % FS_ROWBUF
-// a rank warp may only wait on a row buffer whose previous row it flushed itself (consumer warps can close rows out of
-// order, so the barrier parity of a buffer is only unambiguous to the warp that saw its previous phase)
-static_assert(FS_ROWBUF % FS_RANK_WARPS == 0 && FS_ROWBUF <= 8, "FS_RANK_WARPS must divide FS_ROWBUF");
-#ifndef SKB_X_QCAP
-#define SKB_X_QCAP 64
+#ifndef SKB_X_ABLATE
+#define SKB_X_ABLATE 0  // experiments only (never in the shipped build): 1 = no filter probe, 2 = probe but drop the passers, 4 = no candidate walk
 #endif
-constexpr int FS_QCAP = SKB_X_QCAP;    // per-warp FIFO of filter passers awaiting their table lookup (power of 2, <= 128)
-static_assert((FS_QCAP & (FS_QCAP - 1)) == 0 && FS_QCAP >= 64 && FS_QCAP + 32 < 256, "FIFO size: power of two; outstanding counts are 8 bits");
-constexpr int FS_NHASH = 8;            // hashes per lane per chunk (one chunk = 256 hashes)
+constexpr int FS_SUB = SKB_X_SUB;        // hashes per sub-tile (4 KB): chunks of 8 per lane
+constexpr int FS_STAGES = SKB_X_STAGES;  // staging buffers per warp
+constexpr int FS_WARPS = SKB_X_CW;
+constexpr int FS_THREADS = FS_WARPS * 32;
+constexpr int FS_ROWBUF = SKB_X_ROWBUF;  // rows in flight per CTA: counter buffers are indexed by row % FS_ROWBUF
+static_assert(FS_ROWBUF >= 2 && FS_ROWBUF <= 8, "2..8 row buffers");
+constexpr int FS_NHASH = 8;              // hashes per lane per chunk (one chunk = 256 hashes)
 constexpr int FS_CHUNKS = FS_SUB / (32 * FS_NHASH);
+static_assert(FS_SUB % (32 * FS_NHASH) == 0, "a sub-tile is a whole number of chunks");
 constexpr size_t FS_SMEM_BLOOM = (size_t)SKB_BLOOM_WORDS * 4;
-constexpr size_t FS_SMEM_RING = (size_t)FS_CONSUMER_WARPS * FS_STAGES * FS_SUB * 8;
-constexpr size_t FS_SMEM_QUEUE = (size_t)FS_CONSUMER_WARPS * FS_QCAP * 12;  // 8-byte hash + 4-byte tag per entry (two arrays)
+constexpr size_t FS_SMEM_RING = (size_t)FS_WARPS * FS_STAGES * FS_SUB * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
+// the try_wait suspends the warp in hardware (up to the hint) instead of spinning on the issue port
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -232,38 +215,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(1000000u)  // suspend-time hint (ns): sleep in hardware instead of spinning
-      : "memory");
-}
-// buffer hand-back (a consumer warp waits for the rank warp to flush row lr-4): same loop, kept apart so that profiles
-// tell the two waits apart
-#ifndef SKB_X_FREE_SLEEP
-#define SKB_X_FREE_SLEEP 0  // > 0: poll with a nanosleep of that many ns instead (experiment: the try_wait loop re-issues)
-#endif
-#ifndef SKB_X_RANK_SLEEP
-#define SKB_X_RANK_SLEEP 500
-#endif
-__device__ __forceinline__ void mbar_wait_free(uint64_t* bar, uint32_t parity) {
-  if (SKB_X_FREE_SLEEP > 0) {
-    while (!mbar_try(bar, parity)) __nanosleep(SKB_X_FREE_SLEEP);
-    return;
-  }
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAITF_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONEF_%=;\n\t"
-      "bra WAITF_%=;\n\t"
-      "DONEF_%=:\n\t"
-      "}" ::"r"(smem_u32(bar)),
       "r"(parity), "r"(1000000u)
       : "memory");
-}
-// rank warps wait a whole row (microseconds) and have two rows of slack: poll with a real sleep in between, a
-// try_wait loop alone re-issues every few cycles and takes issue slots from the consumer warps
-__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try(bar, parity)) __nanosleep(SKB_X_RANK_SLEEP);
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier; streamed data is marked
 // evict-first so the query table keeps its place in L2.
@@ -275,6 +228,11 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+__device__ __forceinline__ uint32_t lds_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 
 // two u16 counters per 32-bit word; a per-(row, read) count never exceeds 65535 (checked on the host)
 template <int CPW>
@@ -283,44 +241,39 @@ __device__ __forceinline__ void count_hit(uint32_t* cbuf, uint32_t rd) {
   else atomicAdd(cbuf + (rd >> 2), 1u << (8 * (rd & 3u)));  // u8 counters: the host guarantees counts <= 255
 }
 
-// add the slot's reads to the row's counters
+// add the slot's reads to the row's counters (cnt == 0: the reserved slot of the all-ones key when no read holds it)
 template <int CPW>
-__device__ __forceinline__ void apply_hit(const SkbTable& t, const SkbSlot& s, uint32_t* cbuf) {
-  const uint32_t c = SKB_SLOT_CNT(s.meta);
+__device__ __forceinline__ void apply_hit(const SkbTable& t, unsigned long long meta, uint32_t* cbuf) {
+  const uint32_t c = SKB_SLOT_CNT(meta);
   if (c <= SKB_SLOT_INLINE) {
-    count_hit<CPW>(cbuf, SKB_SLOT_ID(s.meta, 0));
-    if (c > 1) {
-      for (uint32_t j = 1; j < c; ++j) count_hit<CPW>(cbuf, SKB_SLOT_ID(s.meta, j));
+    unsigned long long ids = meta >> SKB_SLOT_CNT_BITS;
+#pragma unroll 1
+    for (uint32_t j = 0; j < c; ++j) {
+      count_hit<CPW>(cbuf, (uint32_t)ids & ((1u << SKB_SLOT_ID_BITS) - 1u));
+      ids >>= SKB_SLOT_ID_BITS;
     }
   } else {
-    const uint32_t st = SKB_SLOT_START(s.meta);
+    const uint32_t st = SKB_SLOT_START(meta);
+#pragma unroll 1
     for (uint32_t j = 0; j < c; ++j) count_hit<CPW>(cbuf, t.reads[st + j]);
   }
 }
 
-// One lookup batch per warp is kept in flight: a lane's slot load is issued when its entry is taken from the
-// queue and the result is consumed only after the warp has probed another tile, so the L2 latency overlaps work.
-// Every lane loads (idle lanes read slot 0) so the loaded registers are written unconditionally. A lookup that
-// lands on another key's slot is put back in the queue with the next slot index instead of being chased in place.
-struct Pending {
-  uint64_t h;
-  uint32_t idx;
-  uint32_t par;  // row buffer (row & 3) the entry belongs to
-  uint4 raw;
-  bool valid;
-};
-#define SKB_Q_FRESH 0x1FFFFFFFu  // queue entry whose home slot is still to be computed (bits 29-31 = row buffer)
-
-// this warp's sub-tiles: global sub-tile numbers w, w+16, w+32, ... over the CTA's rows (a shared claim counter was
-// tried instead: the waits on row buffers stayed and the claim's round trip cost 7 %)
+// A warp's sub-tiles: global sub-tile numbers w, w + FS_WARPS, ... over the CTA's rows (a shared claim counter was
+// tried instead in round 1: the claim's round trip cost 7 %). An empty row counts as one sub-tile of zero hashes so
+// that it is still closed and ranked by somebody.
 struct SubIter {
   uint32_t row, t;    // current row (CTA-local number), sub-tile within it
   uint32_t len;       // hashes in the current row
   const uint64_t* p;  // first hash of the current row
-  uint32_t c0, G;     // local row lr is row c0 + lr * G of the shard
+  uint32_t c0;        // local row lr is row c0 + lr of the shard
+  __device__ __forceinline__ static uint32_t tiles_of(uint32_t len) {
+    const uint32_t n = (len + FS_SUB - 1) / FS_SUB;
+    return n ? n : 1u;
+  }
   __device__ __forceinline__ void load_row(const SkbFusedArgs& a, uint32_t r1) {
     if (row >= r1) { len = 0; p = a.rv.ref; return; }
-    const uint32_t g = c0 + row * G;
+    const uint32_t g = c0 + row;
     if (a.rv.uniform_len) {
       len = a.rv.uniform_len;
       p = a.rv.ref + (size_t)g * a.rv.uniform_pitch;
@@ -331,7 +284,7 @@ struct SubIter {
   }
   __device__ __forceinline__ void settle(const SkbFusedArgs& a, uint32_t r1) {
     while (row < r1) {
-      const uint32_t n = (len + FS_SUB - 1) / FS_SUB;
+      const uint32_t n = tiles_of(len);
       if (t < n) break;
       t -= n;
       ++row;
@@ -339,359 +292,48 @@ struct SubIter {
     }
   }
   __device__ __forceinline__ void next(const SkbFusedArgs& a, uint32_t r1) {
-    t += FS_CONSUMER_WARPS;
+    t += FS_WARPS;
     if (a.rv.uniform_len) {  // every row has the same number of sub-tiles (>= 1): no loads, no loop of loads
-      const uint32_t n = (a.rv.uniform_len + FS_SUB - 1) / FS_SUB;
-      const size_t step = (size_t)a.rv.uniform_pitch * G;
-      while (t >= n && row < r1) { t -= n; ++row; p += step; }
+      const uint32_t n = tiles_of(a.rv.uniform_len);
+      while (t >= n && row < r1) { t -= n; ++row; p += a.rv.uniform_pitch; }
       return;
     }
     settle(a, r1);
   }
 };
 
-// CPW = counters per 32-bit word of a row buffer: 2 (u16, any pass) or 4 (u8, when no read of the pass keeps more than
-// 255 query hashes; more reads fit a pass).
+// Row bookkeeping of one CTA (static shared memory).
+struct FsCtl {
+  unsigned long long carry[FS_ROWBUF];  // running sum of the row in each buffer before this pass
+  unsigned long long lb_min;            // bound of read 0 (bounds never decrease along the reads)
+  uint32_t done[FS_ROWBUF];             // sub-tiles of the buffer's current row that are fully counted
+  uint32_t freed[FS_ROWBUF];            // rows of this buffer that have been ranked (the buffer is zero again)
+  uint32_t li_seg[32];                  // largest bound index within each lane segment of the reads
+};
+
+// Rank work for one finished row, done by the warp whose sub-tile completed it: the counters' total is the row's
+// new running sum; if the row can reach any read's bound, its counters are prefix-scanned and candidate intervals
+// "row gi holds sum sv and meets the bound for reads [b0, b1)" are emitted against the bounds staged in shared memory.
+// The bounds are staged at every 4th read only (0.5 B per read): read b is tested against the bound of read b & ~3,
+// which is lower or equal, so the test can only add candidates; the per-read selection is exact over whatever it is
+// given. On a tie with the bound the row index decides: a row passes when its index does not exceed the LARGEST bound
+// index of the reads in question (`li_cap`), again a superset and free of global loads.
 template <int CPW>
-__global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[FS_CONSUMER_WARPS][FS_STAGES];
-  __shared__ __align__(8) uint64_t row_done[FS_ROWBUF];
-  __shared__ __align__(8) uint64_t row_free[FS_ROWBUF];
-
-  if (*a.abort) return;  // an earlier pass of this batch has to be redone: leave sums and candidates alone
-
-  uint32_t* bloom = reinterpret_cast<uint32_t*>(smem_raw);
-  uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM);
-  uint64_t* queue = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
-  uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE);
-  const uint32_t cwords = a.cnt_stride / CPW;  // 32-bit words per row buffer
-  uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride / 4] bound growth since read 0 at every 4th read, saturating
-
-  // Every CTA owns a contiguous range of rows (balanced by sub-tiles on the host). Dealing the rows round-robin was
-  // tried to spread the rows that contend for a pass's reads: the average CTA took as long, the slowest 10-70 % longer.
-  // r0/r1 and every `row` below are CTA-local numbers; grow() is the row of the shard.
-  const uint32_t c0 = a.cta_row[blockIdx.x], G = 1;
-  const uint32_t r0 = 0, r1 = a.cta_row[blockIdx.x + 1] - c0;
-  auto grow = [&](uint32_t lr) -> uint32_t { return c0 + lr * G; };
-
-  if (threadIdx.x == 0) {
-    for (int w = 0; w < FS_CONSUMER_WARPS; ++w)
-      for (int s = 0; s < FS_STAGES; ++s) mbar_init(&full_bar[w][s], 1);
-    for (int p = 0; p < FS_ROWBUF; ++p) {
-      mbar_init(&row_done[p], FS_CONSUMER_WARPS);
-      mbar_init(&row_free[p], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (!a.skip_stream) {  // stage the filter
-    const uint4* src = reinterpret_cast<const uint4*>(a.table.bloom);
-    uint4* dst = reinterpret_cast<uint4*>(bloom);
-    for (uint32_t i = threadIdx.x; i < SKB_BLOOM_WORDS / 4; i += blockDim.x) dst[i] = src[i];
-  }
-  for (uint32_t i = threadIdx.x; i < FS_ROWBUF * cwords; i += blockDim.x) cnt32[i] = 0;
-  for (uint32_t i = threadIdx.x; 4u * i < a.n_reads; i += blockDim.x) lbrel[i] = (uint16_t)min(a.lb_rel[4u * i], 0xFFFFu);
-  __syncthreads();
-
-  const uint32_t warp = threadIdx.x >> 5, lane = skb_lane();
-
-  if (warp < FS_CONSUMER_WARPS) {
-    // ===== consumers: private TMA staging ring, filter probe, pipelined table verification, shared counters =====
-    // Filter passers are compacted into a per-warp FIFO; lookups run as dense 32-wide batches: every lane issues
-    // one table-slot load, and the results are consumed after the next chunk has been probed, so nothing in this
-    // loop waits on a dependent load. A slot owned by another key re-queues the entry with the next slot index.
-    const uint32_t cw = warp;
-    uint64_t* my_ring = ring + (size_t)cw * FS_STAGES * FS_SUB;
-    // FIFO records: hash in qh[], tag (slot index or SKB_Q_FRESH, row buffer in the top bits) in qt[]
-    uint2* qh = reinterpret_cast<uint2*>(queue) + (size_t)cw * FS_QCAP;
-    uint32_t* qt = reinterpret_cast<uint32_t*>(queue + (size_t)FS_CONSUMER_WARPS * FS_QCAP) + (size_t)cw * FS_QCAP;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const SkbTable& t = a.table;
-    uint32_t qhead = 0, qn = 0;  // FIFO state (warp-uniform)
-    uint64_t outst = 0;          // unfinished entries (queued or in flight) per row buffer, 8 bits each (warp-uniform)
-    Pending pend;
-    pend.valid = false; pend.h = 0; pend.idx = 0; pend.par = 0; pend.raw = make_uint4(0, 0, 0, 0);
-    bool have_pend = false;  // warp-uniform: a lookup batch is in flight
-    uint32_t closing = 0;    // warp-uniform; bit p: the row in buffer p is fully probed, closes when outst[p] == 0
-
-    auto count_now = [&](uint64_t h, uint32_t par) {  // synchronous lookup: only when the FIFO cannot take a burst
-      SkbSlot s;
-      if (table_lookup(t, h, s)) apply_hit<CPW>(t, s, cnt32 + par * cwords);
-    };
-    auto try_close = [&]() {
-      uint32_t nz = 0;
-#pragma unroll
-      for (int p = 0; p < FS_ROWBUF; ++p) nz |= ((outst >> (8 * p)) & 0xFFull) ? (1u << p) : 0u;
-      const uint32_t ready = closing & ~nz;
-      if (ready) {
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (uint32_t p = 0; p < (uint32_t)FS_ROWBUF; ++p)
-            if ((ready >> p) & 1u) mbar_arrive(&row_done[p]);  // every count of that row is in shared memory
-        }
-        closing &= ~ready;
-      }
-    };
-    auto finish_batch = [&]() {
-      if (have_pend) {
-        SkbSlot s;
-        s.key = ((unsigned long long)pend.raw.y << 32) | pend.raw.x;
-        s.meta = ((unsigned long long)pend.raw.w << 32) | pend.raw.z;
-        bool again = false;
-        if (pend.valid) {
-          uint32_t* cb = cnt32 + pend.par * cwords;
-          if (pend.h == SKB_EMPTY_KEY) {
-            if (SKB_SLOT_CNT(s.meta) != 0) apply_hit<CPW>(t, s, cb);
-          } else if (s.key == pend.h) {
-            apply_hit<CPW>(t, s, cb);
-          } else if (s.key != SKB_EMPTY_KEY) {
-            again = true;
-          }
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, again);
-        if (bal) {  // slots owned by other keys: back into the FIFO with the next slot index
-          const uint32_t n = __popc(bal);
-          if (qn + n <= (uint32_t)FS_QCAP) {
-            if (again) {
-              const uint32_t at = (qhead + qn + __popc(bal & lt_mask)) & (FS_QCAP - 1);
-              qh[at] = make_uint2((uint32_t)pend.h, (uint32_t)(pend.h >> 32));
-              qt[at] = ((pend.idx + 1) & (t.cap - 1)) | (pend.par << 29);
-            }
-            qn += n;
-          } else {  // no room (practically never): chase the chain here
-            if (again) {
-              uint32_t slot = pend.idx;
-              for (;;) {
-                slot = (slot + 1) & (t.cap - 1);
-                s = load_slot(&t.slots[slot]);
-                if (s.key == pend.h) { apply_hit<CPW>(t, s, cnt32 + pend.par * cwords); break; }
-                if (s.key == SKB_EMPTY_KEY) break;
-              }
-              again = false;
-            }
-          }
-          __syncwarp();
-        }
-        // resolved entries per row buffer: one packed warp reduction (a field gets at most 32, the fields are 8 bits)
-        {
-          const bool fin = pend.valid && !again;
-          outst -= __reduce_add_sync(0xffffffffu, (fin && pend.par < 4u) ? (1u << (8 * pend.par)) : 0u);
-          if (FS_ROWBUF > 4)
-            outst -= (uint64_t)__reduce_add_sync(0xffffffffu, (fin && pend.par >= 4u) ? (1u << (8 * (pend.par - 4u))) : 0u) << 32;
-        }
-        pend.valid = false;
-        have_pend = false;
-      }
-      if (closing) try_close();
-    };
-    auto start_batch = [&]() {  // oldest (up to) 32 entries of the FIFO, one per lane
-      const uint32_t n = qn < 32u ? qn : 32u;
-      pend.valid = lane < n;
-      const uint32_t qpos = (qhead + (pend.valid ? lane : 0u)) & (FS_QCAP - 1);
-      const uint2 e = qh[qpos];
-      pend.h = ((uint64_t)e.y << 32) | e.x;
-      const uint32_t tag = qt[qpos];
-      pend.par = tag >> 29;
-      const uint32_t qidx = tag & 0x1FFFFFFFu;
-      pend.idx = !pend.valid ? 0u
-                             : (qidx != SKB_Q_FRESH ? qidx
-                                                    : (pend.h == SKB_EMPTY_KEY ? t.cap : table_home(pend.h, t.log2cap)));
-      pend.raw = __ldg(reinterpret_cast<const uint4*>(&t.slots[pend.idx]));  // every lane loads: no predicated merge
-      qhead = (qhead + n) & (FS_QCAP - 1);
-      qn -= n;
-      have_pend = true;
-      __syncwarp();  // FIFO reads done before anyone appends again
-    };
-
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    // bulk copy of the sub-tile `pre` points at into one of this warp's staging buffers (lane 0 only)
-    auto issue_copy = [&](const SubIter& si, uint32_t stage) {
-      const uint32_t first = si.t * FS_SUB;
-      uint32_t n = si.len - first;
-      if (n > (uint32_t)FS_SUB) n = FS_SUB;
-      const uint32_t bytes = ((n + 1u) & ~1u) * 8u;  // multiple of 16; rows start on even offsets
-      mbar_arrive_expect_tx(&full_bar[cw][stage], bytes);
-      bulk_load(my_ring + (size_t)stage * FS_SUB, si.p + first, bytes, &full_bar[cw][stage], policy);
-    };
-
-    SubIter it, pre;
-    it.c0 = c0; it.G = G;
-    it.row = a.skip_stream ? r1 : r0;
-    it.t = cw;
-    it.load_row(a, r1);
-    it.settle(a, r1);
-    pre = it;
-    for (uint32_t s = 0; s < (uint32_t)FS_STAGES; ++s) {  // prime the private ring
-      if (pre.row < r1) {
-        if (lane == 0) issue_copy(pre, s);
-        pre.next(a, r1);
-      }
-    }
-    uint32_t k = 0;  // sub-tiles consumed by this warp: stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1
-
-    for (uint32_t row = r0; row < r1; ++row) {
-      const uint32_t lr = row - r0, par = lr % FS_ROWBUF;
-      if (lr >= (uint32_t)FS_ROWBUF) {
-        while ((closing >> par) & 1u) {  // row lr-4 still open for this warp: finish its lookups now
-          finish_batch();
-          if (qn) start_batch();
-        }
-        mbar_wait_free(&row_free[par], ((lr / FS_ROWBUF) - 1u) & 1u);  // rank warp has flushed row lr-4
-      }
-      const uint32_t fresh_tag = SKB_Q_FRESH | (par << 29);
-      // leftovers of the previous row are looked up as soon as this row starts: the row closes a whole row earlier than
-      // with "two rows back", and the warps no longer wait for the rank warp to hand the buffer back
-      const uint32_t urgent = 1u << ((lr + FS_ROWBUF - 1) % FS_ROWBUF);
-      while (it.row == row) {  // this warp's sub-tiles of the row
-        const uint32_t stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1u;
-        mbar_wait(&full_bar[cw][stage], phase);
-        const uint4* tp = reinterpret_cast<const uint4*>(my_ring + (size_t)stage * FS_SUB);
-        const uint32_t n_sub = it.len - it.t * FS_SUB;  // >= FS_SUB for every sub-tile but a row's last
-#pragma unroll 1
-        for (uint32_t ch = 0; ch < (uint32_t)FS_CHUNKS; ++ch) {
-          uint4 v[FS_NHASH / 2];
-#pragma unroll
-          for (int r = 0; r < FS_NHASH / 2; ++r) v[r] = tp[ch * (FS_NHASH / 2) * 32 + lane + 32 * r];
-          if (ch + 1 == (uint32_t)FS_CHUNKS) {
-            // the staging buffer is fully read: refill it with this warp's next sub-tile
-            __syncwarp();
-            if (pre.row < r1) {
-              if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue_copy(pre, stage);
-              }
-              pre.next(a, r1);
-            }
-            ++k;
-          }
-          const uint32_t base = ch * FS_NHASH * 32;  // first hash index of the chunk within the sub-tile
-          uint32_t pm = 0;                           // bit j: this lane's j-th hash of the chunk passed the filter
-          if ((a.debug & 3) != 1) {
-            if (n_sub >= base + FS_NHASH * 32) {
-#pragma unroll
-              for (int j = 0; j < FS_NHASH; ++j) {
-                const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
-                const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
-                pm += bloom_probe(bloom, lo, hi) << j;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < FS_NHASH; ++j) {
-                const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
-                const uint32_t idx = base + 2u * (lane + 32 * (j >> 1)) + (j & 1);
-                const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
-                pm += (idx < n_sub ? bloom_probe(bloom, lo, hi) : 0u) << j;
-              }
-            }
-          }
-          if ((a.debug & 3) == 2) pm = 0;
-          const uint32_t anyb = __ballot_sync(0xffffffffu, pm != 0u);
-          if (anyb) {  // compact this chunk's passers into the warp FIFO
-            // exclusive prefix of the per-lane passer counts from ballots of the count's bit planes (no shuffle chain);
-            // a lane with four or more passers in one chunk is rare and takes the scan
-            const uint32_t c = __popc(pm);
-            uint32_t excl, total;
-            const uint32_t bh = __ballot_sync(0xffffffffu, c >= 4u);
-            if (bh == 0u) {
-              const uint32_t b0 = __ballot_sync(0xffffffffu, (c & 1u) != 0u);
-              const uint32_t b1 = __ballot_sync(0xffffffffu, (c & 2u) != 0u);
-              excl = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
-              total = __popc(b0) + 2u * __popc(b1);
-            } else {
-              uint32_t incl = c;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)lane >= o) incl += y;
-              }
-              total = __shfl_sync(0xffffffffu, incl, 31);
-              excl = incl - c;
-            }
-            if (qn + total > (uint32_t)FS_QCAP && total <= (uint32_t)FS_QCAP) {
-              while (qn + total > (uint32_t)FS_QCAP) {  // make room (rare): run batches back to back
-                finish_batch();
-                if (qn) start_batch();
-              }
-            }
-            if (qn + total <= (uint32_t)FS_QCAP) {
-              // a passer stores its 8-byte hash (an aligned register pair); the tags of the `total` new records are
-              // written by the first lanes
-              const uint32_t tail = (qhead + qn) & (FS_QCAP - 1);
-              uint32_t at = tail + excl;
-#pragma unroll
-              for (int j = 0; j < FS_NHASH; ++j) {
-                if (pm & (1u << j)) {
-                  qh[at & (FS_QCAP - 1)] =
-                      (j & 1) ? make_uint2(v[j >> 1].z, v[j >> 1].w) : make_uint2(v[j >> 1].x, v[j >> 1].y);
-                  ++at;
-                }
-              }
-              if (lane < total) qt[(tail + lane) & (FS_QCAP - 1)] = fresh_tag;
-              if (total > 32u && lane + 32u < total) qt[(tail + lane + 32u) & (FS_QCAP - 1)] = fresh_tag;
-              if (FS_QCAP > 64)
-                for (uint32_t o = lane + 64u; o < total; o += 32u) qt[(tail + o) & (FS_QCAP - 1)] = fresh_tag;
-              qn += total;
-              outst += (uint64_t)total << (8 * par);
-              __syncwarp();
-            } else {  // a burst larger than the FIFO: look the passers up in place
-#pragma unroll
-              for (int j = 0; j < FS_NHASH; ++j) {
-                if (pm & (1u << j)) {
-                  count_now((j & 1) ? (((uint64_t)v[j >> 1].w << 32) | v[j >> 1].z)
-                                    : (((uint64_t)v[j >> 1].y << 32) | v[j >> 1].x), par);
-                }
-              }
-            }
-          }
-          // lookups: a batch is consumed one chunk after it was issued; the next one starts as soon as 32 passers
-          // are queued, or earlier when a finished row is about to need its buffer back
-          if (have_pend) finish_batch();
-          if (!have_pend && (qn >= 32u || (qn && (closing & urgent)))) start_batch();
-        }
-        it.next(a, r1);
-      }
-      closing |= 1u << par;  // this warp's part of the row is probed; closes when its lookups are resolved
-      try_close();
-    }
-    while (closing) {
-      finish_batch();
-      if (qn) start_batch();
-    }
-    return;
-  }
-
-  // ===== rank warps: cumulative sums over the reads of the pass, candidate test, new running sum =====
-  const uint32_t rp = warp - FS_CONSUMER_WARPS;  // residue of the rows this warp owns
-  const uint32_t per = a.cnt_stride >> 5;        // counters per lane in the segment view (multiple of 8)
+__device__ __forceinline__ void rank_row(const SkbFusedArgs& a, const FsCtl& ctl, const uint16_t* lbrel, uint32_t* cpar,
+                                         uint32_t cwords, uint32_t row_in_shard, unsigned long long carry,
+                                         uint32_t& slot_next, uint32_t& slot_left) {
+  const uint32_t lane = skb_lane();
+  const uint32_t per = a.cnt_stride >> 5;  // counters per lane in the segment view (multiple of 8)
   const uint32_t seg0 = lane * per;
-  const unsigned long long lb_min = a.lb_sum[0];  // bounds are non-decreasing along the reads
-  // The bounds are staged at every 4th read only (0.5 B of shared memory per read): read b is tested against the bound
-  // of read b & ~3, which is lower or equal, so the test can only add candidates; the per-read selection is exact over
-  // whatever it is given. On a tie with the bound the row index decides: here a row passes when its index does not
-  // exceed the LARGEST bound index of the reads the caller looks at (`li_cap`), again a superset and free of global
-  // loads (a load per tied read made single walks take 40 us).
+  const unsigned long long lb_min = ctl.lb_min;
   const unsigned long long lb_seg = seg0 < a.n_reads ? lb_min + lbrel[seg0 >> 2] : ~0ull;
-  uint32_t li_seg = 0;  // largest bound index in this lane's segment / in the whole pass
-  for (uint32_t b = seg0; b < min(seg0 + per, a.n_reads); ++b) li_seg = max(li_seg, a.lb_idx[b]);
-  const uint32_t li_all = __reduce_max_sync(0xffffffffu, li_seg);
+  const uint32_t li_seg = ctl.li_seg[lane];
   auto is_cand = [&](unsigned long long sv, uint32_t gi, uint32_t b, uint32_t li_cap) -> bool {
     const uint32_t rel = lbrel[b >> 2];
     const unsigned long long ls = rel != 0xFFFFu ? lb_min + rel : a.lb_sum[b & ~3u];  // saturated: read the bound
     return sv > ls || (sv == ls && gi <= li_cap);
   };
-  // Candidates leave the kernel as intervals "row gi holds sum sv and meets the bound for reads [b0, b1)": a
-  // contending row produces one record per hit instead of one per read, and slots are reserved 16 at a time per lane
-  // so the rank warp never waits on an atomic per candidate.
-  // (the first block of every lane comes from one reservation per warp: ten thousand lanes hitting the one counter at
-  // kernel start took tens of microseconds to drain)
-  uint32_t slot_next = 0, slot_left = 16;
-  {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(a.ivl_total, 512u);
-    slot_next = __shfl_sync(0xffffffffu, base, 0) + 16u * lane;
-  }
+  // interval slots are reserved 16 at a time per lane, on first use (most rows emit nothing)
   auto emit = [&](unsigned long long sv, uint32_t gi, uint32_t b0, uint32_t b1) {
     if (slot_left == 0) {
       slot_next = atomicAdd(a.ivl_total, 16u);
@@ -704,18 +346,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     }
     ++slot_next; --slot_left;
   };
-  unsigned long long carry_next = (r0 + rp < r1) ? a.sums_in[grow(r0 + rp)] : 0ull;
-  for (uint32_t row = r0 + rp; row < r1; row += FS_RANK_WARPS) {
-    const uint32_t lr = row - r0;
-    const unsigned long long carry = carry_next;
-    if (row + FS_RANK_WARPS < r1) carry_next = a.sums_in[grow(row + FS_RANK_WARPS)];  // in flight while this row is processed
-    const uint32_t rb = lr % FS_ROWBUF;
-    uint32_t* cpar = cnt32 + rb * cwords;
-    mbar_wait_sleepy(&row_done[rb], (lr / FS_ROWBUF) & 1u);
-    // per-lane segment totals of the row's counters; their sum is the row's total for the pass
-    const uint32_t* cseg = cpar + seg0 / CPW;
-    const uint32_t segw = per / CPW;  // words in this lane's segment (multiple of 4)
-    uint32_t tot = 0;
+  // per-lane segment totals of the row's counters; their sum is the row's total for the pass
+  const uint32_t* cseg = cpar ? cpar + seg0 / CPW : nullptr;
+  const uint32_t segw = per / CPW;  // words in this lane's segment (multiple of 4)
+  uint32_t tot = 0;
+  if (cpar) {
     for (uint32_t i = 0; i < segw; i += 4) {
       const uint4 x = *reinterpret_cast<const uint4*>(cseg + i);
       if (CPW == 2) {
@@ -730,74 +365,282 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
         }
       }
     }
-    const uint32_t row_total = __reduce_add_sync(0xffffffffu, tot);
-    if (lane == 0) a.sums_out[grow(row)] = carry + row_total;
-    const uint32_t gi = a.row_base + grow(row);
-    if (row_total) {
-      // sums and bounds never decrease along the reads: a row whose FINAL sum is under the FIRST bound, or a
-      // lane segment whose final sum is under the segment's first bound, cannot hold a candidate
-      if (carry + row_total >= lb_min && !(a.debug & 4)) {
-        uint32_t incl = tot;
+  }
+  const uint32_t row_total = __reduce_add_sync(0xffffffffu, tot);
+  if (lane == 0) a.sums_out[row_in_shard] = carry + row_total;
+  const uint32_t gi = a.row_base + row_in_shard;
+  if (row_total) {
+    // sums and bounds never decrease along the reads: a row whose FINAL sum is under the FIRST bound, or a
+    // lane segment whose final sum is under the segment's first bound, cannot hold a candidate
+    if (carry + row_total >= lb_min && !(SKB_X_ABLATE & 4)) {
+      uint32_t incl = tot;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-          if ((int)lane >= o) incl += y;
-        }
-        if (seg0 < a.n_reads && carry + incl >= lb_seg) {
-          // Walk the segment. Between two hits the row's sum is constant while the bound only tightens, so an
-          // interval opens at a hit (or at the segment start) and closes at the next hit or when the bound overtakes.
-          const uint32_t seg_end = min(seg0 + per, a.n_reads);
-          uint32_t run = incl - tot;
-          bool open = false, first = true;
-          uint32_t ob = 0;
-          unsigned long long os = 0;
-          for (uint32_t i = 0; i < segw; ++i) {
-            const uint32_t x = cseg[i];
-            if (x == 0u && !open && !first) continue;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += y;
+      }
+      if (seg0 < a.n_reads && carry + incl >= lb_seg) {
+        // Walk the segment. Between two hits the row's sum is constant while the bound only tightens, so an
+        // interval opens at a hit (or at the segment start) and closes at the next hit or when the bound overtakes.
+        const uint32_t seg_end = min(seg0 + per, a.n_reads);
+        uint32_t run = incl - tot;
+        bool open = false, first = true;
+        uint32_t ob = 0;
+        unsigned long long os = 0;
+        for (uint32_t i = 0; i < segw; ++i) {
+          const uint32_t x = cseg[i];
+          if (x == 0u && !open && !first) continue;
 #pragma unroll
-            for (int half = 0; half < CPW; ++half) {
-              const uint32_t c = CPW == 2 ? (half ? (x >> 16) : (x & 0xFFFFu)) : ((x >> (8 * half)) & 0xFFu);
-              const uint32_t b = seg0 + CPW * i + half;
-              if (b < seg_end) {
-                bool check = open || first;
-                first = false;
-                if (c) {
-                  if (open) { emit(os, gi, ob, b); open = false; }
-                  run += c;
-                  check = true;
-                }
-                if (check) {
-                  const unsigned long long sv = carry + run;
-                  const bool cand = sv >= lb_seg && is_cand(sv, gi, b, li_seg);
-                  if (cand && !open) { open = true; ob = b; os = sv; }
-                  if (!cand && open) { emit(os, gi, ob, b); open = false; }
-                }
+          for (int half = 0; half < CPW; ++half) {
+            const uint32_t c = CPW == 2 ? (half ? (x >> 16) : (x & 0xFFFFu)) : ((x >> (8 * half)) & 0xFFu);
+            const uint32_t b = seg0 + CPW * i + half;
+            if (b < seg_end) {
+              bool check = open || first;
+              first = false;
+              if (c) {
+                if (open) { emit(os, gi, ob, b); open = false; }
+                run += c;
+                check = true;
+              }
+              if (check) {
+                const unsigned long long sv = carry + run;
+                const bool cand = sv >= lb_seg && is_cand(sv, gi, b, li_seg);
+                if (cand && !open) { open = true; ob = b; os = sv; }
+                if (!cand && open) { emit(os, gi, ob, b); open = false; }
               }
             }
           }
-          if (open) emit(os, gi, ob, seg_end);
         }
-        __syncwarp();
+        if (open) emit(os, gi, ob, seg_end);
       }
-      // clear the buffer for row lr+4 (lane-interleaved 16-byte stores: no bank conflicts)
-      uint4* z = reinterpret_cast<uint4*>(cpar);
-      for (uint32_t i = lane; i < (cwords >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
-    } else if (carry >= lb_min && !(a.debug & 128)) {
-      // no hit in this pass: the row's sum is `carry` for every read, so it meets the bound for a prefix [0, e) of
-      // the reads (first passes of a stream, when most sums tie at the bound)
-      uint32_t e = 0;
-      for (uint32_t b0 = 0; b0 < a.n_reads; b0 += 32) {
-        const uint32_t b = b0 + lane;
-        const bool ok = b < a.n_reads && is_cand(carry, gi, b, li_all);
-        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        if (bal != 0xffffffffu) { e = b0 + (uint32_t)__ffs(~bal) - 1; break; }
-        e = b0 + 32;
-      }
-      if (e > a.n_reads) e = a.n_reads;
-      if (lane == 0 && e) emit(carry, gi, 0, e);
+      __syncwarp();
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&row_free[rb]);
+    // clear the buffer for the next row that uses it (lane-interleaved 16-byte stores: no bank conflicts)
+    uint4* z = reinterpret_cast<uint4*>(cpar);
+    for (uint32_t i = lane; i < (cwords >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
+  } else if (carry >= lb_min) {
+    // no hit in this pass: the row's sum is `carry` for every read, so it meets the bound for a prefix [0, e) of
+    // the reads (first passes of a stream, when most sums tie at the bound)
+    const uint32_t li_all = __reduce_max_sync(0xffffffffu, li_seg);
+    uint32_t e = 0;
+    for (uint32_t b0 = 0; b0 < a.n_reads; b0 += 32) {
+      const uint32_t b = b0 + lane;
+      const bool ok = b < a.n_reads && is_cand(carry, gi, b, li_all);
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      if (bal != 0xffffffffu) { e = b0 + (uint32_t)__ffs(~bal) - 1; break; }
+      e = b0 + 32;
+    }
+    if (e > a.n_reads) e = a.n_reads;
+    if (lane == 0 && e) emit(carry, gi, 0, e);
+  }
+  __syncwarp();
+}
+
+// CPW = counters per 32-bit word of a row buffer: 2 (u16, any pass) or 4 (u8, when no read of the pass keeps more than
+// 255 query hashes; more reads fit a pass).
+//
+// Persistent, one CTA per SM, each owning a contiguous range of reference rows. A row is cut into FS_SUB-hash
+// sub-tiles dealt round-robin to the CTA's warps. Every warp streams its sub-tiles through a PRIVATE ring of
+// cp.async.bulk (TMA) staging buffers that it refills itself, probes each hash against the filter in shared memory
+// (one LDS + a handful of integer instructions), and resolves the few passers on the spot: the lanes that hold one
+// look their hash up in the L2-resident table (a 16-byte load; the next passer's load is in flight while the
+// previous one is counted) and add the key's reads to the row's counters in shared memory. The warp whose sub-tile
+// completes a row turns its counters into the new running sum and the candidate intervals (rank_row) and hands the
+// buffer back. Nothing in the loop is warp-collective except the row hand-over, so a burst of hits in one warp does
+// not stall the others' streams. HBM traffic per pass = the reference matrix, once.
+template <int CPW>
+__global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[FS_WARPS][FS_STAGES];
+  __shared__ FsCtl ctl;
+
+  if (*a.abort) return;  // an earlier pass of this batch has to be redone: leave sums and candidates alone
+
+  uint32_t* bloom = reinterpret_cast<uint32_t*>(smem_raw);
+  uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM);
+  uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
+  const uint32_t cwords = a.cnt_stride / CPW;  // 32-bit words per row buffer
+  uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride / 4] bound growth since read 0 at every 4th read, saturating
+
+  // every `row` below is a CTA-local number; c0 + row is the row of the shard
+  const uint32_t c0 = a.cta_row[blockIdx.x];
+  const uint32_t r1 = a.cta_row[blockIdx.x + 1] - c0;
+
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < FS_WARPS; ++w)
+      for (int s = 0; s < FS_STAGES; ++s) mbar_init(&full_bar[w][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ctl.lb_min = a.lb_sum[0];
+  }
+  if (threadIdx.x < FS_ROWBUF) { ctl.done[threadIdx.x] = 0; ctl.freed[threadIdx.x] = 0; ctl.carry[threadIdx.x] = 0; }
+  if (threadIdx.x < 32) ctl.li_seg[threadIdx.x] = 0;
+  if (!a.skip_stream) {  // stage the filter
+    const uint4* src = reinterpret_cast<const uint4*>(a.table.bloom);
+    uint4* dst = reinterpret_cast<uint4*>(bloom);
+    for (uint32_t i = threadIdx.x; i < SKB_BLOOM_WORDS / 4; i += blockDim.x) dst[i] = src[i];
+  }
+  for (uint32_t i = threadIdx.x; i < FS_ROWBUF * cwords; i += blockDim.x) cnt32[i] = 0;
+  for (uint32_t i = threadIdx.x; 4u * i < a.n_reads; i += blockDim.x) lbrel[i] = (uint16_t)min(a.lb_rel[4u * i], 0xFFFFu);
+  __syncthreads();
+  {
+    const uint32_t per = a.cnt_stride >> 5;
+    for (uint32_t b = threadIdx.x; b < a.n_reads; b += blockDim.x) atomicMax(&ctl.li_seg[b / per], a.lb_idx[b]);
+  }
+  __syncthreads();
+
+  const uint32_t warp = threadIdx.x >> 5, lane = skb_lane();
+  uint32_t slot_next = 0, slot_left = 0;  // this lane's reserved interval slots
+
+  if (a.skip_stream) {  // the pass has no query hashes: rows are ranked from their running sums alone
+    for (uint32_t row = warp; row < r1; row += FS_WARPS)
+      rank_row<CPW>(a, ctl, lbrel, nullptr, cwords, c0 + row, a.sums_in[c0 + row], slot_next, slot_left);
+  } else {
+    const SkbTable& t = a.table;
+    const uint4* tslots = reinterpret_cast<const uint4*>(t.slots);
+    const uint32_t tcap = t.cap, tlog2 = t.log2cap;
+    uint8_t* my_ring = reinterpret_cast<uint8_t*>(ring + (size_t)warp * FS_STAGES * FS_SUB);
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    // bulk copy of the sub-tile `si` points at into one of this warp's staging buffers (lane 0 only)
+    auto issue_copy = [&](const SubIter& si, uint32_t stage) {
+      const uint32_t first = si.t * FS_SUB;
+      uint32_t n = si.len - first;
+      if (n > (uint32_t)FS_SUB) n = FS_SUB;
+      const uint32_t bytes = ((n + 1u) & ~1u) * 8u;  // multiple of 16; rows start on even offsets
+      mbar_arrive_expect_tx(&full_bar[warp][stage], bytes);
+      if (bytes) bulk_load(my_ring + (size_t)stage * FS_SUB * 8, si.p + first, bytes, &full_bar[warp][stage], policy);
+    };
+
+    SubIter it, pre;
+    it.c0 = c0;
+    it.row = 0;
+    it.t = warp;
+    it.load_row(a, r1);
+    it.settle(a, r1);
+    pre = it;
+    for (uint32_t s = 0; s < (uint32_t)FS_STAGES; ++s) {  // prime the private ring
+      if (pre.row < r1) {
+        if (lane == 0) issue_copy(pre, s);
+        pre.next(a, r1);
+      }
+    }
+    uint32_t k = 0;  // sub-tiles consumed by this warp: stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1
+    uint32_t cur_row = 0xFFFFFFFFu, par = 0;
+    uint32_t* cb = cnt32;
+
+    while (it.row < r1) {
+      unsigned long long carry_pref = 0;
+      const bool opens = it.t == 0;  // this warp holds the row's first sub-tile: it fetches the row's running sum
+      if (it.row != cur_row) {
+        cur_row = it.row;
+        par = cur_row % FS_ROWBUF;
+        cb = cnt32 + par * cwords;
+        if (cur_row >= (uint32_t)FS_ROWBUF) {  // the buffer's previous row must have been ranked and cleared
+          const uint32_t need = cur_row / FS_ROWBUF;
+          if (lane == 0)
+            while (lds_acquire_u32(&ctl.freed[par]) < need) __nanosleep(64);
+          __syncwarp();
+        }
+      }
+      if (opens && lane == 0) carry_pref = a.sums_in[c0 + cur_row];  // in flight while the sub-tile is probed
+      const uint32_t stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1u;
+      mbar_wait(&full_bar[warp][stage], phase);
+      const uint8_t* tile = my_ring + (size_t)stage * FS_SUB * 8;
+      const uint32_t n_sub = it.len - it.t * FS_SUB;  // >= FS_SUB for every sub-tile but a row's last
+#pragma unroll 1
+      for (uint32_t ch = 0; ch < (uint32_t)FS_CHUNKS; ++ch) {
+        const uint32_t base = ch * FS_NHASH * 32;  // first hash index of the chunk within the sub-tile
+        if (base >= n_sub) break;
+        const uint8_t* cbase = tile + (size_t)base * 8 + lane * 16;
+        uint4 v[FS_NHASH / 2];
+#pragma unroll
+        for (int r = 0; r < FS_NHASH / 2; ++r) v[r] = *reinterpret_cast<const uint4*>(cbase + 512 * r);
+        uint32_t pm = 0;  // bit 7 - j: this lane's j-th hash of the chunk passed the filter
+        if (!(SKB_X_ABLATE & 1)) {
+          if (n_sub >= base + FS_NHASH * 32) {
+#pragma unroll
+            for (int j = 0; j < FS_NHASH; ++j) {
+              const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
+              const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
+              pm = __funnelshift_l(bloom_probe(bloom, lo, hi), pm, 1);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < FS_NHASH; ++j) {
+              const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
+              const uint32_t idx = base + 2u * (lane + 32 * (j >> 1)) + (j & 1);
+              const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
+              pm = __funnelshift_l(idx < n_sub ? bloom_probe(bloom, lo, hi) : 0u, pm, 1);
+            }
+          }
+        }
+        if (SKB_X_ABLATE & 2) pm = 0;
+        // Divergent: only the lanes that hold a passer run this, two passers per trip. A passer's hash is read back
+        // from the staging buffer by its position (hash j of the chunk sits at byte (j >> 1) * 512 + (j & 1) * 8 of the
+        // lane's column), both table loads are issued before either is resolved, so a lane pays the L2 latency once
+        // per trip; a slot owned by another key is chased in place (load factor 0.125: rare).
+        while (pm) {
+          const uint32_t b0 = 31u - (uint32_t)__clz((int)pm);
+          pm &= ~(1u << b0);
+          const bool two = pm != 0u;
+          const uint32_t b1 = two ? 31u - (uint32_t)__clz((int)pm) : b0;
+          pm &= ~(1u << b1);
+          // bit b holds hash j = 7 - b: offset 0x608 - ((b * 0x108) & 0x608)
+          const uint2 e0 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b0 * 0x108u) & 0x608u));
+          const uint2 e1 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b1 * 0x108u) & 0x608u));
+          const uint64_t h0 = ((uint64_t)e0.y << 32) | e0.x, h1 = ((uint64_t)e1.y << 32) | e1.x;
+          uint32_t s0 = h0 == SKB_EMPTY_KEY ? tcap : table_home(h0, tlog2);
+          uint32_t s1 = h1 == SKB_EMPTY_KEY ? tcap : table_home(h1, tlog2);
+          uint4 r0 = __ldg(tslots + s0);
+          uint4 r1 = __ldg(tslots + s1);
+          for (;;) {  // walk the probe sequence until the key or an empty slot
+            const uint64_t key = ((uint64_t)r0.y << 32) | r0.x;
+            if (key == h0) { apply_hit<CPW>(t, ((unsigned long long)r0.w << 32) | r0.z, cb); break; }
+            if (key == SKB_EMPTY_KEY) break;
+            s0 = (s0 + 1) & (tcap - 1);
+            r0 = __ldg(tslots + s0);
+          }
+          if (two) {
+            for (;;) {
+              const uint64_t key = ((uint64_t)r1.y << 32) | r1.x;
+              if (key == h1) { apply_hit<CPW>(t, ((unsigned long long)r1.w << 32) | r1.z, cb); break; }
+              if (key == SKB_EMPTY_KEY) break;
+              s1 = (s1 + 1) & (tcap - 1);
+              r1 = __ldg(tslots + s1);
+            }
+          }
+        }
+      }
+      // the staging buffer is fully read: refill it with this warp's next sub-tile
+      __syncwarp();
+      if (pre.row < r1) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue_copy(pre, stage);
+        }
+        pre.next(a, r1);
+      }
+      ++k;
+      // this sub-tile's hits are in shared memory: count it done; the warp that completes the row ranks it
+      uint32_t last = 0;
+      if (lane == 0) {
+        if (opens) ctl.carry[par] = carry_pref;
+        __threadfence_block();
+        last = atomicAdd(&ctl.done[par], 1u) + 1u == SubIter::tiles_of(it.len) ? 1u : 0u;
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        __threadfence_block();
+        const unsigned long long carry = ctl.carry[par];
+        rank_row<CPW>(a, ctl, lbrel, cb, cwords, c0 + cur_row, carry, slot_next, slot_left);
+        if (lane == 0) {
+          ctl.done[par] = 0;
+          __threadfence_block();
+          atomicAdd(&ctl.freed[par], 1u);
+        }
+      }
+      it.next(a, r1);
+    }
   }
   // hand back the unused part of the last reservation as empty intervals
   for (; slot_left; --slot_left, ++slot_next) {
@@ -821,7 +664,7 @@ __global__ void __launch_bounds__(256) tracked_counts_kernel(const SkbRefView rv
   uint32_t* cbuf = reinterpret_cast<uint32_t*>(ctr + (size_t)tr * stride);
   for (uint32_t i = part * blockDim.x + threadIdx.x; i < len; i += 8 * blockDim.x) {
     SkbSlot s;
-    if (table_lookup(t, src[i], s)) apply_hit<2>(t, s, cbuf);
+    if (table_lookup(t, src[i], s)) apply_hit<2>(t, s.meta, cbuf);
   }
 }
 
@@ -1213,17 +1056,17 @@ void skb_launch_memb_build(const SkbRefView& rv, uint32_t* memb, uint32_t memb_l
 }
 
 size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 2 * FS_ROWBUF + (size_t)cnt_stride / 2;
+  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 2 * FS_ROWBUF + (size_t)cnt_stride / 2;
 }
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + (size_t)cnt_stride * 1 * FS_ROWBUF + (size_t)cnt_stride / 2;
+  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 1 * FS_ROWBUF + (size_t)cnt_stride / 2;
 }
 uint32_t skb_fused_tile() { return FS_SUB; }
-// Largest pass the kernel's shared memory holds: 227 KB per CTA minus the static barriers, the filter, the staging
-// rings and the FIFOs leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each) plus the bounds staged at
+// Largest pass the kernel's shared memory holds: 227 KB per CTA minus the static barriers and bookkeeping, the filter
+// and the staging rings leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each) plus the bounds staged at
 // every 4th read (0.5 B per read). Pass-local read ids are SKB_SLOT_ID_BITS wide in a table slot: that caps it either way.
 uint32_t skb_fused_max_reads(int narrow) {
-  const size_t fixed = FS_SMEM_BLOOM + FS_SMEM_RING + FS_SMEM_QUEUE + 1024;  // 1 KB: static barriers + slack
+  const size_t fixed = FS_SMEM_BLOOM + FS_SMEM_RING + 1024;  // 1 KB: static barriers + slack
   const size_t budget = 232448;                                             // opt-in maximum per CTA on sm_100
   if (fixed >= budget) return 0;
   const size_t per2 = (narrow ? 2 * FS_ROWBUF : 4 * FS_ROWBUF) + 1;         // bytes per read, times two
