@@ -161,7 +161,7 @@ struct skb_ctx {
   cudaStream_t copy_stream = nullptr;  // batch staging (H2D): lets skb_batch_stage overlap a predict running on `stream`
   std::string err;
   // reference shard
-  DevBuf ref, row_start, row_len, cta_row, memb;
+  DevBuf ref, row_start, row_len, cta_row, tile_cum, memb;
   uint32_t memb_log2 = 0;  // 0 = no membership prefilter
   uint64_t ref_len = 0;  // hashes in the shard (without alignment padding)
   uint32_t n_rows = 0, row_base = 0, uniform_len = 0, uniform_pitch = 0;
@@ -177,7 +177,7 @@ struct skb_ctx {
   DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, cand_pool;
   DevBuf sk_hashes, sk_counts;
   // predict scratch
-  DevBuf q_off, qh, qread, counts, lb_sum, lb_rel, lb_idx, cand, cand_cnt, ivl, scal;
+  DevBuf q_off, qh, qread, counts, lb_sum, lb_idx, cand, cand_cnt, ivl, seg_hdr, seg_words, scal;
   DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
@@ -592,6 +592,11 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
     }
     CU(c, c->cta_row.ensure((G + 1) * 4));
     CU(c, cudaMemcpy(c->cta_row.p, cta.data(), (G + 1) * 4, cudaMemcpyHostToDevice));
+    // sub-tiles before each row: how a CTA of the streaming kernel maps a claimed sub-tile number to its row
+    if (cum[n_rows] > 0xFFFFFFF0ull) return fail(c, SKB_ERR_INVALID_ARG, "reference shard too large (sub-tile count)");
+    std::vector<uint32_t> cum32(cum.begin(), cum.end());
+    CU(c, c->tile_cum.ensure(((size_t)n_rows + 1) * 4));
+    CU(c, cudaMemcpy(c->tile_cum.p, cum32.data(), ((size_t)n_rows + 1) * 4, cudaMemcpyHostToDevice));
   }
   CU(c, c->sums[0].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
   CU(c, c->sums[1].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
@@ -670,8 +675,8 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   struct PassRec { uint32_t r, B; int sums_cur, tracked_cur; };
   std::vector<PassRec> recs;
   uint32_t* d_abort = c->scal.as<uint32_t>() + 24;
-  CU(c, cudaMemsetAsync(d_abort, 0, 16, c->stream));
-  CU(c, cudaMemsetAsync(d_cand_total, 0, 8, c->stream));  // bucket-overflow flag + interval slot counter (the verdict kernel clears them after every pass)
+  CU(c, cudaMemsetAsync(d_abort, 0, 32, c->stream));
+  CU(c, cudaMemsetAsync(d_cand_total, 0, 12, c->stream));  // bucket-overflow flag + interval slot counter (the verdict kernel clears them after every pass)
   const uint32_t kBatch = 8;
   bool force_sync = false;  // after a rollback: one pass at a time until the pass size is back at its maximum
   uint32_t seq = 0;
@@ -699,7 +704,9 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     cudaError_t e;
     if ((e = c->counts.ensure(ctr_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
         (e = c->lb_idx.ensure((size_t)B * 4)) != cudaSuccess || (e = c->cand_cnt.ensure((size_t)B * 4)) != cudaSuccess ||
-        (e = c->lb_rel.ensure((size_t)B * 4)) != cudaSuccess || (e = c->ivl.ensure((size_t)SKB_IVL_CAP * sizeof(SkbInterval))) != cudaSuccess ||
+        (e = c->ivl.ensure((size_t)SKB_IVL_CAP * sizeof(SkbInterval))) != cudaSuccess ||
+        (e = c->seg_hdr.ensure((size_t)SKB_SEG_CAP * 16)) != cudaSuccess ||
+        (e = c->seg_words.ensure((size_t)SKB_SEG_CAP * SKB_SEG_WORDS_MAX * 4)) != cudaSuccess ||
         (e = c->cand.ensure((size_t)B * c->cand_cap * sizeof(SkbCand))) != cudaSuccess ||
         (e = c->tprefix.ensure((size_t)SKB_MAX_TRACKED * stride * 4)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
@@ -716,25 +723,32 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     ra.row_stride = stride; ra.n_reads = B; ra.row_base = c->row_base;
     ra.sums_in = c->sums[c->sums_cur].as<unsigned long long>();
     ra.tracked = c->tracked[c->tracked_cur].as<uint32_t>(); ra.n_tracked = ra.tracked + SKB_MAX_TRACKED;
-    ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>(); ra.lb_rel = c->lb_rel.as<uint32_t>();
+    ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>();
     ra.ivl = c->ivl.as<SkbInterval>(); ra.ivl_cap = SKB_IVL_CAP; ra.ivl_total = d_cand_total + 1;
+    ra.seg_hdr = c->seg_hdr.as<uint4>(); ra.seg_words = c->seg_words.as<uint32_t>(); ra.seg_cap = SKB_SEG_CAP;
+    ra.seg_cpw = narrow ? 4 : 2; ra.seg_words_per = stride / 32 / ra.seg_cpw; ra.seg_total = d_cand_total + 2;
     ra.cand = c->cand.as<SkbCand>(); ra.cand_cap = c->cand_cap; ra.cand_total = d_cand_total;
     ra.cand_cnt = c->cand_cnt.as<uint32_t>(); ra.cand_stat = d_cand_stat;
     ra.top = top; ra.out_idx = d_out_idx + (size_t)r * top;
     ra.out_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)r * top;
     ra.tracked_next = c->tracked[c->tracked_cur ^ 1].as<uint32_t>(); ra.n_tracked_next = ra.tracked_next + SKB_MAX_TRACKED;
     ra.abort = d_abort; ra.seq = seq;
-    { ProfScope ps(c, SKB_K_RANK, nkeys ? 4 : 3);
+    { ProfScope ps(c, SKB_K_RANK, nkeys ? 3 : 2);
       if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, ra.n_tracked, t, c->counts.as<uint16_t>(), stride, c->stream);
       skb_launch_rank_bounds(ra, c->stream); }
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
     fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
     fa.sums_in = ra.sums_in; fa.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
-    fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx; fa.lb_rel = ra.lb_rel;
+    fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx;
     fa.ivl = c->ivl.as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_cand_total + 1; fa.abort = d_abort;
+    fa.seg_hdr = c->seg_hdr.as<uint4>(); fa.seg_words = c->seg_words.as<uint32_t>(); fa.seg_cap = SKB_SEG_CAP;
+    fa.seg_total = d_cand_total + 2;
+    fa.tile_cum = c->tile_cum.as<uint32_t>();
+    fa.tpr = std::max(1u, (c->uniform_len + skb_fused_tile() - 1) / skb_fused_tile());
+    fa.tpr_magic = (uint32_t)((0x100000000ull + fa.tpr - 1) / fa.tpr);
     { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
-    { ProfScope ps(c, SKB_K_RANK, 4);
+    { ProfScope ps(c, SKB_K_RANK, 5);
       skb_launch_rank_expand(ra, c->stream); skb_launch_rank_select(ra, c->stream);
       skb_launch_pass_verdict(ra, c->stream);
       skb_launch_tracked_update(ra, c->stream); }  // from this pass's top lists (skipped on the device after an overflow)
@@ -748,7 +762,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     const bool batchable = !force_sync && B > 1 && c->pass_cur >= c->pass_max;
     if (batchable && recs.size() < kBatch && r < R) continue;
     // ---- checkpoint: did any pass since the last one overflow?
-    if ((e = cudaMemcpyAsync(h_total, d_abort, 16, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+    if ((e = cudaMemcpyAsync(h_total, d_abort, 32, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e));
       break;
@@ -756,10 +770,10 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     if (h_total[0] != 0) {  // more contenders than a bucket / the interval list holds, in the pass numbered h_total[1]
       const PassRec& pr = recs[recs.size() - (seq - h_total[1])];
       if (getenv("SKB_TRACE_PASSES"))
-        fprintf(stderr, "[skb] pass at read %u with %u reads overflowed (bucket flag %u, intervals %u of %u): redo with %u\n", pr.r, pr.B,
-                h_total[2], h_total[3], (unsigned)SKB_IVL_CAP, std::max(1u, pr.B / 2));
+        fprintf(stderr, "[skb] pass at read %u with %u reads overflowed (fullest bucket %u of %u, intervals %u of %u, segment records %u of %u): redo with %u\n", pr.r, pr.B,
+                h_total[2], c->cand_cap, h_total[3], (unsigned)SKB_IVL_CAP, h_total[4], (unsigned)SKB_SEG_CAP, std::max(1u, pr.B / 2));
       c->st_passes -= (seq - h_total[1]) - 1;  // the passes behind the failed one did not run
-      cudaMemsetAsync(d_abort, 0, 16, c->stream);
+      cudaMemsetAsync(d_abort, 0, 32, c->stream);
       if (pr.B > 1) {
         // redo from that pass with fewer reads: the bounds tighten after every pass
         r = pr.r; c->sums_cur = pr.sums_cur; c->tracked_cur = pr.tracked_cur;
@@ -787,7 +801,10 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
       const uint64_t grown = std::min<uint64_t>(c->pass_max, (uint64_t)std::max(lastB, c->pass_cur) * 2);
       const uint64_t cap_grown = std::min<uint64_t>(std::max<uint32_t>(c->n_rows, 64), budget / std::max<uint64_t>(grown, 1));
       // (a short last pass of a call says little about a full one: it never grows the pass)
-      if (lastB >= c->pass_cur && (2ull * h_total[2] <= cap_grown || cap_grown >= c->n_rows)) c->pass_cur = (uint32_t)grown;
+      // (and the interval / segment-record lists: their length follows the lane segments that reach a bound, which
+      // at worst doubles with the reads while the pass is below 32 segments of 16 reads)
+      const bool lists_ok = 2ull * h_total[3] <= SKB_IVL_CAP && 2ull * h_total[4] <= SKB_SEG_CAP;
+      if (lastB >= c->pass_cur && lists_ok && (2ull * h_total[2] <= cap_grown || cap_grown >= c->n_rows)) c->pass_cur = (uint32_t)grown;
       else c->pass_cur = std::max(lastB, c->pass_cur);
       if (c->pass_cur >= c->pass_max) force_sync = false;
     }
@@ -841,7 +858,7 @@ void skb_destroy(skb_ctx* c) {
   DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->memb, &c->sums[0], &c->sums[1], &c->tracked[0], &c->tracked[1], &c->tprefix, &c->g_tau, &c->g_cap,
                     &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->cand_pool,
                     &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->lb_sum,
-                    &c->lb_idx, &c->lb_rel, &c->ivl, &c->cand, &c->cand_cnt, &c->scal,
+                    &c->lb_idx, &c->ivl, &c->seg_hdr, &c->seg_words, &c->tile_cum, &c->cand, &c->cand_cnt, &c->scal,
                     &c->t_slots, &c->t_fill, &c->t_reads, &c->t_slot, &c->t_bloom, &c->out_idx,
                     &c->out_sum, &c->misc};
   for (DevBuf* b : bufs) b->release();

@@ -117,17 +117,24 @@ struct SkbFusedArgs {
   const unsigned long long* sums_in;  // [n_rows]
   unsigned long long* sums_out;       // [n_rows]
   const unsigned long long* lb_sum;   // [n_reads] lower bound of every read's top-th key
-  const uint32_t* lb_rel;             // [n_reads] lb_sum[b] - lb_sum[0] (staged in shared memory by the kernel)
   const uint32_t* lb_idx;             // [n_reads]
-  SkbInterval* ivl;                   // [ivl_cap] candidate intervals produced by the rank warps
+  SkbInterval* ivl;                   // [ivl_cap] candidate intervals (a lane segment without hits that meets its bound)
   uint32_t ivl_cap;
-  uint32_t* ivl_total;                // [1] slots reserved (16 at a time); > ivl_cap = overflow
+  uint32_t* ivl_total;                // [1] intervals produced; > ivl_cap = overflow
+  uint4* seg_hdr;                     // [seg_cap] segment records: {sum at segment start (lo, hi), global row, first read}
+  uint32_t* seg_words;                // [seg_cap][cnt_stride / 32 / counters-per-word] the segment's counters
+  uint32_t seg_cap;
+  uint32_t* seg_total;                // [1] records produced; > seg_cap = overflow
+  const uint32_t* tile_cum;           // [n_rows + 1] sub-tiles before each row of the shard (ragged shards only)
+  uint32_t tpr, tpr_magic;            // uniform shards: sub-tiles per row and ceil(2^32 / tpr) (tile -> row by a multiply)
   const uint32_t* abort;              // [2] {set once an earlier pass of the batch overflowed, its sequence number}: skip
 };
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
 size_t skb_fused_smem_bytes(uint32_t cnt_stride);
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride);
 #define SKB_IVL_CAP ((4u << 20) << (SKB_X_IDBITS - 12))  // candidate intervals per pass (4 M per 4096 reads); more than that shrinks the pass
+#define SKB_SEG_CAP (2u << 20)     // segment records per pass (16 + up to 160 bytes each)
+#define SKB_SEG_WORDS_MAX 40u      // counters of one lane segment, in words: 4096 / 32 / 4 (u8) or 2560 / 32 / 2 (u16)
 uint32_t skb_fused_tile();
 uint32_t skb_fused_max_reads(int narrow);
 
@@ -148,11 +155,14 @@ struct SkbRankArgs {
   const uint32_t* tracked;             // [*n_tracked] local rows
   const uint32_t* n_tracked;           // device scalar, <= SKB_MAX_TRACKED
   unsigned long long* lb_sum;          // [n_reads]
-  uint32_t* lb_rel;                    // [n_reads] lb_sum[b] - lb_sum[0]
   uint32_t* lb_idx;                    // [n_reads] (global index)
   const SkbInterval* ivl;              // candidate intervals of the pass
   uint32_t ivl_cap;
   const uint32_t* ivl_total;
+  const uint4* seg_hdr;                // segment records of the pass (see SkbFusedArgs)
+  const uint32_t* seg_words;
+  uint32_t seg_cap, seg_words_per, seg_cpw;
+  const uint32_t* seg_total;
   SkbCand* cand;                       // [n_reads][cand_cap] per-read candidate buckets
   uint32_t cand_cap;
   uint32_t* cand_total;                // [1] overflow flag
@@ -169,7 +179,7 @@ struct SkbRankArgs {
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st);
 // tracked rows of the next pass = union of the top lists of 16 sampled reads of this pass (last read first)
 void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st);
-void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st);  // intervals -> per-read candidate buckets
+void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st);  // segment records + intervals -> per-read candidate buckets
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st);  // per-read top-N
 // after a pass: record the first pass whose candidates overflowed (abort[0] = 1, abort[1] = seq) and clear the pass's
 // overflow counters; passes enqueued behind a failed one leave the running sums and the tracked rows untouched

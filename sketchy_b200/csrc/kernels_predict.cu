@@ -179,7 +179,7 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 #define SKB_X_CW 16
 #endif
 #ifndef SKB_X_ROWBUF
-#define SKB_X_ROWBUF 6
+#define SKB_X_ROWBUF 8
 #endif
 #ifndef SKB_X_ABLATE
 #define SKB_X_ABLATE 0  // experiments only (never in the shipped build): 1 = no filter probe, 2 = probe but drop the passers, 4 = no candidate walk
@@ -259,96 +259,41 @@ __device__ __forceinline__ void apply_hit(const SkbTable& t, unsigned long long 
   }
 }
 
-// A warp's sub-tiles: global sub-tile numbers w, w + FS_WARPS, ... over the CTA's rows (a shared claim counter was
-// tried instead in round 1: the claim's round trip cost 7 %). An empty row counts as one sub-tile of zero hashes so
-// that it is still closed and ranked by somebody.
-struct SubIter {
-  uint32_t row, t;    // current row (CTA-local number), sub-tile within it
-  uint32_t len;       // hashes in the current row
-  const uint64_t* p;  // first hash of the current row
-  uint32_t c0;        // local row lr is row c0 + lr of the shard
-  __device__ __forceinline__ static uint32_t tiles_of(uint32_t len) {
-    const uint32_t n = (len + FS_SUB - 1) / FS_SUB;
-    return n ? n : 1u;
-  }
-  __device__ __forceinline__ void load_row(const SkbFusedArgs& a, uint32_t r1) {
-    if (row >= r1) { len = 0; p = a.rv.ref; return; }
-    const uint32_t g = c0 + row;
-    if (a.rv.uniform_len) {
-      len = a.rv.uniform_len;
-      p = a.rv.ref + (size_t)g * a.rv.uniform_pitch;
-    } else {
-      len = a.rv.row_len[g];
-      p = a.rv.ref + a.rv.row_start[g];
-    }
-  }
-  __device__ __forceinline__ void settle(const SkbFusedArgs& a, uint32_t r1) {
-    while (row < r1) {
-      const uint32_t n = tiles_of(len);
-      if (t < n) break;
-      t -= n;
-      ++row;
-      load_row(a, r1);
-    }
-  }
-  __device__ __forceinline__ void next(const SkbFusedArgs& a, uint32_t r1) {
-    t += FS_WARPS;
-    if (a.rv.uniform_len) {  // every row has the same number of sub-tiles (>= 1): no loads, no loop of loads
-      const uint32_t n = tiles_of(a.rv.uniform_len);
-      while (t >= n && row < r1) { t -= n; ++row; p += a.rv.uniform_pitch; }
-      return;
-    }
-    settle(a, r1);
-  }
-};
-
 // Row bookkeeping of one CTA (static shared memory).
 struct FsCtl {
-  unsigned long long carry[FS_ROWBUF];  // running sum of the row in each buffer before this pass
-  unsigned long long lb_min;            // bound of read 0 (bounds never decrease along the reads)
-  uint32_t done[FS_ROWBUF];             // sub-tiles of the buffer's current row that are fully counted
-  uint32_t freed[FS_ROWBUF];            // rows of this buffer that have been ranked (the buffer is zero again)
-  uint32_t li_seg[32];                  // largest bound index within each lane segment of the reads
+  unsigned long long lb_seg[32];  // bound of the first read of each lane segment (bounds never decrease along the reads)
+  uint32_t li_seg[32];            // largest bound index within each lane segment of the reads
+  uint32_t done[FS_ROWBUF];       // sub-tiles of the buffer's current row that are fully counted
+  uint32_t freed[FS_ROWBUF];      // rows of this buffer that have been ranked (the buffer is zero again)
+  uint32_t next_tile;             // next unclaimed sub-tile of the CTA's rows (claimed in order)
+  uint4 desc[FS_WARPS][FS_STAGES];  // sub-tile staged in each ring slot: {row (CTA-local), tile in row, row length, -}
 };
+constexpr uint32_t FS_NONE = 0xFFFFFFFFu;
 
-// Rank work for one finished row, done by the warp whose sub-tile completed it: the counters' total is the row's
-// new running sum; if the row can reach any read's bound, its counters are prefix-scanned and candidate intervals
-// "row gi holds sum sv and meets the bound for reads [b0, b1)" are emitted against the bounds staged in shared memory.
-// The bounds are staged at every 4th read only (0.5 B per read): read b is tested against the bound of read b & ~3,
-// which is lower or equal, so the test can only add candidates; the per-read selection is exact over whatever it is
-// given. On a tie with the bound the row index decides: a row passes when its index does not exceed the LARGEST bound
-// index of the reads in question (`li_cap`), again a superset and free of global loads.
+__device__ __forceinline__ uint32_t fs_tiles_of(uint32_t len) {  // an empty row still has one (empty) sub-tile:
+  const uint32_t n = (len + FS_SUB - 1) / FS_SUB;                 // somebody has to close and rank it
+  return n ? n : 1u;
+}
+
+// Rank work for one finished row, done by the warp whose sub-tile completed it. It is deliberately short, because
+// the row's counter buffer is held meanwhile: the counters' total gives the row's new running sum; a lane segment
+// of the reads (cnt_stride / 32 consecutive reads) whose final sum reaches the bound of the segment's first read
+// may hold top-N candidates and is handed to the post-pass kernels, which test every read against its exact bound:
+//   - a segment with hits is copied out as a record {sum at segment start, row, first read, the segment's counters}
+//     (walk_kernel);
+//   - a segment without hits holds one sum for all its reads: an interval (expand_kernel).
+// Sums and bounds never decrease along the reads, so a segment (or a row) whose FINAL sum is under its FIRST bound
+// cannot hold a candidate. On a tie the row index decides: the segment passes when the row's index does not exceed
+// the largest bound index within it (a superset; the exact test comes later).
 template <int CPW>
-__device__ __forceinline__ void rank_row(const SkbFusedArgs& a, const FsCtl& ctl, const uint16_t* lbrel, uint32_t* cpar,
-                                         uint32_t cwords, uint32_t row_in_shard, unsigned long long carry,
-                                         uint32_t& slot_next, uint32_t& slot_left) {
+__device__ __forceinline__ void rank_row(const SkbFusedArgs& a, const FsCtl& ctl, uint32_t* cpar, uint32_t cwords,
+                                         uint32_t row_in_shard) {
   const uint32_t lane = skb_lane();
-  const uint32_t per = a.cnt_stride >> 5;  // counters per lane in the segment view (multiple of 8)
+  const uint32_t per = a.cnt_stride >> 5;  // reads per lane segment (multiple of 16)
   const uint32_t seg0 = lane * per;
-  const unsigned long long lb_min = ctl.lb_min;
-  const unsigned long long lb_seg = seg0 < a.n_reads ? lb_min + lbrel[seg0 >> 2] : ~0ull;
-  const uint32_t li_seg = ctl.li_seg[lane];
-  auto is_cand = [&](unsigned long long sv, uint32_t gi, uint32_t b, uint32_t li_cap) -> bool {
-    const uint32_t rel = lbrel[b >> 2];
-    const unsigned long long ls = rel != 0xFFFFu ? lb_min + rel : a.lb_sum[b & ~3u];  // saturated: read the bound
-    return sv > ls || (sv == ls && gi <= li_cap);
-  };
-  // interval slots are reserved 16 at a time per lane, on first use (most rows emit nothing)
-  auto emit = [&](unsigned long long sv, uint32_t gi, uint32_t b0, uint32_t b1) {
-    if (slot_left == 0) {
-      slot_next = atomicAdd(a.ivl_total, 16u);
-      slot_left = 16;
-    }
-    if (slot_next < a.ivl_cap) {
-      SkbInterval iv;
-      iv.sum = sv; iv.idx = gi; iv.span = b0 | (b1 << 16);
-      a.ivl[slot_next] = iv;
-    }
-    ++slot_next; --slot_left;
-  };
-  // per-lane segment totals of the row's counters; their sum is the row's total for the pass
-  const uint32_t* cseg = cpar ? cpar + seg0 / CPW : nullptr;
   const uint32_t segw = per / CPW;  // words in this lane's segment (multiple of 4)
+  const unsigned long long carry = a.sums_in[row_in_shard];
+  const uint32_t* cseg = cpar ? cpar + seg0 / CPW : nullptr;
   uint32_t tot = 0;
   if (cpar) {
     for (uint32_t i = 0; i < segw; i += 4) {
@@ -369,69 +314,43 @@ __device__ __forceinline__ void rank_row(const SkbFusedArgs& a, const FsCtl& ctl
   const uint32_t row_total = __reduce_add_sync(0xffffffffu, tot);
   if (lane == 0) a.sums_out[row_in_shard] = carry + row_total;
   const uint32_t gi = a.row_base + row_in_shard;
-  if (row_total) {
-    // sums and bounds never decrease along the reads: a row whose FINAL sum is under the FIRST bound, or a
-    // lane segment whose final sum is under the segment's first bound, cannot hold a candidate
-    if (carry + row_total >= lb_min && !(SKB_X_ABLATE & 4)) {
-      uint32_t incl = tot;
+  const unsigned long long fin = carry + row_total;
+  const unsigned long long lb_min = ctl.lb_seg[0];
+  if (fin > lb_min || (fin == lb_min && gi <= __reduce_max_sync(0xffffffffu, ctl.li_seg[lane]))) {
+    uint32_t incl = tot;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += y;
-      }
-      if (seg0 < a.n_reads && carry + incl >= lb_seg) {
-        // Walk the segment. Between two hits the row's sum is constant while the bound only tightens, so an
-        // interval opens at a hit (or at the segment start) and closes at the next hit or when the bound overtakes.
-        const uint32_t seg_end = min(seg0 + per, a.n_reads);
-        uint32_t run = incl - tot;
-        bool open = false, first = true;
-        uint32_t ob = 0;
-        unsigned long long os = 0;
-        for (uint32_t i = 0; i < segw; ++i) {
-          const uint32_t x = cseg[i];
-          if (x == 0u && !open && !first) continue;
-#pragma unroll
-          for (int half = 0; half < CPW; ++half) {
-            const uint32_t c = CPW == 2 ? (half ? (x >> 16) : (x & 0xFFFFu)) : ((x >> (8 * half)) & 0xFFu);
-            const uint32_t b = seg0 + CPW * i + half;
-            if (b < seg_end) {
-              bool check = open || first;
-              first = false;
-              if (c) {
-                if (open) { emit(os, gi, ob, b); open = false; }
-                run += c;
-                check = true;
-              }
-              if (check) {
-                const unsigned long long sv = carry + run;
-                const bool cand = sv >= lb_seg && is_cand(sv, gi, b, li_seg);
-                if (cand && !open) { open = true; ob = b; os = sv; }
-                if (!cand && open) { emit(os, gi, ob, b); open = false; }
-              }
-            }
-          }
-        }
-        if (open) emit(os, gi, ob, seg_end);
-      }
-      __syncwarp();
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += y;
     }
-    // clear the buffer for the next row that uses it (lane-interleaved 16-byte stores: no bank conflicts)
+    const unsigned long long seg_end_sum = carry + incl, lbs = ctl.lb_seg[lane];
+    const bool pass = seg0 < a.n_reads && (seg_end_sum > lbs || (seg_end_sum == lbs && gi <= ctl.li_seg[lane]));
+    const uint32_t seg_hi = min(seg0 + per, a.n_reads);
+    if (pass && tot == 0u) {  // one sum for the whole segment
+      const uint32_t slot = atomicAdd(a.ivl_total, 1u);
+      if (slot < a.ivl_cap) {
+        SkbInterval iv;
+        iv.sum = seg_end_sum; iv.idx = gi; iv.span = seg0 | (seg_hi << 16);
+        a.ivl[slot] = iv;
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass && tot != 0u);
+    if (bal) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(a.seg_total, (uint32_t)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+      if (((bal >> lane) & 1u) && slot < a.seg_cap) {
+        a.seg_hdr[slot] = make_uint4((uint32_t)(seg_end_sum - tot), (uint32_t)((seg_end_sum - tot) >> 32), gi, seg0);
+        uint4* dst = reinterpret_cast<uint4*>(a.seg_words + (size_t)slot * segw);
+        for (uint32_t i = 0; i < segw; i += 4) dst[i >> 2] = *reinterpret_cast<const uint4*>(cseg + i);
+      }
+    }
+  }
+  if (row_total) {  // clear the buffer for the next row that uses it (lane-interleaved 16-byte stores)
+    __syncwarp();
     uint4* z = reinterpret_cast<uint4*>(cpar);
     for (uint32_t i = lane; i < (cwords >> 2); i += 32) z[i] = make_uint4(0, 0, 0, 0);
-  } else if (carry >= lb_min) {
-    // no hit in this pass: the row's sum is `carry` for every read, so it meets the bound for a prefix [0, e) of
-    // the reads (first passes of a stream, when most sums tie at the bound)
-    const uint32_t li_all = __reduce_max_sync(0xffffffffu, li_seg);
-    uint32_t e = 0;
-    for (uint32_t b0 = 0; b0 < a.n_reads; b0 += 32) {
-      const uint32_t b = b0 + lane;
-      const bool ok = b < a.n_reads && is_cand(carry, gi, b, li_all);
-      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-      if (bal != 0xffffffffu) { e = b0 + (uint32_t)__ffs(~bal) - 1; break; }
-      e = b0 + 32;
-    }
-    if (e > a.n_reads) e = a.n_reads;
-    if (lane == 0 && e) emit(carry, gi, 0, e);
   }
   __syncwarp();
 }
@@ -440,19 +359,20 @@ __device__ __forceinline__ void rank_row(const SkbFusedArgs& a, const FsCtl& ctl
 // 255 query hashes; more reads fit a pass).
 //
 // Persistent, one CTA per SM, each owning a contiguous range of reference rows. A row is cut into FS_SUB-hash
-// sub-tiles dealt round-robin to the CTA's warps. Every warp streams its sub-tiles through a PRIVATE ring of
-// cp.async.bulk (TMA) staging buffers that it refills itself, probes each hash against the filter in shared memory
-// (one LDS + a handful of integer instructions), and resolves the few passers on the spot: the lanes that hold one
-// look their hash up in the L2-resident table (a 16-byte load; the next passer's load is in flight while the
-// previous one is counted) and add the key's reads to the row's counters in shared memory. The warp whose sub-tile
-// completes a row turns its counters into the new running sum and the candidate intervals (rank_row) and hands the
-// buffer back. Nothing in the loop is warp-collective except the row hand-over, so a burst of hits in one warp does
-// not stall the others' streams. HBM traffic per pass = the reference matrix, once.
+// sub-tiles; the CTA's warps claim sub-tiles in order from a shared counter, one claim ahead of every free slot of
+// their PRIVATE ring of cp.async.bulk (TMA) staging buffers, so the claim's round trip hides behind the copy. A warp
+// probes each staged hash against the filter in shared memory (one LDS + a handful of integer instructions) and
+// resolves the few passers on the spot: the lanes that hold one look their hash up in the L2-resident table (a
+// 16-byte load; two passers per trip, both loads in flight together) and add the key's reads to the row's counters
+// in shared memory. The warp whose sub-tile completes a row does the row's short rank step (rank_row) and hands the
+// counter buffer back; FS_ROWBUF rows are in flight, and since sub-tiles are claimed in order the warps cannot run
+// far apart, so nobody waits for a buffer. Nothing in the loop is warp-collective except that hand-over.
+// HBM traffic per pass = the reference matrix, once.
 template <int CPW>
 __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[FS_WARPS][FS_STAGES];
-  __shared__ FsCtl ctl;
+  __shared__ __align__(16) FsCtl ctl;
 
   if (*a.abort) return;  // an earlier pass of this batch has to be redone: leave sums and candidates alone
 
@@ -460,27 +380,31 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + FS_SMEM_BLOOM);
   uint32_t* cnt32 = reinterpret_cast<uint32_t*>(smem_raw + FS_SMEM_BLOOM + FS_SMEM_RING);
   const uint32_t cwords = a.cnt_stride / CPW;  // 32-bit words per row buffer
-  uint16_t* lbrel = reinterpret_cast<uint16_t*>(cnt32 + FS_ROWBUF * cwords);  // [cnt_stride / 4] bound growth since read 0 at every 4th read, saturating
 
   // every `row` below is a CTA-local number; c0 + row is the row of the shard
   const uint32_t c0 = a.cta_row[blockIdx.x];
   const uint32_t r1 = a.cta_row[blockIdx.x + 1] - c0;
+  const uint32_t tile0 = a.rv.uniform_len ? 0u : a.tile_cum[c0];
+  const uint32_t n_tiles = a.rv.uniform_len ? r1 * fs_tiles_of(a.rv.uniform_len) : a.tile_cum[c0 + r1] - tile0;
 
   if (threadIdx.x == 0) {
     for (int w = 0; w < FS_WARPS; ++w)
       for (int s = 0; s < FS_STAGES; ++s) mbar_init(&full_bar[w][s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    ctl.lb_min = a.lb_sum[0];
+    ctl.next_tile = 0;
   }
-  if (threadIdx.x < FS_ROWBUF) { ctl.done[threadIdx.x] = 0; ctl.freed[threadIdx.x] = 0; ctl.carry[threadIdx.x] = 0; }
-  if (threadIdx.x < 32) ctl.li_seg[threadIdx.x] = 0;
+  if (threadIdx.x < FS_ROWBUF) { ctl.done[threadIdx.x] = 0; ctl.freed[threadIdx.x] = 0; }
+  if (threadIdx.x < 32) {
+    const uint32_t seg0 = threadIdx.x * (a.cnt_stride >> 5);
+    ctl.li_seg[threadIdx.x] = 0;
+    ctl.lb_seg[threadIdx.x] = seg0 < a.n_reads ? a.lb_sum[seg0] : ~0ull;
+  }
   if (!a.skip_stream) {  // stage the filter
     const uint4* src = reinterpret_cast<const uint4*>(a.table.bloom);
     uint4* dst = reinterpret_cast<uint4*>(bloom);
     for (uint32_t i = threadIdx.x; i < SKB_BLOOM_WORDS / 4; i += blockDim.x) dst[i] = src[i];
   }
   for (uint32_t i = threadIdx.x; i < FS_ROWBUF * cwords; i += blockDim.x) cnt32[i] = 0;
-  for (uint32_t i = threadIdx.x; 4u * i < a.n_reads; i += blockDim.x) lbrel[i] = (uint16_t)min(a.lb_rel[4u * i], 0xFFFFu);
   __syncthreads();
   {
     const uint32_t per = a.cnt_stride >> 5;
@@ -489,165 +413,200 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   __syncthreads();
 
   const uint32_t warp = threadIdx.x >> 5, lane = skb_lane();
-  uint32_t slot_next = 0, slot_left = 0;  // this lane's reserved interval slots
 
   if (a.skip_stream) {  // the pass has no query hashes: rows are ranked from their running sums alone
-    for (uint32_t row = warp; row < r1; row += FS_WARPS)
-      rank_row<CPW>(a, ctl, lbrel, nullptr, cwords, c0 + row, a.sums_in[c0 + row], slot_next, slot_left);
-  } else {
-    const SkbTable& t = a.table;
-    const uint4* tslots = reinterpret_cast<const uint4*>(t.slots);
-    const uint32_t tcap = t.cap, tlog2 = t.log2cap;
-    uint8_t* my_ring = reinterpret_cast<uint8_t*>(ring + (size_t)warp * FS_STAGES * FS_SUB);
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    // bulk copy of the sub-tile `si` points at into one of this warp's staging buffers (lane 0 only)
-    auto issue_copy = [&](const SubIter& si, uint32_t stage) {
-      const uint32_t first = si.t * FS_SUB;
-      uint32_t n = si.len - first;
-      if (n > (uint32_t)FS_SUB) n = FS_SUB;
-      const uint32_t bytes = ((n + 1u) & ~1u) * 8u;  // multiple of 16; rows start on even offsets
-      mbar_arrive_expect_tx(&full_bar[warp][stage], bytes);
-      if (bytes) bulk_load(my_ring + (size_t)stage * FS_SUB * 8, si.p + first, bytes, &full_bar[warp][stage], policy);
-    };
+    for (uint32_t row = warp; row < r1; row += FS_WARPS) rank_row<CPW>(a, ctl, nullptr, cwords, c0 + row);
+    return;
+  }
 
-    SubIter it, pre;
-    it.c0 = c0;
-    it.row = 0;
-    it.t = warp;
-    it.load_row(a, r1);
-    it.settle(a, r1);
-    pre = it;
-    for (uint32_t s = 0; s < (uint32_t)FS_STAGES; ++s) {  // prime the private ring
-      if (pre.row < r1) {
-        if (lane == 0) issue_copy(pre, s);
-        pre.next(a, r1);
+  const SkbTable& t = a.table;
+  const uint4* tslots = reinterpret_cast<const uint4*>(t.slots);
+  const uint32_t tcap = t.cap, tlog2 = t.log2cap;
+  uint8_t* my_ring = reinterpret_cast<uint8_t*>(ring + (size_t)warp * FS_STAGES * FS_SUB);
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+  // lane 0: claim the CTA's next sub-tile, describe it in this ring slot and start its bulk copy
+  auto claim_and_issue = [&](uint32_t stage) {
+    const uint32_t n = atomicAdd(&ctl.next_tile, 1u);
+    uint4 d = make_uint4(FS_NONE, 0u, 0u, 0u);
+    if (n < n_tiles) {
+      uint32_t row, tt, len;
+      const uint64_t* p;
+      if (a.rv.uniform_len) {
+        row = __umulhi(n, a.tpr_magic);  // n / tiles-per-row by a precomputed reciprocal (exact in this range)
+        tt = n - row * a.tpr;
+        len = a.rv.uniform_len;
+        p = a.rv.ref + (size_t)(c0 + row) * a.rv.uniform_pitch;
+      } else {  // ragged rows: the row whose cumulative sub-tile range holds n
+        uint32_t lo = 0, hi = r1;
+        const uint32_t key = tile0 + n;
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (a.tile_cum[c0 + mid] <= key) lo = mid; else hi = mid;
+        }
+        row = lo;
+        tt = key - a.tile_cum[c0 + row];
+        len = a.rv.row_len[c0 + row];
+        p = a.rv.ref + a.rv.row_start[c0 + row];
+      }
+      d = make_uint4(row, tt, len, 0u);
+      const uint32_t first = tt * FS_SUB;
+      uint32_t cnt = len - first;
+      if (cnt > (uint32_t)FS_SUB) cnt = FS_SUB;
+      const uint32_t bytes = ((cnt + 1u) & ~1u) * 8u;  // multiple of 16; rows start on even offsets
+      mbar_arrive_expect_tx(&full_bar[warp][stage], bytes);
+      if (bytes) bulk_load(my_ring + (size_t)stage * FS_SUB * 8, p + first, bytes, &full_bar[warp][stage], policy);
+    }
+    ctl.desc[warp][stage] = d;
+  };
+
+  if (lane == 0)
+    for (uint32_t s = 0; s < (uint32_t)FS_STAGES; ++s) claim_and_issue(s);  // prime the private ring
+
+  for (uint32_t k = 0;; ++k) {  // sub-tiles consumed by this warp: stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1
+    const uint32_t stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1u;
+    __syncwarp();
+    const uint4 d = ctl.desc[warp][stage];
+    if (d.x == FS_NONE) break;  // claims are in order: once one comes back empty, so do all later ones
+    const uint32_t row = d.x, len = d.z;
+    const uint32_t par = row % FS_ROWBUF;
+    uint32_t* cb = cnt32 + par * cwords;
+    if (row >= (uint32_t)FS_ROWBUF) {  // the buffer's previous row must have been ranked and cleared (it almost always has)
+      const uint32_t need = row / FS_ROWBUF;
+      if (lane == 0)
+        while (lds_acquire_u32(&ctl.freed[par]) < need) __nanosleep(100);
+      __syncwarp();
+    }
+    mbar_wait(&full_bar[warp][stage], phase);
+    const uint8_t* tile = my_ring + (size_t)stage * FS_SUB * 8;
+    const uint32_t n_sub = len - d.y * FS_SUB;  // >= FS_SUB for every sub-tile but a row's last
+#pragma unroll 1
+    for (uint32_t ch = 0; ch < (uint32_t)FS_CHUNKS; ++ch) {
+      const uint32_t base = ch * FS_NHASH * 32;  // first hash index of the chunk within the sub-tile
+      if (base >= n_sub) break;
+      const uint8_t* cbase = tile + (size_t)base * 8 + lane * 16;
+      uint4 v[FS_NHASH / 2];
+#pragma unroll
+      for (int r = 0; r < FS_NHASH / 2; ++r) v[r] = *reinterpret_cast<const uint4*>(cbase + 512 * r);
+      uint32_t pm = 0;  // bit 7 - j: this lane's j-th hash of the chunk passed the filter
+      if (!(SKB_X_ABLATE & 1)) {
+        if (n_sub >= base + FS_NHASH * 32) {
+#pragma unroll
+          for (int j = 0; j < FS_NHASH; ++j) {
+            const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
+            const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
+            pm = __funnelshift_l(bloom_probe(bloom, lo, hi), pm, 1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < FS_NHASH; ++j) {
+            const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
+            const uint32_t idx = base + 2u * (lane + 32 * (j >> 1)) + (j & 1);
+            const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
+            pm = __funnelshift_l(idx < n_sub ? bloom_probe(bloom, lo, hi) : 0u, pm, 1);
+          }
+        }
+      }
+      if (SKB_X_ABLATE & 2) pm = 0;
+      // Divergent: only the lanes that hold a passer run this, two passers per trip. A passer's hash is read back
+      // from the staging buffer by its position (hash j of the chunk sits at byte (j >> 1) * 512 + (j & 1) * 8 of the
+      // lane's column), both table loads are issued before either is resolved, so a lane pays the L2 latency once
+      // per trip; a slot owned by another key is chased in place (load factor 0.125: rare).
+      while (pm) {
+        const uint32_t b0 = 31u - (uint32_t)__clz((int)pm);
+        pm &= ~(1u << b0);
+        const bool two = pm != 0u;
+        const uint32_t b1 = two ? 31u - (uint32_t)__clz((int)pm) : b0;
+        pm &= ~(1u << b1);
+        // bit b holds hash j = 7 - b: offset 0x608 - ((b * 0x108) & 0x608)
+        const uint2 e0 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b0 * 0x108u) & 0x608u));
+        const uint2 e1 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b1 * 0x108u) & 0x608u));
+        const uint64_t h0 = ((uint64_t)e0.y << 32) | e0.x, h1 = ((uint64_t)e1.y << 32) | e1.x;
+        uint32_t s0 = h0 == SKB_EMPTY_KEY ? tcap : table_home(h0, tlog2);
+        uint32_t s1 = h1 == SKB_EMPTY_KEY ? tcap : table_home(h1, tlog2);
+        uint4 r0 = __ldg(tslots + s0);
+        uint4 r1v = __ldg(tslots + s1);
+        for (;;) {  // walk the probe sequence until the key or an empty slot
+          const uint64_t key = ((uint64_t)r0.y << 32) | r0.x;
+          if (key == h0) { apply_hit<CPW>(t, ((unsigned long long)r0.w << 32) | r0.z, cb); break; }
+          if (key == SKB_EMPTY_KEY) break;
+          s0 = (s0 + 1) & (tcap - 1);
+          r0 = __ldg(tslots + s0);
+        }
+        if (two) {
+          for (;;) {
+            const uint64_t key = ((uint64_t)r1v.y << 32) | r1v.x;
+            if (key == h1) { apply_hit<CPW>(t, ((unsigned long long)r1v.w << 32) | r1v.z, cb); break; }
+            if (key == SKB_EMPTY_KEY) break;
+            s1 = (s1 + 1) & (tcap - 1);
+            r1v = __ldg(tslots + s1);
+          }
+        }
       }
     }
-    uint32_t k = 0;  // sub-tiles consumed by this warp: stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1
-    uint32_t cur_row = 0xFFFFFFFFu, par = 0;
-    uint32_t* cb = cnt32;
-
-    while (it.row < r1) {
-      unsigned long long carry_pref = 0;
-      const bool opens = it.t == 0;  // this warp holds the row's first sub-tile: it fetches the row's running sum
-      if (it.row != cur_row) {
-        cur_row = it.row;
-        par = cur_row % FS_ROWBUF;
-        cb = cnt32 + par * cwords;
-        if (cur_row >= (uint32_t)FS_ROWBUF) {  // the buffer's previous row must have been ranked and cleared
-          const uint32_t need = cur_row / FS_ROWBUF;
-          if (lane == 0)
-            while (lds_acquire_u32(&ctl.freed[par]) < need) __nanosleep(64);
-          __syncwarp();
-        }
-      }
-      if (opens && lane == 0) carry_pref = a.sums_in[c0 + cur_row];  // in flight while the sub-tile is probed
-      const uint32_t stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1u;
-      mbar_wait(&full_bar[warp][stage], phase);
-      const uint8_t* tile = my_ring + (size_t)stage * FS_SUB * 8;
-      const uint32_t n_sub = it.len - it.t * FS_SUB;  // >= FS_SUB for every sub-tile but a row's last
-#pragma unroll 1
-      for (uint32_t ch = 0; ch < (uint32_t)FS_CHUNKS; ++ch) {
-        const uint32_t base = ch * FS_NHASH * 32;  // first hash index of the chunk within the sub-tile
-        if (base >= n_sub) break;
-        const uint8_t* cbase = tile + (size_t)base * 8 + lane * 16;
-        uint4 v[FS_NHASH / 2];
-#pragma unroll
-        for (int r = 0; r < FS_NHASH / 2; ++r) v[r] = *reinterpret_cast<const uint4*>(cbase + 512 * r);
-        uint32_t pm = 0;  // bit 7 - j: this lane's j-th hash of the chunk passed the filter
-        if (!(SKB_X_ABLATE & 1)) {
-          if (n_sub >= base + FS_NHASH * 32) {
-#pragma unroll
-            for (int j = 0; j < FS_NHASH; ++j) {
-              const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
-              const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
-              pm = __funnelshift_l(bloom_probe(bloom, lo, hi), pm, 1);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < FS_NHASH; ++j) {
-              const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
-              const uint32_t idx = base + 2u * (lane + 32 * (j >> 1)) + (j & 1);
-              const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
-              pm = __funnelshift_l(idx < n_sub ? bloom_probe(bloom, lo, hi) : 0u, pm, 1);
-            }
-          }
-        }
-        if (SKB_X_ABLATE & 2) pm = 0;
-        // Divergent: only the lanes that hold a passer run this, two passers per trip. A passer's hash is read back
-        // from the staging buffer by its position (hash j of the chunk sits at byte (j >> 1) * 512 + (j & 1) * 8 of the
-        // lane's column), both table loads are issued before either is resolved, so a lane pays the L2 latency once
-        // per trip; a slot owned by another key is chased in place (load factor 0.125: rare).
-        while (pm) {
-          const uint32_t b0 = 31u - (uint32_t)__clz((int)pm);
-          pm &= ~(1u << b0);
-          const bool two = pm != 0u;
-          const uint32_t b1 = two ? 31u - (uint32_t)__clz((int)pm) : b0;
-          pm &= ~(1u << b1);
-          // bit b holds hash j = 7 - b: offset 0x608 - ((b * 0x108) & 0x608)
-          const uint2 e0 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b0 * 0x108u) & 0x608u));
-          const uint2 e1 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b1 * 0x108u) & 0x608u));
-          const uint64_t h0 = ((uint64_t)e0.y << 32) | e0.x, h1 = ((uint64_t)e1.y << 32) | e1.x;
-          uint32_t s0 = h0 == SKB_EMPTY_KEY ? tcap : table_home(h0, tlog2);
-          uint32_t s1 = h1 == SKB_EMPTY_KEY ? tcap : table_home(h1, tlog2);
-          uint4 r0 = __ldg(tslots + s0);
-          uint4 r1 = __ldg(tslots + s1);
-          for (;;) {  // walk the probe sequence until the key or an empty slot
-            const uint64_t key = ((uint64_t)r0.y << 32) | r0.x;
-            if (key == h0) { apply_hit<CPW>(t, ((unsigned long long)r0.w << 32) | r0.z, cb); break; }
-            if (key == SKB_EMPTY_KEY) break;
-            s0 = (s0 + 1) & (tcap - 1);
-            r0 = __ldg(tslots + s0);
-          }
-          if (two) {
-            for (;;) {
-              const uint64_t key = ((uint64_t)r1.y << 32) | r1.x;
-              if (key == h1) { apply_hit<CPW>(t, ((unsigned long long)r1.w << 32) | r1.z, cb); break; }
-              if (key == SKB_EMPTY_KEY) break;
-              s1 = (s1 + 1) & (tcap - 1);
-              r1 = __ldg(tslots + s1);
-            }
-          }
-        }
-      }
-      // the staging buffer is fully read: refill it with this warp's next sub-tile
-      __syncwarp();
-      if (pre.row < r1) {
-        if (lane == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          issue_copy(pre, stage);
-        }
-        pre.next(a, r1);
-      }
-      ++k;
-      // this sub-tile's hits are in shared memory: count it done; the warp that completes the row ranks it
-      uint32_t last = 0;
+    // the staging buffer is fully read: refill it with the CTA's next unclaimed sub-tile; then count this one done
+    __syncwarp();
+    uint32_t last = 0;
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      claim_and_issue(stage);
+      __threadfence_block();  // this warp's hits are in shared memory before the count says so
+      last = atomicAdd(&ctl.done[par], 1u) + 1u == fs_tiles_of(len) ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {  // this sub-tile completed the row: rank it and hand the buffer back
+      __threadfence_block();
+      rank_row<CPW>(a, ctl, cb, cwords, c0 + row);
       if (lane == 0) {
-        if (opens) ctl.carry[par] = carry_pref;
+        ctl.done[par] = 0;
         __threadfence_block();
-        last = atomicAdd(&ctl.done[par], 1u) + 1u == SubIter::tiles_of(it.len) ? 1u : 0u;
+        atomicAdd(&ctl.freed[par], 1u);
       }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        __threadfence_block();
-        const unsigned long long carry = ctl.carry[par];
-        rank_row<CPW>(a, ctl, lbrel, cb, cwords, c0 + cur_row, carry, slot_next, slot_left);
-        if (lane == 0) {
-          ctl.done[par] = 0;
-          __threadfence_block();
-          atomicAdd(&ctl.freed[par], 1u);
-        }
-      }
-      it.next(a, r1);
     }
   }
-  // hand back the unused part of the last reservation as empty intervals
-  for (; slot_left; --slot_left, ++slot_next) {
-    if (slot_next < a.ivl_cap) {
-      SkbInterval iv;
-      iv.sum = 0; iv.idx = 0xFFFFFFFFu; iv.span = 0;
-      a.ivl[slot_next] = iv;
+}
+
+// Post-pass: segment records -> per-read candidate buckets. One thread per 16-byte unit of a record's counters: it
+// sums the units before it (a record is at most 160 bytes), then tests each of its reads against the read's exact
+// bound; a row that is at least as good as the bound is a candidate for that read.
+__global__ void __launch_bounds__(256) walk_kernel(const SkbRankArgs a) {
+  const uint32_t total = min(*a.seg_total, a.seg_cap);
+  const uint32_t upr = a.seg_words_per / 4;  // 16-byte units per record
+  const uint32_t cpw = a.seg_cpw;            // counters per word: 2 (u16) or 4 (u8)
+  const uint64_t n_units = (uint64_t)total * upr;
+  for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t rec = (uint32_t)(u / upr), unit = (uint32_t)(u - (uint64_t)rec * upr);
+    const uint4 hd = a.seg_hdr[rec];
+    const uint4* w = reinterpret_cast<const uint4*>(a.seg_words + (size_t)rec * a.seg_words_per);
+    unsigned long long run = ((unsigned long long)hd.y << 32) | hd.x;
+    for (uint32_t q = 0; q < unit; ++q) {
+      const uint4 x = w[q];
+      const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (cpw == 2) run += (w4[i] & 0xFFFFu) + (w4[i] >> 16);
+        else { const uint32_t pair = (w4[i] & 0x00FF00FFu) + ((w4[i] >> 8) & 0x00FF00FFu); run += (pair & 0xFFFFu) + (pair >> 16); }
+      }
+    }
+    const uint4 x = w[unit];
+    const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+    const uint32_t gi = hd.z;
+    uint32_t b = hd.w + unit * 4 * cpw;
+    for (int i = 0; i < 4; ++i) {
+      for (uint32_t h = 0; h < cpw; ++h, ++b) {
+        run += cpw == 2 ? ((w4[i] >> (16 * h)) & 0xFFFFu) : ((w4[i] >> (8 * h)) & 0xFFu);
+        if (b < a.n_reads && !skb_key_better(a.lb_sum[b], a.lb_idx[b], run, gi)) {
+          const uint32_t slot = atomicAdd(&a.cand_cnt[b], 1u);
+          if (slot < a.cand_cap) {
+            SkbCand cd;
+            cd.sum = run; cd.idx = gi; cd.pad = 0;
+            a.cand[(size_t)b * a.cand_cap + slot] = cd;
+          } else {
+            *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
+          }
+        }
+      }
     }
   }
 }
@@ -741,12 +700,8 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
   a.lb_idx[b] = n ? ki[n - 1] : 0xFFFFFFFFu;
 }
 
-__global__ void lb_rel_kernel(const SkbRankArgs a) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.n_reads) a.lb_rel[b] = (uint32_t)(a.lb_sum[b] - a.lb_sum[0]);  // in-pass growth always fits 32 bits
-}
-
-// intervals -> per-read candidate buckets. One warp per interval; the per-read counter is the slot allocator.
+// intervals (one sum over a run of reads) -> per-read candidate buckets. One warp per interval; every read is tested
+// against its exact bound; the per-read counter is the slot allocator.
 __global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
   const uint32_t total = min(*a.ivl_total, a.ivl_cap);
   const uint32_t lane = skb_lane();
@@ -755,6 +710,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
     const SkbInterval iv = a.ivl[w];
     const uint32_t b0 = iv.span & 0xFFFFu, b1 = iv.span >> 16;
     for (uint32_t b = b0 + lane; b < b1; b += 32) {
+      if (skb_key_better(a.lb_sum[b], a.lb_idx[b], iv.sum, iv.idx)) continue;  // under this read's bound
       const uint32_t slot = atomicAdd(&a.cand_cnt[b], 1u);
       if (slot < a.cand_cap) {
         SkbCand cd;
@@ -782,13 +738,15 @@ __global__ void __launch_bounds__(256) pass_verdict_kernel(const SkbRankArgs a) 
   if (a.abort[0] == 0u) {
     a.abort[2] = m;
     a.abort[3] = *a.ivl_total;
-    if (*a.cand_total != 0u || *a.ivl_total > a.ivl_cap) {
+    a.abort[4] = *a.seg_total;
+    if (*a.cand_total != 0u || *a.ivl_total > a.ivl_cap || *a.seg_total > a.seg_cap) {
       a.abort[1] = a.seq;
       a.abort[0] = 1u;
     }
   }
   *a.cand_total = 0u;
   *const_cast<uint32_t*>(a.ivl_total) = 0u;
+  *const_cast<uint32_t*>(a.seg_total) = 0u;
 }
 
 __global__ void __launch_bounds__(1024) tracked_update_kernel(const SkbRankArgs a) {
@@ -1056,20 +1014,20 @@ void skb_launch_memb_build(const SkbRefView& rv, uint32_t* memb, uint32_t memb_l
 }
 
 size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 2 * FS_ROWBUF + (size_t)cnt_stride / 2;
+  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 2 * FS_ROWBUF;
 }
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 1 * FS_ROWBUF + (size_t)cnt_stride / 2;
+  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 1 * FS_ROWBUF;
 }
 uint32_t skb_fused_tile() { return FS_SUB; }
 // Largest pass the kernel's shared memory holds: 227 KB per CTA minus the static barriers and bookkeeping, the filter
-// and the staging rings leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each) plus the bounds staged at
-// every 4th read (0.5 B per read). Pass-local read ids are SKB_SLOT_ID_BITS wide in a table slot: that caps it either way.
+// and the staging rings leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each). Pass-local read ids are
+// SKB_SLOT_ID_BITS wide in a table slot: that caps it either way.
 uint32_t skb_fused_max_reads(int narrow) {
-  const size_t fixed = FS_SMEM_BLOOM + FS_SMEM_RING + 1024;  // 1 KB: static barriers + slack
+  const size_t fixed = FS_SMEM_BLOOM + FS_SMEM_RING + 2048;  // 2 KB: static barriers, row bookkeeping, slack
   const size_t budget = 232448;                                             // opt-in maximum per CTA on sm_100
   if (fixed >= budget) return 0;
-  const size_t per2 = (narrow ? 2 * FS_ROWBUF : 4 * FS_ROWBUF) + 1;         // bytes per read, times two
+  const size_t per2 = narrow ? 2 * FS_ROWBUF : 4 * FS_ROWBUF;               // bytes per read, times two
   const uint32_t gran = narrow ? 512u : 256u;                               // cnt_stride granularity (api.cu)
   uint32_t b = (uint32_t)std::min<size_t>(1u << SKB_SLOT_ID_BITS, 2 * (budget - fixed) / per2);
   return b / gran * gran;
@@ -1095,10 +1053,12 @@ void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, co
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) {
   tracked_prefix_kernel<<<SKB_MAX_TRACKED, 256, 0, st>>>(a);
   rank_bounds_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
-  lb_rel_kernel<<<(a.n_reads + 255) / 256, 256, 0, st>>>(a);
 }
 
-void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st) { expand_kernel<<<148 * 8, 256, 0, st>>>(a); }
+void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st) {
+  walk_kernel<<<148 * 8, 256, 0, st>>>(a);
+  expand_kernel<<<148 * 8, 256, 0, st>>>(a);
+}
 
 void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st) { tracked_update_kernel<<<1, 1024, 0, st>>>(a); }
 

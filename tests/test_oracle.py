@@ -23,6 +23,25 @@ def test_murmur3_known_answers():
         assert pyspec.murmur3_x64_128(v["input"].encode(), v["seed"]) == (h1, h2)
 
 
+def _smhasher_verification(fn) -> int:
+    """SMHasher's VerificationTest (KeysetTest.cpp): hash the keys {}, {0}, {0,1}, ... {0..254} with seed 256 - len,
+    concatenate the 16-byte digests (h1 then h2, little-endian, as MurmurHash3_x64_128 writes them), hash that with
+    seed 0; the first four bytes, little-endian, are the verification value."""
+    import struct
+    digests = b""
+    for i in range(256):
+        digests += struct.pack("<QQ", *fn(bytes(range(i)), 256 - i))
+    return struct.unpack("<I", struct.pack("<QQ", *fn(digests, 0))[:4])[0]
+
+
+def test_murmur3_smhasher_verification_value():
+    """External pin: SMHasher publishes 0x6384BA69 as the verification value of MurmurHash3_x64_128 (main.cpp,
+    g_hashes[]). It covers every tail length 0..15, multi-block inputs and the seed handling, which the four short
+    published vectors do not."""
+    assert _smhasher_verification(oracle.murmur3_x64_128) == 0x6384BA69
+    assert _smhasher_verification(pyspec.murmur3_x64_128) == 0x6384BA69
+
+
 @given(st.binary(min_size=0, max_size=70), st.integers(0, 2**32 - 1))
 @settings(max_examples=300, deadline=None)
 def test_murmur3_matches_pyspec(data, seed):

@@ -1,9 +1,9 @@
 #!/bin/bash
 # tools/build_variant.sh <name> [-DMACRO=..]...  -> sketchy_b200/build/variants/lib_<name>.so
-# api.cu and kernels_predict.cu are rebuilt with the macros (SKB_X_CW consumer warps, SKB_X_SUB hashes per sub-tile, SKB_X_STAGES
-# staging buffers per warp, SKB_X_ROWBUF rows in flight, SKB_X_RANKW rank warps, SKB_BLOOM_K filter bits, SKB_X_QCAP FIFO entries per warp, SKB_X_RANK_SLEEP / SKB_X_FREE_SLEEP barrier polling intervals, SKB_X_IDBITS read-id width = log2 of the
-# largest pass); the other
-# objects come from the in-tree build. Load a variant with SKB_LIB=<path> (sketchy_b200/_lib.py).
+# api.cu and kernels_predict.cu are rebuilt with the macros (SKB_X_CW warps per CTA, SKB_X_SUB hashes per sub-tile,
+# SKB_X_STAGES staging buffers per warp, SKB_X_ROWBUF rows in flight, SKB_BLOOM_K filter bits, SKB_X_IDBITS read-id
+# width = log2 of the largest pass, SKB_X_ABLATE experiment switches); the other objects come from the in-tree build.
+# Load a variant with SKB_LIB=<path> (sketchy_b200/_lib.py).
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
