@@ -120,6 +120,11 @@ int skb_sums_download(skb_ctx* ctx, uint64_t* out /* [n_rows] */);
 int skb_sums_upload(skb_ctx* ctx, const uint64_t* in /* [n_rows] */);
 /* Reads per streaming pass (0 = library default). Any value gives identical results. */
 int skb_set_pass_reads(skb_ctx* ctx, uint32_t max_reads_per_pass);
+/* How a pass turns its counts into every read's top-N; every mode gives identical results (tests run all of them).
+ * 0 = automatic (default): brute-force ranking over all rows right after a reset, for small shards and to redo a
+ * pass whose candidate lists overflowed, candidate lists from per-read lower bounds otherwise;
+ * 1 = candidate lists wherever they are possible (even on small shards); 2 = brute force always. */
+int skb_set_rank_mode(skb_ctx* ctx, int mode);
 
 /* ---- read-set predict (replaces `_shared_hashes`, src/sketchy.rs:281-315) and `shared` (:238-279) ------------- */
 

@@ -45,6 +45,7 @@ SYMBOLS = [
     ("skb_sums_download", _i, [_vp, _vp]),
     ("skb_sums_upload", _i, [_vp, _vp]),
     ("skb_set_pass_reads", _i, [_vp, _u32]),
+    ("skb_set_rank_mode", _i, [_vp, _i]),
     ("skb_shared_counts", _i, [_vp, _vp, _vp, _u32, _vp]),
     ("skb_rank_counts", _i, [_vp, _vp, _u32, _u32, _vp, _vp]),
     ("skb_merge_topn_device", _i, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _vp]),
@@ -191,6 +192,10 @@ class Context:
 
     def set_pass_reads(self, n: int):
         self.check(self.lib.skb_set_pass_reads(self.h, n))
+
+    def set_rank_mode(self, mode: int):
+        """0 = automatic, 1 = candidate lists wherever possible, 2 = brute-force ranking always (same results)."""
+        self.check(self.lib.skb_set_rank_mode(self.h, mode))
 
     def shared_counts(self, q_hashes: np.ndarray, q_off: np.ndarray) -> np.ndarray:
         q_hashes = np.ascontiguousarray(q_hashes, dtype=np.uint64)

@@ -153,6 +153,9 @@ void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uin
 // context / batch
 // ---------------------------------------------------------------------------------------------------------
 struct ProfEvent { int id; cudaEvent_t a, b; };
+#define SKB_NSUMS 4
+#define SKB_NTRACK 3
+#define SKB_NTAB 3
 
 struct skb_ctx {
   int device = 0;
@@ -167,21 +170,31 @@ struct skb_ctx {
   uint32_t n_rows = 0, row_base = 0, uniform_len = 0, uniform_pitch = 0;
   uint64_t hmax = 0;
   bool has_ref = false;
-  DevBuf sums[2];
+  // Rotating state of the pass pipeline (see predict_device): the running sums after the last SKB_NSUMS passes, the
+  // tracked-row sets the last SKB_NTRACK passes proposed, the query tables of the last SKB_NTAB passes.
+  DevBuf sums[SKB_NSUMS];
   int sums_cur = 0;
-  DevBuf tracked[2];         // [SKB_MAX_TRACKED] local rows + (at index SKB_MAX_TRACKED) their count, double buffered
+  DevBuf tracked[SKB_NTRACK];  // [SKB_MAX_TRACKED] local rows + (at index SKB_MAX_TRACKED) their count
   int tracked_cur = 0;
-  DevBuf tprefix;
+  DevBuf tprefix, textra;
+  cudaStream_t side = nullptr;  // pre-pass / post-pass kernels, overlapping the streaming kernel of the neighbouring passes
+  cudaEvent_t ev_pre[SKB_NTAB] = {nullptr, nullptr, nullptr}, ev_fused[2] = {nullptr, nullptr}, ev_join = nullptr;
+  int tab_cur = 0;              // slot of the newest query table
+  bool pass_proven = false;     // a full-size sparse pass has been checked and did not overflow: batch them
+  int rank_mode = 0;            // skb_set_rank_mode
+  uint32_t dense_left = 0;      // upcoming passes that are ranked densely (bounds too loose to be worth candidates)
+  DevBuf dense, part_idx, part_sum;
+  bool pipeline = true;         // steady-state passes take their bounds from two passes back (pre-pass work next to the stream)
   uint32_t tracked_top = 0;  // 0 = invalid
   // per-group scratch (hash/select)
   DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, cand_pool;
   DevBuf sk_hashes, sk_counts;
   // predict scratch
-  DevBuf q_off, qh, qread, counts, lb_sum, lb_idx, cand, cand_cnt, ivl, seg_hdr, seg_words, scal;
-  DevBuf t_slots, t_fill, t_reads, t_slot, t_bloom;
+  DevBuf q_off, qh, qread, counts, lb_sum[SKB_NTAB], lb_idx[SKB_NTAB], cand[2], cand_cnt[2], ivl[2], seg_hdr[2], seg_words[2], scal;
+  DevBuf t_slots[SKB_NTAB], t_fill[SKB_NTAB], t_reads[SKB_NTAB], t_slot[SKB_NTAB], t_bloom[SKB_NTAB];
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = skb_fused_max_reads(1), pass_cur = 64;  // default reads per pass: what the kernel's shared memory holds
+  uint32_t pass_max = skb_fused_max_reads(1);  // reads per pass: what the kernel's shared memory holds
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -231,17 +244,18 @@ int fail(skb_ctx* c, int code, const char* fmt, ...) {
 
 struct ProfScope {
   skb_ctx* c; int id; cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(skb_ctx* ctx, int kid, int n_launches) : c(ctx), id(kid) {
+  cudaStream_t st;
+  ProfScope(skb_ctx* ctx, int kid, int n_launches, cudaStream_t on = nullptr) : c(ctx), id(kid), st(on ? on : ctx->stream) {
     c->launches += n_launches;
     c->prof_n[id] += n_launches;
     if (c->prof_on) {
       cudaEventCreate(&a); cudaEventCreate(&b);
-      cudaEventRecord(a, c->stream);
+      cudaEventRecord(a, st);
     }
   }
   ~ProfScope() {
     if (c->prof_on) {
-      cudaEventRecord(b, c->stream);
+      cudaEventRecord(b, st);
       c->pending.push_back({id, a, b});
     }
   }
@@ -250,6 +264,7 @@ struct ProfScope {
 void prof_resolve(skb_ctx* c) {
   if (c->pending.empty()) return;
   cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->side);
   for (auto& e : c->pending) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.id] += ms;
@@ -444,33 +459,23 @@ int ensure_table(skb_ctx* c, uint32_t max_keys) {
   if (c->t_maxkeys && max_keys <= c->t_maxkeys) return SKB_OK;
   const uint32_t mk = (uint32_t)skb_next_pow2(std::max<uint32_t>(max_keys, 1u << 16));
   const uint32_t cap = mk * 8;  // load factor <= 0.125: a lookup is almost always one 16-byte load
-  CU(c, c->t_slots.ensure(((size_t)cap + 1) * sizeof(SkbSlot)));
-  CU(c, c->t_fill.ensure(((size_t)cap + 1) * 4));
-  CU(c, c->t_reads.ensure((size_t)mk * 4));
-  CU(c, c->t_slot.ensure((size_t)mk * 4));
-  CU(c, c->t_bloom.ensure((size_t)SKB_BLOOM_WORDS * 4));
+  for (int i = 0; i < SKB_NTAB; ++i) {
+    CU(c, c->t_slots[i].ensure(((size_t)cap + 1) * sizeof(SkbSlot)));
+    CU(c, c->t_fill[i].ensure(((size_t)cap + 1) * 4));
+    CU(c, c->t_reads[i].ensure((size_t)mk * 4));
+    CU(c, c->t_slot[i].ensure((size_t)mk * 4));
+    CU(c, c->t_bloom[i].ensure((size_t)SKB_BLOOM_WORDS * 4));
+  }
   c->t_cap = cap;
   c->t_maxkeys = mk;
   return SKB_OK;
 }
 
-// Reads in the first pass after an upload / a reset of the sums. Nothing is known about the ranking yet, so the
-// bounds are loose and a read may have every row as a candidate: start with the largest pass whose per-read bucket
-// still holds the whole shard (it cannot overflow), then grow (see the headroom rule in predict_device).
-uint32_t first_pass_reads(const skb_ctx* c) {
-  uint64_t budget = SKB_CAND_BUDGET;
-  if (const char* eb = getenv("SKB_CAND_BUDGET")) budget = std::max<uint64_t>(64, strtoull(eb, nullptr, 10));  // tests only
-  const uint64_t fit = budget / std::max<uint32_t>(c->n_rows, 64);
-  uint32_t b = 128;
-  while ((uint64_t)b * 2 <= fit && b * 2 <= c->pass_max) b *= 2;
-  return std::min<uint32_t>(b, c->pass_max);
-}
-
-SkbTable table_of(skb_ctx* c) {
+SkbTable table_of(skb_ctx* c, int slot) {
   SkbTable t;
-  t.slots = c->t_slots.as<SkbSlot>(); t.fill = c->t_fill.as<uint32_t>(); t.reads = c->t_reads.as<uint32_t>();
-  t.slot_of = c->t_slot.as<uint32_t>(); t.bloom = c->t_bloom.as<uint32_t>();
-  t.cursor = c->scal.as<uint32_t>() + 4;
+  t.slots = c->t_slots[slot].as<SkbSlot>(); t.fill = c->t_fill[slot].as<uint32_t>(); t.reads = c->t_reads[slot].as<uint32_t>();
+  t.slot_of = c->t_slot[slot].as<uint32_t>(); t.bloom = c->t_bloom[slot].as<uint32_t>();
+  t.cursor = c->scal.as<uint32_t>() + 4 + slot;
   t.cap = c->t_cap;
   t.memb = c->memb_log2 ? c->memb.as<uint32_t>() : nullptr;
   t.memb_log2 = c->memb_log2;
@@ -598,14 +603,14 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
     CU(c, c->tile_cum.ensure(((size_t)n_rows + 1) * 4));
     CU(c, cudaMemcpy(c->tile_cum.p, cum32.data(), ((size_t)n_rows + 1) * 4, cudaMemcpyHostToDevice));
   }
-  CU(c, c->sums[0].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
-  CU(c, c->sums[1].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
+  for (int i = 0; i < SKB_NSUMS; ++i) CU(c, c->sums[i].ensure(std::max<size_t>(8, (size_t)n_rows * 8)));
   CU(c, cudaMemsetAsync(c->sums[0].p, 0, std::max<size_t>(8, (size_t)n_rows * 8), c->stream));
   c->sums_cur = 0;
   c->tracked_top = 0;
-  c->pass_cur = first_pass_reads(c);
-  CU(c, c->tracked[0].ensure((SKB_MAX_TRACKED + 1) * 4));
-  CU(c, c->tracked[1].ensure((SKB_MAX_TRACKED + 1) * 4));
+  c->pass_proven = false;
+  c->dense_left = 1;  // the pass after the first (always dense) one: the tracked rows of a few thousand reads bound little
+  for (int i = 0; i < SKB_NTRACK; ++i) CU(c, c->tracked[i].ensure((SKB_MAX_TRACKED + 1) * 4));
+  c->tracked_cur = 0;
   CU(c, cudaStreamSynchronize(c->stream));
   c->has_ref = true;
   return SKB_OK;
@@ -652,38 +657,105 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   }
   if (int rc = check_launch(c, "compact")) return rc;
 
-  // ---- rows tracked for the bounds: start from the current top rows
-  const uint32_t n_top_rows = std::min(top, c->n_rows);
-  unsigned long long* sums_in = c->sums[c->sums_cur].as<unsigned long long>();
   uint32_t* h_total = c->h_scal;
-  if (c->tracked_top != top) {
-    uint32_t* tr = c->tracked[c->tracked_cur].as<uint32_t>();
-    { ProfScope ps(c, SKB_K_RANK, 1);
-      skb_launch_rank_full(sums_in, c->n_rows, n_top_rows, 0, nullptr, nullptr, tr, c->stream); }
-    h_total[4] = n_top_rows;
-    CU(c, cudaMemcpyAsync(tr + SKB_MAX_TRACKED, &h_total[4], 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    c->tracked_top = top;
-  }
-  CU(c, c->scal.ensure(256));
-  uint32_t* d_cand_total = c->scal.as<uint32_t>() + 8;                                                  // overflow flag
+  uint32_t* d_scal = c->scal.as<uint32_t>();
   unsigned long long* d_cand_stat = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 64);  // statistics
+  uint32_t* d_abort = d_scal + 24;
+  uint32_t* d_dense_ovf = d_scal + 20;
   CU(c, cudaMemsetAsync(d_cand_stat, 0, 16, c->stream));  // candidates, member keys
-
-  // Passes are enqueued back to back and checked on the host only every few passes: a pass whose candidates overflow
-  // records itself in `abort` on the device, the passes enqueued behind it do nothing, and the host rolls back to it.
-  struct PassRec { uint32_t r, B; int sums_cur, tracked_cur; };
-  std::vector<PassRec> recs;
-  uint32_t* d_abort = c->scal.as<uint32_t>() + 24;
   CU(c, cudaMemsetAsync(d_abort, 0, 32, c->stream));
-  CU(c, cudaMemsetAsync(d_cand_total, 0, 12, c->stream));  // bucket-overflow flag + interval slot counter (the verdict kernel clears them after every pass)
+  CU(c, cudaMemsetAsync(d_scal + 8, 0, 32, c->stream));  // per post-slot: bucket-overflow flag, interval count, segment-record count (the verdict kernel clears them after every pass)
+  CU(c, cudaMemsetAsync(d_dense_ovf, 0, 4, c->stream));
+
+  // ---- every buffer a pass may need, sized once for the largest pass: nothing is (re)allocated while passes are in flight
+  uint64_t budget = SKB_CAND_BUDGET;
+  if (const char* eb = getenv("SKB_CAND_BUDGET")) budget = std::max<uint64_t>(64, strtoull(eb, nullptr, 10));  // tests only
+  const uint32_t Bmax = std::max<uint32_t>(1, std::min<uint32_t>(c->pass_max, R));
+  const uint32_t stride_max = (uint32_t)round_up(Bmax, 512);
+  // dense ranking: row groups so that (reads x groups) threads fill the GPU, bounded by the part lists' size
+  uint32_t groups_max = std::max<uint32_t>(1, std::min<uint32_t>(256, (uint32_t)((256ull << 20) / ((uint64_t)Bmax * top * 12))));
+  groups_max = std::min<uint32_t>(groups_max, std::max<uint32_t>(1, c->n_rows / 64));
+  {
+    cudaError_t e = cudaSuccess;
+    auto need = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.ensure(bytes); };
+    need(c->counts, (size_t)SKB_MAX_TRACKED * stride_max * 2);
+    need(c->tprefix, (size_t)SKB_MAX_TRACKED * stride_max * 4);
+    need(c->textra, (size_t)SKB_MAX_TRACKED * 8);
+    for (int i = 0; i < SKB_NTAB; ++i) { need(c->lb_sum[i], (size_t)Bmax * 8); need(c->lb_idx[i], (size_t)Bmax * 4); }
+    for (int i = 0; i < 2; ++i) {
+      need(c->cand_cnt[i], (size_t)Bmax * 4);
+      need(c->cand[i], (size_t)std::max<uint64_t>(budget, std::max<uint32_t>(c->n_rows, 64)) * sizeof(SkbCand));
+      need(c->ivl[i], (size_t)SKB_IVL_CAP * sizeof(SkbInterval));
+      need(c->seg_hdr[i], (size_t)SKB_SEG_CAP * 16);
+      need(c->seg_words[i], (size_t)SKB_SEG_CAP * SKB_SEG_WORDS_MAX * 4);
+    }
+    need(c->dense, (size_t)c->n_rows * stride_max * 2);  // u16 per read (u32 for half as many reads with u16 counters)
+    need(c->part_idx, (size_t)groups_max * Bmax * top * 4);
+    need(c->part_sum, (size_t)groups_max * Bmax * top * 8);
+    if (e != cudaSuccess) return fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
+    const uint64_t key_budget = 32ull * skb_fused_max_reads(1);
+    uint64_t max_keys = 0;
+    for (uint32_t r0 = 0; r0 < R; r0 += Bmax) max_keys = std::max(max_keys, q_off[std::min(R, r0 + Bmax)] - q_off[r0]);
+    if (int rc = ensure_table(c, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(max_keys, 1), key_budget))) return rc;
+  }
+
+  // The pass loop. A pass = a block of consecutive reads against the whole shard:
+  //   pre(i)    query table T_i (+ for a sparse pass: exact per-read sums of the tracked rows X_i -> per-read bounds L_i)
+  //   stream(i) the HBM-bound kernel: sums S_{i-1} -> S_i, plus what the ranking needs
+  //   post(i)   the top-N of every read of the pass, and the tracked rows U_i the next passes take their bounds from
+  // Two ranking modes, same answer:
+  //   sparse  rows are tested against per-read lower bounds of the top-th key (from the tracked rows' exact sums);
+  //           the few that pass become per-read candidate lists (walk / expand / select). Cheap when the bounds are good.
+  //   dense   the stream writes every hit row's prefix sums over the reads of the pass and every read is ranked over all
+  //           rows by brute force (dense_topk + merge). Needs no bounds and cannot overflow: used right after a reset,
+  //           for small shards, and to redo a sparse pass whose candidates overflowed.
+  // stream() kernels run on the main stream, pre() and post() on the side stream. In steady state (sparse passes that
+  // have been seen to fit) passes are enqueued in batches and checked on the host only every few passes; with
+  // `pipeline` the bounds of pass i then come from X_i = U_{i-2} with sums S_{i-2} + (row totals against T_{i-1}), all
+  // exact, so pre(i) does not wait for stream(i-1). A sparse pass whose candidates overflow records itself in `abort` on
+  // the device, the passes behind it do nothing, and the host redoes it as a dense pass.
+  struct PassRec { uint32_t r, B; int sums_in, tracked_in; bool full; };
+  std::vector<PassRec> recs;
+  struct Pending { bool on = false, dense = false; SkbRankArgs ra; SkbDenseArgs da; int fused_ev = 0; } post;
   const uint32_t kBatch = 8;
-  bool force_sync = false;  // after a rollback: one pass at a time until the pass size is back at its maximum
-  uint32_t seq = 0;
-  uint32_t r = 0;
-  int rc_final = SKB_OK;
+  bool prev_pipelined = false;  // the previous pass of this call was enqueued in steady state (S_{i-2}, T_{i-1} are its inputs)
+  uint32_t seq = 0, r = 0, dense_until = 0, dense_max_reads = Bmax;
+  int rc_final = SKB_OK, tracked_prev = c->tracked_cur;
+  const SkbRefView rv = ref_view(c);
+  // (a small shard's prefix-sum vectors are a few MB: dense ranking costs less than the sparse launch train)
+  const bool small_shard = c->rank_mode == 2 || (c->rank_mode == 0 && (uint64_t)c->n_rows * stride_max * 2 <= (32ull << 20));
+
+  auto enqueue_post = [&]() {  // post(i) on the side stream, behind stream(i)
+    if (!post.on) return;
+    cudaStreamWaitEvent(c->side, c->ev_fused[post.fused_ev], 0);
+    if (post.dense) {
+      ProfScope ps(c, SKB_K_RANK, 3, c->side);
+      skb_launch_dense_topk(post.da, c->side);
+      skb_launch_merge_topn(post.da.part_idx, post.da.part_sum, post.da.groups, post.da.n_reads, top, post.ra.out_idx, post.ra.out_sum, c->side);
+      skb_launch_tracked_update(post.ra, c->side);
+    } else {
+      ProfScope ps(c, SKB_K_RANK, 6, c->side);
+      skb_launch_rank_expand(post.ra, c->side); skb_launch_rank_select(post.ra, c->side);
+      skb_launch_pass_verdict(post.ra, c->side);
+      skb_launch_tracked_update(post.ra, c->side);  // from this pass's top lists (skipped on the device after an overflow)
+    }
+    post.on = false;
+  };
+  auto join_streams = [&]() -> cudaError_t {  // main stream waits for everything enqueued on the side stream
+    cudaError_t e = cudaEventRecord(c->ev_join, c->side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+    return e;
+  };
+  // the side stream starts behind whatever the main stream has done so far (hashing, selection, resets)
+  cudaEventRecord(c->ev_join, c->stream);
+  cudaStreamWaitEvent(c->side, c->ev_join, 0);
+
   while (r < R) {
-    uint32_t B = std::min<uint32_t>(std::min(c->pass_cur, c->pass_max), R - r);
+    const bool need_init = c->tracked_top != top;  // no tracked rows yet (first pass after an upload / a reset, or `top` changed)
+    const bool dense = small_shard || need_init || c->dense_left > 0 || r < dense_until;
+    uint32_t B = std::min<uint32_t>(c->pass_max, R - r);
+    if (dense) B = std::min(B, dense_max_reads);
+    const bool full = R - r >= c->pass_max;  // not the short last pass of a call
     // u8 counters need every read of the pass to keep <= 255 query hashes; otherwise u16 counters and fewer reads
     bool narrow = true;
     for (uint32_t i = r; i < r + B; ++i)
@@ -693,124 +765,152 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
     const uint64_t key_budget = 32ull * skb_fused_max_reads(1);  // 2^17 for 4096-read passes
     while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
     const uint32_t nkeys = (uint32_t)(q_off[r + B] - q_off[r]);
-    if (int rc = ensure_table(c, nkeys)) { rc_final = rc; break; }
-    // per-read candidate buckets share one fixed budget: small passes (loose bounds right after a reset) get buckets
-    // as large as the shard itself, full passes still hold thousands of contenders per read
-    uint64_t budget = SKB_CAND_BUDGET;
-    if (const char* eb = getenv("SKB_CAND_BUDGET")) budget = std::max<uint64_t>(64, strtoull(eb, nullptr, 10));  // tests only
+    if (nkeys > c->t_maxkeys) { rc_final = fail(c, SKB_ERR_INVALID_ARG, "a single read keeps %u query hashes; the pass table holds %u", nkeys, c->t_maxkeys); break; }
+    // per-read candidate buckets share one fixed budget
     c->cand_cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(std::max<uint32_t>(c->n_rows, 64), budget / B));
     const uint32_t stride = (uint32_t)round_up(B, narrow ? 512 : 256);
-    const size_t ctr_bytes = (size_t)SKB_MAX_TRACKED * stride * 2;
-    cudaError_t e;
-    if ((e = c->counts.ensure(ctr_bytes)) != cudaSuccess || (e = c->lb_sum.ensure((size_t)B * 8)) != cudaSuccess ||
-        (e = c->lb_idx.ensure((size_t)B * 4)) != cudaSuccess || (e = c->cand_cnt.ensure((size_t)B * 4)) != cudaSuccess ||
-        (e = c->ivl.ensure((size_t)SKB_IVL_CAP * sizeof(SkbInterval))) != cudaSuccess ||
-        (e = c->seg_hdr.ensure((size_t)SKB_SEG_CAP * 16)) != cudaSuccess ||
-        (e = c->seg_words.ensure((size_t)SKB_SEG_CAP * SKB_SEG_WORDS_MAX * 4)) != cudaSuccess ||
-        (e = c->cand.ensure((size_t)B * c->cand_cap * sizeof(SkbCand))) != cudaSuccess ||
-        (e = c->tprefix.ensure((size_t)SKB_MAX_TRACKED * stride * 4)) != cudaSuccess) {
-      rc_final = fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
-      break;
-    }
-    SkbTable t = table_of(c);
-    { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1);
-      skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->stream); }
-    cudaMemsetAsync(c->counts.p, 0, ctr_bytes, c->stream);
-    cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)B * 4, c->stream);
-    const SkbRefView rv = ref_view(c);
+    const bool steady = !dense && c->pass_proven;
+    const bool lag2 = c->pipeline && steady && prev_pipelined;  // bounds from U_{i-2}: pre(i) does not wait for stream(i-1)
+    const int tab = (c->tab_cur + 1) % SKB_NTAB, tab_prev = c->tab_cur;
+    const int qs = seq & 1;                       // post slot (records, buckets, counters)
+    const int s_in = c->sums_cur, s_out = (s_in + 1) % SKB_NSUMS, s_in2 = (s_in + SKB_NSUMS - 1) % SKB_NSUMS;
+    const int x_in = lag2 ? tracked_prev : c->tracked_cur, x_out = (c->tracked_cur + 1) % SKB_NTRACK;
+    if (!lag2) enqueue_post();  // X_i = U_{i-1}: post(i-1) first
+
+    // ---- pre(i) on the side stream
+    const SkbTable t = table_of(c, tab);
+    { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1, c->side);
+      skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->side); }
     SkbRankArgs ra{};
     ra.tracked_counts = c->counts.as<uint16_t>(); ra.tracked_prefix = c->tprefix.as<uint32_t>();
+    ra.tracked_extra = c->textra.as<unsigned long long>();
     ra.row_stride = stride; ra.n_reads = B; ra.row_base = c->row_base;
-    ra.sums_in = c->sums[c->sums_cur].as<unsigned long long>();
-    ra.tracked = c->tracked[c->tracked_cur].as<uint32_t>(); ra.n_tracked = ra.tracked + SKB_MAX_TRACKED;
-    ra.lb_sum = c->lb_sum.as<unsigned long long>(); ra.lb_idx = c->lb_idx.as<uint32_t>();
-    ra.ivl = c->ivl.as<SkbInterval>(); ra.ivl_cap = SKB_IVL_CAP; ra.ivl_total = d_cand_total + 1;
-    ra.seg_hdr = c->seg_hdr.as<uint4>(); ra.seg_words = c->seg_words.as<uint32_t>(); ra.seg_cap = SKB_SEG_CAP;
-    ra.seg_cpw = narrow ? 4 : 2; ra.seg_words_per = stride / 32 / ra.seg_cpw; ra.seg_total = d_cand_total + 2;
-    ra.cand = c->cand.as<SkbCand>(); ra.cand_cap = c->cand_cap; ra.cand_total = d_cand_total;
-    ra.cand_cnt = c->cand_cnt.as<uint32_t>(); ra.cand_stat = d_cand_stat;
+    ra.sums_in = c->sums[lag2 ? s_in2 : s_in].as<unsigned long long>();
+    ra.tracked = c->tracked[x_in].as<uint32_t>(); ra.n_tracked = ra.tracked + SKB_MAX_TRACKED;
+    ra.lb_sum = c->lb_sum[tab].as<unsigned long long>(); ra.lb_idx = c->lb_idx[tab].as<uint32_t>();
+    ra.ivl = c->ivl[qs].as<SkbInterval>(); ra.ivl_cap = SKB_IVL_CAP; ra.ivl_total = d_scal + 8 + 4 * qs + 1;
+    ra.seg_hdr = c->seg_hdr[qs].as<uint4>(); ra.seg_words = c->seg_words[qs].as<uint32_t>(); ra.seg_cap = SKB_SEG_CAP;
+    ra.seg_cpw = narrow ? 4 : 2; ra.seg_words_per = stride / 32 / ra.seg_cpw; ra.seg_total = d_scal + 8 + 4 * qs + 2;
+    ra.cand = c->cand[qs].as<SkbCand>(); ra.cand_cap = c->cand_cap; ra.cand_total = d_scal + 8 + 4 * qs;
+    ra.cand_cnt = c->cand_cnt[qs].as<uint32_t>(); ra.cand_stat = d_cand_stat;
     ra.top = top; ra.out_idx = d_out_idx + (size_t)r * top;
     ra.out_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)r * top;
-    ra.tracked_next = c->tracked[c->tracked_cur ^ 1].as<uint32_t>(); ra.n_tracked_next = ra.tracked_next + SKB_MAX_TRACKED;
+    ra.tracked_next = c->tracked[x_out].as<uint32_t>(); ra.n_tracked_next = ra.tracked_next + SKB_MAX_TRACKED;
     ra.abort = d_abort; ra.seq = seq;
-    { ProfScope ps(c, SKB_K_RANK, nkeys ? 3 : 2);
-      if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, ra.n_tracked, t, c->counts.as<uint16_t>(), stride, c->stream);
-      skb_launch_rank_bounds(ra, c->stream); }
+    cudaError_t e = cudaSuccess;
+    if (!dense) {
+      e = cudaMemsetAsync(c->counts.p, 0, (size_t)SKB_MAX_TRACKED * stride * 2, c->side);
+      if (e == cudaSuccess) e = cudaMemsetAsync(c->textra.p, 0, (size_t)SKB_MAX_TRACKED * 8, c->side);
+      if (e != cudaSuccess) { rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e)); break; }
+      ProfScope ps(c, SKB_K_RANK, (nkeys ? 3 : 2) + (lag2 ? 1 : 0), c->side);
+      if (lag2) skb_launch_tracked_totals(rv, ra.tracked, ra.n_tracked, table_of(c, tab_prev), ra.tracked_extra, c->side);
+      if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, ra.n_tracked, t, c->counts.as<uint16_t>(), stride, c->side);
+      skb_launch_rank_bounds(ra, c->side);
+    }
+    cudaEventRecord(c->ev_pre[tab], c->side);
+    if (lag2) enqueue_post();  // post(i-1) behind pre(i): it runs next to stream(i)
+
+    // ---- stream(i) on the main stream
+    cudaStreamWaitEvent(c->stream, c->ev_pre[tab], 0);
+    if (!dense) cudaMemsetAsync(c->cand_cnt[qs].p, 0, (size_t)B * 4, c->stream);
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
     fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
-    fa.sums_in = ra.sums_in; fa.sums_out = c->sums[c->sums_cur ^ 1].as<unsigned long long>();
+    fa.sums_in = c->sums[s_in].as<unsigned long long>(); fa.sums_out = c->sums[s_out].as<unsigned long long>();
     fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx;
-    fa.ivl = c->ivl.as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_cand_total + 1; fa.abort = d_abort;
-    fa.seg_hdr = c->seg_hdr.as<uint4>(); fa.seg_words = c->seg_words.as<uint32_t>(); fa.seg_cap = SKB_SEG_CAP;
-    fa.seg_total = d_cand_total + 2;
+    fa.ivl = c->ivl[qs].as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_scal + 8 + 4 * qs + 1; fa.abort = d_abort;
+    fa.seg_hdr = c->seg_hdr[qs].as<uint4>(); fa.seg_words = c->seg_words[qs].as<uint32_t>(); fa.seg_cap = SKB_SEG_CAP;
+    fa.seg_total = d_scal + 8 + 4 * qs + 2;
+    fa.dense = dense ? c->dense.p : nullptr; fa.dense_overflow = d_dense_ovf;
     fa.tile_cum = c->tile_cum.as<uint32_t>();
     fa.tpr = std::max(1u, (c->uniform_len + skb_fused_tile() - 1) / skb_fused_tile());
     fa.tpr_magic = (uint32_t)((0x100000000ull + fa.tpr - 1) / fa.tpr);
     { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
-    { ProfScope ps(c, SKB_K_RANK, 5);
-      skb_launch_rank_expand(ra, c->stream); skb_launch_rank_select(ra, c->stream);
-      skb_launch_pass_verdict(ra, c->stream);
-      skb_launch_tracked_update(ra, c->stream); }  // from this pass's top lists (skipped on the device after an overflow)
+    cudaEventRecord(c->ev_fused[qs], c->stream);
     if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
-    recs.push_back({r, B, c->sums_cur, c->tracked_cur});
+    post.on = true; post.dense = dense; post.ra = ra; post.fused_ev = qs;
+    if (dense) {
+      SkbDenseArgs da{};
+      da.dense = c->dense.p; da.wide = narrow ? 0 : 1; da.cnt_stride = stride; da.n_rows = c->n_rows; da.n_reads = B;
+      da.row_base = c->row_base; da.top = top;
+      // row groups: enough CTAs (64 reads x one group each) to fill the GPU a few times over, at least 64 rows per group
+      da.groups = std::max<uint32_t>(1, std::min<uint32_t>(groups_max, (uint32_t)((8ull * c->num_sms * 64 + B - 1) / B)));
+      da.sums_in = fa.sums_in; da.sums_out = fa.sums_out;
+      da.part_idx = c->part_idx.as<uint32_t>(); da.part_sum = c->part_sum.as<unsigned long long>();
+      post.da = da;
+    }
+    recs.push_back({r, B, s_in, c->tracked_cur, full});
     c->st_passes += 1;
-    c->sums_cur ^= 1;
-    c->tracked_cur ^= 1;
+    c->sums_cur = s_out;
+    tracked_prev = c->tracked_cur;
+    c->tracked_cur = x_out;
+    c->tab_cur = tab;
+    prev_pipelined = steady;
     r += B;
     ++seq;
-    const bool batchable = !force_sync && B > 1 && c->pass_cur >= c->pass_max;
-    if (batchable && recs.size() < kBatch && r < R) continue;
+    if (steady && recs.size() < kBatch && r < R) continue;
+
     // ---- checkpoint: did any pass since the last one overflow?
-    if ((e = cudaMemcpyAsync(h_total, d_abort, 32, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+    enqueue_post();
+    if ((e = join_streams()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(h_total, d_abort, 32, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(h_total + 8, d_dense_ovf, 4, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
       rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e));
       break;
     }
-    if (h_total[0] != 0) {  // more contenders than a bucket / the interval list holds, in the pass numbered h_total[1]
-      const PassRec& pr = recs[recs.size() - (seq - h_total[1])];
+    prev_pipelined = false;  // everything is finished: the next pass may use S_{i-1} and U_{i-1} directly
+    if (getenv("SKB_TRACE_PASSES"))
+      fprintf(stderr, "[skb] checkpoint after %zu pass(es), last %s at read %u with %u reads: fullest bucket %u of %u, intervals %u, segment records %u%s\n",
+              recs.size(), dense ? "dense" : "sparse", recs.back().r, recs.back().B, h_total[2], c->cand_cap, h_total[3], h_total[4],
+              h_total[0] || h_total[8] ? " OVERFLOW" : "");
+    if (h_total[8] != 0) {  // a 16-bit prefix sum overflowed in the dense pass just checked (dense passes are checked one by one)
+      const PassRec pr = recs.back();
+      if ((e = cudaMemsetAsync(d_dense_ovf, 0, 4, c->stream)) != cudaSuccess) { rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e)); break; }
+      r = pr.r; c->sums_cur = pr.sums_in; c->tracked_cur = pr.tracked_in; tracked_prev = pr.tracked_in;
+      c->st_passes -= 1;
+      dense_until = std::max(dense_until, pr.r + pr.B);
+      dense_max_reads = 256;  // 255 * 256 < 2^16: cannot overflow
+      recs.clear();
+      cudaEventRecord(c->ev_join, c->stream);
+      cudaStreamWaitEvent(c->side, c->ev_join, 0);
+      continue;
+    }
+    if (h_total[0] != 0) {  // more contenders than a bucket / a record list holds, in the sparse pass numbered h_total[1]
+      const PassRec pr = recs[recs.size() - (seq - h_total[1])];
       if (getenv("SKB_TRACE_PASSES"))
-        fprintf(stderr, "[skb] pass at read %u with %u reads overflowed (fullest bucket %u of %u, intervals %u of %u, segment records %u of %u): redo with %u\n", pr.r, pr.B,
-                h_total[2], c->cand_cap, h_total[3], (unsigned)SKB_IVL_CAP, h_total[4], (unsigned)SKB_SEG_CAP, std::max(1u, pr.B / 2));
-      c->st_passes -= (seq - h_total[1]) - 1;  // the passes behind the failed one did not run
-      cudaMemsetAsync(d_abort, 0, 32, c->stream);
-      if (pr.B > 1) {
-        // redo from that pass with fewer reads: the bounds tighten after every pass
-        r = pr.r; c->sums_cur = pr.sums_cur; c->tracked_cur = pr.tracked_cur;
-        c->pass_cur = std::max(1u, pr.B / 2);
-        force_sync = true;
-        recs.clear();
-        continue;
+        fprintf(stderr, "[skb] pass at read %u with %u reads overflowed (fullest bucket %u of %u, intervals %u of %u, segment records %u of %u): redo dense\n", pr.r, pr.B,
+                h_total[2], c->cand_cap, h_total[3], (unsigned)SKB_IVL_CAP, h_total[4], (unsigned)SKB_SEG_CAP);
+      c->st_passes -= (seq - h_total[1]) - 1;  // the passes behind the failed one did nothing (the failed one did stream)
+      if ((e = cudaMemsetAsync(d_abort, 0, 32, c->stream)) != cudaSuccess ||
+          (e = cudaMemsetAsync(d_scal + 8, 0, 32, c->stream)) != cudaSuccess) {
+        rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e));
+        break;
       }
-      // a single read (always the newest pass: single-read passes are checked one by one): its ranking is simply
-      // the top of the new sums (exact, no candidates needed)
-      ProfScope ps(c, SKB_K_RANK, 2);
-      unsigned long long* sums_new = c->sums[c->sums_cur].as<unsigned long long>();
-      uint32_t* o_idx = d_out_idx + (size_t)pr.r * top;
-      unsigned long long* o_sum = reinterpret_cast<unsigned long long*>(d_out_sum) + (size_t)pr.r * top;
-      skb_launch_rank_full(sums_new, c->n_rows, n_top_rows, c->row_base, o_idx, o_sum, nullptr, c->stream);
-      if (n_top_rows < top) {
-        cudaMemsetAsync(o_idx + n_top_rows, 0xFF, (size_t)(top - n_top_rows) * 4, c->stream);
-        cudaMemsetAsync(o_sum + n_top_rows, 0, (size_t)(top - n_top_rows) * 8, c->stream);
-      }
-      skb_launch_tracked_update(ra, c->stream);  // the guard is clear again
-    } else {
-      // grow the pass only when the fullest bucket of the last pass leaves headroom: twice the reads means half the
-      // bucket, and the tracked rows are staler towards the end of a longer pass (assume twice the contenders)
-      const uint32_t lastB = recs.back().B;
-      const uint64_t grown = std::min<uint64_t>(c->pass_max, (uint64_t)std::max(lastB, c->pass_cur) * 2);
-      const uint64_t cap_grown = std::min<uint64_t>(std::max<uint32_t>(c->n_rows, 64), budget / std::max<uint64_t>(grown, 1));
-      // (a short last pass of a call says little about a full one: it never grows the pass)
-      // (and the interval / segment-record lists: their length follows the lane segments that reach a bound, which
-      // at worst doubles with the reads while the pass is below 32 segments of 16 reads)
-      const bool lists_ok = 2ull * h_total[3] <= SKB_IVL_CAP && 2ull * h_total[4] <= SKB_SEG_CAP;
-      if (lastB >= c->pass_cur && lists_ok && (2ull * h_total[2] <= cap_grown || cap_grown >= c->n_rows)) c->pass_cur = (uint32_t)grown;
-      else c->pass_cur = std::max(lastB, c->pass_cur);
-      if (c->pass_cur >= c->pass_max) force_sync = false;
+      // redo from that pass, densely. Its input sums and the tracked rows it started from are intact: the passes
+      // behind it left everything alone.
+      r = pr.r; c->sums_cur = pr.sums_in; c->tracked_cur = pr.tracked_in; tracked_prev = pr.tracked_in;
+      dense_until = std::max(dense_until, pr.r + pr.B);
+      c->dense_left = 1;  // and the pass after it: its bounds would be as loose
+      c->pass_proven = false;
+      recs.clear();
+      cudaEventRecord(c->ev_join, c->stream);
+      cudaStreamWaitEvent(c->side, c->ev_join, 0);
+      continue;
+    }
+    if (dense) {
+      c->tracked_top = top;  // the dense pass proposed tracked rows: bounds exist from here on
+      if (!need_init && recs.back().r >= dense_until && c->dense_left > 0) c->dense_left -= 1;
+    } else if (recs.back().full) {
+      c->pass_proven = true;  // full-size sparse passes fit: from here on they are enqueued in batches
     }
     recs.clear();
   }
-  if (rc_final) return rc_final;
+  if (rc_final) {  // leave nothing in flight behind an error
+    cudaStreamSynchronize(c->side);
+    cudaStreamSynchronize(c->stream);
+    return rc_final;
+  }
   unsigned long long cands[2] = {0, 0};
   CU(c, cudaMemcpyAsync(cands, d_cand_stat, 16, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -841,8 +941,14 @@ int skb_create(int device, skb_ctx** out) {
   skb_ctx* c = new skb_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SKB_ERR_CUDA; }
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < SKB_NTAB; ++i) ok = cudaEventCreateWithFlags(&c->ev_pre[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&c->ev_fused[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { delete c; return SKB_ERR_CUDA; }
+  if (const char* e = getenv("SKB_PIPELINE")) c->pipeline = e[0] != '0';  // experiments: 0 = every pass waits for the one before
   if (cudaHostAlloc((void**)&c->h_scal, 64, cudaHostAllocDefault) != cudaSuccess) {
     cudaStreamDestroy(c->stream); delete c; return SKB_ERR_OOM;
   }
@@ -854,17 +960,26 @@ void skb_destroy(skb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->side) cudaStreamSynchronize(c->side);
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-  DevBuf* bufs[] = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->memb, &c->sums[0], &c->sums[1], &c->tracked[0], &c->tracked[1], &c->tprefix, &c->g_tau, &c->g_cap,
-                    &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->cand_pool,
-                    &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->lb_sum,
-                    &c->lb_idx, &c->ivl, &c->seg_hdr, &c->seg_words, &c->tile_cum, &c->cand, &c->cand_cnt, &c->scal,
-                    &c->t_slots, &c->t_fill, &c->t_reads, &c->t_slot, &c->t_bloom, &c->out_idx,
-                    &c->out_sum, &c->misc};
+  std::vector<DevBuf*> bufs = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->tile_cum, &c->memb, &c->tprefix, &c->textra,
+                               &c->g_tau, &c->g_cap, &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status,
+                               &c->cand_pool, &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->scal,
+                               &c->out_idx, &c->out_sum, &c->misc, &c->dense, &c->part_idx, &c->part_sum};
+  for (auto& x : c->sums) bufs.push_back(&x);
+  for (auto& x : c->tracked) bufs.push_back(&x);
+  for (int i = 0; i < SKB_NTAB; ++i)
+    for (DevBuf* x : {&c->lb_sum[i], &c->lb_idx[i], &c->t_slots[i], &c->t_fill[i], &c->t_reads[i], &c->t_slot[i], &c->t_bloom[i]}) bufs.push_back(x);
+  for (int i = 0; i < 2; ++i)
+    for (DevBuf* x : {&c->cand[i], &c->cand_cnt[i], &c->ivl[i], &c->seg_hdr[i], &c->seg_words[i]}) bufs.push_back(x);
   for (DevBuf* b : bufs) b->release();
   if (c->h_scal) cudaFreeHost(c->h_scal);
   cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (cudaEvent_t e : c->ev_pre) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_fused) if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -872,6 +987,7 @@ const char* skb_last_error(const skb_ctx* c) { return c ? c->err.c_str() : "null
 void* skb_stream(skb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int skb_synchronize(skb_ctx* c) {
   if (!c) return SKB_ERR_INVALID_ARG;
+  CU(c, cudaStreamSynchronize(c->side));
   CU(c, cudaStreamSynchronize(c->stream));
   return SKB_OK;
 }
@@ -1064,7 +1180,8 @@ int skb_sums_reset(skb_ctx* c) {
   if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
   CU(c, cudaMemsetAsync(c->sums[c->sums_cur].p, 0, std::max<size_t>(8, (size_t)c->n_rows * 8), c->stream));
   c->tracked_top = 0;
-  c->pass_cur = first_pass_reads(c);
+  c->pass_proven = false;
+  c->dense_left = 1;  // the pass after the first (always dense) one: the tracked rows of a few thousand reads bound little
   return SKB_OK;
 }
 
@@ -1084,13 +1201,22 @@ int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
   if (c->n_rows) CU(c, cudaMemcpyAsync(c->sums[c->sums_cur].p, in, (size_t)c->n_rows * 8, cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   c->tracked_top = 0;
+  c->pass_proven = false;
+  c->dense_left = 1;
+  return SKB_OK;
+}
+
+int skb_set_rank_mode(skb_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 2) return SKB_ERR_INVALID_ARG;
+  c->rank_mode = mode;
+  c->pass_proven = false;
   return SKB_OK;
 }
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
   c->pass_max = m ? std::min<uint32_t>(m, skb_fused_max_reads(1)) : skb_fused_max_reads(1);
-  c->pass_cur = std::min(c->pass_cur, c->pass_max);
+  c->pass_proven = false;
   return SKB_OK;
 }
 

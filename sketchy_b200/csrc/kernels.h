@@ -125,6 +125,8 @@ struct SkbFusedArgs {
   uint32_t* seg_words;                // [seg_cap][cnt_stride / 32 / counters-per-word] the segment's counters
   uint32_t seg_cap;
   uint32_t* seg_total;                // [1] records produced; > seg_cap = overflow
+  void* dense;                        // non-null: dense pass, [n_rows][cnt_stride] prefix sums (u16 / u32) instead of candidates
+  uint32_t* dense_overflow;           // [1] set when a u16 prefix sum overflows
   const uint32_t* tile_cum;           // [n_rows + 1] sub-tiles before each row of the shard (ragged shards only)
   uint32_t tpr, tpr_magic;            // uniform shards: sub-tiles per row and ceil(2^32 / tpr) (tile -> row by a multiply)
   const uint32_t* abort;              // [2] {set once an earlier pass of the batch overflowed, its sequence number}: skip
@@ -141,6 +143,9 @@ uint32_t skb_fused_max_reads(int narrow);
 // per-read counts of the tracked rows only (they define the bounds): ctr[t][read], u16, row stride `stride`
 void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
                                const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st);
+// totals of the tracked rows against a pass's table (all reads of that pass): extra[t] += hits of tracked row t
+void skb_launch_tracked_totals(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
+                               const SkbTable& t, unsigned long long* extra, cudaStream_t st);
 #define SKB_CAND_BUDGET ((24u << 20) << (SKB_X_IDBITS - 12))  // candidate records per pass over all reads (384 MB per 4096 reads); bucket = budget / reads
 
 #define SKB_MAX_TRACKED 192u  // rows whose exact per-read sums define the bounds
@@ -148,6 +153,7 @@ void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, co
 struct SkbRankArgs {
   uint16_t* tracked_counts;        // [SKB_MAX_TRACKED][row_stride] per-read counts of the tracked rows
   uint32_t* tracked_prefix;        // [SKB_MAX_TRACKED][row_stride] inclusive prefix sums of the above
+  unsigned long long* tracked_extra;  // [SKB_MAX_TRACKED] added to sums_in of each tracked row (its total of the pass that is still streaming; zero otherwise)
   uint32_t row_stride;
   uint32_t n_reads;  // reads in this pass
   uint32_t row_base; // global index of local row 0
@@ -188,6 +194,18 @@ void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st);
 // top-N of a plain value array by (value desc, index asc); one CTA. idx_base is added to reported indices.
 void skb_launch_rank_full(const unsigned long long* vals, uint32_t n, uint32_t top, uint32_t idx_base,
                           uint32_t* out_idx, unsigned long long* out_val, uint32_t* out_local, cudaStream_t st);
+
+// dense ranking of one pass: per (read, row group) top lists from the prefix-sum vectors (see dense_topk_kernel)
+struct SkbDenseArgs {
+  const void* dense;                   // [n_rows][cnt_stride] u16 (wide == 0) or u32 (wide == 1)
+  int wide;
+  uint32_t cnt_stride, n_rows, n_reads, row_base, top, groups;
+  const unsigned long long* sums_in;   // [n_rows] before the pass
+  const unsigned long long* sums_out;  // [n_rows] after the pass (== sums_in: the row had no hit, its vector is all zero)
+  uint32_t* part_idx;                  // [groups][n_reads][top]
+  unsigned long long* part_sum;
+};
+void skb_launch_dense_topk(const SkbDenseArgs& a, cudaStream_t st);
 
 void skb_launch_merge_topn(const uint32_t* idx_parts, const unsigned long long* sum_parts, uint32_t n_parts,
                            uint64_t n_reads, uint32_t top, uint32_t* out_idx, unsigned long long* out_sum,

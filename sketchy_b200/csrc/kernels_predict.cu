@@ -170,13 +170,13 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 // mbarrier / bulk-copy primitives
 // ---------------------------------------------------------------------------------------------------------
 #ifndef SKB_X_SUB
-#define SKB_X_SUB 512
+#define SKB_X_SUB 256
 #endif
 #ifndef SKB_X_STAGES
 #define SKB_X_STAGES 2
 #endif
 #ifndef SKB_X_CW
-#define SKB_X_CW 16
+#define SKB_X_CW 32
 #endif
 #ifndef SKB_X_ROWBUF
 #define SKB_X_ROWBUF 8
@@ -184,7 +184,7 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 #ifndef SKB_X_ABLATE
 #define SKB_X_ABLATE 0  // experiments only (never in the shipped build): 1 = no filter probe, 2 = probe but drop the passers, 4 = no candidate walk
 #endif
-constexpr int FS_SUB = SKB_X_SUB;        // hashes per sub-tile (4 KB): chunks of 8 per lane
+constexpr int FS_SUB = SKB_X_SUB;        // hashes per sub-tile (2 KB): chunks of 8 per lane
 constexpr int FS_STAGES = SKB_X_STAGES;  // staging buffers per warp
 constexpr int FS_WARPS = SKB_X_CW;
 constexpr int FS_THREADS = FS_WARPS * 32;
@@ -316,7 +316,44 @@ __device__ __forceinline__ void rank_row(const SkbFusedArgs& a, const FsCtl& ctl
   const uint32_t gi = a.row_base + row_in_shard;
   const unsigned long long fin = carry + row_total;
   const unsigned long long lb_min = ctl.lb_seg[0];
-  if (fin > lb_min || (fin == lb_min && gi <= __reduce_max_sync(0xffffffffu, ctl.li_seg[lane]))) {
+  if (a.dense) {
+    // Dense pass (no bounds yet, or the bounds let too many rows through): the row's sum after every read of the pass,
+    // relative to `carry`, goes out as one prefix-sum vector (u16 per read with u8 counters, u32 with u16 counters);
+    // dense_topk_kernel ranks every read over all rows from these.
+    if (row_total) {  // (a row without a hit keeps sums_out == sums_in: dense_topk_kernel never reads its vector)
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += y;
+      }
+      uint32_t run = incl - tot;
+      if (CPW == 4) {
+        if (row_total > 0xFFFFu) *a.dense_overflow = 1u;  // does not fit 16 bits: the host redoes the pass with <= 256 reads
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.dense) + (size_t)row_in_shard * a.cnt_stride + seg0);
+        for (uint32_t i = 0; i < segw; i += 2) {
+          uint32_t o4[4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t x = cseg[i + q];
+            const uint32_t p0 = run + (x & 0xFFu), p1 = p0 + ((x >> 8) & 0xFFu), p2 = p1 + ((x >> 16) & 0xFFu);
+            run = p2 + (x >> 24);
+            o4[2 * q] = (p0 & 0xFFFFu) | (p1 << 16);
+            o4[2 * q + 1] = (p2 & 0xFFFFu) | (run << 16);
+          }
+          dst[i >> 1] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(a.dense) + (size_t)row_in_shard * a.cnt_stride + seg0);
+        for (uint32_t i = 0; i < segw; i += 2) {
+          const uint32_t x0 = cseg[i], x1 = cseg[i + 1];
+          const uint32_t p0 = run + (x0 & 0xFFFFu), p1 = p0 + (x0 >> 16), p2 = p1 + (x1 & 0xFFFFu);
+          run = p2 + (x1 >> 16);
+          dst[i >> 1] = make_uint4(p0, p1, p2, run);
+        }
+      }
+    }
+  } else if (fin > lb_min || (fin == lb_min && gi <= __reduce_max_sync(0xffffffffu, ctl.li_seg[lane]))) {
     uint32_t incl = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -434,7 +471,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
       uint32_t row, tt, len;
       const uint64_t* p;
       if (a.rv.uniform_len) {
-        row = __umulhi(n, a.tpr_magic);  // n / tiles-per-row by a precomputed reciprocal (exact in this range)
+        row = a.tpr == 1u ? n : __umulhi(n, a.tpr_magic);  // n / tiles-per-row by a precomputed reciprocal (exact while n * tpr < 2^32)
         tt = n - row * a.tpr;
         len = a.rv.uniform_len;
         p = a.rv.ref + (size_t)(c0 + row) * a.rv.uniform_pitch;
@@ -627,6 +664,24 @@ __global__ void __launch_bounds__(256) tracked_counts_kernel(const SkbRefView rv
   }
 }
 
+// total hits of every tracked row against a pass's table (summed over the reads of that pass); 8 CTAs share a row
+__global__ void __launch_bounds__(256) tracked_totals_kernel(const SkbRefView rv, const uint32_t* __restrict__ tracked,
+                                                             const uint32_t* __restrict__ n_tracked, const SkbTable t,
+                                                             unsigned long long* extra) {
+  const uint32_t tr = blockIdx.x / 8, part = blockIdx.x % 8;
+  if (tr >= *n_tracked) return;
+  const uint32_t row = tracked[tr];
+  const uint64_t* src = rv.ref + rv.row_start[row];
+  const uint32_t len = rv.row_len[row];
+  uint32_t n = 0;
+  for (uint32_t i = part * blockDim.x + threadIdx.x; i < len; i += 8 * blockDim.x) {
+    SkbSlot s;
+    if (table_lookup(t, src[i], s)) n += SKB_SLOT_CNT(s.meta);
+  }
+  n = __reduce_add_sync(0xffffffffu, n);
+  if (skb_lane() == 0 && n) atomicAdd(&extra[tr], (unsigned long long)n);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // rank kernels
 // ---------------------------------------------------------------------------------------------------------
@@ -685,7 +740,7 @@ __global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
   uint32_t n = 0;
   for (uint32_t t = 0; t < nt; ++t) {
     const uint32_t row = a.tracked[t];
-    const unsigned long long s = a.sums_in[row] + a.tracked_prefix[(size_t)t * a.row_stride + b];
+    const unsigned long long s = a.sums_in[row] + a.tracked_extra[t] + a.tracked_prefix[(size_t)t * a.row_stride + b];
     const uint32_t gi = a.row_base + row;
     if (n == keep && !skb_key_better(s, gi, ks[n - 1], ki[n - 1])) continue;
     uint32_t pos = n < keep ? n : n - 1;  // insert, dropping the worst when full
@@ -909,6 +964,134 @@ __global__ void __launch_bounds__(1024) rank_full_kernel(const unsigned long lon
   }
 }
 
+// Dense ranking: per read, the `top` best rows by (sum desc, index asc) among one group of rows, from the per-row
+// prefix-sum vectors the streaming kernel wrote (dense[row][read], relative to sums_in[row]). One thread per
+// (read, row group): consecutive threads hold consecutive reads, so every row step is one coalesced load. Rows are
+// visited in increasing index, so a later row must be strictly better to displace an earlier one (the tie rule of
+// the reference's stable sort). Output: parts[g][read][top] for merge_topn_kernel. A vector of rows without a hit in
+// the pass is not written: such a row has sums_out == sums_in and counts as all-zero.
+template <int KREG, typename P>
+__global__ void __launch_bounds__(128) dense_topk_kernel(const SkbDenseArgs a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t g = blockIdx.y;
+  const uint32_t r_lo = (uint32_t)(((uint64_t)a.n_rows * g) / gridDim.y), r_hi = (uint32_t)(((uint64_t)a.n_rows * (g + 1)) / gridDim.y);
+  if (b >= a.n_reads) return;
+  const P* col = reinterpret_cast<const P*>(a.dense) + b;
+  const uint32_t top = a.top;
+  unsigned long long ks[KREG];
+  uint32_t ki[KREG];
+#pragma unroll
+  for (int t = 0; t < KREG; ++t) { ks[t] = 0; ki[t] = 0xFFFFFFFFu; }
+  for (uint32_t row = r_lo; row < r_hi; ++row) {
+    const unsigned long long s_in = a.sums_in[row];
+    const unsigned long long v = s_in + (a.sums_out[row] != s_in ? (unsigned long long)col[(size_t)row * a.cnt_stride] : 0ull);
+    const uint32_t gi = a.row_base + row;
+    if (KREG <= 16) {  // the list lives in registers: compare-and-shift through the whole list
+      if (skb_key_better(v, gi, ks[KREG - 1], ki[KREG - 1])) {
+        unsigned long long cs = v;
+        uint32_t ci = gi;
+#pragma unroll
+        for (int t = 0; t < KREG; ++t) {
+          const bool better = skb_key_better(cs, ci, ks[t], ki[t]);
+          const unsigned long long ts = ks[t];
+          const uint32_t ti = ki[t];
+          if (better) { ks[t] = cs; ki[t] = ci; cs = ts; ci = ti; }
+        }
+      }
+    } else {  // long lists (local memory): insertion from the tail
+      if (skb_key_better(v, gi, ks[top - 1], ki[top - 1])) {
+        uint32_t pos = top - 1;
+        while (pos > 0 && skb_key_better(v, gi, ks[pos - 1], ki[pos - 1])) { ks[pos] = ks[pos - 1]; ki[pos] = ki[pos - 1]; --pos; }
+        ks[pos] = v; ki[pos] = gi;
+      }
+    }
+  }
+  const size_t o = ((size_t)g * a.n_reads + b) * top;
+  if (KREG <= 16) {
+#pragma unroll
+    for (int t = 0; t < KREG; ++t)
+      if ((uint32_t)t < top) { a.part_sum[o + t] = ks[t]; a.part_idx[o + t] = ki[t]; }
+  } else {
+    for (uint32_t t = 0; t < top; ++t) { a.part_sum[o + t] = ks[t]; a.part_idx[o + t] = ki[t]; }
+  }
+}
+
+// Dense ranking for top <= 32, the fast form: a CTA takes 64 consecutive reads and one group of rows; row tiles of
+// 32 rows x 64 reads are staged in shared memory (coalesced row segments), then every warp ranks its 8 reads with one
+// lane per row of the tile. The `top` best rows of a read so far live across the warp's lanes (lane t holds the t-th
+// best); a row enters only when it beats the current top-th entry (a ballot: almost always empty once the list has
+// warmed up), by a shuffle-insert. Same order as above: rows arrive in increasing index and must be strictly better.
+template <typename P>
+__global__ void __launch_bounds__(256) dense_topk_warp_kernel(const SkbDenseArgs a) {
+  constexpr int PADW = sizeof(P) == 2 ? 33 : 65;  // 32-bit words per tile row: 64 reads + one word of padding (no bank conflicts)
+  __shared__ uint32_t tile[32 * PADW];
+  const uint32_t b0 = blockIdx.x * 64, g = blockIdx.y;
+  const uint32_t r_lo = (uint32_t)(((uint64_t)a.n_rows * g) / gridDim.y), r_hi = (uint32_t)(((uint64_t)a.n_rows * (g + 1)) / gridDim.y);
+  const uint32_t warp = threadIdx.x >> 5, lane = skb_lane(), top = a.top;
+  unsigned long long ks[8], thr_s[8];
+  uint32_t ki[8], thr_i[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ks[j] = 0; ki[j] = 0xFFFFFFFFu; thr_s[j] = 0; thr_i[j] = 0xFFFFFFFFu; }
+  const uint32_t lrow = threadIdx.x >> 3, lcol = (threadIdx.x & 7u) * 8;  // tile loader: 8 threads per row, 8 reads each
+  for (uint32_t r0 = r_lo; r0 < r_hi; r0 += 32) {
+    __syncthreads();  // the previous tile has been consumed
+    {
+      const uint32_t row = r0 + lrow;
+      uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 8 values: 4 words (u16) or 8 words (u32)
+      if (row < r_hi && a.sums_out[row] != a.sums_in[row]) {  // (a row without a hit in the pass: all zero, never written)
+        const P* src = reinterpret_cast<const P*>(a.dense) + (size_t)row * a.cnt_stride + b0 + lcol;
+        const uint4 x = *reinterpret_cast<const uint4*>(src);
+        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+        if (sizeof(P) == 4) {
+          const uint4 y = *reinterpret_cast<const uint4*>(src + 4);
+          w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+        }
+      }
+      uint32_t* dst = tile + lrow * PADW + lcol * sizeof(P) / 4;
+#pragma unroll
+      for (int q = 0; q < (int)(2 * sizeof(P)); ++q) dst[q] = w[q];
+    }
+    __syncthreads();
+    const uint32_t row = r0 + lane;
+    const bool valid = row < r_hi;
+    const unsigned long long s_in = valid ? a.sums_in[row] : 0ull;
+    const uint32_t gi = a.row_base + row;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t col = warp * 8 + j;
+      if (b0 + col >= a.n_reads) break;
+      uint32_t pv;
+      if (sizeof(P) == 2) pv = (tile[lane * PADW + (col >> 1)] >> (16 * (col & 1u))) & 0xFFFFu;
+      else pv = tile[lane * PADW + col];
+      const unsigned long long v = s_in + pv;
+      uint32_t bal = __ballot_sync(0xffffffffu, valid && skb_key_better(v, gi, thr_s[j], thr_i[j]));
+      while (bal) {
+        const int src = __ffs((int)bal) - 1;
+        bal &= bal - 1;
+        const unsigned long long cs = __shfl_sync(0xffffffffu, v, src);
+        const uint32_t ci = __shfl_sync(0xffffffffu, gi, src);
+        if (!skb_key_better(cs, ci, thr_s[j], thr_i[j])) continue;  // the threshold rose since the ballot
+        const uint32_t pos = __popc(__ballot_sync(0xffffffffu, lane < top && skb_key_better(ks[j], ki[j], cs, ci)));
+        const unsigned long long us = __shfl_up_sync(0xffffffffu, ks[j], 1);
+        const uint32_t ui = __shfl_up_sync(0xffffffffu, ki[j], 1);
+        if (lane > pos) { ks[j] = us; ki[j] = ui; }
+        else if (lane == pos) { ks[j] = cs; ki[j] = ci; }
+        thr_s[j] = __shfl_sync(0xffffffffu, ks[j], top - 1);
+        thr_i[j] = __shfl_sync(0xffffffffu, ki[j], top - 1);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t b = b0 + warp * 8 + j;
+    if (b < a.n_reads && lane < top) {
+      const size_t o = ((size_t)g * a.n_reads + b) * top + lane;
+      a.part_sum[o] = ks[j];
+      a.part_idx[o] = ki[j];
+    }
+  }
+}
+
 // multi-GPU: per read, merge n_parts lists of `top` (sum, idx) into the best `top`. One warp per read.
 __global__ void __launch_bounds__(256) merge_topn_kernel(const uint32_t* __restrict__ idx_parts,
                                                          const unsigned long long* __restrict__ sum_parts,
@@ -1050,6 +1233,11 @@ void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, co
   tracked_counts_kernel<<<SKB_MAX_TRACKED * 8, 256, 0, st>>>(rv, tracked, n_tracked, t, ctr, stride);
 }
 
+void skb_launch_tracked_totals(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
+                               const SkbTable& t, unsigned long long* extra, cudaStream_t st) {
+  tracked_totals_kernel<<<SKB_MAX_TRACKED * 8, 256, 0, st>>>(rv, tracked, n_tracked, t, extra);
+}
+
 void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) {
   tracked_prefix_kernel<<<SKB_MAX_TRACKED, 256, 0, st>>>(a);
   rank_bounds_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
@@ -1075,6 +1263,24 @@ void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st) {
 void skb_launch_rank_full(const unsigned long long* vals, uint32_t n, uint32_t top, uint32_t idx_base,
                           uint32_t* out_idx, unsigned long long* out_val, uint32_t* out_local, cudaStream_t st) {
   rank_full_kernel<<<1, 1024, 0, st>>>(vals, n, top, idx_base, out_idx, out_val, out_local);
+}
+
+void skb_launch_dense_topk(const SkbDenseArgs& a, cudaStream_t st) {
+  if (a.n_reads == 0 || a.groups == 0) return;
+  if (a.top <= 32) {
+    const dim3 wgrid((a.n_reads + 63) / 64, a.groups);
+    if (a.wide) dense_topk_warp_kernel<uint32_t><<<wgrid, 256, 0, st>>>(a);
+    else dense_topk_warp_kernel<uint16_t><<<wgrid, 256, 0, st>>>(a);
+    return;
+  }
+  const dim3 grid((a.n_reads + 127) / 128, a.groups);
+  if (a.top <= 16) {
+    if (a.wide) dense_topk_kernel<16, uint32_t><<<grid, 128, 0, st>>>(a);
+    else dense_topk_kernel<16, uint16_t><<<grid, 128, 0, st>>>(a);
+  } else {
+    if (a.wide) dense_topk_kernel<SKB_MAX_TOP, uint32_t><<<grid, 128, 0, st>>>(a);
+    else dense_topk_kernel<SKB_MAX_TOP, uint16_t><<<grid, 128, 0, st>>>(a);
+  }
 }
 
 void skb_launch_merge_topn(const uint32_t* idx_parts, const unsigned long long* sum_parts, uint32_t n_parts,

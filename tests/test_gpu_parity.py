@@ -111,28 +111,33 @@ def _world(seed, n_lineages, per_lineage, glen, s, n_reads, rlen, k=16, hseed=0,
     return ref, off, blob, roff
 
 
-def _check_predict(ctx, ref, off, blob, roff, k, s_query, hseed, top, pass_reads, chunks=1):
-    ctx.ref_upload(ref, off)
-    ctx.set_pass_reads(pass_reads)
+def _check_predict(ctx, ref, off, blob, roff, k, s_query, hseed, top, pass_reads, chunks=1, modes=(0, 1)):
+    """Streaming predict through the C ABI == the oracle, in every ranking mode (0 = automatic: these small worlds
+    are ranked by brute force; 1 = candidate lists from per-read bounds wherever possible)."""
     n = roff.size - 1
     ei, es, esums = oracle.predict_stream(ref, off, (blob, roff), k, s_query, hseed, top)
-    gi_all, gs_all = [], []
-    bounds = np.linspace(0, n, chunks + 1).astype(int)
-    for c in range(chunks):
-        lo, hi = bounds[c], bounds[c + 1]
-        b = ctx.batch()
-        sub_off = roff[lo:hi + 1] - roff[lo]
-        b.add(blob[int(roff[lo]):int(roff[hi])] if hi > lo else np.zeros(1, np.uint8), sub_off)
-        gi, gs = ctx.predict_stream(b, k, s_query, hseed, top)
-        gi_all.append(gi)
-        gs_all.append(gs)
-        b.close()
-    gi = np.concatenate(gi_all)
-    gs = np.concatenate(gs_all)
-    assert gi.shape == ei.shape
-    bad = np.flatnonzero((gi != ei).any(axis=1) | (gs != es).any(axis=1))
-    assert bad.size == 0, (bad[:5], gi[bad[:2]], ei[bad[:2]], gs[bad[:2]], es[bad[:2]])
-    assert (ctx.sums_download() == esums).all()
+    for mode in modes:
+        ctx.set_rank_mode(mode)
+        ctx.ref_upload(ref, off)
+        ctx.set_pass_reads(pass_reads)
+        gi_all, gs_all = [], []
+        bounds = np.linspace(0, n, chunks + 1).astype(int)
+        for c in range(chunks):
+            lo, hi = bounds[c], bounds[c + 1]
+            b = ctx.batch()
+            sub_off = roff[lo:hi + 1] - roff[lo]
+            b.add(blob[int(roff[lo]):int(roff[hi])] if hi > lo else np.zeros(1, np.uint8), sub_off)
+            gi, gs = ctx.predict_stream(b, k, s_query, hseed, top)
+            gi_all.append(gi)
+            gs_all.append(gs)
+            b.close()
+        gi = np.concatenate(gi_all)
+        gs = np.concatenate(gs_all)
+        assert gi.shape == ei.shape
+        bad = np.flatnonzero((gi != ei).any(axis=1) | (gs != es).any(axis=1))
+        assert bad.size == 0, (mode, bad[:5], gi[bad[:2]], ei[bad[:2]], gs[bad[:2]], es[bad[:2]])
+        assert (ctx.sums_download() == esums).all(), mode
+    ctx.set_rank_mode(0)
 
 
 @pytest.mark.parametrize("pass_reads", [1, 7, 64, 0])
@@ -172,8 +177,8 @@ def test_predict_medium_scale(ctx):
 
 
 def test_predict_more_contenders_than_a_bucket(ctx, monkeypatch):
-    """4500 references beat the tracked row at once while the candidate budget is forced tiny: buckets overflow, the
-    pass is halved down to single reads and those are ranked exactly from the new sums."""
+    """4500 references beat the tracked row at once while the candidate budget is forced tiny: buckets overflow and the
+    pass is redone with the brute-force ranking."""
     monkeypatch.setenv("SKB_CAND_BUDGET", "4096")
     ga = synth.random_genome(20_000, 901)
     gb = synth.random_genome(20_000, 902)
@@ -269,10 +274,50 @@ def test_error_codes(ctx):
     b.close()
 
 
-def test_predict_large_scale_against_independent_gpu_path(ctx):
-    """Scale the oracle cannot reach in seconds (6,000 x s=2,000 reference, 3,000 reads of 5 kb): the streaming
-    path (fused kernel, bounds, candidates) must equal the result assembled from the independent dense path
-    (per-read sketches -> skb_shared_counts binary-search kernel -> cumulative sums -> numpy ranking)."""
+def _dense_second_opinion(ctx, blob, roff, k, s, reads_to_check, gi, gs, final):
+    """Independent GPU path as a second opinion: one sketch per read -> skb_shared_counts (binary-search kernel) ->
+    cumulative sums -> numpy ranking on the host."""
+    qb = ctx.batch().add(blob, roff)
+    qs, _, _ = ctx.sketch(qb, k, s, 0)
+    qb.close()
+    qoff = np.zeros(len(qs) + 1, dtype=np.uint64)
+    qoff[1:] = np.cumsum([h.size for h, _ in qs])
+    counts = ctx.shared_counts(np.concatenate([h for h, _ in qs]), qoff)   # [N, R]
+    cum = np.cumsum(counts, axis=1)
+    assert (cum[:, -1] == final).all()
+    idx = np.arange(cum.shape[0])
+    for r in reads_to_check:
+        order = np.lexsort((idx, -cum[:, r].astype(np.int64)))[:10]
+        assert gi[r].tolist() == order.tolist(), r
+        assert gs[r].tolist() == cum[order, r].tolist(), r
+
+
+def _check_predict_large(ctx, ref, off, blob, roff, k, s, top, modes):
+    """Every read of a large case against the oracle (its N merges per read spread over all host threads: the same
+    arithmetic as the single-threaded loop, checked in tests/test_oracle.py), in several ranking modes."""
+    import os
+    ei, es, esums = oracle.predict_stream(ref, off, (blob, roff), k, s, 0, top, nthreads=os.cpu_count() or 1)
+    out = None
+    for mode in modes:
+        ctx.set_rank_mode(mode)
+        ctx.ref_upload(ref, off)
+        ctx.set_pass_reads(0)
+        rb = ctx.batch().add(blob, roff)
+        gi, gs = ctx.predict_stream(rb, k, s, 0, top)
+        final = ctx.sums_download()
+        stats = ctx.last_predict_stats()
+        rb.close()
+        bad = np.flatnonzero((gi != ei).any(axis=1) | (gs != es).any(axis=1))
+        assert bad.size == 0, (mode, bad[:5], gi[bad[:2]], ei[bad[:2]], gs[bad[:2]], es[bad[:2]])
+        assert (final == esums).all(), mode
+        out = (gi, gs, final, stats)
+    ctx.set_rank_mode(0)
+    return out
+
+
+def test_predict_large_scale_against_oracle(ctx):
+    """6,000 x s=2,000 reference, 3,000 reads of 5 kb: the streaming path (fused kernel, bounds, candidate lists, and the
+    brute-force ranking) against the oracle on every read, plus the independent dense GPU path on a sample."""
     base = [synth.random_genome(200_000, 7000 + l) for l in range(12)]
     b = ctx.batch().add_records([g.tobytes() for g in base])
     sk, _, _ = ctx.sketch(b, 16, 2000, 0)
@@ -289,32 +334,14 @@ def test_predict_large_scale_against_independent_gpu_path(ctx):
     off[1:] = np.cumsum([r.size for r in rows])
     ref = np.concatenate(rows)
     blob, roff, _ = synth.sample_reads(base, 3000, 5000, 99)
-    ctx.ref_upload(ref, off)
-    ctx.set_pass_reads(0)
-    rb = ctx.batch().add(blob, roff)
-    gi, gs = ctx.predict_stream(rb, 16, 2000, 0, 10)
-    final = ctx.sums_download()
-    rb.close()
-    # independent path: one sketch per read, dense counts, cumulative sums, stable ranking on the host
-    qb = ctx.batch().add(blob, roff)
-    qs, _, _ = ctx.sketch(qb, 16, 2000, 0)
-    qb.close()
-    qoff = np.zeros(len(qs) + 1, dtype=np.uint64)
-    qoff[1:] = np.cumsum([h.size for h, _ in qs])
-    counts = ctx.shared_counts(np.concatenate([h for h, _ in qs]), qoff)   # [N, R]
-    cum = np.cumsum(counts, axis=1)
-    assert (cum[:, -1] == final).all()
-    idx = np.arange(cum.shape[0])
-    for r in list(range(0, 64)) + list(range(64, 3000, 97)) + [2999]:
-        order = np.lexsort((idx, -cum[:, r].astype(np.int64)))[:10]
-        assert gi[r].tolist() == order.tolist(), r
-        assert gs[r].tolist() == cum[order, r].tolist(), r
+    gi, gs, final, _ = _check_predict_large(ctx, ref, off, blob, roff, 16, 2000, 10, modes=(0, 1, 2))
+    _dense_second_opinion(ctx, blob, roff, 16, 2000, list(range(0, 64)) + list(range(64, 3000, 97)) + [2999], gi, gs, final)
 
 
-def test_predict_full_size_passes_against_independent_gpu_path(ctx):
+def test_predict_full_size_passes_against_oracle(ctx):
     """Passes of the maximum size (4096 reads in the default build: u8 counters, every pass-local read id in use, a
-    ragged last pass). 20,000 short reads vs 2,000 x s=500: the candidate buckets hold the whole shard, so the very
-    first pass is a full one. Checked against the dense path like the test above, around every multiple of 4096."""
+    ragged last pass): 20,000 short reads vs 2,000 x s=500, every read against the oracle in all ranking modes, and the
+    independent dense GPU path around every multiple of 4096."""
     base = [synth.random_genome(60_000, 7100 + l) for l in range(8)]
     b = ctx.batch().add_records([g.tobytes() for g in base])
     sk, _, _ = ctx.sketch(b, 16, 500, 0)
@@ -331,30 +358,12 @@ def test_predict_full_size_passes_against_independent_gpu_path(ctx):
     ref = np.concatenate(rows)
     n_reads = 20_000
     blob, roff, _ = synth.sample_reads(base, n_reads, 600, 98)
-    ctx.ref_upload(ref, off)
-    ctx.set_pass_reads(0)
-    rb = ctx.batch().add(blob, roff)
-    gi, gs = ctx.predict_stream(rb, 16, 500, 0, 10)
-    final = ctx.sums_download()
-    stats = ctx.last_predict_stats()
-    rb.close()
+    gi, gs, final, stats = _check_predict_large(ctx, ref, off, blob, roff, 16, 500, 10, modes=(0, 1, 2))
     assert stats["passes"] <= 5, stats   # 4 x 4096 + 3616 (fewer with a build whose passes are larger)
-    qb = ctx.batch().add(blob, roff)
-    qs, _, _ = ctx.sketch(qb, 16, 500, 0)
-    qb.close()
-    qoff = np.zeros(len(qs) + 1, dtype=np.uint64)
-    qoff[1:] = np.cumsum([h.size for h, _ in qs])
-    counts = ctx.shared_counts(np.concatenate([h for h, _ in qs]), qoff)   # [N, R]
-    cum = np.cumsum(counts, axis=1)
-    assert (cum[:, -1] == final).all()
-    idx = np.arange(cum.shape[0])
     picks = set(list(range(0, 32)) + list(range(32, n_reads, 131)) + [n_reads - 1])
     for edge in range(4096, n_reads, 4096):
         picks.update(range(edge - 24, edge + 24))
-    for r in sorted(picks):
-        order = np.lexsort((idx, -cum[:, r].astype(np.int64)))[:10]
-        assert gi[r].tolist() == order.tolist(), r
-        assert gs[r].tolist() == cum[order, r].tolist(), r
+    _dense_second_opinion(ctx, blob, roff, 16, 500, sorted(picks), gi, gs, final)
 
 
 def test_limits_and_edge_cases(ctx):
@@ -435,8 +444,8 @@ def test_membership_prefilter_does_not_change_results(monkeypatch):
 def test_overflow_inside_a_batch_of_passes_rolls_back(ctx, monkeypatch):
     """Steady state (passes enqueued eight at a time, checked on the host afterwards): the stream switches from lineage A
     to lineage B, whose 3,000 identical rows overtake the tracked rows at the same read and overflow every bucket. The
-    device marks the failing pass, the passes queued behind it do nothing, the host rolls back to it, halves the pass
-    down to single reads and ranks those from the sums. Results must still equal the oracle's."""
+    device marks the failing pass, the passes queued behind it do nothing, the host rolls back to it and redoes it with
+    the brute-force ranking. Results must still equal the oracle's."""
     monkeypatch.setenv("SKB_CAND_BUDGET", str(16 * 512))
     ga = [synth.random_genome(20_000, 910 + i) for i in range(3)]
     gb = synth.random_genome(20_000, 920)
@@ -449,5 +458,5 @@ def test_overflow_inside_a_batch_of_passes_rolls_back(ctx, monkeypatch):
     blob_b, roff_b, _ = synth.sample_reads([gb], 260, 1200, 6, sub=0.0, ins=0.0, dele=0.0)
     blob = np.concatenate([blob_a, blob_b])
     roff = np.concatenate([roff_a, roff_b[1:] + roff_a[-1]])
-    _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, 3, 16)
-    assert ctx.last_predict_stats()["passes"] > (460 + 15) // 16     # some passes were redone smaller
+    _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, 3, 16, modes=(1,))
+    assert ctx.last_predict_stats()["passes"] > (460 + 15) // 16     # a pass streamed twice: once overflowing, once dense
