@@ -37,6 +37,7 @@ extern "C" {
 #define SKB_ERR_OOM (-8)
 #define SKB_ERR_INTERNAL (-9)
 #define SKB_ERR_STATE (-10) /* call order violated (e.g. adding to a staged batch) */
+#define SKB_ERR_COMM (-11)  /* NCCL could not be loaded or a collective failed */
 
 #define SKB_MAX_K 32
 #define SKB_MAX_TOP 128
@@ -143,6 +144,34 @@ int skb_rank_counts(skb_ctx* ctx, const uint64_t* counts, uint32_t n, uint32_t t
 int skb_merge_topn_device(skb_ctx* ctx, const uint32_t* d_idx_parts, const uint64_t* d_sum_parts,
                           uint32_t n_parts, uint64_t n_reads, uint32_t top, uint32_t* d_out_idx,
                           uint64_t* d_out_sum);
+
+/* ---- multi-GPU predict: one process per GPU, the reference rows sharded by contiguous range over the ranks (each
+ *      rank uploads its range with its global_row_base), one NCCL communicator over NVLink / NVSwitch. The reference
+ *      is single-process; this is the scale-out of `_sum_of_shared_hashes` (src/sketchy.rs:317-356): every rank ranks
+ *      every read against its rows, the per-rank top-N lists are gathered and merged. ---------------------------- */
+
+#define SKB_COMM_ID_BYTES 128
+/* On ONE rank: make the communicator's id; hand the bytes to every rank by any means (a file, MPI, a socket). */
+int skb_comm_unique_id(uint8_t id[SKB_COMM_ID_BYTES]);
+/* On every rank (collective): join the communicator as `rank` of `world`. libnccl.so.2 is loaded at this point. */
+int skb_comm_init(skb_ctx* ctx, const uint8_t id[SKB_COMM_ID_BYTES], int rank, int world);
+int skb_comm_destroy(skb_ctx* ctx);
+int skb_comm_rank(const skb_ctx* ctx);
+int skb_comm_world(const skb_ctx* ctx);
+/* The contiguous split every collective call assumes: items [*begin, *begin + *count) of n belong to `rank`
+ * (ceil(n / world) items per rank, the last ranks may get fewer or none). Use it for reference rows and for reads. */
+void skb_dist_range(uint64_t n, int rank, int world, uint64_t* begin, uint64_t* count);
+/* Collective streaming predict of `reads_total` reads. `local` holds ONLY this rank's reads,
+ * skb_dist_range(reads_total, rank, world), one group each: a rank packs, copies and hashes 1/world of the reads and
+ * the per-read query-hash lists are exchanged. out_idx / out_sum ([reads_total * top], host; may be NULL on ranks that
+ * do not report) receive the merged ranking of EVERY read, identical on all ranks and identical to a single GPU
+ * holding all rows. Without a communicator it is skb_predict_stream. */
+int skb_predict_stream_dist(skb_ctx* ctx, skb_batch* local, uint64_t reads_total, uint32_t k, uint32_t s_query,
+                            uint64_t seed, uint32_t top, uint32_t* out_idx, uint64_t* out_sum);
+/* Same with DEVICE output pointers. */
+int skb_predict_stream_dist_device(skb_ctx* ctx, skb_batch* local, uint64_t reads_total, uint32_t k,
+                                   uint32_t s_query, uint64_t seed, uint32_t top, uint32_t* d_out_idx,
+                                   uint64_t* d_out_sum);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------------------- */
 

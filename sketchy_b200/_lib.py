@@ -14,7 +14,8 @@ SO_PATH = os.environ.get("SKB_LIB") or os.path.join(_HERE, "libsketchy_b200.so")
 
 ERRORS = {0: "SKB_OK", -1: "SKB_ERR_INVALID_ARG", -2: "SKB_ERR_CUDA", -3: "SKB_ERR_NO_DEVICE",
           -4: "SKB_ERR_REF_NOT_SORTED", -5: "SKB_ERR_TOP_GT_N", -6: "SKB_ERR_NO_REFERENCE",
-          -7: "SKB_ERR_UNSUPPORTED_K", -8: "SKB_ERR_OOM", -9: "SKB_ERR_INTERNAL", -10: "SKB_ERR_STATE"}
+          -7: "SKB_ERR_UNSUPPORTED_K", -8: "SKB_ERR_OOM", -9: "SKB_ERR_INTERNAL", -10: "SKB_ERR_STATE",
+          -11: "SKB_ERR_COMM"}
 KERNEL_IDS = {"hash": 0, "select": 1, "table": 2, "stream": 3, "rank": 4, "merge": 5, "shared": 6, "misc": 7}
 MAX_TOP = 128
 
@@ -46,6 +47,14 @@ SYMBOLS = [
     ("skb_sums_upload", _i, [_vp, _vp]),
     ("skb_set_pass_reads", _i, [_vp, _u32]),
     ("skb_set_rank_mode", _i, [_vp, _i]),
+    ("skb_comm_unique_id", _i, [_vp]),
+    ("skb_comm_init", _i, [_vp, _vp, _i, _i]),
+    ("skb_comm_destroy", _i, [_vp]),
+    ("skb_comm_rank", _i, [_vp]),
+    ("skb_comm_world", _i, [_vp]),
+    ("skb_dist_range", None, [_u64, _i, _i, C.POINTER(_u64), C.POINTER(_u64)]),
+    ("skb_predict_stream_dist", _i, [_vp, _vp, _u64, _u32, _u32, _u64, _u32, _vp, _vp]),
+    ("skb_predict_stream_dist_device", _i, [_vp, _vp, _u64, _u32, _u32, _u64, _u32, _vp, _vp]),
     ("skb_shared_counts", _i, [_vp, _vp, _vp, _u32, _vp]),
     ("skb_rank_counts", _i, [_vp, _vp, _u32, _u32, _vp, _vp]),
     ("skb_merge_topn_device", _i, [_vp, _vp, _vp, _u32, _u64, _u32, _vp, _vp]),
@@ -59,6 +68,13 @@ SYMBOLS = [
     ("skb_batch_record_start", _i, [_vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     ("skb_debug_kmer_hashes", _i, [_vp, _vp, _u32, _u64, _vp, _vp]),
 ]
+
+
+def dist_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """[begin, begin + count) of `n` items that belong to `rank` (the split every collective call assumes)."""
+    b, c = _u64(), _u64()
+    load_library().skb_dist_range(n, rank, world, C.byref(b), C.byref(c))
+    return int(b.value), int(c.value)
 
 
 class SkbError(RuntimeError):
@@ -176,6 +192,41 @@ class Context:
                               d_sum: int, pad: bool = False):
         self.check(self.lib.skb_predict_stream_device(self.h, batch.h, k, s_query, seed, top, int(pad), _ptr(d_idx),
                                                       _ptr(d_sum)))
+
+    # ---- multi-GPU (one process per GPU; see include/sketchy_b200.h) ----
+    def comm_unique_id(self) -> np.ndarray:
+        """On one rank: the communicator's id (128 bytes) to hand to every rank."""
+        uid = np.zeros(128, dtype=np.uint8)
+        rc = self.lib.skb_comm_unique_id(_ptr(uid))
+        if rc != 0:
+            raise SkbError(rc, "skb_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return uid
+
+    def comm_init(self, uid: np.ndarray, rank: int, world: int):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        assert uid.size == 128
+        self.check(self.lib.skb_comm_init(self.h, _ptr(uid), rank, world))
+
+    def comm_destroy(self):
+        self.check(self.lib.skb_comm_destroy(self.h))
+
+    def predict_stream_dist(self, batch: "Batch", reads_total: int, k: int, s_query: int, seed: int, top: int,
+                            out=None, report: bool = True):
+        """Collective: `batch` holds this rank's reads (dist_range(reads_total, rank, world)); returns the merged
+        ranking of every read (report=False: this rank takes part but does not copy the result to the host)."""
+        if not report:
+            self.check(self.lib.skb_predict_stream_dist(self.h, batch.h, reads_total, k, s_query, seed, top, None, None))
+            return None, None
+        if out is None:
+            out = (np.zeros((max(reads_total, 1), top), dtype=np.uint32), np.zeros((max(reads_total, 1), top), dtype=np.uint64))
+        oi, os_ = out
+        self.check(self.lib.skb_predict_stream_dist(self.h, batch.h, reads_total, k, s_query, seed, top, _ptr(oi), _ptr(os_)))
+        return oi[:reads_total], os_[:reads_total]
+
+    def predict_stream_dist_device(self, batch: "Batch", reads_total: int, k: int, s_query: int, seed: int, top: int,
+                                   d_idx: int, d_sum: int):
+        self.check(self.lib.skb_predict_stream_dist_device(self.h, batch.h, reads_total, k, s_query, seed, top,
+                                                           _ptr(d_idx), _ptr(d_sum)))
 
     def sums_reset(self):
         self.check(self.lib.skb_sums_reset(self.h))

@@ -8,6 +8,9 @@
 #include <cstring>
 #include <thread>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl is loaded with dlopen when a communicator is asked for
+
 #include "kernels.h"
 
 #define SKB_VERSION_STR "sketchy_b200 0.1.0 (sm_100a)"
@@ -152,6 +155,42 @@ void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uin
 // ---------------------------------------------------------------------------------------------------------
 // context / batch
 // ---------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (skb_comm_init): a single-GPU caller never needs the library to be present, and inside a
+// process that already carries NCCL (PyTorch) the same copy is used.
+struct SkbNccl {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+      lib = dlopen(name, RTLD_NOW | RTLD_NOLOAD);
+      if (!lib) lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    bool ok = true;
+    auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) { ok = false; err = std::string("libnccl lacks ") + n; } return p; };
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(sym("ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(sym("ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(sym("ncclAllGather"));
+    Broadcast = reinterpret_cast<decltype(Broadcast)>(sym("ncclBroadcast"));
+    GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+    GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+    if (!ok) { lib = nullptr; }
+    return ok;
+  }
+};
+SkbNccl g_nccl;
+
 struct ProfEvent { int id; cudaEvent_t a, b; };
 #define SKB_NSUMS 4
 #define SKB_NTRACK 3
@@ -183,8 +222,12 @@ struct skb_ctx {
   bool pass_proven = false;     // a full-size sparse pass has been checked and did not overflow: batch them
   int rank_mode = 0;            // skb_set_rank_mode
   uint32_t dense_left = 0;      // upcoming passes that are ranked densely (bounds too loose to be worth candidates)
-  DevBuf dense, part_idx, part_sum;
-  bool pipeline = true;         // steady-state passes take their bounds from two passes back (pre-pass work next to the stream)
+  DevBuf dense, part_idx, part_sum, piece_idx, piece_sum, piece_row;
+  bool pipeline = false;        // steady-state passes take their bounds from two passes back (pre-pass work enqueued next to the stream)
+  // multi-GPU: one process per GPU, reference rows sharded by contiguous range, NCCL over NVLink for the exchange steps
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  DevBuf qn_all, gath_idx, gath_sum, hmax_all;
   uint32_t tracked_top = 0;  // 0 = invalid
   // per-group scratch (hash/select)
   DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, cand_pool;
@@ -616,14 +659,82 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   return SKB_OK;
 }
 
-int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top, int pad,
-                   uint32_t* d_out_idx, uint64_t* d_out_sum) {
+// ---- per-read query sets -----------------------------------------------------------------------------------
+// The reads of a call as the pass loop sees them: R "pass reads" with their query hashes (<= tau, distinct, ascending,
+// at most s_query) flat in c->qh / c->qread. A read that keeps more than 65535 query hashes (the range of the u16
+// per-(row, read) counters) is cut into consecutive pass reads: the running sums are cumulative, so the ranking after
+// its last piece is the read's ranking and the pieces before it are simply not reported (`last_piece`).
+struct QuerySet {
+  uint32_t R = 0;                    // pass reads
+  std::vector<uint32_t> qn;          // [R] query hashes per pass read
+  std::vector<uint64_t> q_off;       // [R + 1]
+  std::vector<uint32_t> out_row;     // [R] caller's read (row of the output arrays) of a last piece, UINT32_MAX otherwise; empty = identity
+};
+constexpr uint32_t kMaxPieceKeys = 65535;
+
+// qn_reads[i] = query hashes of caller read i (already on the device, compacted read after read in c->qh)
+int finish_query_set(skb_ctx* c, const std::vector<uint32_t>& qn_reads, QuerySet& qs) {
+  const uint32_t n = (uint32_t)qn_reads.size();
+  bool split = false;
+  for (uint32_t v : qn_reads) split = split || v > kMaxPieceKeys;
+  if (!split) {
+    qs.R = n; qs.qn = qn_reads;
+  } else {
+    for (uint32_t i = 0; i < n; ++i) {
+      uint32_t left = qn_reads[i];
+      do {
+        const uint32_t take = std::min(left, kMaxPieceKeys);
+        qs.qn.push_back(take);
+        left -= take;
+        qs.out_row.push_back(left == 0 ? i : 0xFFFFFFFFu);
+      } while (left > 0);
+    }
+    qs.R = (uint32_t)qs.qn.size();
+  }
+  qs.q_off.assign((size_t)qs.R + 1, 0);
+  for (uint32_t r = 0; r < qs.R; ++r) qs.q_off[r + 1] = qs.q_off[r] + qs.qn[r];
+  const uint64_t QN = qs.q_off[qs.R];
+  c->st_qhashes = QN;
+  CU(c, c->q_off.ensure(((size_t)qs.R + 1) * 8));
+  CU(c, c->qread.ensure(std::max<uint64_t>(QN, 1) * 4));
+  CU(c, cudaMemcpyAsync(c->q_off.p, qs.q_off.data(), ((size_t)qs.R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  { ProfScope ps(c, SKB_K_SELECT, 1);
+    skb_launch_fill_qread(c->q_off.as<uint64_t>(), qs.R, c->qread.as<uint32_t>(), c->stream); }
+  return check_launch(c, "fill_qread");
+}
+
+int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum);
+
+int predict_checks(skb_ctx* c, uint32_t k, uint32_t s_query, uint32_t top, int pad) {
   if (!c->has_ref) return fail(c, SKB_ERR_NO_REFERENCE, "no reference uploaded");
   if (k < 1 || k > SKB_MAX_K) return fail(c, SKB_ERR_UNSUPPORTED_K, "k=%u unsupported (1..%d)", k, SKB_MAX_K);
   if (top < 1 || top > SKB_MAX_TOP) return fail(c, SKB_ERR_INVALID_ARG, "top=%u unsupported (1..%d)", top, SKB_MAX_TOP);
   if (top > c->n_rows && !pad)
     return fail(c, SKB_ERR_TOP_GT_N, "top (%u) exceeds the number of reference sketches (%u)", top, c->n_rows);
   if (s_query < 1) return fail(c, SKB_ERR_INVALID_ARG, "s_query must be >= 1");
+  return SKB_OK;
+}
+
+// passes over a query set whose pass reads may be pieces of the caller's reads: rank into scratch, report last pieces
+int run_passes_reported(skb_ctx* c, const QuerySet& qs, uint32_t n_reads, uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  if (qs.out_row.empty()) return run_passes(c, qs, top, d_out_idx, d_out_sum);
+  CU(c, c->piece_idx.ensure((size_t)qs.R * top * 4));
+  CU(c, c->piece_sum.ensure((size_t)qs.R * top * 8));
+  CU(c, c->piece_row.ensure((size_t)qs.R * 4));
+  CU(c, cudaMemcpyAsync(c->piece_row.p, qs.out_row.data(), (size_t)qs.R * 4, cudaMemcpyHostToDevice, c->stream));
+  if (int rc = run_passes(c, qs, top, c->piece_idx.as<uint32_t>(), c->piece_sum.as<uint64_t>())) return rc;
+  { ProfScope ps(c, SKB_K_RANK, 1);
+    skb_launch_report_pieces(c->piece_idx.as<uint32_t>(), c->piece_sum.as<unsigned long long>(), c->piece_row.as<uint32_t>(), qs.R, top,
+                             d_out_idx, reinterpret_cast<unsigned long long*>(d_out_sum), c->stream); }
+  if (int rc = check_launch(c, "report_pieces")) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  (void)n_reads;
+  return SKB_OK;
+}
+
+int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top, int pad,
+                   uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  if (int rc = predict_checks(c, k, s_query, top, pad)) return rc;
   if (int rc = stage_batch(b)) return rc;
   const uint32_t R = (uint32_t)b->g_first.size();
   c->st_passes = 0; c->st_qhashes = 0; c->st_cands = 0; c->st_ref_bytes = c->ref_len * 8;
@@ -639,24 +750,29 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   std::vector<uint64_t> kmers;
   SelectPlan plan;
   if (int rc = run_hash_select(c, b, k, s_query, seed, true, c->hmax, nullptr, nullptr, qn, kmers, plan)) return rc;
-  std::vector<uint64_t> q_off(R + 1, 0);
-  uint32_t qmax = 0;
-  for (uint32_t r = 0; r < R; ++r) { q_off[r + 1] = q_off[r] + qn[r]; qmax = std::max(qmax, qn[r]); }
-  if (qmax > 65535u)
-    return fail(c, SKB_ERR_INVALID_ARG, "a read keeps %u query hashes under the reference maximum; limit is 65535", qmax);
-  const uint64_t QN = q_off[R];
-  c->st_qhashes = QN;
-  CU(c, c->q_off.ensure((R + 1) * 8));
+  uint64_t QN = 0;
+  for (uint32_t v : qn) QN += v;
   CU(c, c->qh.ensure(std::max<uint64_t>(QN, 1) * 8));
-  CU(c, c->qread.ensure(std::max<uint64_t>(QN, 1) * 4));
-  CU(c, cudaMemcpyAsync(c->q_off.p, q_off.data(), (R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   {
+    std::vector<uint64_t> off(R + 1, 0);
+    for (uint32_t r = 0; r < R; ++r) off[r + 1] = off[r] + qn[r];
+    CU(c, c->q_off.ensure(((size_t)R + 1) * 8));
+    CU(c, cudaMemcpyAsync(c->q_off.p, off.data(), ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     ProfScope ps(c, SKB_K_SELECT, 1);
     skb_launch_compact_queries(c->cand_pool.as<uint64_t>(), c->g_base.as<uint64_t>(), c->g_outn.as<uint32_t>(), c->q_off.as<uint64_t>(),
-                               R, c->qh.as<uint64_t>(), c->qread.as<uint32_t>(), c->stream);
+                               R, c->qh.as<uint64_t>(), c->stream);
+    CU(c, cudaStreamSynchronize(c->stream));  // `off` is a local: the copy must have read it
   }
   if (int rc = check_launch(c, "compact")) return rc;
+  QuerySet qs;
+  if (int rc = finish_query_set(c, qn, qs)) return rc;
+  return run_passes_reported(c, qs, R, top, d_out_idx, d_out_sum);
+}
 
+int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  const uint32_t R = qs.R;
+  const std::vector<uint32_t>& qn = qs.qn;
+  const std::vector<uint64_t>& q_off = qs.q_off;
   uint32_t* h_total = c->h_scal;
   uint32_t* d_scal = c->scal.as<uint32_t>();
   unsigned long long* d_cand_stat = reinterpret_cast<unsigned long long*>(c->scal.as<uint8_t>() + 64);  // statistics
@@ -919,6 +1035,122 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   return SKB_OK;
 }
 
+#define NC(c, call)                                                                                         \
+  do {                                                                                                      \
+    ncclResult_t r__ = (call);                                                                              \
+    if (r__ != ncclSuccess) return fail((c), SKB_ERR_COMM, "%s: %s", #call, g_nccl.GetErrorString(r__));   \
+  } while (0)
+
+void dist_range(uint64_t n, int rank, int world, uint64_t* begin, uint64_t* count) {
+  const uint64_t per = world > 0 ? (n + world - 1) / world : n;
+  const uint64_t b = std::min<uint64_t>(n, per * (uint64_t)rank), e = std::min<uint64_t>(n, per * ((uint64_t)rank + 1));
+  if (begin) *begin = b;
+  if (count) *count = e - b;
+}
+
+// Streaming predict over a reference sharded across the ranks of the communicator. Rank r holds the reads
+// dist_range(reads_total, r, world) of the call in `b` (it packed and staged only those) and hashes only those; the
+// per-read query lists are exchanged (all-gather of the counts, then of the hashes), every rank runs the passes of ALL
+// reads against its row shard, the per-rank top-N lists (global row indices) are all-gathered and merged by
+// (sum desc, index asc). Exact: every member of the global top-N is in its shard's local top-N, and a read's query
+// list only matters below a shard's largest reference hash, so the list cut at the largest hash of ANY shard serves
+// them all. The merged ranking of every read ends up in d_out_* on every rank.
+int predict_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t k, uint32_t s_query, uint64_t seed,
+                        uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  if (!c->comm || c->world <= 1) {
+    if (reads_total != b->g_first.size()) return fail(c, SKB_ERR_INVALID_ARG, "no communicator: the batch must hold all %llu reads", (unsigned long long)reads_total);
+    return predict_device(c, b, k, s_query, seed, top, 0, d_out_idx, d_out_sum);
+  }
+  if (int rc = predict_checks(c, k, s_query, top, 1)) return rc;
+  if (reads_total > 0xFFFFFFF0ull) return fail(c, SKB_ERR_INVALID_ARG, "too many reads in one call");
+  if (int rc = stage_batch(b)) return rc;
+  const int W = c->world;
+  const uint32_t R = (uint32_t)reads_total, R_loc = (uint32_t)b->g_first.size();
+  uint64_t my_begin = 0, my_count = 0;
+  dist_range(R, c->rank, W, &my_begin, &my_count);
+  if (R_loc != my_count)
+    return fail(c, SKB_ERR_INVALID_ARG, "rank %d of %d must hold reads [%llu, %llu) of the call, the batch has %u", c->rank, W,
+                (unsigned long long)my_begin, (unsigned long long)(my_begin + my_count), R_loc);
+  c->st_passes = 0; c->st_qhashes = 0; c->st_cands = 0; c->st_ref_bytes = c->ref_len * 8;
+  if (R == 0) return SKB_OK;
+  const uint32_t Rmax = (R + W - 1) / W;
+  // ---- the largest reference hash of any shard
+  CU(c, c->hmax_all.ensure((size_t)W * 8));
+  unsigned long long* d_hmax = c->hmax_all.as<unsigned long long>();
+  unsigned long long my_hmax = c->n_rows ? c->hmax : 0ull;
+  CU(c, cudaMemcpyAsync(d_hmax + c->rank, &my_hmax, 8, cudaMemcpyHostToDevice, c->stream));
+  NC(c, g_nccl.AllGather(d_hmax + c->rank, d_hmax, 1, ncclUint64, c->comm, c->stream));
+  std::vector<unsigned long long> hm(W);
+  CU(c, cudaMemcpyAsync(hm.data(), d_hmax, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const uint64_t tau = *std::max_element(hm.begin(), hm.end());
+  // ---- this rank's reads: query lists
+  std::vector<uint32_t> qn_loc;
+  std::vector<uint64_t> kmers;
+  SelectPlan plan;
+  if (int rc = run_hash_select(c, b, k, s_query, seed, true, tau, nullptr, nullptr, qn_loc, kmers, plan)) return rc;
+  // ---- everybody's counts
+  CU(c, c->qn_all.ensure((size_t)W * Rmax * 4));
+  uint32_t* d_qn = c->qn_all.as<uint32_t>();
+  CU(c, cudaMemsetAsync(d_qn + (size_t)c->rank * Rmax, 0, (size_t)Rmax * 4, c->stream));
+  if (R_loc) CU(c, cudaMemcpyAsync(d_qn + (size_t)c->rank * Rmax, c->g_outn.p, (size_t)R_loc * 4, cudaMemcpyDeviceToDevice, c->stream));
+  NC(c, g_nccl.AllGather(d_qn + (size_t)c->rank * Rmax, d_qn, Rmax, ncclUint32, c->comm, c->stream));
+  std::vector<uint32_t> qn_pad((size_t)W * Rmax), qn(R);
+  CU(c, cudaMemcpyAsync(qn_pad.data(), d_qn, qn_pad.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  std::vector<uint64_t> off(R + 1, 0);
+  for (int g = 0; g < W; ++g) {
+    uint64_t gb, gc;
+    dist_range(R, g, W, &gb, &gc);
+    for (uint64_t i = 0; i < gc; ++i) qn[gb + i] = qn_pad[(size_t)g * Rmax + i];
+  }
+  for (uint32_t r = 0; r < R; ++r) off[r + 1] = off[r] + qn[r];
+  const uint64_t QN = off[R];
+  CU(c, c->qh.ensure(std::max<uint64_t>(QN, 1) * 8));
+  CU(c, c->q_off.ensure(((size_t)R + 1) * 8));
+  CU(c, cudaMemcpyAsync(c->q_off.p, off.data(), ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  if (R_loc) {
+    ProfScope ps(c, SKB_K_SELECT, 1);
+    skb_launch_compact_queries(c->cand_pool.as<uint64_t>(), c->g_base.as<uint64_t>(), c->g_outn.as<uint32_t>(),
+                               c->q_off.as<uint64_t>() + my_begin, R_loc, c->qh.as<uint64_t>(), c->stream);
+  }
+  if (int rc = check_launch(c, "compact")) return rc;
+  // ---- everybody's hashes: rank g broadcasts its slice of the flat list in place
+  NC(c, g_nccl.GroupStart());
+  for (int g = 0; g < W; ++g) {
+    uint64_t gb, gc;
+    dist_range(R, g, W, &gb, &gc);
+    const uint64_t n = off[gb + gc] - off[gb];
+    if (n == 0) continue;
+    uint64_t* p = c->qh.as<uint64_t>() + off[gb];
+    ncclResult_t r = g_nccl.Broadcast(p, p, n, ncclUint64, g, c->comm, c->stream);
+    if (r != ncclSuccess) { g_nccl.GroupEnd(); return fail(c, SKB_ERR_COMM, "ncclBroadcast: %s", g_nccl.GetErrorString(r)); }
+  }
+  NC(c, g_nccl.GroupEnd());
+  CU(c, cudaStreamSynchronize(c->stream));  // `off` is a local: its copy must be done; and the exchange is complete
+  QuerySet qs;
+  if (int rc = finish_query_set(c, qn, qs)) return rc;
+  // ---- passes of every read against this rank's rows, then the exchange of the local top-N lists
+  CU(c, c->out_idx.ensure(std::max<size_t>(4, (size_t)R * top * 4)));
+  CU(c, c->out_sum.ensure(std::max<size_t>(8, (size_t)R * top * 8)));
+  CU(c, c->gath_idx.ensure((size_t)W * R * top * 4));
+  CU(c, c->gath_sum.ensure((size_t)W * R * top * 8));
+  if (c->n_rows == 0) {
+    CU(c, cudaMemsetAsync(c->out_idx.p, 0xFF, (size_t)R * top * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->out_sum.p, 0, (size_t)R * top * 8, c->stream));
+  } else if (int rc = run_passes_reported(c, qs, R, top, c->out_idx.as<uint32_t>(), c->out_sum.as<uint64_t>())) {
+    return rc;
+  }
+  NC(c, g_nccl.AllGather(c->out_idx.p, c->gath_idx.p, (size_t)R * top, ncclUint32, c->comm, c->stream));
+  NC(c, g_nccl.AllGather(c->out_sum.p, c->gath_sum.p, (size_t)R * top, ncclUint64, c->comm, c->stream));
+  { ProfScope ps(c, SKB_K_MERGE, 1);
+    skb_launch_merge_topn(c->gath_idx.as<uint32_t>(), c->gath_sum.as<unsigned long long>(), (uint32_t)W, R, top, d_out_idx,
+                          reinterpret_cast<unsigned long long*>(d_out_sum), c->stream); }
+  if (int rc = check_launch(c, "merge")) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -961,11 +1193,12 @@ void skb_destroy(skb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->side) cudaStreamSynchronize(c->side);
+  if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   std::vector<DevBuf*> bufs = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->tile_cum, &c->memb, &c->tprefix, &c->textra,
                                &c->g_tau, &c->g_cap, &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status,
                                &c->cand_pool, &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->scal,
-                               &c->out_idx, &c->out_sum, &c->misc, &c->dense, &c->part_idx, &c->part_sum};
+                               &c->out_idx, &c->out_sum, &c->misc, &c->dense, &c->part_idx, &c->part_sum, &c->piece_idx, &c->piece_sum, &c->piece_row, &c->qn_all, &c->gath_idx, &c->gath_sum, &c->hmax_all};
   for (auto& x : c->sums) bufs.push_back(&x);
   for (auto& x : c->tracked) bufs.push_back(&x);
   for (int i = 0; i < SKB_NTAB; ++i)
@@ -1169,6 +1402,71 @@ int skb_predict_stream(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, u
   if (R) {
     CU(c, cudaMemcpyAsync(out_idx, c->out_idx.p, R * top * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaMemcpyAsync(out_sum, c->out_sum.p, R * top * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return SKB_OK;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------------
+int skb_comm_unique_id(uint8_t* id) {
+  if (!id) return SKB_ERR_INVALID_ARG;
+  std::string err;
+  if (!g_nccl.load(err)) return SKB_ERR_COMM;
+  static_assert(sizeof(ncclUniqueId) == SKB_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId u;
+  if (g_nccl.GetUniqueId(&u) != ncclSuccess) return SKB_ERR_COMM;
+  std::memcpy(id, &u, sizeof u);
+  return SKB_OK;
+}
+
+int skb_comm_init(skb_ctx* c, const uint8_t* id, int rank, int world) {
+  if (!c || !id || world < 1 || rank < 0 || rank >= world) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (c->comm) return fail(c, SKB_ERR_STATE, "communicator already initialised");
+  if (!g_nccl.load(c->err)) return SKB_ERR_COMM;
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof u);
+  NC(c, g_nccl.CommInitRank(&c->comm, world, u, rank));
+  c->rank = rank; c->world = world;
+  return SKB_OK;
+}
+
+int skb_comm_destroy(skb_ctx* c) {
+  if (!c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (c->comm) {
+    cudaStreamSynchronize(c->stream);
+    g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr; c->rank = 0; c->world = 1;
+  }
+  return SKB_OK;
+}
+
+int skb_comm_rank(const skb_ctx* c) { return c ? c->rank : 0; }
+int skb_comm_world(const skb_ctx* c) { return c ? c->world : 1; }
+
+void skb_dist_range(uint64_t n, int rank, int world, uint64_t* begin, uint64_t* count) { dist_range(n, rank, world, begin, count); }
+
+int skb_predict_stream_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t k, uint32_t s_query,
+                                   uint64_t seed, uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum) {
+  if (!c || !b || b->ctx != c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (reads_total && (!d_out_idx || !d_out_sum)) return fail(c, SKB_ERR_INVALID_ARG, "null output");
+  return predict_dist_device(c, b, reads_total, k, s_query, seed, top, d_out_idx, d_out_sum);
+}
+
+int skb_predict_stream_dist(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t k, uint32_t s_query, uint64_t seed,
+                            uint32_t top, uint32_t* out_idx, uint64_t* out_sum) {
+  if (!c || !b || b->ctx != c) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (top < 1 || top > SKB_MAX_TOP) return fail(c, SKB_ERR_INVALID_ARG, "top=%u unsupported (1..%d)", top, SKB_MAX_TOP);
+  CU(c, c->misc.ensure(std::max<size_t>(16, (size_t)reads_total * top * 12)));
+  uint64_t* d_sum = c->misc.as<uint64_t>();
+  uint32_t* d_idx = reinterpret_cast<uint32_t*>(d_sum + reads_total * top);
+  if (int rc = predict_dist_device(c, b, reads_total, k, s_query, seed, top, d_idx, d_sum)) return rc;
+  if (reads_total && out_idx && out_sum) {  // (a rank that does not report may pass NULL)
+    CU(c, cudaMemcpyAsync(out_idx, d_idx, (size_t)reads_total * top * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(out_sum, d_sum, (size_t)reads_total * top * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
   }
   return SKB_OK;

@@ -42,10 +42,15 @@ struct SkbSelectArgs {
 };
 void skb_launch_select(const SkbSelectArgs& a, cudaStream_t st);
 
-// predict: gather every read's selected hashes into one flat (hash, read) list
+// predict: gather every read's selected hashes into one flat list (read after read, at q_off[read])
 void skb_launch_compact_queries(const uint64_t* cand, const uint64_t* cand_base, const uint32_t* out_n,
-                                const uint64_t* q_off, uint32_t n_reads, uint64_t* qh, uint32_t* qread,
-                                cudaStream_t st);
+                                const uint64_t* q_off, uint32_t n_reads, uint64_t* qh, cudaStream_t st);
+// qread[j] = pass read of flat query position j (q_off: [n_reads + 1])
+void skb_launch_fill_qread(const uint64_t* q_off, uint32_t n_reads, uint32_t* qread, cudaStream_t st);
+// copy the scratch ranking of every piece that ends a read (out_row != UINT32_MAX) to the caller's row
+void skb_launch_report_pieces(const uint32_t* idx, const unsigned long long* sum, const uint32_t* out_row,
+                              uint32_t n_pieces, uint32_t top, uint32_t* out_idx, unsigned long long* out_sum,
+                              cudaStream_t st);
 
 // ---- predict ---------------------------------------------------------------------------------------------
 #define SKB_BLOOM_WORDS 16384u  // 64 KB shared-memory filter (2^19 bits)

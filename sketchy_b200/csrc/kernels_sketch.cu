@@ -287,15 +287,32 @@ __global__ void select_kernel(const SkbSelectArgs a) {
 
 __global__ void compact_queries_kernel(const uint64_t* __restrict__ cand, const uint64_t* __restrict__ cand_base,
                                        const uint32_t* __restrict__ out_n, const uint64_t* __restrict__ q_off,
-                                       uint32_t n_reads, uint64_t* __restrict__ qh, uint32_t* __restrict__ qread) {
+                                       uint32_t n_reads, uint64_t* __restrict__ qh) {
   const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n_reads) return;
   const uint32_t n = out_n[r];
   const uint64_t src = cand_base[r], dst = q_off[r];
-  for (uint32_t j = skb_lane(); j < n; j += 32) {
-    qh[dst + j] = cand[src + j];
-    qread[dst + j] = r;
-  }
+  for (uint32_t j = skb_lane(); j < n; j += 32) qh[dst + j] = cand[src + j];
+}
+
+// qread[j] = the pass read whose query list holds flat position j
+__global__ void fill_qread_kernel(const uint64_t* __restrict__ q_off, uint32_t n_reads, uint32_t* __restrict__ qread) {
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_reads) return;
+  for (uint64_t j = q_off[r] + skb_lane(); j < q_off[r + 1]; j += 32) qread[j] = r;
+}
+
+// rows of the scratch ranking that belong to the last piece of a read go to the caller's arrays
+__global__ void report_pieces_kernel(const uint32_t* __restrict__ idx, const unsigned long long* __restrict__ sum,
+                                     const uint32_t* __restrict__ out_row, uint32_t n_pieces, uint32_t top,
+                                     uint32_t* __restrict__ out_idx, unsigned long long* __restrict__ out_sum) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (uint64_t)n_pieces * top) return;
+  const uint32_t p = (uint32_t)(e / top), t = (uint32_t)(e % top);
+  const uint32_t row = out_row[p];
+  if (row == 0xFFFFFFFFu) return;
+  out_idx[(size_t)row * top + t] = idx[e];
+  out_sum[(size_t)row * top + t] = sum[e];
 }
 
 }  // namespace
@@ -324,10 +341,24 @@ void skb_launch_select(const SkbSelectArgs& a, cudaStream_t st) {
 }
 
 void skb_launch_compact_queries(const uint64_t* cand, const uint64_t* cand_base, const uint32_t* out_n,
-                                const uint64_t* q_off, uint32_t n_reads, uint64_t* qh, uint32_t* qread,
-                                cudaStream_t st) {
+                                const uint64_t* q_off, uint32_t n_reads, uint64_t* qh, cudaStream_t st) {
   if (n_reads == 0) return;
   const int threads = 256;
   const unsigned blocks = (unsigned)(((uint64_t)n_reads * 32 + threads - 1) / threads);
-  compact_queries_kernel<<<blocks, threads, 0, st>>>(cand, cand_base, out_n, q_off, n_reads, qh, qread);
+  compact_queries_kernel<<<blocks, threads, 0, st>>>(cand, cand_base, out_n, q_off, n_reads, qh);
+}
+
+void skb_launch_fill_qread(const uint64_t* q_off, uint32_t n_reads, uint32_t* qread, cudaStream_t st) {
+  if (n_reads == 0) return;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)(((uint64_t)n_reads * 32 + threads - 1) / threads);
+  fill_qread_kernel<<<blocks, threads, 0, st>>>(q_off, n_reads, qread);
+}
+
+void skb_launch_report_pieces(const uint32_t* idx, const unsigned long long* sum, const uint32_t* out_row,
+                              uint32_t n_pieces, uint32_t top, uint32_t* out_idx, unsigned long long* out_sum,
+                              cudaStream_t st) {
+  const uint64_t n = (uint64_t)n_pieces * top;
+  if (n == 0) return;
+  report_pieces_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, sum, out_row, n_pieces, top, out_idx, out_sum);
 }

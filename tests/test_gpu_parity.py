@@ -366,6 +366,27 @@ def test_predict_full_size_passes_against_oracle(ctx):
     _dense_second_opinion(ctx, blob, roff, 16, 500, sorted(picks), gi, gs, final)
 
 
+def test_read_with_more_than_65535_query_hashes(ctx):
+    """A contig fed as a read against large sketches keeps > 65535 query hashes under the reference maximum, more than a
+    16-bit per-(row, read) counter holds: its query list is cut into pieces that stream as consecutive pass reads (the
+    sums are cumulative) and only the ranking after the last piece is reported. Short reads before and after it."""
+    base = [synth.random_genome(150_000, 8100 + l) for l in range(3)]
+    s = 120_000
+    sk, _, _ = oracle.sketch_groups([g.tobytes() for g in base], [0, 1, 2], 3, 16, s, 0)
+    rows = [sk[i % 3][0] for i in range(7)]
+    assert all(r.size > 70_000 for r in rows)
+    off = np.zeros(len(rows) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([r.size for r in rows])
+    ref = np.concatenate(rows)
+    short, soff, _ = synth.sample_reads(base, 6, 2000, 3)
+    recs = [short[int(soff[i]):int(soff[i + 1])].tobytes() for i in range(6)]
+    recs.insert(3, base[1][10_000:140_000].tobytes())      # ~130,000 distinct k-mers, all under the reference maximum
+    blob = np.frombuffer(b"".join(recs), dtype=np.uint8)
+    roff = np.zeros(len(recs) + 1, dtype=np.uint64)
+    roff[1:] = np.cumsum([len(r) for r in recs])
+    _check_predict(ctx, ref, off, blob, roff, 16, s, 0, 3, 0, modes=(0, 1))
+
+
 def test_limits_and_edge_cases(ctx):
     from sketchy_b200._lib import SkbError
     g = synth.random_genome(3000, 1)
