@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — predict reads/s of the B200 MinHash hot path on the BASELINE.json C3 workload
-(100,000 synthetic 5 kb ONT-like reads vs a 40,000-genome k=16 s=10,000 reference, --top 10).
+"""bench.py — predict reads/s of the B200 MinHash hot path on the BASELINE.json workloads.
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU)
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one process per GPU (torchrun for N > 1)
   python bench.py --impl reference --steps K --warmup W    # the CPU oracle port, timed on the host cores
+  python bench.py --config c4|c5|c3i ...                    # the other BASELINE configs (records kept under profiles/)
 
-One JSON line on stdout (rank 0). A step = streaming predict of ALL reads (running sums reset at step start) =
-ceil(reads / reads_per_pass) passes over the HBM-resident reference matrix. `value` times it with the packed
-reads already in HBM; `e2e` times the same job from host ASCII buffers through the C ABI (2-bit packing into
-pinned memory, H2D, kernels, D2H of the top-N). Multi-GPU: reference rows are sharded by contiguous range, every
-rank sees every read, local top-N are all-gathered over NCCL and merged by (sum desc, index asc).
+Default = C3 (100,000 synthetic 5 kb ONT-like reads vs a 40,000-genome k=16 s=10,000 reference, --top 10), the
+configuration BASELINE.json's metric is quoted on. One JSON line on stdout (rank 0).
+
+A step = streaming predict of ALL reads (running sums reset at step start) = ceil(reads / reads_per_pass) passes over the
+HBM-resident reference matrix. `value` times it with the packed reads already in HBM; `e2e` times the same job from host
+ASCII buffers through the C ABI (2-bit packing into pinned memory, H2D, kernels, D2H of the top-N). Multi-GPU: the
+reference rows are sharded by contiguous range over the ranks, every rank packs / copies / hashes 1/N of the reads, the
+per-read query-hash lists and the local top-N lists are exchanged over the library's own NCCL communicator
+(skb_predict_stream_dist) and merged by (sum desc, index asc).
 """
 from __future__ import annotations
 
@@ -20,6 +24,7 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -28,6 +33,15 @@ sys.path.insert(0, ROOT)
 
 K, SEED = 16, 0
 GENOME_LEN = 2_800_000
+PASS_READS = 4096  # the library's full pass (u8 counters)
+
+CONFIGS = {
+    # name: (refs, sketch size, reads, top, lineages, row distribution, consensus)
+    "c3": (40_000, 10_000, 100_000, 10, 40, "lineage", False),
+    "c3i": (40_000, 10_000, 100_000, 10, 40, "independent", False),
+    "c4": (40_000, 1_000, 1_000_000, 5, 40, "lineage", True),
+    "c5": (1_000_000, 10_000, 1_000_000, 10, 1000, "lineage", False),
+}
 
 
 def log(*a):
@@ -40,19 +54,29 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--refs", type=int, default=40_000)
-    p.add_argument("--sketch-size", type=int, default=10_000)
-    p.add_argument("--reads", type=int, default=100_000)
+    p.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    p.add_argument("--refs", type=int, default=0)
+    p.add_argument("--sketch-size", type=int, default=0)
+    p.add_argument("--reads", type=int, default=0)
     p.add_argument("--read-len", type=int, default=5_000)
-    p.add_argument("--lineages", type=int, default=40)
-    p.add_argument("--top", type=int, default=10)
+    p.add_argument("--lineages", type=int, default=0)
+    p.add_argument("--top", type=int, default=0)
     p.add_argument("--pass-reads", type=int, default=0, help="reads per streaming pass (0 = library default)")
+    p.add_argument("--rank-mode", type=int, default=0, help="0 automatic, 1 candidate lists wherever possible, 2 brute force always")
     p.add_argument("--cpu-sample", type=int, default=12, help="reads in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--verify", action="store_true", help="N>1: check the merged ranking against one GPU holding all rows")
-    p.add_argument("--sketch-genomes", type=int, default=64, help="genomes in the bounded sketch-throughput sample (0 = skip)")
-    return p.parse_args()
+    p.add_argument("--no-extras", action="store_true", help="skip the zero-hit variant and the sketch leg")
+    p.add_argument("--sketch-genomes", type=int, default=128, help="genomes in the bounded sketch-throughput sample (0 = skip)")
+    a = p.parse_args()
+    refs, s, reads, top, lin, dist_kind, cons = CONFIGS[a.config]
+    a.refs = a.refs or refs
+    a.sketch_size = a.sketch_size or s
+    a.reads = a.reads or reads
+    a.top = a.top or top
+    a.lineages = a.lineages or lin
+    a.row_dist, a.consensus = dist_kind, cons
+    return a
 
 
 class ClockSampler:
@@ -103,25 +127,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def ncu_traffic_bytes() -> float | None:
-    """DRAM bytes (read + write) of one fused_kernel launch from the committed `ncu --set full` capture of this
-    workload (profiles/r01_fused_kernel_ncu.md); None when the summary is missing."""
-    try:
-        rd = wr = None
-        for line in open(os.path.join(ROOT, "profiles", "r01_fused_kernel_ncu.md")):
-            f = [x.strip() for x in line.split("|")]
-            if len(f) >= 4 and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                v = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[3]]
-                rd, wr = (v, wr) if f[1].endswith("read.sum") else (rd, v)
-        return rd + wr if rd is not None and wr is not None else None
-    except Exception:
-        return None
+def ncu_traffic_bytes() -> tuple[float | None, str]:
+    """DRAM bytes (read + write) of one fused_kernel launch from the committed `ncu --set full` capture of the C3
+    workload; None when the summary is missing."""
+    for name in ("r02_fused_kernel_ncu.md", "r01_fused_kernel_ncu.md"):
+        try:
+            rd = wr = None
+            for line in open(os.path.join(ROOT, "profiles", name)):
+                f = [x.strip() for x in line.split("|")]
+                if len(f) >= 4 and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[3]]
+                    rd, wr = (v, wr) if f[1].endswith("read.sum") else (rd, v)
+            if rd is not None and wr is not None:
+                return rd + wr, f"profiles/{name} (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        except Exception:
+            pass
+    return None, "no ncu summary under profiles/"
 
 
-def workload_name(N: int, s: int, R: int, top: int) -> str:
+def workload_name(cfg: str, N: int, s: int, R: int, top: int) -> str:
     """config.workload: the same string for this repo's arm and the reference arm."""
-    if (N, s, R, top) == (40000, 10000, 100000, 10):
+    if (cfg, N, s, R, top) == ("c3", 40000, 10000, 100000, 10):
         return "C3: predict 100,000 synthetic ONT reads vs 40,000-genome reference, k=16, s=10000, --top 10"
+    if (cfg, N, s, top) == ("c4", 40000, 1000, 5):
+        return f"C4: streaming predict + genotype consensus, {R} synthetic ONT reads vs 40,000-genome s=1000 reference, --top 5 --consensus"
+    if (cfg, N, s, top) == ("c5", 1000000, 10000, 10):
+        return f"C5: scale-out, {R} reads vs 1,000,000-genome s=10000 reference sharded over the GPUs, --top 10"
+    if cfg == "c3i":
+        return f"C3 zero-hit variant: {R} reads vs {N} independent rows x s={s}, k=16, --top {top}"
     return f"predict {R} reads vs {N} x s={s}, k=16, --top {top}"
 
 
@@ -131,17 +164,6 @@ def measured_peak_gbs() -> tuple[float, str]:
         return float(d["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
-
-
-def make_workload(args, device, rank, world, need_host_matrix):
-    """Synthetic C3 data. Returns dict with base genomes (torch), local reference rows (torch int64 on `device`),
-    reads ([R, read_len] uint8 numpy) and offsets."""
-    import torch
-    from sketchy_b200 import synth_torch as st
-    t0 = time.time()
-    genomes = st.random_genomes(args.lineages, GENOME_LEN, 3000, device)
-    log(f"[rank {rank}] genomes {time.time() - t0:.1f}s")
-    return genomes
 
 
 def sketch_base_rows_gpu(ctx, genomes, s):
@@ -154,11 +176,54 @@ def sketch_base_rows_gpu(ctx, genomes, s):
     return rows
 
 
+def independent_rows(n_rows: int, s: int, row0: int, device):
+    """SURVEY §8d second distribution: every row = s fresh sorted uniform draws in [0, 2^64 * s / 2.8e6): no read ever
+    hits a row (the zero-hit extreme: the stream and the filter probe alone)."""
+    import torch
+    from sketchy_b200 import synth_torch as st
+    top = float(2 ** 63) * 2.0 * s / GENOME_LEN
+    out = torch.empty((n_rows, s), dtype=torch.int64, device=device)
+    for b0 in range(0, n_rows, st.ROW_BLOCK):
+        nb = min(st.ROW_BLOCK, n_rows - b0)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(5000 + (row0 + b0) // st.ROW_BLOCK)
+        rows = (torch.rand((nb, s), generator=gen, device=device, dtype=torch.float64) * top).to(torch.int64)
+        rows, _ = torch.sort(rows, dim=1)
+        dup = rows[:, 1:] <= rows[:, :-1]
+        if bool(dup.any()):
+            fix = torch.cumsum(torch.cat([torch.zeros((nb, 1), dtype=torch.int64, device=device), dup.to(torch.int64)], 1), 1)
+            rows = rows + fix
+        out[b0:b0 + nb] = rows
+    return out
+
+
+def genotype_table(n_rows: int, lineages: int) -> np.ndarray:
+    """C4 genotype index: 6 categorical columns per reference (an MLST-like value tied to the lineage, 5 binary R/S)."""
+    rng = np.random.default_rng(99)
+    lin = np.arange(n_rows) % lineages
+    cols = [lin.astype(np.int32)]
+    for c in range(5):
+        per_lineage = rng.integers(0, 2, size=lineages)
+        flip = rng.random(n_rows) < 0.05
+        cols.append(np.where(flip, 1 - per_lineage[lin], per_lineage[lin]).astype(np.int32))
+    return np.stack(cols, axis=1)   # [N, 6]
+
+
+def consensus_calls(idx: np.ndarray, table: np.ndarray) -> np.ndarray:
+    """Per read and genotype column the most frequent value among the read's top rows; ties go to the value that comes
+    first in rank order (api.consensus_value; the reference's HashMap max_by is nondeterministic on ties,
+    src/sketchy.rs:380-387, 408). idx [R, top] -> [R, columns]."""
+    v = table[idx.astype(np.int64)]                              # [R, top, C]
+    same = (v[:, :, None, :] == v[:, None, :, :]).sum(axis=2)    # [R, top, C] occurrences of the value at each rank
+    first_best = same.argmax(axis=1)                             # first rank position holding the most frequent value
+    return np.take_along_axis(v, first_best[:, None, :], axis=1)[:, 0, :]
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from sketchy_b200 import synth_torch as st
-    from sketchy_b200._lib import Context
+    from sketchy_b200._lib import Context, dist_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -169,21 +234,34 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     ctx = Context(local)  # raises without a B200: no CPU fallback
+    if world > 1:  # the library's own communicator; its id travels over the launcher's process group
+        uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(device)
+        dist.broadcast(uid, 0)
+        ctx.comm_init(uid.cpu().numpy(), rank, world)
     if args.pass_reads:
         ctx.set_pass_reads(args.pass_reads)
+    if args.rank_mode:
+        ctx.set_rank_mode(args.rank_mode)
     N, s, R, top = args.refs, args.sketch_size, args.reads, args.top
+    cfg = args.config
 
     # ---------------- synthetic data (untimed) ----------------
     t0 = time.time()
-    genomes = st.random_genomes(args.lineages, GENOME_LEN, 3000, device)
-    base_rows = sketch_base_rows_gpu(ctx, genomes, s)
-    assert all(r.size == s for r in base_rows)
-    base_t = torch.from_numpy(np.stack(base_rows).astype(np.int64))
-    assert int(base_t.min()) >= 0
-    from sketchy_b200.dist import shard_rows
-    lo, hi = shard_rows(N, rank, world, st.ROW_BLOCK)
-    ref = st.expand_reference_block(base_t.to(device), lo, hi - lo, 0.02, 4000, device)
-    off = np.arange(hi - lo + 1, dtype=np.uint64) * np.uint64(s)
+    n_base = min(args.lineages, 40)   # distinct base genomes (C5's 1000 lineages reuse the 40 genomes with different replaced entries)
+    genomes = st.random_genomes(n_base, GENOME_LEN, 3000, device)
+    lo, cnt = dist_range(N, rank, world)
+    lo_al = lo // st.ROW_BLOCK * st.ROW_BLOCK           # row blocks are seeded independently of the sharding
+    hi = lo + cnt
+    if args.row_dist == "independent":
+        ref = independent_rows(hi - lo_al, s, lo_al, device)[lo - lo_al:]
+        base_t = None
+    else:
+        base_rows = sketch_base_rows_gpu(ctx, genomes, s)
+        assert all(r.size == s for r in base_rows)
+        base_t = torch.from_numpy(np.stack(base_rows).astype(np.int64))
+        assert int(base_t.min()) >= 0
+        ref = st.expand_reference_block(base_t.to(device), lo_al, hi - lo_al, 0.02, 4000, device)[lo - lo_al:]
+    off = np.arange(cnt + 1, dtype=np.uint64) * np.uint64(s)
     ctx.ref_upload_device(ref.data_ptr(), off, row_base=lo)
     reads = st.sample_reads(genomes, R, args.read_len, 777)
     roff = np.arange(R + 1, dtype=np.uint64) * np.uint64(args.read_len)
@@ -191,8 +269,8 @@ def run_b200(args):
     blob = blob_pinned.numpy()
     log(f"[rank {rank}] data ready in {time.time() - t0:.1f}s: rows [{lo},{hi}) x {s}, {R} reads x {args.read_len}")
 
-    # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only) + parity gate ----------------
-    cpu_baseline = None
+    # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only) + parity gates ----------------
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle  # the checker / baseline, never the thing measured as `value`
         ref_host = ref.cpu().numpy().view(np.uint64).reshape(-1)
@@ -219,31 +297,47 @@ def run_b200(args):
         gi, gs = ctx.predict_stream(b, K, s, SEED, top)
         b.close()
         assert (gi == ei).all() and (gs == es).all(), "GPU predict differs from the oracle on the CPU sample"
-        log(f"[rank 0] parity gate ok on {n_s} reads; cpu {n_s / dt:.2f} reads/s")
-        del ref_host
+        # second gate: full-size passes. 2 x 4096 + 300 reads (two full passes and a short one) against every 32nd row
+        # of the matrix, every read checked against the oracle (its merges spread over the host threads)
+        n_g = min(R, 2 * PASS_READS + 300)
+        sel = np.arange(0, N, 32)
+        sub_ref = np.ascontiguousarray(ref_host.reshape(N, s)[sel]).reshape(-1)
+        sub_off = np.arange(sel.size + 1, dtype=np.uint64) * np.uint64(s)
+        t1 = time.time()
+        ei2, es2, _ = oracle.predict_stream(sub_ref, sub_off, (blob[:n_g * args.read_len], roff[:n_g + 1]), K, s, SEED, top,
+                                            nthreads=ncores)
+        c2 = Context(local)
+        gate_modes = {}
+        for mode in (1, 2):
+            c2.set_rank_mode(mode)
+            c2.ref_upload(sub_ref, sub_off)
+            b2 = c2.batch().add(blob[:n_g * args.read_len], roff[:n_g + 1])
+            gi2, gs2 = c2.predict_stream(b2, K, s, SEED, top)
+            b2.close()
+            assert (gi2 == ei2).all() and (gs2 == es2).all(), f"GPU predict (rank mode {mode}) differs from the oracle on full passes"
+            gate_modes[mode] = c2.last_predict_stats()["passes"]
+        c2.close()
+        parity = {"sample_reads_vs_full_matrix": n_s, "full_pass_reads": n_g, "full_pass_rows": int(sel.size),
+                  "rank_modes_checked": sorted(gate_modes), "seconds": round(time.time() - t1, 1)}
+        log(f"[rank 0] parity gates ok: {n_s} reads vs the full matrix, {n_g} reads vs {sel.size} rows in both rank modes; "
+            f"cpu {n_s / dt:.2f} reads/s")
+        del ref_host, sub_ref
     del ref
     torch.cuda.empty_cache()
 
-    # ---------------- resident batch ----------------
-    batch = ctx.batch().add(blob, roff)
+    # ---------------- resident batch: this rank's slice of the reads ----------------
+    r_lo, r_cnt = dist_range(R, rank, world)
+    batch = ctx.batch()
+    if r_cnt:
+        batch.add(blob[r_lo * args.read_len:(r_lo + r_cnt) * args.read_len], roff[r_lo:r_lo + r_cnt + 1] - roff[r_lo])
     batch.stage()
     d_idx = torch.zeros((R, top), dtype=torch.int32, device=device)
     d_sum = torch.zeros((R, top), dtype=torch.int64, device=device)
-    if world > 1:
-        g_idx = torch.zeros((world, R, top), dtype=torch.int32, device=device)
-        g_sum = torch.zeros((world, R, top), dtype=torch.int64, device=device)
-        m_idx = torch.zeros((R, top), dtype=torch.int32, device=device)
-        m_sum = torch.zeros((R, top), dtype=torch.int64, device=device)
     ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=device)
 
     def step_resident():
         ctx.sums_reset()
-        ctx.predict_stream_device(batch, K, s, SEED, top, d_idx.data_ptr(), d_sum.data_ptr(), pad=world > 1)
-        if world > 1:
-            dist.all_gather_into_tensor(g_idx.view(-1), d_idx.view(-1))
-            dist.all_gather_into_tensor(g_sum.view(-1), d_sum.view(-1))
-            torch.cuda.current_stream().synchronize()
-            ctx.merge_topn_device(g_idx.data_ptr(), g_sum.data_ptr(), world, R, top, m_idx.data_ptr(), m_sum.data_ptr())
+        ctx.predict_stream_dist_device(batch, R, K, s, SEED, top, d_idx.data_ptr(), d_sum.data_ptr())
 
     def sync_all():
         torch.cuda.synchronize()
@@ -255,25 +349,6 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sync_all()
-    if world > 1 and args.verify:
-        # parity gate of the sharded path: the merged ranking of the first reads == one GPU holding every row
-        n_v = min(4096, R)
-        ok = torch.ones(1, device=device)
-        if rank == 0:
-            full = st.expand_reference_block(base_t.to(device), 0, N, 0.02, 4000, device)
-            c2 = Context(local)
-            c2.ref_upload_device(full.data_ptr(), np.arange(N + 1, dtype=np.uint64) * np.uint64(s), row_base=0)
-            del full
-            vb = c2.batch().add(blob[:n_v * args.read_len], roff[:n_v + 1])
-            vi, vs = c2.predict_stream(vb, K, s, SEED, top)
-            vb.close(); c2.close()
-            mi = m_idx[:n_v].cpu().numpy().view(np.uint32)
-            ms = m_sum[:n_v].cpu().numpy().view(np.uint64)
-            good = bool((mi == vi).all() and (ms == vs).all())
-            log(f"[rank 0] sharded ({world} GPUs) vs unsharded on {n_v} reads: {'ok' if good else 'MISMATCH'}")
-            ok[0] = 1.0 if good else 0.0
-        dist.broadcast(ok, 0)
-        assert ok.item() == 1.0, "sharded predict differs from unsharded"
     ctx.prof_reset()
     ctx.prof_enable(True)
     launches0 = ctx.launch_count
@@ -295,11 +370,9 @@ def run_b200(args):
     prof = {k: ctx.prof_get(k) for k in ("hash", "select", "table", "stream", "rank", "merge")}
     ctx.prof_enable(False)
     stats = ctx.last_predict_stats()
-    # checksum of the whole job's answer (every read's top-N rows and sums): equal across builds, pass sizes and GPU
-    # counts when the results are identical, so kernel variants and shardings can be compared at full size
-    import zlib
-    r_idx, r_sum = (m_idx, m_sum) if world > 1 else (d_idx, d_sum)
-    result_crc = zlib.crc32(r_sum.cpu().numpy().tobytes(), zlib.crc32(r_idx.cpu().numpy().tobytes()))
+    # checksum of the whole job's answer (every read's top-N rows and sums): equal across builds, pass sizes, ranking
+    # modes and GPU counts when the results are identical
+    result_crc = zlib.crc32(d_sum.cpu().numpy().tobytes(), zlib.crc32(d_idx.cpu().numpy().tobytes()))
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -307,36 +380,29 @@ def run_b200(args):
 
     # ---------------- end to end through the C ABI with host buffers ----------------
     e2e = None
+    consensus_info = None
     if not args.no_e2e:
-        hb = ctx.batch()
         # caller-owned page-locked result arrays: the D2H of every chunk's top-N is a DMA straight into them
         oi = torch.zeros((R, top), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
         os_ = torch.zeros((R, top), dtype=torch.int64).pin_memory().numpy().view(np.uint64)
-
-        # a streaming caller feeds reads in chunks: chunk i+1 is normalised + 2-bit packed into pinned memory by the
-        # library's host threads while the GPU works on chunk i (two batches, double buffered)
-        # chunk sizes grow so that packing + copying chunk i+1 always fits inside the GPU time of chunk i, and they are
-        # multiples of the library's pass sizes (ramp, then 4096 per pass): no partial passes
-        b0 = 128   # the library's first pass size after a reset (largest pass whose buckets hold the whole shard) ...
-        while b0 * 2 <= (24 << 20) // max(hi - lo, 64) and b0 * 2 <= 4096:
-            b0 *= 2
-        ramp = sum(b0 << i for i in range(8) if (b0 << i) < 4096)   # ... and the reads of the passes that ramp up to 4096
-        sizes, c_lo = [ramp if ramp else 4_096, 4 * 4_096], 0
-        chunks = []
-        while c_lo < R:
-            n_c = sizes[len(chunks)] if len(chunks) < len(sizes) else 10 * 4_096
-            chunks.append((c_lo, min(c_lo + n_c, R)))
-            c_lo = chunks[-1][1]
+        # a streaming caller feeds reads in chunks of whole passes: chunk i+1 is normalised + 2-bit packed into pinned
+        # memory by the library's host threads and copied to the device while the GPU works on chunk i (two batches,
+        # double buffered). With N ranks every rank packs, copies and hashes 1/N of each chunk.
+        chunk_reads = 5 * PASS_READS
+        chunks = [(c_lo, min(c_lo + chunk_reads, R)) for c_lo in range(0, R, chunk_reads)]
         pack_s = [0.0]
-        hbs = [hb, ctx.batch()]
-        # every rank packs every read: share the host cores between the ranks of the box instead of oversubscribing them
-        pack_threads = max(1, (os.cpu_count() or 1) // world)
+        hbs = [ctx.batch(), ctx.batch()]
+        pack_threads = max(1, (os.cpu_count() or 1) // world)   # the ranks of one box share its host cores
+        gt = genotype_table(N, args.lineages) if args.consensus else None
+        calls = [None]
 
         def pack(j, p_lo, p_hi):
             t0 = time.perf_counter()
             hbs[j].clear()
-            hbs[j].add(blob[p_lo * args.read_len:p_hi * args.read_len], roff[p_lo:p_hi + 1] - roff[p_lo],
-                       nthreads=pack_threads)
+            m_lo, m_cnt = dist_range(p_hi - p_lo, rank, world)
+            a, b = p_lo + m_lo, p_lo + m_lo + m_cnt
+            if m_cnt:
+                hbs[j].add(blob[a * args.read_len:b * args.read_len], roff[a:b + 1] - roff[a], nthreads=pack_threads)
             pack_s[0] += time.perf_counter() - t0
             hbs[j].stage()   # H2D on the copy stream, overlapping the kernels of the previous chunk
 
@@ -348,21 +414,12 @@ def run_b200(args):
                 if ci + 1 < len(chunks):
                     th = threading.Thread(target=pack, args=((ci + 1) & 1, *chunks[ci + 1]))
                     th.start()
-                b = hbs[ci & 1]
-                if world > 1:
-                    ctx.predict_stream_device(b, K, s, SEED, top, d_idx[q_lo:q_hi].data_ptr(), d_sum[q_lo:q_hi].data_ptr(), pad=True)
-                else:
-                    ctx.predict_stream(b, K, s, SEED, top, out=(oi[q_lo:q_hi], os_[q_lo:q_hi]))   # H2D + kernels + D2H of the top-N
+                ctx.predict_stream_dist(hbs[ci & 1], q_hi - q_lo, K, s, SEED, top, out=(oi[q_lo:q_hi], os_[q_lo:q_hi]),
+                                        report=rank == 0)   # H2D + kernels (+ exchange) + D2H of the merged top-N
                 if th is not None:
                     th.join()
-            if world > 1:
-                dist.all_gather_into_tensor(g_idx.view(-1), d_idx.view(-1))
-                dist.all_gather_into_tensor(g_sum.view(-1), d_sum.view(-1))
-                torch.cuda.current_stream().synchronize()
-                ctx.merge_topn_device(g_idx.data_ptr(), g_sum.data_ptr(), world, R, top, m_idx.data_ptr(),
-                                      m_sum.data_ptr())
-                oi[:] = m_idx.cpu().numpy().view(np.uint32)
-                os_[:] = m_sum.cpu().numpy().view(np.uint64)
+            if gt is not None and rank == 0:   # C4: the genotype consensus of every read, formed on the host from the top rows
+                calls[0] = consensus_calls(oi, gt)
 
         for _ in range(2):
             step_e2e()
@@ -379,83 +436,76 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         packed = sum(-(-((b1 - b0) * (args.read_len + 1)) // 32) * 32 for b0, b1 in chunks)
-        h2d = packed // 4 + packed // 8 + (packed // 1024 + R) * 9
+        h2d = (packed // 4 + packed // 8 + (packed // 1024 + R) * 9) // world
         e2e = {"value": R / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(R * top * 12), "ms_per_step": dt * 1e3,
-               "includes": "host normalise+2-bit pack into pinned memory (a first chunk covering the ramp passes, 16384, then chunks of 40960 reads, packed and copied "
-                           "to the device while the GPU works on the previous chunk), all kernels, D2H of top-N into page-locked host arrays",
-               "host_threads": pack_threads, "host_pack_ms_per_step": pack_s[0] / n_e2e * 1e3}
-        # the e2e result must equal the resident result
-        if world == 1:
+               "includes": f"host normalise + 2-bit pack into pinned memory (chunks of {chunk_reads} reads, each rank its 1/{world} "
+                           "of a chunk, packed and copied to the device while the GPU works on the previous chunk), all kernels, "
+                           + ("the NCCL exchanges, " if world > 1 else "") + "D2H of the top-N into page-locked host arrays"
+                           + (", the per-read genotype consensus on the host" if gt is not None else ""),
+               "host_threads": pack_threads, "host_pack_ms_per_step": pack_s[0] / n_e2e * 1e3,
+               "h2d_bytes_note": "per rank"}
+        if rank == 0:
+            # the e2e result must equal the resident result
             assert (oi == d_idx.cpu().numpy().view(np.uint32)).all() and (os_ == d_sum.cpu().numpy().view(np.uint64)).all()
+            if gt is not None:
+                from sketchy_b200.api import consensus_value
+                chk = np.linspace(0, R - 1, 2000).astype(int)
+                for r_ in chk:   # the vectorised consensus == the per-read rule of the host mirror
+                    for c_ in range(gt.shape[1]):
+                        assert str(calls[0][r_, c_]) == consensus_value([str(x) for x in gt[oi[r_].astype(np.int64), c_]])
+                consensus_info = {"columns": int(gt.shape[1]), "reads": R, "calls_crc32": f"{zlib.crc32(calls[0].tobytes()):08x}",
+                                  "checked_against_host_mirror": int(chk.size)}
         for x in hbs:
             x.close()
 
-    # ---------------- sketch throughput on a bounded C2 sample (k=16, s=1000), rank 0 at N=1 ----------------
-    sketch_info = None
-    if rank == 0 and world == 1 and args.sketch_genomes > 0:
-        ng = args.sketch_genomes
-        recs = [st.random_genomes(1, GENOME_LEN, 9000 + g, device)[0].cpu().numpy() for g in range(min(ng, 8))]
-        recs = [recs[g % len(recs)] for g in range(ng)]           # 8 distinct genomes, repeated (hashing cost is data independent)
-        sb = ctx.batch().add_records(recs)
-        sb.stage()
-        ctx.sketch(sb, K, 1000, SEED)                               # warm-up
-        ctx.prof_reset(); ctx.prof_enable(True)
-        ctx.synchronize()
-        t1 = time.perf_counter()
-        n_it = 3
-        for _ in range(n_it):
-            sk_out, _, _ = ctx.sketch(sb, K, 1000, SEED)
-        ctx.synchronize()
-        dt = (time.perf_counter() - t1) / n_it
-        hash_ms, _ = ctx.prof_get("hash")
-        sel_ms, _ = ctx.prof_get("select")
-        ctx.prof_enable(False)
-        gbp = ng * GENOME_LEN / 1e9
-        sketch_info = {"workload": f"C2 sample: {ng} x 2.8 Mbp assemblies, k=16, s=1000, packed batch resident in HBM",
-                       "gbp_per_s": gbp / dt, "kernel_gbp_per_s": gbp / ((hash_ms + sel_ms) / n_it * 1e-3),
-                       "hash_kernel_ms": hash_ms / n_it, "select_kernel_ms": sel_ms / n_it, "call_ms": dt * 1e3,
-                       "bound": "integer pipes (about 100 instructions per k-mer, ~0.4 B/base of traffic)"}
-        assert all(h.size == 1000 for h, _ in sk_out)
-        sb.close()
+    # ---------------- extras (rank 0 at N=1): the zero-hit variant of C3 and the sketch leg ----------------
+    zero_hit, sketch_info = None, None
+    peak, how = measured_peak_gbs()
+    if rank == 0 and world == 1 and not args.no_extras and cfg == "c3":
+        zero_hit = zero_hit_variant(ctx, args, device, blob, roff, peak, how)
+    if rank == 0 and world == 1 and not args.no_extras and args.sketch_genomes > 0:
+        sketch_info = sketch_leg(ctx, args, device)
 
     if rank == 0:
-        peak, how = measured_peak_gbs()
-        rows_local = hi - lo
         passes = stats["passes"]
         # query hashes that actually enter a pass (the membership prefilter drops the ones no reference row holds)
         keys_per_pass = stats.get("member_hashes", stats["query_hashes"]) / max(passes, 1)
-        bytes_per_launch = rows_local * s * 8 + keys_per_pass * 8
+        bytes_per_launch = cnt * s * 8 + keys_per_pass * 8
         avg_ms = stream_ms / max(stream_n, 1)
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         ms_per_step = ms / args.steps
+        traffic, traffic_src = ncu_traffic_bytes()
         out = {
-            "metric": "predict reads/s (streaming, 100k 5kb reads vs 40k x s=10000 reference, top 10)",
+            "metric": f"predict reads/s (streaming, {R // 1000}k 5kb reads vs {N // 1000}k x s={s} reference, top {top})",
             "value": R / (ms_per_step * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(N, s, R, top), "refs": N, "sketch_size": s, "reads": R,
-                       "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages,
-                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or 4096,
+            "scaling": "weak" if cfg == "c5" else "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, N, s, R, top), "refs": N, "sketch_size": s, "reads": R,
+                       "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages, "rows": args.row_dist,
+                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or PASS_READS,
                        "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass"
-                             % (rows_local * s * 8 / 1e9),
-                       "parallelism": f"reference rows sharded over {world} GPU(s); NCCL all-gather of local top-N"
-                       if world > 1 else "1 GPU"},
+                             % (cnt * s * 8 / 1e9),
+                       "parallelism": f"reference rows sharded over {world} GPUs, reads hashed 1/{world} per rank; NCCL all-gather of "
+                                      "the query lists and of the local top-N (library communicator)" if world > 1 else "1 GPU"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "fused_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": f"of {how}",
-                         # ncu capture of a full single-GPU pass: comparable with bytes_per_launch at N=1 only
-                         "traffic": ncu_traffic_bytes() if world == 1 and (N, s) == (40000, 10000) else None,
-                         "traffic_source": "profiles/r01_fused_kernel_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                         # ncu capture of a full single-GPU C3 pass: comparable with bytes_per_launch there only
+                         "traffic": traffic if world == 1 and (N, s) == (40000, 10000) else None,
+                         "traffic_source": traffic_src,
                          "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
-                         "launches": stream_n,
+                         "launches": stream_n, "reads_per_launch": R / max(passes, 1),
                          "stream_share_of_step": stream_ms / ms if ms > 0 else None},
+            "roofline_zero_hit": zero_hit,
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
             "predict_stats": stats,
             "result_crc32": f"{result_crc:08x}",
+            "parity": parity,
             "cpu_baseline": cpu_baseline,
+            "consensus": consensus_info,
             "sketch": sketch_info,
         }
         print(json.dumps(out), flush=True)
@@ -463,6 +513,142 @@ def run_b200(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def zero_hit_variant(ctx, args, device, blob, roff, peak, how):
+    """The same reads against 40,000 independent rows: no read hits any row, so a pass is the stream and
+    the filter probe alone — the upper bracket of the streaming kernel next to the hit-heavy lineage matrix. (The
+    reference-membership prefilter drops nearly every query hash here; the few false positives keep the passes honest:
+    they stream the whole matrix against a nearly empty filter.)"""
+    import torch
+    from sketchy_b200._lib import Context
+    N, s, R, top = args.refs, args.sketch_size, args.reads, args.top
+    c2 = Context(ctx.device)
+    ref = independent_rows(N, s, 0, device)
+    c2.ref_upload_device(ref.data_ptr(), np.arange(N + 1, dtype=np.uint64) * np.uint64(s), row_base=0)
+    del ref
+    torch.cuda.empty_cache()
+    b2 = c2.batch().add(blob, roff)
+    b2.stage()
+    d_i = torch.zeros((R, top), dtype=torch.int32, device=device)
+    d_s = torch.zeros((R, top), dtype=torch.int64, device=device)
+
+    def step():
+        c2.sums_reset()
+        c2.predict_stream_device(b2, K, s, SEED, top, d_i.data_ptr(), d_s.data_ptr())
+
+    for _ in range(2):
+        step()
+    c2.synchronize()
+    c2.prof_reset(); c2.prof_enable(True)
+    t1 = time.perf_counter()
+    n_it = 3
+    for _ in range(n_it):
+        step()
+    c2.synchronize()
+    dt = (time.perf_counter() - t1) / n_it
+    sm, sn = c2.prof_get("stream")
+    c2.prof_enable(False)
+    st_ = c2.last_predict_stats()
+    # with all sums zero the ranking is the first `top` rows for every read
+    assert (d_i.cpu().numpy() == np.arange(top)[None, :]).all() and int(d_s.abs().sum()) == 0
+    b2.close(); c2.close()
+    avg_ms = sm / max(sn, 1)
+    bytes_per_launch = N * s * 8 + st_.get("member_hashes", 0) / max(st_["passes"], 1) * 8
+    ach = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": "fused_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "peak_source": f"of {how}", "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches": sn,
+            "value": R / dt, "value_unit": "reads/s", "passes_per_step": st_["passes"],
+            "member_hashes_per_step": st_.get("member_hashes"),
+            "workload": workload_name("c3i", N, s, R, top)}
+
+
+def sketch_leg(ctx, args, device):
+    """C2 on a bounded sample (k=16, s=1000, 2.8 Mbp assemblies): kernel-only Gbp/s from a packed batch resident in HBM,
+    Gbp/s per library call from host ASCII, FASTA on a RAM disk -> .msh through the `sketchy sketch` binary, and the
+    oracle's `_sketch_files` port on all host cores (one file per thread, as the reference's rayon pool does,
+    src/sketchy.rs:470-472) on a smaller sample."""
+    import shutil
+    import tempfile
+    import oracle
+    from sketchy_b200 import synth_torch as st
+    from sketchy_b200 import build as skb_build
+    ng = args.sketch_genomes
+    distinct = [st.random_genomes(1, GENOME_LEN, 9000 + g, device)[0].cpu().numpy() for g in range(min(ng, 8))]
+    recs = [distinct[g % len(distinct)] for g in range(ng)]      # 8 distinct genomes, repeated (hashing cost is data independent)
+    gbp = ng * GENOME_LEN / 1e9
+    sb = ctx.batch().add_records(recs)
+    sb.stage()
+    ctx.sketch(sb, K, 1000, SEED)                                  # warm-up
+    ctx.prof_reset(); ctx.prof_enable(True)
+    ctx.synchronize()
+    t1 = time.perf_counter()
+    n_it = 3
+    for _ in range(n_it):
+        sk_out, _, _ = ctx.sketch(sb, K, 1000, SEED)
+    ctx.synchronize()
+    dt_res = (time.perf_counter() - t1) / n_it
+    hash_ms, _ = ctx.prof_get("hash")
+    sel_ms, _ = ctx.prof_get("select")
+    ctx.prof_enable(False)
+    assert all(h.size == 1000 for h, _ in sk_out)
+    sb.close()
+    # per call from host ASCII: normalise + pack into pinned memory, H2D, kernels, D2H of the sketches
+    t1 = time.perf_counter()
+    hb = ctx.batch().add_records(recs)
+    sk2, _, _ = ctx.sketch(hb, K, 1000, SEED)
+    dt_host = time.perf_counter() - t1
+    hb.close()
+    assert all((a[0] == b[0]).all() for a, b in zip(sk2, sk_out))
+    # FASTA on a RAM disk -> .msh through the C++ host (process start and CUDA context creation included)
+    cli = None
+    try:
+        tmp = tempfile.mkdtemp(prefix="skb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        paths = []
+        for g in range(ng):
+            pth = os.path.join(tmp, f"g{g:05d}.fa")
+            with open(pth, "wb") as f:
+                f.write(b">g%d\n" % g); f.write(recs[g].tobytes()); f.write(b"\n")
+            paths.append(pth)
+        exe = skb_build.CLI
+        t1 = time.perf_counter()
+        r = subprocess.run([exe, "sketch", "-k", "16", "-s", "1000", "-o", os.path.join(tmp, "ref.msh"), "-i", *paths],
+                           capture_output=True, text=True, timeout=600)
+        dt_cli = time.perf_counter() - t1
+        if r.returncode == 0:
+            t1 = time.perf_counter()   # the same binary on one file: what of the wall time is process start + context creation
+            subprocess.run([exe, "sketch", "-k", "16", "-s", "1000", "-o", os.path.join(tmp, "one.msh"), "-i", paths[0]],
+                           capture_output=True, text=True, timeout=600)
+            dt_one = time.perf_counter() - t1
+            cli = {"gbp_per_s": gbp / dt_cli, "wall_s": dt_cli, "one_file_wall_s": dt_one,
+                   "gbp_per_s_beyond_start_up": gbp * (ng - 1) / ng / max(dt_cli - dt_one, 1e-9),
+                   "msh_bytes": os.path.getsize(os.path.join(tmp, "ref.msh"))}
+        else:
+            cli = {"error": r.stderr[-300:]}
+        shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as e:   # the sketch leg is an extra: never take the predict line down with it
+        cli = {"error": repr(e)}
+    # CPU: the oracle's sketch driver, one file per host thread
+    ncores = os.cpu_count() or 1
+    n_cpu = min(ng, 2 * ncores)
+    t1 = time.perf_counter()
+    osk, _, _ = oracle.sketch_groups([r_.tobytes() for r_ in recs[:n_cpu]], list(range(n_cpu)), n_cpu, K, 1000, SEED, nthreads=ncores)
+    dt_cpu = time.perf_counter() - t1
+    assert all((osk[g][0] == sk_out[g][0]).all() for g in range(n_cpu)), "GPU sketches differ from the oracle"
+    kern_gbp = gbp / ((hash_ms + sel_ms) / n_it * 1e-3)
+    bound = 600.0   # SURVEY App. D.2: ~30 IMAD + ~25 ALU per k-mer at 64 lanes/clk/SM x 148 SMs x 1.965 GHz
+    return {"workload": f"C2 sample: {ng} x 2.8 Mbp assemblies, k=16, s=1000",
+            "kernel_gbp_per_s": kern_gbp, "hash_kernel_ms": hash_ms / n_it, "select_kernel_ms": sel_ms / n_it,
+            "resident_call_gbp_per_s": gbp / dt_res, "resident_call_ms": dt_res * 1e3,
+            "host_call_gbp_per_s": gbp / dt_host, "host_call_ms": dt_host * 1e3,
+            "host_call_includes": "normalise + 2-bit pack into pinned memory (all host threads), H2D, kernels, D2H of the sketches",
+            "cli_fasta_to_msh": cli,
+            "roofline": {"bound": "integer pipes", "achieved": kern_gbp, "peak": bound, "unit": "Gbp/s", "frac": kern_gbp / bound,
+                         "peak_source": "estimate (SURVEY App. D.2 instruction count at the 1965 MHz maximum clock); pipe "
+                                        "utilisation from ncu in profiles/r02_hash_kernel_ncu.md"},
+            "cpu_baseline": {"value": n_cpu * GENOME_LEN / 1e9 / dt_cpu, "unit": "Gbp/s", "cores": ncores, "kind": "port",
+                             "sample": f"{n_cpu} of the assemblies, one file per host thread as rayon does "
+                                       f"(src/sketchy.rs:470-472), {dt_cpu:.1f}s; sketches equal the GPU's"}}
 
 
 def run_reference(args):
@@ -475,13 +661,19 @@ def run_reference(args):
     from sketchy_b200 import synth_torch as st
     device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     N, s, R, top = args.refs, args.sketch_size, args.reads, args.top
+    if args.config == "c5":   # bounded sample of the 80 GB reference: the rows one of eight GPUs would hold
+        N = N // 8
     t0 = time.time()
-    genomes = st.random_genomes(args.lineages, GENOME_LEN, 3000, device)
-    gh = [genomes[l].cpu().numpy().tobytes() for l in range(args.lineages)]
+    n_base = min(args.lineages, 40)
+    genomes = st.random_genomes(n_base, GENOME_LEN, 3000, device)
     ncores = os.cpu_count() or 1
-    sk, _, _ = oracle.sketch_groups(gh, list(range(args.lineages)), args.lineages, K, s, SEED, nthreads=ncores)
-    base_t = torch.from_numpy(np.stack([h for h, _ in sk]).astype(np.int64))
-    ref = st.expand_reference_block(base_t.to(device), 0, N, 0.02, 4000, device).cpu().numpy().view(np.uint64).reshape(-1)
+    if args.row_dist == "independent":
+        ref = independent_rows(N, s, 0, device).cpu().numpy().view(np.uint64).reshape(-1)
+    else:
+        gh = [genomes[l].cpu().numpy().tobytes() for l in range(n_base)]
+        sk, _, _ = oracle.sketch_groups(gh, list(range(n_base)), n_base, K, s, SEED, nthreads=ncores)
+        base_t = torch.from_numpy(np.stack([h for h, _ in sk]).astype(np.int64))
+        ref = st.expand_reference_block(base_t.to(device), 0, N, 0.02, 4000, device).cpu().numpy().view(np.uint64).reshape(-1)
     off = np.arange(N + 1, dtype=np.uint64) * np.uint64(s)
     n_s = min(args.cpu_sample, R)
     total_reads = n_s * (max(args.warmup, 1) + args.steps)
@@ -501,16 +693,17 @@ def run_reference(args):
     t1 = time.perf_counter()   # labelled extra: one step with the merges spread over all host threads
     oracle.predict_stream(ref, off, (blob, roff), K, s, SEED, top, nthreads=ncores)
     v_all = n_s / (time.perf_counter() - t1)
-    out = {"impl": "reference", "metric": "predict reads/s (streaming, 100k 5kb reads vs 40k x s=10000 reference, top 10)",
+    R_, N_ = args.reads, args.refs
+    out = {"impl": "reference", "metric": f"predict reads/s (streaming, {R_ // 1000}k 5kb reads vs {N_ // 1000}k x s={s} reference, top {top})",
            "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
-           "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "u64", "data": "synthetic",
-           "config": {"workload": workload_name(N, s, R, top), "refs": N, "sketch_size": s, "reads": R,
-                      "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages,
-                      "sample": f"each step = a bounded sample of {n_s} consecutive reads of the workload against the "
-                                f"full {N} x {s} matrix"},
+           "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak" if args.config == "c5" else "strong",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": workload_name(args.config, N_, s, R_, top), "refs": N_, "sketch_size": s, "reads": R_,
+                      "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages, "rows": args.row_dist,
+                      "sample": f"each step = a bounded sample of {n_s} consecutive reads of the workload against "
+                                + (f"the full {N} x {s} matrix" if N == N_ else f"{N} x {s} rows (one GPU's shard of the {N_}-row reference)")},
            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",
-                            "sample": f"{n_s} reads per step vs the full {N}x{s} matrix; C++ restatement of sketchy "
+                            "sample": f"{n_s} reads per step vs {N}x{s} rows; C++ restatement of sketchy "
                                       f"0.6.0 (oracle/oracle.cpp), single thread like the reference's predict loop",
                             "all_cores": {"value": v_all, "unit": "reads/s", "cores": ncores,
                                           "note": "not the reference's behaviour: the N merges per read spread over "

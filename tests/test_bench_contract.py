@@ -35,8 +35,24 @@ def test_reference_arm_is_silent_on_other_ranks():
 def test_roofline_helpers():
     sys.path.insert(0, ROOT)
     import bench
-    t = bench.ncu_traffic_bytes()
-    assert t is not None and 3.2e9 < t < 3.3e9        # one pass over the 3.2 GB matrix, no re-reads
-    assert bench.workload_name(40000, 10000, 100000, 10).startswith("C3: predict 100,000 synthetic ONT reads")
+    t, src = bench.ncu_traffic_bytes()
+    assert t is not None and 3.2e9 < t < 3.3e9 and src.startswith("profiles/")   # one pass over the 3.2 GB matrix, no re-reads
+    assert bench.workload_name("c3", 40000, 10000, 100000, 10).startswith("C3: predict 100,000 synthetic ONT reads")
+    assert bench.workload_name("c4", 40000, 1000, 1000000, 5).startswith("C4: streaming predict + genotype consensus")
+
+
+def test_consensus_calls_match_the_host_mirror():
+    """bench.py's vectorised per-read consensus (C4) == api.consensus_value on every read, ties included."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from sketchy_b200.api import consensus_value
+    rng = np.random.default_rng(3)
+    table = rng.integers(0, 3, size=(50, 4)).astype(np.int32)
+    idx = rng.integers(0, 50, size=(200, 5)).astype(np.uint32)
+    calls = bench.consensus_calls(idx, table)
+    for r in range(200):
+        for c in range(4):
+            assert str(calls[r, c]) == consensus_value([str(x) for x in table[idx[r].astype(np.int64), c]])
     peak, how = bench.measured_peak_gbs()
     assert peak > 1000 and how in ("measured", "fallback")
