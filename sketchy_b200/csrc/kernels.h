@@ -141,7 +141,8 @@ size_t skb_fused_smem_bytes(uint32_t cnt_stride);
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride);
 #define SKB_IVL_CAP ((4u << 20) << (SKB_X_IDBITS - 12))  // candidate intervals per pass (4 M per 4096 reads); more than that shrinks the pass
 #define SKB_SEG_CAP (2u << 20)     // segment records per pass (16 + up to 160 bytes each)
-#define SKB_SEG_WORDS_MAX 40u      // counters of one lane segment, in words: 4096 / 32 / 4 (u8) or 2560 / 32 / 2 (u16)
+// counters of one lane segment, in words: reads / 32 / 4 with u8 counters, at most 2560 / 32 / 2 = 40 with u16 counters
+#define SKB_SEG_WORDS_MAX ((1u << SKB_X_IDBITS) / 128u > 40u ? (1u << SKB_X_IDBITS) / 128u : 40u)
 uint32_t skb_fused_tile();
 uint32_t skb_fused_max_reads(int narrow);
 

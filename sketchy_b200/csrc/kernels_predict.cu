@@ -265,13 +265,13 @@ struct FsCtl {
   uint32_t li_seg[32];            // largest bound index within each lane segment of the reads
   uint32_t done[FS_ROWBUF];       // sub-tiles of the buffer's current row that are fully counted
   uint32_t freed[FS_ROWBUF];      // rows of this buffer that have been ranked (the buffer is zero again)
-  uint32_t next_tile;             // next unclaimed sub-tile of the CTA's rows (claimed in order)
-  uint4 desc[FS_WARPS][FS_STAGES];  // sub-tile staged in each ring slot: {row (CTA-local), tile in row, row length, -}
+  uint32_t next_tile;             // next unclaimed claim unit of the CTA's rows (claimed in order)
 };
 constexpr uint32_t FS_NONE = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint32_t fs_tiles_of(uint32_t len) {  // an empty row still has one (empty) sub-tile:
-  const uint32_t n = (len + FS_SUB - 1) / FS_SUB;                 // somebody has to close and rank it
+constexpr uint32_t FS_CLAIM = (uint32_t)FS_SUB * FS_STAGES;       // hashes per claim: one ring's worth of a row
+__device__ __forceinline__ uint32_t fs_claims_of(uint32_t len) {  // an empty row still has one (empty) claim:
+  const uint32_t n = (len + FS_CLAIM - 1) / FS_CLAIM;             // somebody has to close and rank it
   return n ? n : 1u;
 }
 
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   const uint32_t c0 = a.cta_row[blockIdx.x];
   const uint32_t r1 = a.cta_row[blockIdx.x + 1] - c0;
   const uint32_t tile0 = a.rv.uniform_len ? 0u : a.tile_cum[c0];
-  const uint32_t n_tiles = a.rv.uniform_len ? r1 * fs_tiles_of(a.rv.uniform_len) : a.tile_cum[c0 + r1] - tile0;
+  const uint32_t n_tiles = a.rv.uniform_len ? r1 * fs_claims_of(a.rv.uniform_len) : a.tile_cum[c0 + r1] - tile0;
 
   if (threadIdx.x == 0) {
     for (int w = 0; w < FS_WARPS; ++w)
@@ -463,136 +463,149 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
   uint64_t policy;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
-  // lane 0: claim the CTA's next sub-tile, describe it in this ring slot and start its bulk copy
-  auto claim_and_issue = [&](uint32_t stage) {
-    const uint32_t n = atomicAdd(&ctl.next_tile, 1u);
-    uint4 d = make_uint4(FS_NONE, 0u, 0u, 0u);
-    if (n < n_tiles) {
-      uint32_t row, tt, len;
-      const uint64_t* p;
-      if (a.rv.uniform_len) {
-        row = a.tpr == 1u ? n : __umulhi(n, a.tpr_magic);  // n / tiles-per-row by a precomputed reciprocal (exact while n * tpr < 2^32)
-        tt = n - row * a.tpr;
-        len = a.rv.uniform_len;
-        p = a.rv.ref + (size_t)(c0 + row) * a.rv.uniform_pitch;
-      } else {  // ragged rows: the row whose cumulative sub-tile range holds n
-        uint32_t lo = 0, hi = r1;
-        const uint32_t key = tile0 + n;
-        while (hi - lo > 1) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (a.tile_cum[c0 + mid] <= key) lo = mid; else hi = mid;
-        }
-        row = lo;
-        tt = key - a.tile_cum[c0 + row];
-        len = a.rv.row_len[c0 + row];
-        p = a.rv.ref + a.rv.row_start[c0 + row];
+  // A claim = FS_STAGES consecutive sub-tiles of one row (its "claim unit", one ring's worth); the warp's ring slot j
+  // holds sub-tile j of the current claim. All lanes keep the claim in registers: {row, first sub-tile, row length}.
+  auto claim = [&](uint32_t& row, uint32_t& t0, uint32_t& len, const uint64_t*& p) {
+    uint32_t n = 0;
+    if (lane == 0) n = atomicAdd(&ctl.next_tile, 1u);
+    n = __shfl_sync(0xffffffffu, n, 0);
+    row = FS_NONE; t0 = 0; len = 0; p = a.rv.ref;
+    if (n >= n_tiles) return;
+    if (a.rv.uniform_len) {
+      row = a.tpr == 1u ? n : __umulhi(n, a.tpr_magic);  // n / claims-per-row by a precomputed reciprocal (exact while n * tpr < 2^32)
+      t0 = (n - row * a.tpr) * FS_STAGES;
+      len = a.rv.uniform_len;
+      p = a.rv.ref + (size_t)(c0 + row) * a.rv.uniform_pitch;
+    } else {  // ragged rows: the row whose cumulative claim range holds n
+      uint32_t lo = 0, hi = r1;
+      const uint32_t key = tile0 + n;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.tile_cum[c0 + mid] <= key) lo = mid; else hi = mid;
       }
-      d = make_uint4(row, tt, len, 0u);
-      const uint32_t first = tt * FS_SUB;
-      uint32_t cnt = len - first;
-      if (cnt > (uint32_t)FS_SUB) cnt = FS_SUB;
-      const uint32_t bytes = ((cnt + 1u) & ~1u) * 8u;  // multiple of 16; rows start on even offsets
-      mbar_arrive_expect_tx(&full_bar[warp][stage], bytes);
-      if (bytes) bulk_load(my_ring + (size_t)stage * FS_SUB * 8, p + first, bytes, &full_bar[warp][stage], policy);
+      row = lo;
+      t0 = (key - a.tile_cum[c0 + row]) * FS_STAGES;
+      len = a.rv.row_len[c0 + row];
+      p = a.rv.ref + a.rv.row_start[c0 + row];
     }
-    ctl.desc[warp][stage] = d;
+  };
+  // lane 0: bulk copy of sub-tile (t0 + j) of a claimed row into ring slot j (nothing to copy past the row's end)
+  auto issue = [&](uint32_t j, uint32_t t0, uint32_t len, const uint64_t* p) {
+    const uint32_t first = (t0 + j) * FS_SUB;
+    uint32_t cnt = first < len ? len - first : 0u;
+    if (cnt > (uint32_t)FS_SUB) cnt = FS_SUB;
+    const uint32_t bytes = ((cnt + 1u) & ~1u) * 8u;  // multiple of 16; rows start on even offsets
+    mbar_arrive_expect_tx(&full_bar[warp][j], bytes);
+    if (bytes) bulk_load(my_ring + (size_t)j * FS_SUB * 8, p + first, bytes, &full_bar[warp][j], policy);
   };
 
-  if (lane == 0)
-    for (uint32_t s = 0; s < (uint32_t)FS_STAGES; ++s) claim_and_issue(s);  // prime the private ring
+  uint32_t row, t0, len;
+  const uint64_t* rp;
+  claim(row, t0, len, rp);
+  if (row != FS_NONE && lane == 0)
+    for (uint32_t j = 0; j < (uint32_t)FS_STAGES; ++j) issue(j, t0, len, rp);  // prime the private ring
 
-  for (uint32_t k = 0;; ++k) {  // sub-tiles consumed by this warp: stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1
-    const uint32_t stage = k % FS_STAGES, phase = (k / FS_STAGES) & 1u;
-    __syncwarp();
-    const uint4 d = ctl.desc[warp][stage];
-    if (d.x == FS_NONE) break;  // claims are in order: once one comes back empty, so do all later ones
-    const uint32_t row = d.x, len = d.z;
+  for (uint32_t k = 0; row != FS_NONE; ++k) {  // claims consumed by this warp: every ring slot's barrier flips once per claim
+    const uint32_t phase = k & 1u;
+    // the next claim is made now, so that its round trip is over when the first ring slot is free again
+    uint32_t nrow, nt0, nlen;
+    const uint64_t* np;
+    claim(nrow, nt0, nlen, np);
     const uint32_t par = row % FS_ROWBUF;
     uint32_t* cb = cnt32 + par * cwords;
     if (row >= (uint32_t)FS_ROWBUF) {  // the buffer's previous row must have been ranked and cleared (it almost always has)
       const uint32_t need = row / FS_ROWBUF;
-      if (lane == 0)
-        while (lds_acquire_u32(&ctl.freed[par]) < need) __nanosleep(100);
-      __syncwarp();
+      if (lds_acquire_u32(&ctl.freed[par]) < need) {
+        if (lane == 0)
+          while (lds_acquire_u32(&ctl.freed[par]) < need) __nanosleep(100);
+        __syncwarp();
+      }
     }
-    mbar_wait(&full_bar[warp][stage], phase);
-    const uint8_t* tile = my_ring + (size_t)stage * FS_SUB * 8;
-    const uint32_t n_sub = len - d.y * FS_SUB;  // >= FS_SUB for every sub-tile but a row's last
 #pragma unroll 1
-    for (uint32_t ch = 0; ch < (uint32_t)FS_CHUNKS; ++ch) {
-      const uint32_t base = ch * FS_NHASH * 32;  // first hash index of the chunk within the sub-tile
-      if (base >= n_sub) break;
-      const uint8_t* cbase = tile + (size_t)base * 8 + lane * 16;
-      uint4 v[FS_NHASH / 2];
+    for (uint32_t j = 0; j < (uint32_t)FS_STAGES; ++j) {
+      mbar_wait(&full_bar[warp][j], phase);
+      const uint8_t* tile = my_ring + (size_t)j * FS_SUB * 8;
+      const uint32_t first = (t0 + j) * FS_SUB;
+      const uint32_t n_sub = first < len ? len - first : 0u;  // >= FS_SUB for every sub-tile but a row's last
+#pragma unroll 1
+      for (uint32_t ch = 0; ch < (uint32_t)FS_CHUNKS; ++ch) {
+        const uint32_t base = ch * FS_NHASH * 32;  // first hash index of the chunk within the sub-tile
+        if (base >= n_sub) break;
+        const uint8_t* cbase = tile + (size_t)base * 8 + lane * 16;
+        uint4 v[FS_NHASH / 2];
 #pragma unroll
-      for (int r = 0; r < FS_NHASH / 2; ++r) v[r] = *reinterpret_cast<const uint4*>(cbase + 512 * r);
-      uint32_t pm = 0;  // bit 7 - j: this lane's j-th hash of the chunk passed the filter
-      if (!(SKB_X_ABLATE & 1)) {
-        if (n_sub >= base + FS_NHASH * 32) {
+        for (int r = 0; r < FS_NHASH / 2; ++r) v[r] = *reinterpret_cast<const uint4*>(cbase + 512 * r);
+        uint32_t pm = 0;  // bit 7 - j: this lane's j-th hash of the chunk passed the filter
+        if (!(SKB_X_ABLATE & 1)) {
+          if (n_sub >= base + FS_NHASH * 32) {
 #pragma unroll
-          for (int j = 0; j < FS_NHASH; ++j) {
-            const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
-            const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
-            pm = __funnelshift_l(bloom_probe(bloom, lo, hi), pm, 1);
+            for (int q = 0; q < FS_NHASH; ++q) {
+              const uint32_t lo = (q & 1) ? v[q >> 1].z : v[q >> 1].x;
+              const uint32_t hi = (q & 1) ? v[q >> 1].w : v[q >> 1].y;
+              pm = __funnelshift_l(bloom_probe(bloom, lo, hi), pm, 1);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < FS_NHASH; ++q) {
+              const uint32_t lo = (q & 1) ? v[q >> 1].z : v[q >> 1].x;
+              const uint32_t idx = base + 2u * (lane + 32 * (q >> 1)) + (q & 1);
+              const uint32_t hi = (q & 1) ? v[q >> 1].w : v[q >> 1].y;
+              pm = __funnelshift_l(idx < n_sub ? bloom_probe(bloom, lo, hi) : 0u, pm, 1);
+            }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < FS_NHASH; ++j) {
-            const uint32_t lo = (j & 1) ? v[j >> 1].z : v[j >> 1].x;
-            const uint32_t idx = base + 2u * (lane + 32 * (j >> 1)) + (j & 1);
-            const uint32_t hi = (j & 1) ? v[j >> 1].w : v[j >> 1].y;
-            pm = __funnelshift_l(idx < n_sub ? bloom_probe(bloom, lo, hi) : 0u, pm, 1);
+        }
+        if (SKB_X_ABLATE & 2) pm = 0;
+        // Divergent: only the lanes that hold a passer run this, two passers per trip. A passer's hash is read back
+        // from the staging buffer by its position (hash q of the chunk sits at byte (q >> 1) * 512 + (q & 1) * 8 of
+        // the lane's column), both table loads are issued before either is resolved, so a lane pays the L2 latency
+        // once per trip; a slot owned by another key is chased in place (load factor 0.125: rare).
+        while (pm) {
+          const uint32_t b0 = 31u - (uint32_t)__clz((int)pm);
+          pm &= ~(1u << b0);
+          const bool two = pm != 0u;
+          const uint32_t b1 = two ? 31u - (uint32_t)__clz((int)pm) : b0;
+          pm &= ~(1u << b1);
+          // bit b holds hash q = 7 - b: offset 0x608 - ((b * 0x108) & 0x608)
+          const uint2 e0 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b0 * 0x108u) & 0x608u));
+          const uint2 e1 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b1 * 0x108u) & 0x608u));
+          const uint64_t h0 = ((uint64_t)e0.y << 32) | e0.x, h1 = ((uint64_t)e1.y << 32) | e1.x;
+          uint32_t s0 = h0 == SKB_EMPTY_KEY ? tcap : table_home(h0, tlog2);
+          uint32_t s1 = h1 == SKB_EMPTY_KEY ? tcap : table_home(h1, tlog2);
+          uint4 r0 = __ldg(tslots + s0);
+          uint4 r1v = __ldg(tslots + s1);
+          for (;;) {  // walk the probe sequence until the key or an empty slot
+            const uint64_t key = ((uint64_t)r0.y << 32) | r0.x;
+            if (key == h0) { apply_hit<CPW>(t, ((unsigned long long)r0.w << 32) | r0.z, cb); break; }
+            if (key == SKB_EMPTY_KEY) break;
+            s0 = (s0 + 1) & (tcap - 1);
+            r0 = __ldg(tslots + s0);
+          }
+          if (two) {
+            for (;;) {
+              const uint64_t key = ((uint64_t)r1v.y << 32) | r1v.x;
+              if (key == h1) { apply_hit<CPW>(t, ((unsigned long long)r1v.w << 32) | r1v.z, cb); break; }
+              if (key == SKB_EMPTY_KEY) break;
+              s1 = (s1 + 1) & (tcap - 1);
+              r1v = __ldg(tslots + s1);
+            }
           }
         }
       }
-      if (SKB_X_ABLATE & 2) pm = 0;
-      // Divergent: only the lanes that hold a passer run this, two passers per trip. A passer's hash is read back
-      // from the staging buffer by its position (hash j of the chunk sits at byte (j >> 1) * 512 + (j & 1) * 8 of the
-      // lane's column), both table loads are issued before either is resolved, so a lane pays the L2 latency once
-      // per trip; a slot owned by another key is chased in place (load factor 0.125: rare).
-      while (pm) {
-        const uint32_t b0 = 31u - (uint32_t)__clz((int)pm);
-        pm &= ~(1u << b0);
-        const bool two = pm != 0u;
-        const uint32_t b1 = two ? 31u - (uint32_t)__clz((int)pm) : b0;
-        pm &= ~(1u << b1);
-        // bit b holds hash j = 7 - b: offset 0x608 - ((b * 0x108) & 0x608)
-        const uint2 e0 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b0 * 0x108u) & 0x608u));
-        const uint2 e1 = *reinterpret_cast<const uint2*>(cbase + 0x608u - ((b1 * 0x108u) & 0x608u));
-        const uint64_t h0 = ((uint64_t)e0.y << 32) | e0.x, h1 = ((uint64_t)e1.y << 32) | e1.x;
-        uint32_t s0 = h0 == SKB_EMPTY_KEY ? tcap : table_home(h0, tlog2);
-        uint32_t s1 = h1 == SKB_EMPTY_KEY ? tcap : table_home(h1, tlog2);
-        uint4 r0 = __ldg(tslots + s0);
-        uint4 r1v = __ldg(tslots + s1);
-        for (;;) {  // walk the probe sequence until the key or an empty slot
-          const uint64_t key = ((uint64_t)r0.y << 32) | r0.x;
-          if (key == h0) { apply_hit<CPW>(t, ((unsigned long long)r0.w << 32) | r0.z, cb); break; }
-          if (key == SKB_EMPTY_KEY) break;
-          s0 = (s0 + 1) & (tcap - 1);
-          r0 = __ldg(tslots + s0);
-        }
-        if (two) {
-          for (;;) {
-            const uint64_t key = ((uint64_t)r1v.y << 32) | r1v.x;
-            if (key == h1) { apply_hit<CPW>(t, ((unsigned long long)r1v.w << 32) | r1v.z, cb); break; }
-            if (key == SKB_EMPTY_KEY) break;
-            s1 = (s1 + 1) & (tcap - 1);
-            r1v = __ldg(tslots + s1);
-          }
-        }
+      // ring slot j is fully read: refill it with sub-tile j of the next claim
+      __syncwarp();
+      if (lane == 0 && nrow != FS_NONE) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(j, nt0, nlen, np);
       }
     }
-    // the staging buffer is fully read: refill it with the CTA's next unclaimed sub-tile; then count this one done
-    __syncwarp();
+    // this claim's hits are in shared memory: count it done; the warp whose claim completes the row ranks it
     uint32_t last = 0;
     if (lane == 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      claim_and_issue(stage);
-      __threadfence_block();  // this warp's hits are in shared memory before the count says so
-      last = atomicAdd(&ctl.done[par], 1u) + 1u == fs_tiles_of(len) ? 1u : 0u;
+      __threadfence_block();
+      last = atomicAdd(&ctl.done[par], 1u) + 1u == fs_claims_of(len) ? 1u : 0u;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {  // this sub-tile completed the row: rank it and hand the buffer back
+    if (last) {  // hand the buffer back after the row's short rank step
       __threadfence_block();
       rank_row<CPW>(a, ctl, cb, cwords, c0 + row);
       if (lane == 0) {
@@ -601,6 +614,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
         atomicAdd(&ctl.freed[par], 1u);
       }
     }
+    row = nrow; t0 = nt0; len = nlen; rp = np;
   }
 }
 
@@ -1202,7 +1216,7 @@ size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
 size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
   return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 1 * FS_ROWBUF;
 }
-uint32_t skb_fused_tile() { return FS_SUB; }
+uint32_t skb_fused_tile() { return FS_CLAIM; }  // hashes per claim unit (what tile_cum / tpr count)
 // Largest pass the kernel's shared memory holds: 227 KB per CTA minus the static barriers and bookkeeping, the filter
 // and the staging rings leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each). Pass-local read ids are
 // SKB_SLOT_ID_BITS wide in a table slot: that caps it either way.

@@ -1,6 +1,3 @@
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_l_bench.json 2> gpurun_out/r02_l_bench.log; tail -3 gpurun_out/r02_l_bench.log; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r02_l_bench.json').read().strip().splitlines()[-1])
-for k in ('value','ms_per_step','e2e','roofline','roofline_zero_hit','kernel_ms_per_step','parity','cpu_baseline','sketch','result_crc32','gpu_launches'):
-    print(k, json.dumps(d.get(k))[:700])
-PY
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
+AB_ARGS="--no-extras" bash tools/ab.sh base b8k 2>&1 | tee gpurun_out/r02_o_ab.txt
+SKB_LIB=$PWD/sketchy_b200/build/variants/lib_b8k.so python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
