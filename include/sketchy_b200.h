@@ -161,6 +161,10 @@ int skb_comm_world(const skb_ctx* ctx);
 /* The contiguous split every collective call assumes: items [*begin, *begin + *count) of n belong to `rank`
  * (ceil(n / world) items per rank, the last ranks may get fewer or none). Use it for reference rows and for reads. */
 void skb_dist_range(uint64_t n, int rank, int world, uint64_t* begin, uint64_t* count);
+/* Collective: every rank contributes `bytes` bytes (host memory); recv ([world * bytes], host) holds rank r's
+ * contribution at r * bytes on every rank. For the small host-side exchanges of a sharded run (local top-N of the
+ * read-set mode, the sketches of a rank's share of the input files). */
+int skb_comm_allgather_host(skb_ctx* ctx, const void* send, void* recv, uint64_t bytes);
 /* Collective streaming predict of `reads_total` reads. `local` holds ONLY this rank's reads,
  * skb_dist_range(reads_total, rank, world), one group each: a rank packs, copies and hashes 1/world of the reads and
  * the per-read query-hash lists are exchanged. out_idx / out_sum ([reads_total * top], host; may be NULL on ranks that

@@ -52,6 +52,7 @@ SYMBOLS = [
     ("skb_comm_destroy", _i, [_vp]),
     ("skb_comm_rank", _i, [_vp]),
     ("skb_comm_world", _i, [_vp]),
+    ("skb_comm_allgather_host", _i, [_vp, _vp, _vp, _u64]),
     ("skb_dist_range", None, [_u64, _i, _i, C.POINTER(_u64), C.POINTER(_u64)]),
     ("skb_predict_stream_dist", _i, [_vp, _vp, _u64, _u32, _u32, _u64, _u32, _vp, _vp]),
     ("skb_predict_stream_dist_device", _i, [_vp, _vp, _u64, _u32, _u32, _u64, _u32, _vp, _vp]),

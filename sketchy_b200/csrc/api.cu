@@ -1447,6 +1447,20 @@ int skb_comm_world(const skb_ctx* c) { return c ? c->world : 1; }
 
 void skb_dist_range(uint64_t n, int rank, int world, uint64_t* begin, uint64_t* count) { dist_range(n, rank, world, begin, count); }
 
+int skb_comm_allgather_host(skb_ctx* c, const void* send, void* recv, uint64_t bytes) {
+  if (!c || (bytes && (!send || !recv))) return SKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  if (bytes == 0) return SKB_OK;
+  if (!c->comm || c->world <= 1) { std::memcpy(recv, send, bytes); return SKB_OK; }
+  CU(c, c->misc.ensure((size_t)bytes * c->world));
+  uint8_t* d = c->misc.as<uint8_t>();
+  CU(c, cudaMemcpyAsync(d + (size_t)bytes * c->rank, send, bytes, cudaMemcpyHostToDevice, c->stream));
+  NC(c, g_nccl.AllGather(d + (size_t)bytes * c->rank, d, bytes, ncclUint8, c->comm, c->stream));
+  CU(c, cudaMemcpyAsync(recv, d, (size_t)bytes * c->world, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SKB_OK;
+}
+
 int skb_predict_stream_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t k, uint32_t s_query,
                                    uint64_t seed, uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum) {
   if (!c || !b || b->ctx != c) return SKB_ERR_INVALID_ARG;

@@ -11,6 +11,8 @@
 #include <map>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
+#include <unistd.h>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -46,8 +48,12 @@ Args parse(int argc, char** argv) {
     std::string t = argv[i];
     if (t.size() >= 2 && t[0] == '-' && !(t.size() > 1 && (isdigit((unsigned char)t[1]) || t[1] == '.'))) {
       std::string name;
+      std::string inline_value;
+      bool has_inline = false;
       if (t.rfind("--", 0) == 0) {
         name = t.substr(2);
+        const size_t eq = name.find('=');  // clap also takes --name=value
+        if (eq != std::string::npos) { inline_value = name.substr(eq + 1); name = name.substr(0, eq); has_inline = true; }
       } else {
         auto it = kShort.find(t);
         if (it == kShort.end()) throw std::runtime_error("unknown option " + t);
@@ -59,6 +65,7 @@ Args parse(int argc, char** argv) {
       }
       cur = name;
       a.opt[cur];
+      if (has_inline) a.opt[cur].push_back(inline_value);
     } else {
       if (cur.empty()) throw std::runtime_error("unexpected argument " + t);
       a.opt[cur].push_back(t);
@@ -83,15 +90,57 @@ void require_msh(const std::string& path) {
   if (e != "msh") throw std::runtime_error("reference sketch file must have Mash (.msh) or Finch (.fsh) extension");
 }
 
+// One process per GPU. A launcher (torchrun, mpirun, a shell loop) starts `world` copies with the usual environment:
+// rank / world size / local rank from SKETCHY_B200_RANK / _WORLD / _DEVICE, else RANK / WORLD_SIZE / LOCAL_RANK (torchrun),
+// else OMPI_COMM_WORLD_*; the NCCL id travels through the file SKETCHY_B200_COMM_FILE (rank 0 writes it, the others wait
+// for it). Every rank reads the same inputs; rank 0 prints / writes the output.
+int env_int(std::initializer_list<const char*> names, int dflt) {
+  for (const char* n : names)
+    if (const char* v = getenv(n)) return atoi(v);
+  return dflt;
+}
+
 struct Ctx {
   skb_ctx* c = nullptr;
+  int rank = 0, world = 1;
   Ctx() {
-    const char* dev = getenv("SKETCHY_B200_DEVICE");
-    const int rc = skb_create(dev ? atoi(dev) : 0, &c);
+    rank = env_int({"SKETCHY_B200_RANK", "RANK", "OMPI_COMM_WORLD_RANK"}, 0);
+    world = env_int({"SKETCHY_B200_WORLD", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE"}, 1);
+    if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad rank / world size in the environment");
+    const int dev = env_int({"SKETCHY_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, 0);
+    const int rc = skb_create(dev, &c);
     if (rc != SKB_OK) throw std::runtime_error("no B200 (sm_100) device: the B200 build has no CPU fallback");
+    if (world > 1) join();
   }
-  ~Ctx() { if (c) skb_destroy(c); }
+  ~Ctx() { if (c) { skb_comm_destroy(c); skb_destroy(c); } }
   void check(int rc) const { if (rc != SKB_OK) throw std::runtime_error(skb_last_error(c)); }
+  void join() {
+    const char* path = getenv("SKETCHY_B200_COMM_FILE");
+    if (!path) throw std::runtime_error("multi-GPU run: set SKETCHY_B200_COMM_FILE to a path every rank can reach");
+    uint8_t id[SKB_COMM_ID_BYTES];
+    if (rank == 0) {
+      if (skb_comm_unique_id(id) != SKB_OK) throw std::runtime_error("NCCL is not available (libnccl.so.2)");
+      const std::string tmp = std::string(path) + ".tmp";
+      FILE* fp = fopen(tmp.c_str(), "wb");
+      if (!fp || fwrite(id, 1, sizeof id, fp) != sizeof id) throw std::runtime_error("cannot write the communicator file");
+      fclose(fp);
+      if (rename(tmp.c_str(), path) != 0) throw std::runtime_error("cannot publish the communicator file");
+    } else {
+      for (int waited = 0;; ++waited) {
+        FILE* fp = fopen(path, "rb");
+        if (fp) {
+          const size_t n = fread(id, 1, sizeof id, fp);
+          fclose(fp);
+          if (n == sizeof id) break;
+        }
+        if (waited > 6000) throw std::runtime_error("timed out waiting for the communicator file");
+        usleep(10000);
+      }
+    }
+    check(skb_comm_init(c, id, rank, world));
+  }
+  // contiguous share of n items of this rank
+  void range(uint64_t n, uint64_t& begin, uint64_t& count) const { skb_dist_range(n, rank, world, &begin, &count); }
 };
 
 using ingest::Blob;
@@ -180,13 +229,17 @@ void print_results(const msh::File& ref, const Genotypes& g, uint64_t read, cons
   }
 }
 
+// this rank's contiguous range of the reference sketches (all of them on one GPU); indices reported by the library are global
 void upload_reference(const Ctx& c, const msh::File& ref) {
+  uint64_t lo = 0, cnt = 0;
+  c.range(ref.sketches.size(), lo, cnt);
   std::vector<uint64_t> flat, off{0};
-  for (const auto& s : ref.sketches) {
+  for (uint64_t i = lo; i < lo + cnt; ++i) {
+    const auto& s = ref.sketches[i];
     flat.insert(flat.end(), s.hashes.begin(), s.hashes.end());
     off.push_back(flat.size());
   }
-  c.check(skb_ref_upload(c.c, flat.data(), off.data(), (uint32_t)ref.sketches.size(), 0));
+  c.check(skb_ref_upload(c.c, flat.data(), off.data(), (uint32_t)cnt, (uint32_t)lo));
 }
 
 // ---- sub-commands -----------------------------------------------------------------------------------------------
@@ -202,39 +255,81 @@ int cmd_sketch(const Args& a) {
   std::vector<std::string> files;
   if (a.has("input")) files = a.opt.at("input");
   else for (std::string l; std::getline(std::cin, l);) if (!l.empty()) files.push_back(l);  // src/sketchy.rs:137-146
-  FILE* fp = fopen(out.c_str(), "wb");  // created before sketching, like the reference (:153)
-  if (!fp) throw std::runtime_error("failed to open file");
-  fclose(fp);
   Ctx c;
+  if (c.rank == 0) {
+    FILE* fp = fopen(out.c_str(), "wb");  // created before sketching, like the reference (:153)
+    if (!fp) throw std::runtime_error("failed to open file");
+    fclose(fp);
+  }
+  // The reference runs its files on a rayon pool, one sketcher per file (src/sketchy.rs:470-473). Here: the files are
+  // partitioned over the GPUs by contiguous range (no collective in the hashing); a rank takes its files in windows
+  // (<= 1 GB on disk each): window i+1 is read, decompressed and split into records on the host threads while window
+  // i is packed, copied and sketched, one skb_sketch call per window; results are kept in file order.
+  const uint32_t G = (uint32_t)files.size();
+  uint64_t f_lo = 0, f_cnt = 0;
+  c.range(G, f_lo, f_cnt);
+  const size_t per_file = 24 + (size_t)s * 12;  // n, bases, kmers, hashes[s], counts[s]
+  uint64_t share = 0, dummy = 0;
+  skb_dist_range(G, 0, c.world, &dummy, &share);  // the largest share: the fixed record size of the exchange
+  std::vector<uint8_t> mine((size_t)share * per_file, 0);
+  auto rec = [&](std::vector<uint8_t>& buf, size_t i) { return buf.data() + i * per_file; };
   skb_batch* b = nullptr;
   c.check(skb_batch_create(c.c, &b));
-  msh::File f;
-  f.kmer_size = k; f.sketch_size = s; f.hash_seed = seed;
-  for (const std::string& p : files) {
-    msh::Sketch sk;
-    sk.name = basename_of(p);
-    f.sketches.push_back(sk);
-  }
-  // windows of files (<= 1 GB on disk each) are read, decompressed and split into records on all host threads, then
-  // packed in file order: the reference runs its files on a rayon pool (src/sketchy.rs:470-472)
-  for (size_t g0 = 0; g0 < files.size();) {
-    const size_t g1 = ingest::window_end(files, g0, 1ull << 30);
-    const Blob blob = ingest::read_files(files, g0, g1);
-    if (blob.n()) c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), blob.grp.data(), blob.n(), 0));
-    g0 = g1;
-  }
-  const uint32_t G = (uint32_t)files.size();
-  const uint32_t have = skb_batch_num_groups(b);  // trailing empty files have no group yet
-  std::vector<uint64_t> hs((size_t)G * s), bases(G, 0), kmers(G, 0);
-  std::vector<uint32_t> cnt((size_t)G * s), n(G, 0);
-  if (have) c.check(skb_sketch(c.c, b, k, s, seed, hs.data(), cnt.data(), n.data(), bases.data(), kmers.data()));
-  for (uint32_t g = 0; g < G; ++g) {
-    auto& sk = f.sketches[g];
-    sk.seq_length = bases[g]; sk.num_valid_kmers = kmers[g];
-    sk.hashes.assign(hs.begin() + (size_t)g * s, hs.begin() + (size_t)g * s + n[g]);
-    sk.counts.assign(cnt.begin() + (size_t)g * s, cnt.begin() + (size_t)g * s + n[g]);
+  {
+    Blob cur, nxt;
+    std::exception_ptr err;
+    size_t g0 = f_lo, g1 = ingest::window_end(files, g0, 1ull << 30);
+    const size_t g_end = f_lo + f_cnt;
+    if (g1 > g_end) g1 = g_end;
+    if (g0 < g_end) cur = ingest::read_files(files, g0, g1);
+    while (g0 < g_end) {
+      size_t n0 = g1, n1 = n0 < g_end ? std::min(g_end, ingest::window_end(files, n0, 1ull << 30)) : n0;
+      std::thread reader;
+      if (n0 < g_end) reader = std::thread([&]() { try { nxt = ingest::read_files(files, n0, n1); } catch (...) { err = std::current_exception(); } });
+      const uint32_t W = (uint32_t)(g1 - g0);
+      for (uint32_t& g : cur.grp) g -= (uint32_t)g0;  // groups of a window start at 0
+      c.check(skb_batch_clear(b));
+      if (cur.n()) c.check(skb_batch_add(b, cur.bytes.data(), cur.off.data(), cur.grp.data(), cur.n(), 0));
+      const uint32_t have = skb_batch_num_groups(b);  // trailing empty files have no group
+      std::vector<uint64_t> hs((size_t)W * s), bases(W, 0), kmers(W, 0);
+      std::vector<uint32_t> cnt((size_t)W * s), n(W, 0);
+      if (have) c.check(skb_sketch(c.c, b, k, s, seed, hs.data(), cnt.data(), n.data(), bases.data(), kmers.data()));
+      for (uint32_t g = 0; g < W; ++g) {
+        uint8_t* r = rec(mine, g0 - f_lo + g);
+        const uint64_t nn = n[g];
+        memcpy(r, &nn, 8); memcpy(r + 8, &bases[g], 8); memcpy(r + 16, &kmers[g], 8);
+        memcpy(r + 24, &hs[(size_t)g * s], (size_t)s * 8);
+        memcpy(r + 24 + (size_t)s * 8, &cnt[(size_t)g * s], (size_t)s * 4);
+      }
+      if (reader.joinable()) reader.join();
+      if (err) std::rethrow_exception(err);
+      cur = std::move(nxt);
+      nxt.clear();
+      g0 = n0; g1 = n1;
+    }
   }
   skb_batch_destroy(b);
+  std::vector<uint8_t> all;
+  if (c.world > 1) {
+    all.resize(mine.size() * c.world);
+    c.check(skb_comm_allgather_host(c.c, mine.data(), all.data(), mine.size()));
+  }
+  if (c.rank != 0) return 0;
+  msh::File f;
+  f.kmer_size = k; f.sketch_size = s; f.hash_seed = seed;
+  for (uint32_t g = 0; g < G; ++g) {
+    const int owner = share ? (int)(g / share) : 0;
+    const uint8_t* r = c.world > 1 ? all.data() + (size_t)owner * mine.size() + (size_t)(g - owner * share) * per_file
+                                   : rec(mine, g);
+    uint64_t nn;
+    msh::Sketch sk;
+    sk.name = basename_of(files[g]);
+    memcpy(&nn, r, 8); memcpy(&sk.seq_length, r + 8, 8); memcpy(&sk.num_valid_kmers, r + 16, 8);
+    sk.hashes.resize(nn); sk.counts.resize(nn);
+    memcpy(sk.hashes.data(), r + 24, nn * 8);
+    memcpy(sk.counts.data(), r + 24 + (size_t)s * 8, nn * 4);
+    f.sketches.push_back(std::move(sk));
+  }
   msh::write_file(out, f);
   return 0;
 }
@@ -297,19 +392,23 @@ int cmd_predict(const Args& a) {
   const uint64_t limit = std::stoull(a.one("limit", "0"));
   const bool stream = a.has("stream"), consensus = a.has("consensus"), header = a.has("header");
   if (consensus && top % 2 != 1) throw std::runtime_error("--top must be an odd number when using --consensus");
+  if (top < 1 || top > SKB_MAX_TOP)  // checked before anything is printed (the reference has no such limit)
+    throw std::runtime_error("--top must be between 1 and " + std::to_string(SKB_MAX_TOP) + " in the B200 build");
   require_msh(a.one("reference"));
   const msh::File ref = msh::read_file(a.one("reference"));
   if (ref.sketches.empty()) throw std::runtime_error("reference sketch file holds no sketches");
   const uint32_t k = ref.kmer_size;
   const uint32_t s_query = (uint32_t)std::max<size_t>(1, ref.sketches[0].hashes.size());  // src/sketchy.rs:82, 522
   const uint64_t seed = ref.hash_seed;
+  Ctx c;
+  if (c.world > 1 && !a.has("input")) throw std::runtime_error("a multi-GPU run reads its reads from a file (-i): stdin cannot be shared by the ranks");
+  const bool speaker = c.rank == 0;  // rank 0 prints; every rank computes
   fastx::Reader rd(a.has("input") ? a.one("input") : std::string("-"));
   const Genotypes g = read_genotypes(a.one("genotypes"));
   for (const auto& s : ref.sketches)
     if (!g.map.count(s.name)) throw std::runtime_error("reference sketch identifier " + s.name + " has no genotype row");
-  if (header) printf("reads\tsketch_id\tshared_hashes\t%s\n", g.header.c_str());
+  if (header && speaker) printf("reads\tsketch_id\tshared_hashes\t%s\n", g.header.c_str());
   if (top > ref.sketches.size()) throw std::runtime_error("--top exceeds the number of reference sketches");
-  Ctx c;
   upload_reference(c, ref);
   skb_batch* b = nullptr;
   c.check(skb_batch_create(c.c, &b));
@@ -325,15 +424,22 @@ int cmd_predict(const Args& a) {
       while (blob.n() < 65536 && (more = rd.next(r))) {
         blob.add(r.seq, 0);
         if (limit && read + blob.n() - 1 == limit) { more = false; break; }
-        if (rd.input_idle()) break;  // a live stream that is pausing: predict what has arrived instead of waiting for 65536 reads
+        if (c.world == 1 && rd.input_idle()) break;  // a live stream that is pausing: predict what has arrived instead of waiting for 65536 reads
       }
       if (!blob.n()) break;
+      // every rank has parsed the chunk; it packs, copies and hashes only its share of it
+      uint64_t lo = 0, cnt = 0;
+      c.range(blob.n(), lo, cnt);
+      std::vector<uint64_t> off(blob.off.begin() + lo, blob.off.begin() + lo + cnt + 1);
       c.check(skb_batch_clear(b));
-      c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), nullptr, blob.n(), 0));
+      if (cnt) c.check(skb_batch_add(b, blob.bytes.data(), off.data(), nullptr, cnt, 0));
       idx.resize(blob.n() * top); sum.resize(blob.n() * top);
-      c.check(skb_predict_stream(c.c, b, k, s_query, seed, top, 0, idx.data(), sum.data()));
-      for (size_t i = 0; i < blob.n(); ++i, ++read) print_results(ref, g, read, &idx[i * top], &sum[i * top], top, consensus);
-      fflush(stdout);  // the reference's println! reaches a pipe line by line: a consumer of the live stream sees each chunk at once
+      c.check(skb_predict_stream_dist(c.c, b, blob.n(), k, s_query, seed, top, speaker ? idx.data() : nullptr, speaker ? sum.data() : nullptr));
+      if (speaker) {
+        for (size_t i = 0; i < blob.n(); ++i) print_results(ref, g, read + i, &idx[i * top], &sum[i * top], top, consensus);
+        fflush(stdout);  // the reference's println! reaches a pipe line by line: a consumer of the live stream sees each chunk at once
+      }
+      read += blob.n();
     }
   } else {  // src/sketchy.rs:281-315: one sketcher for all reads
     uint64_t read = 0;
@@ -356,13 +462,33 @@ int cmd_predict(const Args& a) {
     uint64_t bases = 0, kmers = 0;
     if (any) c.check(skb_sketch(c.c, b, k, s_query, seed, q.data(), nullptr, &qn, &bases, &kmers));
     const uint64_t qoff[2] = {0, qn};
-    const uint32_t N = (uint32_t)ref.sketches.size();
-    std::vector<uint64_t> counts(N);
-    c.check(skb_shared_counts(c.c, q.data(), qoff, 1, counts.data()));
-    std::vector<uint32_t> idx(top);
-    std::vector<uint64_t> sum(top);
-    c.check(skb_rank_counts(c.c, counts.data(), N, top, idx.data(), sum.data()));
-    print_results(ref, g, read, idx.data(), sum.data(), top, consensus);
+    // shared hashes against this rank's rows, its best `top` of them, then the ranks' lists merged by (count desc, index asc)
+    uint64_t lo = 0, cnt = 0;
+    c.range(ref.sketches.size(), lo, cnt);
+    std::vector<uint64_t> counts(std::max<uint64_t>(cnt, 1));
+    if (cnt) c.check(skb_shared_counts(c.c, q.data(), qoff, 1, counts.data()));
+    const uint32_t ltop = (uint32_t)std::min<uint64_t>(top, cnt);
+    std::vector<uint32_t> idx(top, 0xFFFFFFFFu);
+    std::vector<uint64_t> sum(top, 0);
+    if (ltop) c.check(skb_rank_counts(c.c, counts.data(), (uint32_t)cnt, ltop, idx.data(), sum.data()));
+    for (uint32_t t = 0; t < ltop; ++t) idx[t] += (uint32_t)lo;
+    if (c.world > 1) {
+      std::vector<uint8_t> mine((size_t)top * 12), all((size_t)top * 12 * c.world);
+      memcpy(mine.data(), sum.data(), (size_t)top * 8);
+      memcpy(mine.data() + (size_t)top * 8, idx.data(), (size_t)top * 4);
+      c.check(skb_comm_allgather_host(c.c, mine.data(), all.data(), mine.size()));
+      std::vector<std::pair<uint64_t, uint32_t>> cand;
+      for (int w = 0; w < c.world; ++w)
+        for (uint32_t t = 0; t < top; ++t) {
+          uint64_t sv; uint32_t iv;
+          memcpy(&sv, all.data() + (size_t)w * mine.size() + (size_t)t * 8, 8);
+          memcpy(&iv, all.data() + (size_t)w * mine.size() + (size_t)top * 8 + (size_t)t * 4, 4);
+          if (iv != 0xFFFFFFFFu) cand.push_back({sv, iv});
+        }
+      std::sort(cand.begin(), cand.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+      for (uint32_t t = 0; t < top; ++t) { sum[t] = cand[t].first; idx[t] = cand[t].second; }
+    }
+    if (speaker) print_results(ref, g, read, idx.data(), sum.data(), top, consensus);
   }
   skb_batch_destroy(b);
   return 0;

@@ -76,6 +76,25 @@ int skb_predict_stream(skb_ctx*, skb_batch* b, uint32_t k, uint32_t s_query, uin
     for (uint32_t t = 0; t < top; ++t) { oi[(size_t)r * top + t] = t; os[(size_t)r * top + t] = 7; }
   return SKB_OK;
 }
+// multi-GPU entry points: one rank, no exchange (the real ones are exercised by tests/test_multi_gpu.py on GPUs)
+int skb_comm_unique_id(uint8_t* id) { memset(id, 0, SKB_COMM_ID_BYTES); return SKB_OK; }
+int skb_comm_init(skb_ctx*, const uint8_t*, int rank, int world) { logf("comm_init %d %d\n", rank, world); return SKB_OK; }
+int skb_comm_destroy(skb_ctx*) { return SKB_OK; }
+void skb_dist_range(uint64_t n, int rank, int world, uint64_t* begin, uint64_t* count) {
+  const uint64_t per = (n + world - 1) / world;
+  const uint64_t b = per * rank < n ? per * rank : n, e = per * (rank + 1) < n ? per * (rank + 1) : n;
+  if (begin) *begin = b;
+  if (count) *count = e - b;
+}
+int skb_comm_allgather_host(skb_ctx*, const void* send, void* recv, uint64_t bytes) { memcpy(recv, send, bytes); return SKB_OK; }
+int skb_predict_stream_dist(skb_ctx*, skb_batch* b, uint64_t reads_total, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top,
+                            uint32_t* oi, uint64_t* os) {
+  logf("predict_stream k=%u s_query=%u seed=%llu top=%u reads_total=%llu reads=%u\n", k, s_query, (unsigned long long)seed, top,
+       (unsigned long long)reads_total, b->groups);
+  for (uint64_t r = 0; r < reads_total; ++r)
+    for (uint32_t t = 0; t < top; ++t) { oi[(size_t)r * top + t] = t; os[(size_t)r * top + t] = 7; }
+  return SKB_OK;
+}
 int skb_shared_counts(skb_ctx* c, const uint64_t*, const uint64_t* qoff, uint32_t Q, uint64_t* out) {
   logf("shared_counts Q=%u qhashes=%llu\n", Q, (unsigned long long)qoff[Q]);
   for (size_t i = 0; i < (size_t)c->n_rows * Q; ++i) out[i] = i;
