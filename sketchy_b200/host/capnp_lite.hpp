@@ -147,6 +147,12 @@ inline ListView as_list(const Reader& r, const Loc& l) {
     v.count = n;
     v.first = l.word;
   }
+  // the whole list must lie inside its segment BEFORE anybody sizes a buffer from `count` (a truncated or crafted file
+  // would otherwise ask for gigabytes)
+  static const uint32_t kBits[8] = {0, 1, 8, 16, 32, 64, 64, 0};
+  const uint64_t span = v.esize == 7 ? (uint64_t)v.count * (v.dwords + v.pwords) : ((uint64_t)v.count * kBits[v.esize] + 63) / 64;
+  if (v.seg >= r.msg().segs.size() || v.first + span > r.msg().segs[v.seg].size())
+    throw std::runtime_error("Cap'n Proto pointer out of bounds");
   return v;
 }
 

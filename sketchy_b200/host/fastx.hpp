@@ -303,7 +303,7 @@ class Reader {
       bool first = true;
       while (peek() != -1 && peek() != '>') {  // sequence lines go straight into the record, joined by '\n'
         if (!first) r.seq.push_back('\n');
-        append_line(r.seq);
+        append_line(r.seq, true);  // the raw slice, '\r' of a CRLF file included: seq_length counts what needletail's slice holds
         first = false;
       }
       while (!r.seq.empty() && (r.seq.back() == '\n' || r.seq.back() == '\r')) r.seq.pop_back();
@@ -312,6 +312,7 @@ class Reader {
       if (!getline(r.seq)) throw open_error();
       std::string plus, qual;
       if (!getline(plus) || plus.empty() || plus[0] != '+' || !getline(qual)) throw open_error();
+      if (qual.size() != r.seq.size()) throw open_error();  // needletail rejects a record whose quality length differs
     }
     return true;
   }
@@ -336,7 +337,7 @@ class Reader {
     return (unsigned char)buf_[pos_];
   }
   // appends the next line, without its terminator, to `out`; false at the end of the input
-  bool append_line(std::string& out) {
+  bool append_line(std::string& out, bool keep_cr = false) {
     if (peek() == -1) return false;
     for (;;) {
       const char* p = buf_.data() + pos_;
@@ -353,7 +354,7 @@ class Reader {
       fill();
       if (pos_ >= len_) break;
     }
-    if (!out.empty() && out.back() == '\r') out.pop_back();
+    if (!keep_cr && !out.empty() && out.back() == '\r') out.pop_back();
     return true;
   }
   bool getline(std::string& out) {

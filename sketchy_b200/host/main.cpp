@@ -115,6 +115,7 @@ struct Ctx {
   ~Ctx() { if (c) { skb_comm_destroy(c); skb_destroy(c); } }
   void check(int rc) const { if (rc != SKB_OK) throw std::runtime_error(skb_last_error(c)); }
   void join() {
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);  // stdout carries the result rows: NCCL's own messages (version banner) go to stderr
     const char* path = getenv("SKETCHY_B200_COMM_FILE");
     if (!path) throw std::runtime_error("multi-GPU run: set SKETCHY_B200_COMM_FILE to a path every rank can reach");
     uint8_t id[SKB_COMM_ID_BYTES];
@@ -316,7 +317,7 @@ int cmd_sketch(const Args& a) {
   }
   if (c.rank != 0) return 0;
   msh::File f;
-  f.kmer_size = k; f.sketch_size = s; f.hash_seed = seed;
+  f.kmer_size = k; f.sketch_size = 0; f.hash_seed = seed;  // minHashesPerWindow = the largest sketch, as finch writes it [RECALLED]
   for (uint32_t g = 0; g < G; ++g) {
     const int owner = share ? (int)(g / share) : 0;
     const uint8_t* r = c.world > 1 ? all.data() + (size_t)owner * mine.size() + (size_t)(g - owner * share) * per_file
@@ -328,6 +329,7 @@ int cmd_sketch(const Args& a) {
     sk.hashes.resize(nn); sk.counts.resize(nn);
     memcpy(sk.hashes.data(), r + 24, nn * 8);
     memcpy(sk.counts.data(), r + 24 + (size_t)s * 8, nn * 4);
+    f.sketch_size = std::max<uint32_t>(f.sketch_size, (uint32_t)sk.hashes.size());
     f.sketches.push_back(std::move(sk));
   }
   msh::write_file(out, f);

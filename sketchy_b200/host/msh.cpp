@@ -45,9 +45,12 @@ std::vector<uint8_t> encode(const File& f) {
   Writer w;
   const uint64_t root = w.alloc(3 + 4);
   w.set_struct_ptr(0, root, 3, 4);
-  w.at(root + 0) = (uint64_t)f.kmer_size;                                        // windowSize left 0
-  w.at(root + 1) = (uint64_t)f.sketch_size;                                      // minHashesPerWindow; bools false
+  // the field set finch's write_mash_file fills [RECALLED]: kmerSize, windowSize = k, minHashesPerWindow, concatenated,
+  // alphabet "ACGT", hashSeed (stored XOR its default 42); error, noncanonical, preserveCase stay at their defaults
+  w.at(root + 0) = (uint64_t)f.kmer_size | ((uint64_t)f.kmer_size << 32);        // kmerSize, windowSize
+  w.at(root + 1) = (uint64_t)f.sketch_size | (1ull << 32);                       // minHashesPerWindow, concatenated = true (bit 96)
   w.at(root + 2) = ((uint64_t)((uint32_t)f.hash_seed ^ 42u)) << 32;              // error 0.0, hashSeed XOR default
+  w.write_text(root + 3 + 2, "ACGT");                                            // alphabet
   const uint64_t plist = w.alloc(1);  // ReferenceList: 0 data words, 1 pointer
   w.set_struct_ptr(root + 3 + 3, plist, 0, 1);
   const uint32_t n = (uint32_t)f.sketches.size();
@@ -58,8 +61,8 @@ std::vector<uint8_t> encode(const File& f) {
   for (uint32_t i = 0; i < n; ++i) {
     const Sketch& s = f.sketches[i];
     const uint64_t e = tag + 1 + (uint64_t)i * ew;
-    w.at(e + 0) = (uint64_t)(uint32_t)std::min<uint64_t>(s.seq_length, 0xFFFFFFFFull);
-    w.at(e + 1) = s.seq_length;
+    w.at(e + 0) = 0;             // Reference.length (u32, pre-length64 Mash): left 0 as finch does
+    w.at(e + 1) = s.seq_length;  // length64
     w.at(e + 2) = s.num_valid_kmers;
     w.write_text(e + 3 + 2, s.name);
     w.write_text(e + 3 + 3, s.comment);

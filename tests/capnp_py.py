@@ -76,6 +76,16 @@ def decode_msh(data: bytes):
     return out
 
 
+def decode_msh_header(data: bytes) -> dict:
+    """The file-level fields next to k / s / seed: windowSize, concatenated, alphabet (what Mash tooling reads and finch's
+    writer fills)."""
+    m = Msg(data)
+    seg, w, dw, pw = m.struct_at(m.follow(0, 0))
+    d = m.segs[seg][w:w + dw]
+    return {"window": (d[0] >> 32) & 0xFFFFFFFF, "concatenated": bool((d[1] >> 32) & 1), "noncanonical": bool((d[1] >> 33) & 1),
+            "alphabet": m.text(m.follow(seg, w + dw + 2))}
+
+
 def encode_msh_multiseg(f: dict) -> bytes:
     """Segment 0 holds only a FAR root pointer; the root struct lives in segment 1; every sketch's hash list lives in
     its own segment behind a far pointer; names use DOUBLE-far pointers (landing pads in segment 2)."""

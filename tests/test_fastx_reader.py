@@ -69,18 +69,19 @@ def _fnv(b: bytes) -> int:
 
 
 def _expected(raw: bytes, kind: str) -> bytes:
-    """Independent parse: id = header line minus its marker; FASTA sequence = its lines (CR stripped) joined by LF (the
-    raw slice needletail hands on); FASTQ sequence = line 2 of the record."""
+    """Independent parse: id = header line minus its marker; FASTA sequence = the raw slice between the header line and
+    the next record, interior line breaks kept as they are in the file (CR included: the length needletail's slice has,
+    SURVEY.md Appendix F-3), trailing line break dropped; FASTQ sequence = line 2 of the record."""
     lines = [l[:-1] if l.endswith(b"\r") else l for l in raw.split(b"\n")]
     out = []
     if kind == "fasta":
         rid, seq = None, []
-        for l in lines + [b">"]:
+        for l in raw.split(b"\n") + [b">"]:
             if l.startswith(b">"):
                 if rid is not None:
-                    body = b"\n".join(seq).rstrip(b"\n")
+                    body = b"\n".join(seq).rstrip(b"\r\n")
                     out.append(b"%s\t%d\t%d\n" % (rid, len(body), _fnv(body)))
-                rid, seq = l[1:], []
+                rid, seq = l[1:].rstrip(b"\r"), []
             elif rid is not None:
                 seq.append(l)
     else:
@@ -222,3 +223,12 @@ def test_parallel_file_reader_equals_the_sequential_one(tmp_path):
     p = subprocess.run([exe, "8", str(1 << 30)] + files[:3] + [str(tmp_path / "bad.fa")] + files[3:] + [str(tmp_path / "nope.fa")],
                        capture_output=True, text=True)
     assert p.returncode == 1 and "failed to open Fastx file or record with Needletail" in p.stderr
+
+
+def test_fastq_quality_length_must_match(harness, tmp_path):
+    """needletail rejects a FASTQ record whose quality string is not as long as its sequence; so does the host reader."""
+    good = b"@a\nACGT\n+\nIIII\n"
+    rc, out, _ = _run(harness, data=good + good.replace(b"@a", b"@b"))
+    assert rc == 0 and out.count(b"\n") == 2
+    rc, out, err = _run(harness, data=good + b"@b\nACGT\n+\nIII\n")
+    assert rc != 0

@@ -60,6 +60,8 @@ def test_msh_writer_decodes_with_independent_reader_and_round_trips(tmp_path):
     run("msh-from-text", str(txt), str(out))
     dec = capnp_py.decode_msh(out.read_bytes())
     assert dec == f
+    assert capnp_py.decode_msh_header(out.read_bytes()) == {"window": f["k"], "concatenated": True, "noncanonical": False,
+                                                            "alphabet": "ACGT"}
     assert run("msh-to-text", str(out)).stdout == _to_text(f)
 
 

@@ -75,4 +75,4 @@ def test_cli_two_ranks_equal_one(tmp_path):
     for extra in (["-s", "-t", "3"], ["-s", "-t", "3", "-c"], ["-t", "4"]):
         a = run(1, "predict", "-i", str(fq), "-r", str(one), "-g", str(geno), *extra)
         b = run(2, "predict", "-i", str(fq), "-r", str(one), "-g", str(geno), *extra)
-        assert a == b and a.count(b"\n") >= 1, extra
+        assert a == b and a.count(b"\n") >= 1, (extra, a[:300], b[:300])

@@ -1,3 +1,4 @@
+python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -8
 for n in 4 2; do
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/r02_p_n$n.json 2> gpurun_out/r02_p_n$n.log
 python - <<PY
