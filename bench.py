@@ -388,7 +388,7 @@ def run_b200(args):
         # a streaming caller feeds reads in chunks of whole passes: chunk i+1 is normalised + 2-bit packed into pinned
         # memory by the library's host threads and copied to the device while the GPU works on chunk i (two batches,
         # double buffered). With N ranks every rank packs, copies and hashes 1/N of each chunk.
-        chunk_reads = 5 * PASS_READS
+        chunk_reads = 5 * (args.pass_reads or PASS_READS)
         chunks = [(c_lo, min(c_lo + chunk_reads, R)) for c_lo in range(0, R, chunk_reads)]
         pack_s = [0.0]
         hbs = [ctx.batch(), ctx.batch()]

@@ -119,7 +119,8 @@ int skb_predict_stream_device(skb_ctx* ctx, skb_batch* b, uint32_t k, uint32_t s
 int skb_sums_reset(skb_ctx* ctx);
 int skb_sums_download(skb_ctx* ctx, uint64_t* out /* [n_rows] */);
 int skb_sums_upload(skb_ctx* ctx, const uint64_t* in /* [n_rows] */);
-/* Reads per streaming pass (0 = library default). Any value gives identical results. */
+/* Reads per streaming pass: 0 = library default (4096: the streaming kernel's best fraction of the HBM roofline), up
+ * to 8192 (fewer passes over the matrix: more reads per second at a lower fraction). Any value gives identical results. */
 int skb_set_pass_reads(skb_ctx* ctx, uint32_t max_reads_per_pass);
 /* How a pass turns its counts into every read's top-N; every mode gives identical results (tests run all of them).
  * 0 = automatic (default): brute-force ranking over all rows right after a reset, for small shards and to redo a

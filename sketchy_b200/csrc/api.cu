@@ -192,6 +192,8 @@ struct SkbNccl {
 SkbNccl g_nccl;
 
 struct ProfEvent { int id; cudaEvent_t a, b; };
+#define SKB_DEFAULT_PASS_READS 4096u  // the streaming kernel runs closest to the HBM roofline here; 8192 gives more reads/s
+#define SKB_PASS_KEY_BUDGET (1ull << 18)  // query hashes per pass before the membership prefilter (which typically drops more than half of them; the 2^19-bit filter is designed for ~2^17 keys at three bits each)
 #define SKB_NSUMS 4
 #define SKB_NTRACK 3
 #define SKB_NTAB 3
@@ -237,7 +239,7 @@ struct skb_ctx {
   DevBuf t_slots[SKB_NTAB], t_fill[SKB_NTAB], t_reads[SKB_NTAB], t_slot[SKB_NTAB], t_bloom[SKB_NTAB];
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = skb_fused_max_reads(1);  // reads per pass: what the kernel's shared memory holds
+  uint32_t pass_max = SKB_DEFAULT_PASS_READS;  // reads per pass (skb_set_pass_reads: up to what the kernel's shared memory holds)
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -805,11 +807,12 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       need(c->seg_hdr[i], (size_t)SKB_SEG_CAP * 16);
       need(c->seg_words[i], (size_t)SKB_SEG_CAP * SKB_SEG_WORDS_MAX * 4);
     }
-    need(c->dense, (size_t)c->n_rows * stride_max * 2);  // u16 per read (u32 for half as many reads with u16 counters)
+    // u16 per read with u8 counters, u32 per read with u16 counters (whose passes hold at most skb_fused_max_reads(0) reads)
+    need(c->dense, (size_t)c->n_rows * std::max<size_t>((size_t)stride_max * 2, (size_t)std::min<uint32_t>(stride_max, skb_fused_max_reads(0)) * 4));
     need(c->part_idx, (size_t)groups_max * Bmax * top * 4);
     need(c->part_sum, (size_t)groups_max * Bmax * top * 8);
     if (e != cudaSuccess) return fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
-    const uint64_t key_budget = 32ull * skb_fused_max_reads(1);
+    const uint64_t key_budget = SKB_PASS_KEY_BUDGET;
     uint64_t max_keys = 0;
     for (uint32_t r0 = 0; r0 < R; r0 += Bmax) max_keys = std::max(max_keys, q_off[std::min(R, r0 + Bmax)] - q_off[r0]);
     if (int rc = ensure_table(c, (uint32_t)std::min<uint64_t>(std::max<uint64_t>(max_keys, 1), key_budget))) return rc;
@@ -878,7 +881,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       if (qn[i] > 255u) { narrow = false; break; }
     if (!narrow) B = std::min<uint32_t>(B, skb_fused_max_reads(0));
     // keep the pass's key count inside the filter's design load (and the table)
-    const uint64_t key_budget = 32ull * skb_fused_max_reads(1);  // 2^17 for 4096-read passes
+    const uint64_t key_budget = SKB_PASS_KEY_BUDGET;
     while (B > 1 && q_off[r + B] - q_off[r] > key_budget) B = std::max(1u, B / 2);
     const uint32_t nkeys = (uint32_t)(q_off[r + B] - q_off[r]);
     if (nkeys > c->t_maxkeys) { rc_final = fail(c, SKB_ERR_INVALID_ARG, "a single read keeps %u query hashes; the pass table holds %u", nkeys, c->t_maxkeys); break; }
@@ -932,6 +935,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
     fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
+    fa.rowbuf = skb_fused_rowbuf(stride, fa.narrow); fa.rowbuf_log2 = fa.rowbuf == 8 ? 3 : 2;
     fa.sums_in = c->sums[s_in].as<unsigned long long>(); fa.sums_out = c->sums[s_out].as<unsigned long long>();
     fa.lb_sum = ra.lb_sum; fa.lb_idx = ra.lb_idx;
     fa.ivl = c->ivl[qs].as<SkbInterval>(); fa.ivl_cap = SKB_IVL_CAP; fa.ivl_total = d_scal + 8 + 4 * qs + 1; fa.abort = d_abort;
@@ -1527,7 +1531,7 @@ int skb_set_rank_mode(skb_ctx* c, int mode) {
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
-  c->pass_max = m ? std::min<uint32_t>(m, skb_fused_max_reads(1)) : skb_fused_max_reads(1);
+  c->pass_max = m ? std::min<uint32_t>(m, skb_fused_max_reads(1)) : SKB_DEFAULT_PASS_READS;
   c->pass_proven = false;
   return SKB_OK;
 }

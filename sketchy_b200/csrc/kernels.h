@@ -59,9 +59,9 @@ void skb_launch_report_pieces(const uint32_t* idx, const unsigned long long* sum
 // meta: the low SKB_SLOT_CNT_BITS bits = cnt, the number of reads of the pass that hold `key` (0 .. 2^ID_BITS);
 // cnt <= SKB_SLOT_INLINE: their pass-local read ids sit inline above cnt, so a lookup is one 16-byte load;
 // more: the 32 bits above cnt are the start of the slot's read list in `reads`.
-// Default: 12-bit ids (4096 reads per pass), 13-bit cnt, 4 inline ids. SKB_X_IDBITS=13: 8192 reads, 14-bit cnt, 3 inline.
+// Default: 13-bit ids (up to 8192 reads per pass), 14-bit cnt, 3 inline ids. SKB_X_IDBITS=12: 4096 reads, 13-bit cnt, 4 inline.
 #ifndef SKB_X_IDBITS
-#define SKB_X_IDBITS 12
+#define SKB_X_IDBITS 13
 #endif
 #define SKB_SLOT_ID_BITS SKB_X_IDBITS
 #define SKB_SLOT_CNT_BITS (SKB_X_IDBITS + 1)
@@ -74,9 +74,9 @@ struct __align__(16) SkbSlot {
 #define SKB_SLOT_ID_SHIFT(i) (SKB_SLOT_CNT_BITS + SKB_SLOT_ID_BITS * (i))
 #define SKB_SLOT_ID(m, i) ((uint32_t)(((m) >> SKB_SLOT_ID_SHIFT(i)) & ((1ull << SKB_SLOT_ID_BITS) - 1ull)))
 #define SKB_SLOT_START(m) ((uint32_t)(((m) >> SKB_SLOT_CNT_BITS) & 0xFFFFFFFFull))
-// Reads per pass are bounded by the fused kernel's shared memory: skb_fused_max_reads(narrow) (kernels_predict.cu).
-// Default build: 2560 with u16 counters (4 row buffers + bounds at every 4th read = 8.5 B per read), 4096 with u8
-// counters (reads with <= 255 query hashes: 4.5 B per read; also the range of the 12-bit read ids in a slot).
+// Reads per pass are bounded by the fused kernel's shared memory: skb_fused_max_reads(narrow) (kernels_predict.cu):
+// 8192 with u8 counters (every read of the pass keeps <= 255 query hashes) and 4 counter buffers, 4096 with u16
+// counters; passes of half that size get 8 counter buffers. The library's default pass is 4096 reads.
 
 struct SkbTable {
   SkbSlot* slots;     // [cap + 1]; slot `cap` is reserved for the key that equals SKB_EMPTY_KEY
@@ -117,6 +117,7 @@ struct SkbFusedArgs {
   uint32_t n_reads;     // reads in this pass
   uint32_t cnt_stride;  // counters per row buffer (multiple of 512, >= n_reads)
   int narrow;           // counters are u8 (every read of the pass keeps <= 255 query hashes) instead of u16
+  uint32_t rowbuf, rowbuf_log2;  // counter buffers (rows in flight) per CTA: 4 or 8 (skb_fused_rowbuf)
   int skip_stream;      // the pass has no query hashes: rows are ranked without being streamed
   uint32_t row_base;    // global index of local row 0
   const unsigned long long* sums_in;  // [n_rows]
@@ -137,8 +138,8 @@ struct SkbFusedArgs {
   const uint32_t* abort;              // [2] {set once an earlier pass of the batch overflowed, its sequence number}: skip
 };
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st);
-size_t skb_fused_smem_bytes(uint32_t cnt_stride);
-size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride);
+size_t skb_fused_smem_bytes(uint32_t cnt_stride, int narrow, uint32_t rowbuf);
+uint32_t skb_fused_rowbuf(uint32_t cnt_stride, int narrow);
 #define SKB_IVL_CAP ((4u << 20) << (SKB_X_IDBITS - 12))  // candidate intervals per pass (4 M per 4096 reads); more than that shrinks the pass
 #define SKB_SEG_CAP (2u << 20)     // segment records per pass (16 + up to 160 bytes each)
 // counters of one lane segment, in words: reads / 32 / 4 with u8 counters, at most 2560 / 32 / 2 = 40 with u16 counters

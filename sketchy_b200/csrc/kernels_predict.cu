@@ -178,9 +178,6 @@ __device__ __forceinline__ bool table_lookup(const SkbTable& t, uint64_t h, SkbS
 #ifndef SKB_X_CW
 #define SKB_X_CW 32
 #endif
-#ifndef SKB_X_ROWBUF
-#define SKB_X_ROWBUF 8
-#endif
 #ifndef SKB_X_ABLATE
 #define SKB_X_ABLATE 0  // experiments only (never in the shipped build): 1 = no filter probe, 2 = probe but drop the passers, 4 = no candidate walk
 #endif
@@ -188,8 +185,7 @@ constexpr int FS_SUB = SKB_X_SUB;        // hashes per sub-tile (2 KB): chunks o
 constexpr int FS_STAGES = SKB_X_STAGES;  // staging buffers per warp
 constexpr int FS_WARPS = SKB_X_CW;
 constexpr int FS_THREADS = FS_WARPS * 32;
-constexpr int FS_ROWBUF = SKB_X_ROWBUF;  // rows in flight per CTA: counter buffers are indexed by row % FS_ROWBUF
-static_assert(FS_ROWBUF >= 2 && FS_ROWBUF <= 8, "2..8 row buffers");
+constexpr int FS_ROWBUF_MAX = 8;         // rows in flight per CTA: a.rowbuf (4 or 8) counter buffers, indexed by row % a.rowbuf
 constexpr int FS_NHASH = 8;              // hashes per lane per chunk (one chunk = 256 hashes)
 constexpr int FS_CHUNKS = FS_SUB / (32 * FS_NHASH);
 static_assert(FS_SUB % (32 * FS_NHASH) == 0, "a sub-tile is a whole number of chunks");
@@ -263,8 +259,8 @@ __device__ __forceinline__ void apply_hit(const SkbTable& t, unsigned long long 
 struct FsCtl {
   unsigned long long lb_seg[32];  // bound of the first read of each lane segment (bounds never decrease along the reads)
   uint32_t li_seg[32];            // largest bound index within each lane segment of the reads
-  uint32_t done[FS_ROWBUF];       // sub-tiles of the buffer's current row that are fully counted
-  uint32_t freed[FS_ROWBUF];      // rows of this buffer that have been ranked (the buffer is zero again)
+  uint32_t done[FS_ROWBUF_MAX];   // sub-tiles of the buffer's current row that are fully counted
+  uint32_t freed[FS_ROWBUF_MAX];  // rows of this buffer that have been ranked (the buffer is zero again)
   uint32_t next_tile;             // next unclaimed claim unit of the CTA's rows (claimed in order)
 };
 constexpr uint32_t FS_NONE = 0xFFFFFFFFu;
@@ -402,7 +398,7 @@ __device__ __forceinline__ void rank_row(const SkbFusedArgs& a, const FsCtl& ctl
 // resolves the few passers on the spot: the lanes that hold one look their hash up in the L2-resident table (a
 // 16-byte load; two passers per trip, both loads in flight together) and add the key's reads to the row's counters
 // in shared memory. The warp whose sub-tile completes a row does the row's short rank step (rank_row) and hands the
-// counter buffer back; FS_ROWBUF rows are in flight, and since sub-tiles are claimed in order the warps cannot run
+// counter buffer back; a.rowbuf rows are in flight, and since sub-tiles are claimed in order the warps cannot run
 // far apart, so nobody waits for a buffer. Nothing in the loop is warp-collective except that hand-over.
 // HBM traffic per pass = the reference matrix, once.
 template <int CPW>
@@ -430,7 +426,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     ctl.next_tile = 0;
   }
-  if (threadIdx.x < FS_ROWBUF) { ctl.done[threadIdx.x] = 0; ctl.freed[threadIdx.x] = 0; }
+  if (threadIdx.x < FS_ROWBUF_MAX) { ctl.done[threadIdx.x] = 0; ctl.freed[threadIdx.x] = 0; }
   if (threadIdx.x < 32) {
     const uint32_t seg0 = threadIdx.x * (a.cnt_stride >> 5);
     ctl.li_seg[threadIdx.x] = 0;
@@ -441,7 +437,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     uint4* dst = reinterpret_cast<uint4*>(bloom);
     for (uint32_t i = threadIdx.x; i < SKB_BLOOM_WORDS / 4; i += blockDim.x) dst[i] = src[i];
   }
-  for (uint32_t i = threadIdx.x; i < FS_ROWBUF * cwords; i += blockDim.x) cnt32[i] = 0;
+  for (uint32_t i = threadIdx.x; i < a.rowbuf * cwords; i += blockDim.x) cnt32[i] = 0;
   __syncthreads();
   {
     const uint32_t per = a.cnt_stride >> 5;
@@ -511,10 +507,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
     uint32_t nrow, nt0, nlen;
     const uint64_t* np;
     claim(nrow, nt0, nlen, np);
-    const uint32_t par = row % FS_ROWBUF;
+    const uint32_t par = row & (a.rowbuf - 1u);
     uint32_t* cb = cnt32 + par * cwords;
-    if (row >= (uint32_t)FS_ROWBUF) {  // the buffer's previous row must have been ranked and cleared (it almost always has)
-      const uint32_t need = row / FS_ROWBUF;
+    if (row >= a.rowbuf) {  // the buffer's previous row must have been ranked and cleared (it almost always has)
+      const uint32_t need = row >> a.rowbuf_log2;
       if (lds_acquire_u32(&ctl.freed[par]) < need) {
         if (lane == 0)
           while (lds_acquire_u32(&ctl.freed[par]) < need) __nanosleep(100);
@@ -1210,29 +1206,30 @@ void skb_launch_memb_build(const SkbRefView& rv, uint32_t* memb, uint32_t memb_l
   memb_build_kernel<<<blocks, 256, 0, st>>>(rv, memb, memb_log2);
 }
 
-size_t skb_fused_smem_bytes(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 2 * FS_ROWBUF;
-}
-size_t skb_fused_smem_bytes_narrow(uint32_t cnt_stride) {
-  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * 1 * FS_ROWBUF;
+size_t skb_fused_smem_bytes(uint32_t cnt_stride, int narrow, uint32_t rowbuf) {
+  return FS_SMEM_BLOOM + FS_SMEM_RING + (size_t)cnt_stride * (narrow ? 1 : 2) * rowbuf;
 }
 uint32_t skb_fused_tile() { return FS_CLAIM; }  // hashes per claim unit (what tile_cum / tpr count)
-// Largest pass the kernel's shared memory holds: 227 KB per CTA minus the static barriers and bookkeeping, the filter
-// and the staging rings leaves room for FS_ROWBUF counter rows (1 or 2 bytes per read each). Pass-local read ids are
-// SKB_SLOT_ID_BITS wide in a table slot: that caps it either way.
+// Counter buffers (rows in flight) a pass of `reads` reads gets: 8 when they fit next to the filter and the staging
+// rings in the 227 KB of a CTA, else 4; 0 = the pass does not fit at all.
+uint32_t skb_fused_rowbuf(uint32_t cnt_stride, int narrow) {
+  const size_t budget = 232448 - 2048;  // opt-in maximum per CTA on sm_100 minus the static barriers, row bookkeeping, slack
+  for (uint32_t rb : {8u, 4u})
+    if (skb_fused_smem_bytes(cnt_stride, narrow, rb) <= budget) return rb;
+  return 0;
+}
+// Largest pass the kernel's shared memory holds (with 4 counter buffers); pass-local read ids are SKB_SLOT_ID_BITS
+// wide in a table slot: that caps it either way.
 uint32_t skb_fused_max_reads(int narrow) {
-  const size_t fixed = FS_SMEM_BLOOM + FS_SMEM_RING + 2048;  // 2 KB: static barriers, row bookkeeping, slack
-  const size_t budget = 232448;                                             // opt-in maximum per CTA on sm_100
-  if (fixed >= budget) return 0;
-  const size_t per2 = narrow ? 2 * FS_ROWBUF : 4 * FS_ROWBUF;               // bytes per read, times two
-  const uint32_t gran = narrow ? 512u : 256u;                               // cnt_stride granularity (api.cu)
-  uint32_t b = (uint32_t)std::min<size_t>(1u << SKB_SLOT_ID_BITS, 2 * (budget - fixed) / per2);
+  const uint32_t gran = narrow ? 512u : 256u;  // cnt_stride granularity (api.cu)
+  uint32_t b = 1u << SKB_SLOT_ID_BITS;
+  while (b >= gran && skb_fused_rowbuf(b, narrow) == 0) b -= gran;
   return b / gran * gran;
 }
 
 void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st) {
   if (a.rv.n_rows == 0) return;
-  const size_t smem = a.narrow ? skb_fused_smem_bytes_narrow(a.cnt_stride) : skb_fused_smem_bytes(a.cnt_stride);
+  const size_t smem = skb_fused_smem_bytes(a.cnt_stride, a.narrow, a.rowbuf);
   static SkbSmemOptIn opt_in;
   if (opt_in.needs(smem)) {
     cudaFuncSetAttribute(fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

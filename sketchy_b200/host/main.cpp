@@ -115,7 +115,12 @@ struct Ctx {
   ~Ctx() { if (c) { skb_comm_destroy(c); skb_destroy(c); } }
   void check(int rc) const { if (rc != SKB_OK) throw std::runtime_error(skb_last_error(c)); }
   void join() {
-    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);  // stdout carries the result rows: NCCL's own messages (version banner) go to stderr
+    // stdout carries the result rows: whatever NCCL prints while the communicator is set up (its version banner goes to
+    // stdout under NCCL_DEBUG=VERSION) is sent to stderr instead
+    fflush(stdout);
+    const int saved_stdout = dup(1);
+    dup2(2, 1);
+    struct Restore { int fd; ~Restore() { fflush(stdout); dup2(fd, 1); close(fd); } } restore{saved_stdout};
     const char* path = getenv("SKETCHY_B200_COMM_FILE");
     if (!path) throw std::runtime_error("multi-GPU run: set SKETCHY_B200_COMM_FILE to a path every rank can reach");
     uint8_t id[SKB_COMM_ID_BYTES];

@@ -292,7 +292,7 @@ def _dense_second_opinion(ctx, blob, roff, k, s, reads_to_check, gi, gs, final):
         assert gs[r].tolist() == cum[order, r].tolist(), r
 
 
-def _check_predict_large(ctx, ref, off, blob, roff, k, s, top, modes):
+def _check_predict_large(ctx, ref, off, blob, roff, k, s, top, modes, pass_reads=0):
     """Every read of a large case against the oracle (its N merges per read spread over all host threads: the same
     arithmetic as the single-threaded loop, checked in tests/test_oracle.py), in several ranking modes."""
     import os
@@ -301,12 +301,13 @@ def _check_predict_large(ctx, ref, off, blob, roff, k, s, top, modes):
     for mode in modes:
         ctx.set_rank_mode(mode)
         ctx.ref_upload(ref, off)
-        ctx.set_pass_reads(0)
+        ctx.set_pass_reads(pass_reads)
         rb = ctx.batch().add(blob, roff)
         gi, gs = ctx.predict_stream(rb, k, s, 0, top)
         final = ctx.sums_download()
         stats = ctx.last_predict_stats()
         rb.close()
+        ctx.set_pass_reads(0)
         bad = np.flatnonzero((gi != ei).any(axis=1) | (gs != es).any(axis=1))
         assert bad.size == 0, (mode, bad[:5], gi[bad[:2]], ei[bad[:2]], gs[bad[:2]], es[bad[:2]])
         assert (final == esums).all(), mode
@@ -359,7 +360,10 @@ def test_predict_full_size_passes_against_oracle(ctx):
     n_reads = 20_000
     blob, roff, _ = synth.sample_reads(base, n_reads, 600, 98)
     gi, gs, final, stats = _check_predict_large(ctx, ref, off, blob, roff, 16, 500, 10, modes=(0, 1, 2))
-    assert stats["passes"] <= 5, stats   # 4 x 4096 + 3616 (fewer with a build whose passes are larger)
+    assert stats["passes"] <= 5, stats   # 4 x 4096 + 3616
+    # the largest pass the kernel holds (8192 reads: 13-bit read ids, four counter buffers)
+    _, _, _, stats8 = _check_predict_large(ctx, ref, off, blob, roff, 16, 500, 10, modes=(1, 2), pass_reads=8192)
+    assert stats8["passes"] <= 3, stats8
     picks = set(list(range(0, 32)) + list(range(32, n_reads, 131)) + [n_reads - 1])
     for edge in range(4096, n_reads, 4096):
         picks.update(range(edge - 24, edge + 24))
