@@ -812,6 +812,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     need(c->part_idx, (size_t)groups_max * Bmax * top * 4);
     need(c->part_sum, (size_t)groups_max * Bmax * top * 8);
     if (e != cudaSuccess) return fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 2; ++i) CU(c, cudaMemsetAsync(c->cand_cnt[i].p, 0, (size_t)Bmax * 4, c->stream));  // (a pass's last kernel clears them again)
     const uint64_t key_budget = SKB_PASS_KEY_BUDGET;
     uint64_t max_keys = 0;
     for (uint32_t r0 = 0; r0 < R; r0 += Bmax) max_keys = std::max(max_keys, q_off[std::min(R, r0 + Bmax)] - q_off[r0]);
@@ -851,12 +852,11 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       ProfScope ps(c, SKB_K_RANK, 3, c->side);
       skb_launch_dense_topk(post.da, c->side);
       skb_launch_merge_topn(post.da.part_idx, post.da.part_sum, post.da.groups, post.da.n_reads, top, post.ra.out_idx, post.ra.out_sum, c->side);
-      skb_launch_tracked_update(post.ra, c->side);
+      skb_launch_verdict_update(post.ra, false, c->side);
     } else {
-      ProfScope ps(c, SKB_K_RANK, 6, c->side);
+      ProfScope ps(c, SKB_K_RANK, 3, c->side);
       skb_launch_rank_expand(post.ra, c->side); skb_launch_rank_select(post.ra, c->side);
-      skb_launch_pass_verdict(post.ra, c->side);
-      skb_launch_tracked_update(post.ra, c->side);  // from this pass's top lists (skipped on the device after an overflow)
+      skb_launch_verdict_update(post.ra, true, c->side);  // (the update is skipped on the device after an overflow)
     }
     post.on = false;
   };
@@ -918,20 +918,17 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     ra.abort = d_abort; ra.seq = seq;
     cudaError_t e = cudaSuccess;
     if (!dense) {
-      e = cudaMemsetAsync(c->counts.p, 0, (size_t)SKB_MAX_TRACKED * stride * 2, c->side);
-      if (e == cudaSuccess) e = cudaMemsetAsync(c->textra.p, 0, (size_t)SKB_MAX_TRACKED * 8, c->side);
+      e = cudaMemsetAsync(c->textra.p, 0, (size_t)SKB_MAX_TRACKED * 8, c->side);
       if (e != cudaSuccess) { rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e)); break; }
-      ProfScope ps(c, SKB_K_RANK, (nkeys ? 3 : 2) + (lag2 ? 1 : 0), c->side);
+      ProfScope ps(c, SKB_K_RANK, 2 + (lag2 ? 1 : 0), c->side);
       if (lag2) skb_launch_tracked_totals(rv, ra.tracked, ra.n_tracked, table_of(c, tab_prev), ra.tracked_extra, c->side);
-      if (nkeys) skb_launch_tracked_counts(rv, ra.tracked, ra.n_tracked, t, c->counts.as<uint16_t>(), stride, c->side);
-      skb_launch_rank_bounds(ra, c->side);
+      skb_launch_rank_bounds(rv, t, ra, nkeys != 0, c->side);
     }
     cudaEventRecord(c->ev_pre[tab], c->side);
     if (lag2) enqueue_post();  // post(i-1) behind pre(i): it runs next to stream(i)
 
     // ---- stream(i) on the main stream
     cudaStreamWaitEvent(c->stream, c->ev_pre[tab], 0);
-    if (!dense) cudaMemsetAsync(c->cand_cnt[qs].p, 0, (size_t)B * 4, c->stream);
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
     fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;

@@ -147,9 +147,6 @@ uint32_t skb_fused_rowbuf(uint32_t cnt_stride, int narrow);
 uint32_t skb_fused_tile();
 uint32_t skb_fused_max_reads(int narrow);
 
-// per-read counts of the tracked rows only (they define the bounds): ctr[t][read], u16, row stride `stride`
-void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
-                               const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st);
 // totals of the tracked rows against a pass's table (all reads of that pass): extra[t] += hits of tracked row t
 void skb_launch_tracked_totals(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
                                const SkbTable& t, unsigned long long* extra, cudaStream_t st);
@@ -189,14 +186,15 @@ struct SkbRankArgs {
   uint32_t* abort;                     // [2] see SkbFusedArgs::abort
   uint32_t seq;                        // sequence number of this pass within the call
 };
-void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st);
-// tracked rows of the next pass = union of the top lists of 16 sampled reads of this pass (last read first)
-void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st);
+// bounds of a sparse pass: per-read counts of the tracked rows against the pass's table and their prefix sums (one CTA
+// per tracked row), then every read's top-th best tracked key (one warp per read)
+void skb_launch_rank_bounds(const SkbRefView& rv, const SkbTable& t, const SkbRankArgs& a, bool has_keys, cudaStream_t st);
 void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st);  // segment records + intervals -> per-read candidate buckets
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st);  // per-read top-N
-// after a pass: record the first pass whose candidates overflowed (abort[0] = 1, abort[1] = seq) and clear the pass's
-// overflow counters; passes enqueued behind a failed one leave the running sums and the tracked rows untouched
-void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st);
+// last launch of a pass (one CTA). with_verdict: record the first pass whose candidates overflowed (abort[0] = 1,
+// abort[1] = seq) and clear the pass's counters and bucket fill counts; then the tracked rows for the next passes = union
+// of the top lists of 16 sampled reads of this pass (last read first), unless a pass is being redone
+void skb_launch_verdict_update(const SkbRankArgs& a, bool with_verdict, cudaStream_t st);
 
 // top-N of a plain value array by (value desc, index asc); one CTA. idx_base is added to reported indices.
 void skb_launch_rank_full(const unsigned long long* vals, uint32_t n, uint32_t top, uint32_t idx_base,

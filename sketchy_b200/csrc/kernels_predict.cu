@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) fused_kernel(const SkbFusedArgs
 // Post-pass: segment records -> per-read candidate buckets. One thread per 16-byte unit of a record's counters: it
 // sums the units before it (a record is at most 160 bytes), then tests each of its reads against the read's exact
 // bound; a row that is at least as good as the bound is a candidate for that read.
-__global__ void __launch_bounds__(256) walk_kernel(const SkbRankArgs a) {
+__device__ __forceinline__ void walk_records(const SkbRankArgs& a) {
   const uint32_t total = min(*a.seg_total, a.seg_cap);
   const uint32_t upr = a.seg_words_per / 4;  // 16-byte units per record
   const uint32_t cpw = a.seg_cpw;            // counters per word: 2 (u16) or 4 (u8)
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(256) walk_kernel(const SkbRankArgs a) {
             cd.sum = run; cd.idx = gi; cd.pad = 0;
             a.cand[(size_t)b * a.cand_cap + slot] = cd;
           } else {
-            *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
+            *a.cand_total = 1u;  // bucket overflow: the host redoes the pass densely
           }
         }
       }
@@ -658,19 +658,60 @@ __global__ void __launch_bounds__(256) walk_kernel(const SkbRankArgs a) {
   }
 }
 
-// per-read counts of the tracked rows (the rows that define the bounds); one CTA per tracked row
-__global__ void __launch_bounds__(256) tracked_counts_kernel(const SkbRefView rv, const uint32_t* __restrict__ tracked,
-                                                             const uint32_t* __restrict__ n_tracked, const SkbTable t,
-                                                             uint16_t* ctr, uint32_t stride) {
-  const uint32_t tr = blockIdx.x / 8, part = blockIdx.x % 8;  // 8 CTAs share one tracked row
-  if (tr >= *n_tracked) return;
-  const uint32_t row = tracked[tr];
-  const uint64_t* src = rv.ref + rv.row_start[row];
-  const uint32_t len = rv.row_len[row];
-  uint32_t* cbuf = reinterpret_cast<uint32_t*>(ctr + (size_t)tr * stride);
-  for (uint32_t i = part * blockDim.x + threadIdx.x; i < len; i += 8 * blockDim.x) {
-    SkbSlot s;
-    if (table_lookup(t, src[i], s)) apply_hit<2>(t, s.meta, cbuf);
+// inclusive scan of one u32 per thread across the CTA; returns inclusive prefix, *total = sum
+__device__ __forceinline__ uint32_t cta_scan_u32(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+  const uint32_t lane = skb_lane(), wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
+    if ((int)lane >= o) v += y;
+  }
+  if (lane == 31) warp_sums[wid] = v;
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+  for (uint32_t w = 0; w < nw; ++w) {
+    const uint32_t s = warp_sums[w];
+    if (w < wid) off += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return v + off;
+}
+
+// Bounds, step 1: the per-read counts of one tracked row against the pass's table, accumulated in shared memory, then
+// their inclusive prefix sums over the reads of the pass (what the row adds to its running sum after each read).
+// One CTA per tracked row (they define the bounds; at most SKB_MAX_TRACKED of them).
+__global__ void __launch_bounds__(1024) tracked_prefix_kernel(const SkbRefView rv, const SkbTable t, const SkbRankArgs a, int has_keys) {
+  extern __shared__ __align__(16) uint32_t tk_cnt[];  // [row_stride / 2] u16 counters, two per word
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t tr = blockIdx.x;
+  if (tr >= *a.n_tracked) return;
+  const uint32_t row = a.tracked[tr];
+  for (uint32_t i = threadIdx.x; i < a.row_stride / 2; i += blockDim.x) tk_cnt[i] = 0;
+  __syncthreads();
+  if (has_keys) {
+    const uint64_t* src = rv.ref + rv.row_start[row];
+    const uint32_t len = rv.row_len[row];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+      SkbSlot s;
+      if (table_lookup(t, src[i], s)) apply_hit<2>(t, s.meta, tk_cnt);
+    }
+  }
+  __syncthreads();
+  const uint16_t* c = reinterpret_cast<const uint16_t*>(tk_cnt);
+  uint32_t* p = a.tracked_prefix + (size_t)tr * a.row_stride;
+  const uint32_t per = (a.n_reads + blockDim.x - 1) / blockDim.x;
+  const uint32_t b0 = threadIdx.x * per;
+  const uint32_t b1 = min(b0 + per, a.n_reads);
+  uint32_t local = 0;
+  for (uint32_t b = b0; b < b1; ++b) local += c[b];
+  uint32_t tot;
+  const uint32_t incl = cta_scan_u32(local, warp_sums, &tot);
+  uint32_t run = incl - local;
+  for (uint32_t b = b0; b < b1; ++b) {
+    run += c[b];
+    p[b] = run;
   }
 }
 
@@ -695,79 +736,66 @@ __global__ void __launch_bounds__(256) tracked_totals_kernel(const SkbRefView rv
 // ---------------------------------------------------------------------------------------------------------
 // rank kernels
 // ---------------------------------------------------------------------------------------------------------
-// inclusive scan of one u32 per thread across the CTA; returns inclusive prefix, *total = sum
-__device__ __forceinline__ uint32_t cta_scan_u32(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
-  const uint32_t lane = skb_lane(), wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
-    if ((int)lane >= o) v += y;
-  }
-  if (lane == 31) warp_sums[wid] = v;
-  __syncthreads();
-  uint32_t off = 0, tot = 0;
-  for (uint32_t w = 0; w < nw; ++w) {
-    const uint32_t s = warp_sums[w];
-    if (w < wid) off += s;
-    tot += s;
-  }
-  __syncthreads();
-  *total = tot;
-  return v + off;
-}
-
-// Bounds, step 1: inclusive prefix sums of every tracked row's per-read counts. One CTA per tracked row.
-__global__ void __launch_bounds__(256) tracked_prefix_kernel(const SkbRankArgs a) {
-  __shared__ uint32_t warp_sums[32];
-  const uint32_t t = blockIdx.x;
-  if (t >= *a.n_tracked) return;
-  const uint16_t* c = a.tracked_counts + (size_t)t * a.row_stride;
-  uint32_t* p = a.tracked_prefix + (size_t)t * a.row_stride;
-  const uint32_t per = (a.n_reads + blockDim.x - 1) / blockDim.x;
-  const uint32_t b0 = threadIdx.x * per;
-  const uint32_t b1 = min(b0 + per, a.n_reads);
-  uint32_t local = 0;
-  for (uint32_t b = b0; b < b1; ++b) local += c[b];
-  uint32_t tot;
-  const uint32_t incl = cta_scan_u32(local, warp_sums, &tot);
-  uint32_t run = incl - local;
-  for (uint32_t b = b0; b < b1; ++b) {
-    run += c[b];
-    p[b] = run;
-  }
-}
-
 // Bounds, step 2: for every read the `top`-th best key among the tracked rows (exact sums, so a valid lower bound of
-// the read's true `top`-th key: sums never decrease and the tracked rows are distinct). One thread per read keeps the
-// best `top` keys seen so far in a small sorted list. With fewer than `top` tracked rows the bound is their worst.
-__global__ void __launch_bounds__(128) rank_bounds_kernel(const SkbRankArgs a) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= a.n_reads) return;
+// the read's true `top`-th key: sums never decrease and the tracked rows are distinct). One warp per read: every lane
+// holds up to six tracked rows' keys at this read, the warp takes out its best key `top` times. With fewer than `top`
+// tracked rows the bound is their worst.
+__global__ void __launch_bounds__(256) rank_bounds_kernel(const SkbRankArgs a) {
+  __shared__ unsigned long long base_s[SKB_MAX_TRACKED];
+  __shared__ uint32_t base_i[SKB_MAX_TRACKED];
   const uint32_t nt = *a.n_tracked;
-  const uint32_t keep = a.top < nt ? a.top : nt;
-  unsigned long long ks[SKB_MAX_TOP];
-  uint32_t ki[SKB_MAX_TOP];
-  uint32_t n = 0;
-  for (uint32_t t = 0; t < nt; ++t) {
+  for (uint32_t t = threadIdx.x; t < nt; t += blockDim.x) {
     const uint32_t row = a.tracked[t];
-    const unsigned long long s = a.sums_in[row] + a.tracked_extra[t] + a.tracked_prefix[(size_t)t * a.row_stride + b];
-    const uint32_t gi = a.row_base + row;
-    if (n == keep && !skb_key_better(s, gi, ks[n - 1], ki[n - 1])) continue;
-    uint32_t pos = n < keep ? n : n - 1;  // insert, dropping the worst when full
-    while (pos > 0 && skb_key_better(s, gi, ks[pos - 1], ki[pos - 1])) {
-      ks[pos] = ks[pos - 1]; ki[pos] = ki[pos - 1];
-      --pos;
-    }
-    ks[pos] = s; ki[pos] = gi;
-    if (n < keep) ++n;
+    base_s[t] = a.sums_in[row] + a.tracked_extra[t];
+    base_i[t] = a.row_base + row;
   }
-  a.lb_sum[b] = n ? ks[n - 1] : 0ull;
-  a.lb_idx[b] = n ? ki[n - 1] : 0xFFFFFFFFu;
+  __syncthreads();
+  const uint32_t lane = skb_lane();
+  const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= a.n_reads) return;
+  constexpr int PER = (SKB_MAX_TRACKED + 31) / 32;
+  unsigned long long ks[PER];
+  uint32_t ki[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t t = lane + 32 * j;
+    const bool have = t < nt;
+    ks[j] = have ? base_s[t] + a.tracked_prefix[(size_t)t * a.row_stride + b] : 0ull;
+    ki[j] = have ? base_i[t] : 0xFFFFFFFFu;   // (0, UINT32_MAX): worse than any real key
+  }
+  const uint32_t keep = a.top < nt ? a.top : nt;
+  unsigned long long bs = 0;
+  uint32_t bi = 0xFFFFFFFFu;
+  for (uint32_t r = 0; r < keep; ++r) {
+    // this lane's best remaining key, then the warp's
+    unsigned long long ls = ks[0];
+    uint32_t li = ki[0];
+    int lj = 0;
+#pragma unroll
+    for (int j = 1; j < PER; ++j)
+      if (skb_key_better(ks[j], ki[j], ls, li)) { ls = ks[j]; li = ki[j]; lj = j; }
+    bs = ls; bi = li;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long s2 = __shfl_xor_sync(0xffffffffu, bs, o);
+      const uint32_t i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (skb_key_better(s2, i2, bs, bi)) { bs = s2; bi = i2; }
+    }
+    if (li == bi && ls == bs) {  // the owner retires it (keys are distinct: the row index is part of the key)
+#pragma unroll
+      for (int j = 0; j < PER; ++j)
+        if (j == lj) { ks[j] = 0; ki[j] = 0xFFFFFFFFu; }
+    }
+  }
+  if (lane == 0) {
+    a.lb_sum[b] = keep ? bs : 0ull;
+    a.lb_idx[b] = keep ? bi : 0xFFFFFFFFu;
+  }
 }
 
 // intervals (one sum over a run of reads) -> per-read candidate buckets. One warp per interval; every read is tested
 // against its exact bound; the per-read counter is the slot allocator.
-__global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
+__device__ __forceinline__ void expand_intervals(const SkbRankArgs& a) {
   const uint32_t total = min(*a.ivl_total, a.ivl_cap);
   const uint32_t lane = skb_lane();
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -782,42 +810,55 @@ __global__ void __launch_bounds__(256) expand_kernel(const SkbRankArgs a) {
         cd.sum = iv.sum; cd.idx = iv.idx; cd.pad = 0;
         a.cand[(size_t)b * a.cand_cap + slot] = cd;
       } else {
-        *a.cand_total = 1u;  // bucket overflow: the host redoes the pass with fewer reads
+        *a.cand_total = 1u;  // bucket overflow: the host redoes the pass densely
       }
     }
   }
 }
 
-// Tracked rows of the next pass: the union of the top lists of 16 evenly spaced reads of this pass, the last read's
-// list first (it alone guarantees `top` distinct rows). Rows that led at any point of the pass stay tracked, so a
-// lineage that overtakes and falls back does not loosen the bounds. One CTA.
-__global__ void __launch_bounds__(256) pass_verdict_kernel(const SkbRankArgs a) {
-  __shared__ uint32_t wmax[8];
-  uint32_t m = 0;  // fullest candidate bucket of the pass: the host grows the next pass only when there is headroom
-  for (uint32_t b = threadIdx.x; b < a.n_reads; b += blockDim.x) m = max(m, a.cand_cnt[b]);
-  m = __reduce_max_sync(0xffffffffu, m);
-  if ((threadIdx.x & 31u) == 0) wmax[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  for (int w = 1; w < 8; ++w) m = max(m, wmax[w]);
-  if (a.abort[0] == 0u) {
-    a.abort[2] = m;
-    a.abort[3] = *a.ivl_total;
-    a.abort[4] = *a.seg_total;
-    if (*a.cand_total != 0u || *a.ivl_total > a.ivl_cap || *a.seg_total > a.seg_cap) {
-      a.abort[1] = a.seq;
-      a.abort[0] = 1u;
-    }
-  }
-  *a.cand_total = 0u;
-  *const_cast<uint32_t*>(a.ivl_total) = 0u;
-  *const_cast<uint32_t*>(a.seg_total) = 0u;
+// post-pass, first launch: segment records and intervals -> per-read candidate buckets
+__global__ void __launch_bounds__(256) candidates_kernel(const SkbRankArgs a) {
+  walk_records(a);
+  expand_intervals(a);
 }
 
-__global__ void __launch_bounds__(1024) tracked_update_kernel(const SkbRankArgs a) {
-  if (a.abort[0]) return;  // this pass (or one before it) is redone: keep the tracked rows it started from
+// Post-pass, last launch (one CTA): the overflow verdict of the pass, then the tracked rows of the next passes.
+//   verdict: the fullest candidate bucket and the record counts go to `abort` for the host; a pass whose buckets or
+//            record lists overflowed marks itself there (the passes behind it then do nothing); the counters and the
+//            bucket fill counts are cleared for the slot's next pass.
+//   update:  the union of the top lists of 16 evenly spaced reads of this pass, the last read's list first (it alone
+//            guarantees `top` distinct rows). Rows that led at any point of the pass stay tracked, so a lineage that
+//            overtakes and falls back does not loosen the bounds. Skipped while a pass is being redone.
+__global__ void __launch_bounds__(1024) verdict_update_kernel(const SkbRankArgs a, int with_verdict) {
+  __shared__ uint32_t wmax[32];
   __shared__ uint32_t list[16 * SKB_MAX_TOP];
   __shared__ uint32_t keep[16 * SKB_MAX_TOP];
+  __shared__ uint32_t stop;
+  if (with_verdict) {
+    uint32_t m = 0;
+    for (uint32_t b = threadIdx.x; b < a.n_reads; b += blockDim.x) { m = max(m, a.cand_cnt[b]); a.cand_cnt[b] = 0; }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31u) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (uint32_t w = 1; w < (blockDim.x >> 5); ++w) m = max(m, wmax[w]);
+      if (a.abort[0] == 0u) {
+        a.abort[2] = m;
+        a.abort[3] = *a.ivl_total;
+        a.abort[4] = *a.seg_total;
+        if (*a.cand_total != 0u || *a.ivl_total > a.ivl_cap || *a.seg_total > a.seg_cap) {
+          a.abort[1] = a.seq;
+          a.abort[0] = 1u;
+        }
+      }
+      *a.cand_total = 0u;
+      *const_cast<uint32_t*>(a.ivl_total) = 0u;
+      *const_cast<uint32_t*>(a.seg_total) = 0u;
+    }
+  }
+  if (threadIdx.x == 0) stop = a.abort[0];
+  __syncthreads();
+  if (stop) return;  // this pass (or one before it) is redone: keep the tracked rows it started from
   const uint32_t n_s = 16, total = n_s * a.top;
   for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
     const uint32_t j = e / a.top, tpos = e % a.top;
@@ -833,11 +874,17 @@ __global__ void __launch_bounds__(1024) tracked_update_kernel(const SkbRankArgs 
     keep[e] = first ? 1u : 0u;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {  // order-preserving compaction (a few thousand entries at most)
+  if (threadIdx.x < 32) {  // order-preserving compaction by one warp
     uint32_t n = 0;
-    for (uint32_t e = 0; e < total && n < SKB_MAX_TRACKED; ++e)
-      if (keep[e]) a.tracked_next[n++] = list[e] - a.row_base;
-    *a.n_tracked_next = n;
+    for (uint32_t e0 = 0; e0 < total && n < SKB_MAX_TRACKED; e0 += 32) {
+      const uint32_t e = e0 + threadIdx.x;
+      const bool k = e < total && keep[e];
+      const uint32_t bal = __ballot_sync(0xffffffffu, k);
+      const uint32_t at = n + __popc(bal & ((1u << threadIdx.x) - 1u));
+      if (k && at < SKB_MAX_TRACKED) a.tracked_next[at] = list[e] - a.row_base;
+      n += __popc(bal);
+    }
+    if (threadIdx.x == 0) *a.n_tracked_next = n < SKB_MAX_TRACKED ? n : SKB_MAX_TRACKED;
   }
 }
 
@@ -1239,29 +1286,21 @@ void skb_launch_fused(const SkbFusedArgs& a, cudaStream_t st) {
   else fused_kernel<2><<<a.num_ctas, FS_THREADS, smem, st>>>(a);
 }
 
-void skb_launch_tracked_counts(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
-                               const SkbTable& t, uint16_t* ctr, uint32_t stride, cudaStream_t st) {
-  tracked_counts_kernel<<<SKB_MAX_TRACKED * 8, 256, 0, st>>>(rv, tracked, n_tracked, t, ctr, stride);
-}
-
 void skb_launch_tracked_totals(const SkbRefView& rv, const uint32_t* tracked, const uint32_t* n_tracked,
                                const SkbTable& t, unsigned long long* extra, cudaStream_t st) {
   tracked_totals_kernel<<<SKB_MAX_TRACKED * 8, 256, 0, st>>>(rv, tracked, n_tracked, t, extra);
 }
 
-void skb_launch_rank_bounds(const SkbRankArgs& a, cudaStream_t st) {
-  tracked_prefix_kernel<<<SKB_MAX_TRACKED, 256, 0, st>>>(a);
-  rank_bounds_kernel<<<(a.n_reads + 127) / 128, 128, 0, st>>>(a);
+void skb_launch_rank_bounds(const SkbRefView& rv, const SkbTable& t, const SkbRankArgs& a, bool has_keys, cudaStream_t st) {
+  tracked_prefix_kernel<<<SKB_MAX_TRACKED, 1024, (size_t)a.row_stride * 2, st>>>(rv, t, a, has_keys ? 1 : 0);
+  rank_bounds_kernel<<<(a.n_reads + 7) / 8, 256, 0, st>>>(a);
 }
 
-void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st) {
-  walk_kernel<<<148 * 8, 256, 0, st>>>(a);
-  expand_kernel<<<148 * 8, 256, 0, st>>>(a);
+void skb_launch_rank_expand(const SkbRankArgs& a, cudaStream_t st) { candidates_kernel<<<148 * 8, 256, 0, st>>>(a); }
+
+void skb_launch_verdict_update(const SkbRankArgs& a, bool with_verdict, cudaStream_t st) {
+  verdict_update_kernel<<<1, 1024, 0, st>>>(a, with_verdict ? 1 : 0);
 }
-
-void skb_launch_tracked_update(const SkbRankArgs& a, cudaStream_t st) { tracked_update_kernel<<<1, 1024, 0, st>>>(a); }
-
-void skb_launch_pass_verdict(const SkbRankArgs& a, cudaStream_t st) { pass_verdict_kernel<<<1, 256, 0, st>>>(a); }
 
 void skb_launch_rank_select(const SkbRankArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)RS_WARPS * RS_CACHE * 16;
