@@ -214,7 +214,9 @@ def consensus_calls(idx: np.ndarray, table: np.ndarray) -> np.ndarray:
     first in rank order (api.consensus_value; the reference's HashMap max_by is nondeterministic on ties,
     src/sketchy.rs:380-387, 408). idx [R, top] -> [R, columns]."""
     v = table[idx.astype(np.int64)]                              # [R, top, C]
-    same = (v[:, :, None, :] == v[:, None, :, :]).sum(axis=2)    # [R, top, C] occurrences of the value at each rank
+    same = np.zeros(v.shape, dtype=np.int8)                      # occurrences of the value at each rank position
+    for t in range(v.shape[1]):
+        same += (v == v[:, t:t + 1, :])
     first_best = same.argmax(axis=1)                             # first rank position holding the most frequent value
     return np.take_along_axis(v, first_best[:, None, :], axis=1)[:, 0, :]
 
@@ -247,7 +249,7 @@ def run_b200(args):
 
     # ---------------- synthetic data (untimed) ----------------
     t0 = time.time()
-    n_base = min(args.lineages, 40)   # distinct base genomes (C5's 1000 lineages reuse the 40 genomes with different replaced entries)
+    n_base = args.lineages
     genomes = st.random_genomes(n_base, GENOME_LEN, 3000, device)
     lo, cnt = dist_range(N, rank, world)
     lo_al = lo // st.ROW_BLOCK * st.ROW_BLOCK           # row blocks are seeded independently of the sharding
@@ -388,13 +390,18 @@ def run_b200(args):
         # a streaming caller feeds reads in chunks of whole passes: chunk i+1 is normalised + 2-bit packed into pinned
         # memory by the library's host threads and copied to the device while the GPU works on chunk i (two batches,
         # double buffered). With N ranks every rank packs, copies and hashes 1/N of each chunk.
-        chunk_reads = 5 * (args.pass_reads or PASS_READS)
+        chunk_reads = (10 if R >= 500_000 else 5) * (args.pass_reads or PASS_READS)
         chunks = [(c_lo, min(c_lo + chunk_reads, R)) for c_lo in range(0, R, chunk_reads)]
         pack_s = [0.0]
         hbs = [ctx.batch(), ctx.batch()]
         pack_threads = max(1, (os.cpu_count() or 1) // world)   # the ranks of one box share its host cores
-        gt = genotype_table(N, args.lineages) if args.consensus else None
-        calls = [None]
+        gt = genotype_table(N, args.lineages).astype(np.int16) if args.consensus else None
+        calls = [np.zeros((R, gt.shape[1]), dtype=np.int16) if gt is not None else None]
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=4)   # C4: the genotype consensus of a chunk, formed on the host while the GPU works on the next
+
+        def consensus_chunk(q_lo, q_hi):
+            calls[0][q_lo:q_hi] = consensus_calls(oi[q_lo:q_hi], gt)
 
         def pack(j, p_lo, p_hi):
             t0 = time.perf_counter()
@@ -409,6 +416,7 @@ def run_b200(args):
         def step_e2e():
             ctx.sums_reset()
             pack(0, *chunks[0])
+            pending = []
             for ci, (q_lo, q_hi) in enumerate(chunks):
                 th = None
                 if ci + 1 < len(chunks):
@@ -416,10 +424,12 @@ def run_b200(args):
                     th.start()
                 ctx.predict_stream_dist(hbs[ci & 1], q_hi - q_lo, K, s, SEED, top, out=(oi[q_lo:q_hi], os_[q_lo:q_hi]),
                                         report=rank == 0)   # H2D + kernels (+ exchange) + D2H of the merged top-N
+                if gt is not None and rank == 0:
+                    pending.append(pool.submit(consensus_chunk, q_lo, q_hi))
                 if th is not None:
                     th.join()
-            if gt is not None and rank == 0:   # C4: the genotype consensus of every read, formed on the host from the top rows
-                calls[0] = consensus_calls(oi, gt)
+            for f in pending:
+                f.result()
 
         for _ in range(2):
             step_e2e()
@@ -456,6 +466,7 @@ def run_b200(args):
                         assert str(calls[0][r_, c_]) == consensus_value([str(x) for x in gt[oi[r_].astype(np.int64), c_]])
                 consensus_info = {"columns": int(gt.shape[1]), "reads": R, "calls_crc32": f"{zlib.crc32(calls[0].tobytes()):08x}",
                                   "checked_against_host_mirror": int(chk.size)}
+        pool.shutdown()
         for x in hbs:
             x.close()
 
@@ -664,7 +675,7 @@ def run_reference(args):
     if args.config == "c5":   # bounded sample of the 80 GB reference: the rows one of eight GPUs would hold
         N = N // 8
     t0 = time.time()
-    n_base = min(args.lineages, 40)
+    n_base = args.lineages
     genomes = st.random_genomes(n_base, GENOME_LEN, 3000, device)
     ncores = os.cpu_count() or 1
     if args.row_dist == "independent":
