@@ -68,6 +68,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the zero-hit variant and the sketch leg")
     p.add_argument("--sketch-genomes", type=int, default=128, help="genomes in the bounded sketch-throughput sample (0 = skip)")
+    p.add_argument("--sketch-only", action="store_true", help="run the sketch leg alone and print its record (profiling aid)")
     a = p.parse_args()
     refs, s, reads, top, lin, dist_kind, cons = CONFIGS[a.config]
     a.refs = a.refs or refs
@@ -240,6 +241,10 @@ def run_b200(args):
         uid = torch.from_numpy(ctx.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(device)
         dist.broadcast(uid, 0)
         ctx.comm_init(uid.cpu().numpy(), rank, world)
+    if args.sketch_only:
+        print(json.dumps({"sketch": sketch_leg(ctx, args, device)}), flush=True)
+        ctx.close()
+        return
     if args.pass_reads:
         ctx.set_pass_reads(args.pass_reads)
     if args.rank_mode:

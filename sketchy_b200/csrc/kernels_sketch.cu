@@ -40,13 +40,6 @@ __device__ __forceinline__ uint64_t mm3_finish_h1(uint64_t h1, uint64_t h2, uint
   return h1 + h2;
 }
 
-// k = 16: exactly one block, no tail.
-__device__ __forceinline__ uint64_t mm3_h1_k16(uint64_t k1, uint64_t k2, uint64_t seed) {
-  uint64_t h1 = seed, h2 = seed;
-  mm3_block(h1, h2, k1, k2);
-  return mm3_finish_h1(h1, h2, 16);
-}
-
 // generic length <= 32: w[i] holds bytes 8i..8i+7 little-endian, bytes >= len are zero.
 __device__ __forceinline__ uint64_t mm3_h1_upto32(const uint64_t w[4], uint32_t len, uint64_t seed) {
   uint64_t h1 = seed, h2 = seed;
@@ -93,10 +86,86 @@ __device__ __forceinline__ void emit_hash(const SkbHashArgs& a, uint32_t g, uint
   }
 }
 
+// ---- k = 16 fast path: MurmurHash3_x64_128.h1 of one 16-byte block on explicit 32-bit halves -------------------
+// The integer pipes bound this kernel, so the arithmetic is spelled the way the SASS should come out: a 64-bit
+// multiply by a constant is IMAD.WIDE + 2 IMAD, a rotate is two funnel shifts, x ^= x >> 33 touches the low word only.
+struct U2 { uint32_t lo, hi; };
+__device__ __forceinline__ U2 mulc(U2 a, uint64_t c) {
+  const uint32_t clo = (uint32_t)c, chi = (uint32_t)(c >> 32);
+  U2 r;
+  // spelled in PTX so that the three multiply-adds stay three (the compiler's own form is four: two products, the wide
+  // product and an add)
+  asm("{\n\t"
+      ".reg .u64 t;\n\t"
+      ".reg .u32 th;\n\t"
+      "mul.wide.u32 t, %2, %4;\n\t"
+      "mov.b64 {%0, th}, t;\n\t"
+      "mad.lo.u32 th, %2, %5, th;\n\t"
+      "mad.lo.u32 %1, %3, %4, th;\n\t"
+      "}"
+      : "=r"(r.lo), "=r"(r.hi)
+      : "r"(a.lo), "r"(a.hi), "r"(clo), "r"(chi));
+  return r;
+}
+template <int R>
+__device__ __forceinline__ U2 rotl2(U2 a) {
+  U2 o;
+  if constexpr (R < 32) { o.hi = __funnelshift_l(a.lo, a.hi, R); o.lo = __funnelshift_l(a.hi, a.lo, R); }
+  else { o.hi = __funnelshift_l(a.hi, a.lo, R - 32); o.lo = __funnelshift_l(a.lo, a.hi, R - 32); }
+  return o;
+}
+__device__ __forceinline__ U2 add2(U2 a, U2 b) {
+  const uint64_t x = (((uint64_t)a.hi << 32) | a.lo) + (((uint64_t)b.hi << 32) | b.lo);
+  U2 r; r.lo = (uint32_t)x; r.hi = (uint32_t)(x >> 32);
+  return r;
+}
+// a * 5 + c; c64 = c in a 64-bit register pair the caller keeps live (IMAD.WIDE takes it as its addend)
+__device__ __forceinline__ U2 mul5add(U2 a, uint64_t c64) {
+  const uint64_t t = (uint64_t)a.lo * 5u + c64;
+  U2 r; r.lo = (uint32_t)t; r.hi = a.hi * 5u + (uint32_t)(t >> 32);
+  return r;
+}
+// fmix64 without its last step (x ^= x >> 33 changes the low word only: the caller applies it when it needs the
+// low word at all)
+__device__ __forceinline__ U2 fmix_head(U2 x) {
+  x.lo ^= x.hi >> 1;
+  x = mulc(x, 0xff51afd7ed558ccdull);
+  x.lo ^= x.hi >> 1;
+  return mulc(x, 0xc4ceb9fe1a85ec53ull);
+}
+// A, B with h = (A ^ (A >> 33)) + (B ^ (B >> 33)); k1 = bytes 0..7 of the k-mer (little endian), k2 = bytes 8..15
+template <bool SEED0>
+__device__ __forceinline__ void mm3_k16_heads(U2 k1, U2 k2, uint32_t seed_lo, uint32_t seed_hi, uint64_t c52, uint64_t c38,
+                                              U2& A, U2& B) {
+  k1 = mulc(k1, MM_C1); k1 = rotl2<31>(k1); k1 = mulc(k1, MM_C2);
+  k2 = mulc(k2, MM_C2); k2 = rotl2<33>(k2); k2 = mulc(k2, MM_C1);
+  U2 h1 = k1, h2 = k2;
+  if (!SEED0) { h1.lo ^= seed_lo; h1.hi ^= seed_hi; h2.lo ^= seed_lo; h2.hi ^= seed_hi; }
+  h1 = rotl2<27>(h1);
+  if (!SEED0) { U2 sd; sd.lo = seed_lo; sd.hi = seed_hi; h1 = add2(h1, sd); }
+  h1 = mul5add(h1, c52);
+  h2 = rotl2<31>(h2);
+  h2 = add2(h2, h1);
+  h2 = mul5add(h2, c38);
+  h1.lo ^= 16u; h2.lo ^= 16u;  // len
+  h1 = add2(h1, h2);
+  h2 = add2(h2, h1);
+  A = fmix_head(h1);
+  B = fmix_head(h2);
+}
+__device__ __forceinline__ uint64_t mm3_k16_finish(U2 A, U2 B) {
+  A.lo ^= A.hi >> 1; B.lo ^= B.hi >> 1;
+  return (((uint64_t)A.hi << 32) | A.lo) + (((uint64_t)B.hi << 32) | B.lo);
+}
+
+#ifndef SKB_X_HASH_UNROLL
+#define SKB_X_HASH_UNROLL 8  // 4, 8 or 16: k-mers per unrolled body (the fully unrolled chunk was 64 KB of SASS: instruction-fetch stalls)
+#endif
+
 // One warp per segment (<= 32 chunks of one group); one lane per chunk of 32 k-mer start positions.
-template <bool K16, bool DUMP>
+template <bool K16, bool DUMP, bool SEED0>
 __global__ void __launch_bounds__(256) hash_kernel(const SkbHashArgs a) {
-  __shared__ uint32_t lut[256];
+  __shared__ __align__(1024) uint32_t lut[256];
   if (K16) {
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = ascii4(i);
     __syncthreads();
@@ -116,32 +185,61 @@ __global__ void __launch_bounds__(256) hash_kernel(const SkbHashArgs a) {
     nvalid = __popc(valid);
     if (valid != 0u || DUMP) {
       const uint64_t tau = DUMP ? 0 : a.tau[g];
-      const uint64_t base = DUMP ? 0 : a.cand_base[g];
-      const uint32_t cap = DUMP ? 0 : a.cand_cap[g];
       const uint64_t pos0 = chunk * SKB_CHUNK;
       const uint32_t* cw = a.pv.codes + chunk * 2;
       if (K16) {
         const uint32_t w0 = __ldg(cw), w1 = __ldg(cw + 1), w2 = __ldg(cw + 2);
-        uint32_t fwd_le = w0;
-        uint32_t x = __brev(fwd_le);
-        uint32_t fwd_be = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+        // Values the loop keeps in registers; they pass through an empty asm so that the compiler does not rebuild them
+        // from their definitions for every k-mer. lut_base: byte address of the table in the shared window, 1 KB
+        // aligned, so (index bits | base) is one LOP3. tau_hi1: a hash can be <= tau only if its high word (without the
+        // carry of the low words) + 1 <= tau's high word + 1 (saturating).
+        uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(lut);
+        uint32_t tau_hi1 = (uint32_t)(tau >> 32) == 0xFFFFFFFFu ? 0xFFFFFFFFu : (uint32_t)(tau >> 32) + 1u;
+        uint64_t c52 = 0x52dce729ull, c38 = 0x38495ab5ull;
+        asm volatile("" : "+r"(lut_base), "+r"(tau_hi1), "+l"(c52), "+l"(c38));
+        const uint32_t seed_lo = (uint32_t)a.seed, seed_hi = (uint32_t)(a.seed >> 32);
+        uint32_t x = __brev(w0);
+        uint32_t fwd_be = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);  // the window, first base most significant
+        fwd_be >>= 2;  // (the loop shifts the incoming base in before use)
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < 32; j0 += SKB_X_HASH_UNROLL) {
+          // bases j0 .. j0 + 31 of the lane's 48-base window (w3 would be the next lane's: not needed, k - 1 + 32 <= 48)
+          const bool up = j0 >= 16;
+          const uint32_t sh0 = 2u * (j0 & 15u);
+          const uint32_t wa = up ? w1 : w0, wb = up ? w2 : w1, wc = up ? 0u : w2;
+          const uint32_t lo = __funnelshift_r(wa, wb, sh0), hi = __funnelshift_r(wb, wc, sh0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j > 0) {
-            const uint32_t lo = (j < 16) ? w0 : w1, hi = (j < 16) ? w1 : w2;
-            const int sh = 2 * (j & 15);
-            fwd_le = sh ? __funnelshift_r(lo, hi, sh) : lo;
+          for (uint32_t jj = 0; jj < SKB_X_HASH_UNROLL; ++jj) {
+            const uint32_t j = j0 + jj;
+            const uint32_t fwd_le = jj ? __funnelshift_r(lo, hi, 2 * jj) : lo;  // base j + i at bits 2i
             fwd_be = (fwd_be << 2) | (fwd_le >> 30);
+            // reverse complement, first base most significant, is ~fwd_le; in the little-endian layout it is ~fwd_be
+            const uint32_t canon = (~fwd_le) < fwd_be ? ~fwd_be : fwd_le;
+            uint32_t a0, a1, a2, a3;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(((canon << 2) & 0x3FCu) | lut_base));
+            asm("ld.shared.u32 %0, [%1];" : "=r"(a1) : "r"(((canon >> 6) & 0x3FCu) | lut_base));
+            asm("ld.shared.u32 %0, [%1];" : "=r"(a2) : "r"(((canon >> 14) & 0x3FCu) | lut_base));
+            asm("ld.shared.u32 %0, [%1];" : "=r"(a3) : "r"(((canon >> 22) & 0x3FCu) | lut_base));
+            U2 k1, k2, A, B;
+            k1.lo = a0; k1.hi = a1; k2.lo = a2; k2.hi = a3;
+            mm3_k16_heads<SEED0>(k1, k2, seed_lo, seed_hi, c52, c38, A, B);
+            if (DUMP) {
+              const uint64_t h = mm3_k16_finish(A, B);
+              const bool ok = (valid >> j) & 1u;
+              a.dump_hash[pos0 + j] = ok ? h : 0ull;
+              a.dump_valid[pos0 + j] = ok ? 1 : 0;
+            } else if (A.hi + B.hi + 1u <= tau_hi1) {  // rare
+              const uint64_t h = mm3_k16_finish(A, B);
+              if (((valid >> j) & 1u) && h <= tau) {
+                const uint32_t slot = atomicAdd(&a.cand_cnt[g], 1u);
+                if (slot < __ldg(a.cand_cap + g)) a.cand[__ldg(a.cand_base + g) + slot] = h;
+              }
+            }
           }
-          // reverse complement, first base most significant, is ~fwd_le; in the little-endian layout it is ~fwd_be
-          const bool use_rc = (~fwd_le) < fwd_be;
-          const uint32_t canon = use_rc ? ~fwd_be : fwd_le;
-          const uint64_t k1 = (uint64_t)lut[canon & 0xFFu] | ((uint64_t)lut[(canon >> 8) & 0xFFu] << 32);
-          const uint64_t k2 = (uint64_t)lut[(canon >> 16) & 0xFFu] | ((uint64_t)lut[canon >> 24] << 32);
-          const uint64_t h = mm3_h1_k16(k1, k2, a.seed);
-          emit_hash<DUMP>(a, g, tau, base, cap, pos0 + j, h, (valid >> j) & 1u);
         }
       } else {
+        const uint64_t base = DUMP ? 0 : a.cand_base[g];
+        const uint32_t cap = DUMP ? 0 : a.cand_cap[g];
         const uint32_t k = a.k;
         const uint64_t lo = (uint64_t)__ldg(cw) | ((uint64_t)__ldg(cw + 1) << 32);
         const uint64_t hi = (uint64_t)__ldg(cw + 2) | ((uint64_t)__ldg(cw + 3) << 32);
@@ -323,11 +421,12 @@ void skb_launch_hash(const SkbHashArgs& a, cudaStream_t st) {
   const unsigned blocks = (unsigned)(((uint64_t)a.pv.nseg * 32 + threads - 1) / threads);
   const bool dump = a.dump_hash != nullptr;
   if (a.k == 16) {
-    if (dump) hash_kernel<true, true><<<blocks, threads, 0, st>>>(a);
-    else hash_kernel<true, false><<<blocks, threads, 0, st>>>(a);
+    if (dump) hash_kernel<true, true, false><<<blocks, threads, 0, st>>>(a);
+    else if (a.seed == 0) hash_kernel<true, false, true><<<blocks, threads, 0, st>>>(a);
+    else hash_kernel<true, false, false><<<blocks, threads, 0, st>>>(a);
   } else {
-    if (dump) hash_kernel<false, true><<<blocks, threads, 0, st>>>(a);
-    else hash_kernel<false, false><<<blocks, threads, 0, st>>>(a);
+    if (dump) hash_kernel<false, true, false><<<blocks, threads, 0, st>>>(a);
+    else hash_kernel<false, false, false><<<blocks, threads, 0, st>>>(a);
   }
 }
 
