@@ -249,6 +249,7 @@ def run_b200(args):
         ctx.set_pass_reads(args.pass_reads)
     if args.rank_mode:
         ctx.set_rank_mode(args.rank_mode)
+    pass_reads_eff = None
     N, s, R, top = args.refs, args.sketch_size, args.reads, args.top
     cfg = args.config
 
@@ -270,6 +271,7 @@ def run_b200(args):
         ref = st.expand_reference_block(base_t.to(device), lo_al, hi - lo_al, 0.02, 4000, device)[lo - lo_al:]
     off = np.arange(cnt + 1, dtype=np.uint64) * np.uint64(s)
     ctx.ref_upload_device(ref.data_ptr(), off, row_base=lo)
+    pass_reads_eff = ctx.pass_reads   # automatic: by the size of this rank's shard (or --pass-reads)
     reads = st.sample_reads(genomes, R, args.read_len, 777)
     roff = np.arange(R + 1, dtype=np.uint64) * np.uint64(args.read_len)
     blob_pinned = torch.from_numpy(reads.reshape(-1)).pin_memory()
@@ -395,14 +397,23 @@ def run_b200(args):
         # a streaming caller feeds reads in chunks of whole passes: chunk i+1 is normalised + 2-bit packed into pinned
         # memory by the library's host threads and copied to the device while the GPU works on chunk i (two batches,
         # double buffered). With N ranks every rank packs, copies and hashes 1/N of each chunk.
-        chunk_reads = (10 if R >= 500_000 else 5) * (args.pass_reads or PASS_READS)
-        chunks = [(c_lo, min(c_lo + chunk_reads, R)) for c_lo in range(0, R, chunk_reads)]
+        # The first chunks are short (one pass, then two): the GPU starts after 4 % of the packing instead of 20 %.
+        P = ctx.pass_reads
+        chunk_reads = (10 if R >= 500_000 else 5) * P
+        chunks, c_lo = [], 0
+        for n_pass in (1, 2):
+            if c_lo + n_pass * P < R:
+                chunks.append((c_lo, c_lo + n_pass * P))
+                c_lo += n_pass * P
+        chunks += [(x, min(x + chunk_reads, R)) for x in range(c_lo, R, chunk_reads)]
         pack_s = [0.0]
-        hbs = [ctx.batch(), ctx.batch()]
+        NB = 3                                  # ring of batches: one being packed, one being copied, one being read by the kernels
+        hbs = [ctx.batch() for _ in range(NB)]
         pack_threads = max(1, (os.cpu_count() or 1) // world)   # the ranks of one box share its host cores
         gt = genotype_table(N, args.lineages).astype(np.int16) if args.consensus else None
         calls = [np.zeros((R, gt.shape[1]), dtype=np.int16) if gt is not None else None]
         from concurrent.futures import ThreadPoolExecutor
+        import queue
         pool = ThreadPoolExecutor(max_workers=4)   # C4: the genotype consensus of a chunk, formed on the host while the GPU works on the next
 
         def consensus_chunk(q_lo, q_hi):
@@ -410,29 +421,47 @@ def run_b200(args):
 
         def pack(j, p_lo, p_hi):
             t0 = time.perf_counter()
-            hbs[j].clear()
+            hbs[j].clear()                      # (waits for the batch's previous copies: they are long over)
             m_lo, m_cnt = dist_range(p_hi - p_lo, rank, world)
             a, b = p_lo + m_lo, p_lo + m_lo + m_cnt
             if m_cnt:
                 hbs[j].add(blob[a * args.read_len:b * args.read_len], roff[a:b + 1] - roff[a], nthreads=pack_threads)
+            hbs[j].stage()                      # enqueues the H2D on the copy stream and returns: the packer goes on
             pack_s[0] += time.perf_counter() - t0
-            hbs[j].stage()   # H2D on the copy stream, overlapping the kernels of the previous chunk
+
+        trace = {"first_pack_ms": 0.0, "call_ms": [0.0] * len(chunks), "wait_pack_ms": [0.0] * len(chunks)}
 
         def step_e2e():
             ctx.sums_reset()
-            pack(0, *chunks[0])
+            free = threading.Semaphore(NB)
+            ready = queue.Queue()
+
+            def producer():                     # the caller's reader thread: packs chunk after chunk, NB - 1 ahead at most
+                for ci, (p_lo, p_hi) in enumerate(chunks):
+                    free.acquire()
+                    pack(ci % NB, p_lo, p_hi)
+                    ready.put(ci)
+
+            th = threading.Thread(target=producer)
+            t_a = time.perf_counter()
+            th.start()
             pending = []
             for ci, (q_lo, q_hi) in enumerate(chunks):
-                th = None
-                if ci + 1 < len(chunks):
-                    th = threading.Thread(target=pack, args=((ci + 1) & 1, *chunks[ci + 1]))
-                    th.start()
-                ctx.predict_stream_dist(hbs[ci & 1], q_hi - q_lo, K, s, SEED, top, out=(oi[q_lo:q_hi], os_[q_lo:q_hi]),
-                                        report=rank == 0)   # H2D + kernels (+ exchange) + D2H of the merged top-N
+                t_w = time.perf_counter()
+                got = ready.get()
+                assert got == ci
+                t_a2 = time.perf_counter()
+                if ci == 0:
+                    trace["first_pack_ms"] += (t_a2 - t_a) * 1e3
+                else:
+                    trace["wait_pack_ms"][ci] += (t_a2 - t_w) * 1e3
+                ctx.predict_stream_dist(hbs[ci % NB], q_hi - q_lo, K, s, SEED, top, out=(oi[q_lo:q_hi], os_[q_lo:q_hi]),
+                                        report=rank == 0)   # H2D wait + kernels (+ exchange) + D2H of the merged top-N
+                trace["call_ms"][ci] += (time.perf_counter() - t_a2) * 1e3
+                free.release()
                 if gt is not None and rank == 0:
                     pending.append(pool.submit(consensus_chunk, q_lo, q_hi))
-                if th is not None:
-                    th.join()
+            th.join()
             for f in pending:
                 f.result()
 
@@ -442,6 +471,9 @@ def run_b200(args):
         t1 = time.perf_counter()
         n_e2e = max(2, min(args.steps, 3))
         pack_s[0] = 0.0
+        trace["first_pack_ms"] = 0.0
+        trace["call_ms"] = [0.0] * len(chunks)
+        trace["wait_pack_ms"] = [0.0] * len(chunks)
         for _ in range(n_e2e):
             step_e2e()
         sync_all()
@@ -451,15 +483,19 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         packed = sum(-(-((b1 - b0) * (args.read_len + 1)) // 32) * 32 for b0, b1 in chunks)
-        h2d = (packed // 4 + packed // 8 + (packed // 1024 + R) * 9) // world
+        h2d = (packed // 4 + packed // 8 + (packed // 1024 + R) * 9 + R * 8) // world
         e2e = {"value": R / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(R * top * 12), "ms_per_step": dt * 1e3,
-               "includes": f"host normalise + 2-bit pack into pinned memory (chunks of {chunk_reads} reads, each rank its 1/{world} "
-                           "of a chunk, packed and copied to the device while the GPU works on the previous chunk), all kernels, "
+               "includes": f"host normalise + 2-bit pack into pinned memory (chunks of {P}, {2 * P}, then {chunk_reads} reads, each rank its 1/{world} "
+                           f"of a chunk; a reader thread packs up to {NB - 1} chunks ahead, copies run on the copy stream), all kernels, "
                            + ("the NCCL exchanges, " if world > 1 else "") + "D2H of the top-N into page-locked host arrays"
                            + (", the per-read genotype consensus on the host" if gt is not None else ""),
                "host_threads": pack_threads, "host_pack_ms_per_step": pack_s[0] / n_e2e * 1e3,
-               "h2d_bytes_note": "per rank"}
+               "h2d_bytes_note": "per rank",
+               "timeline_ms": {"chunk_reads": [b1 - b0 for b0, b1 in chunks],
+                               "first_pack_and_copy": round(trace["first_pack_ms"] / n_e2e, 3),
+                               "library_call_per_chunk": [round(x / n_e2e, 3) for x in trace["call_ms"]],
+                               "wait_for_chunk_packed": [round(x / n_e2e, 3) for x in trace["wait_pack_ms"]]}}
         if rank == 0:
             # the e2e result must equal the resident result
             assert (oi == d_idx.cpu().numpy().view(np.uint32)).all() and (os_ == d_sum.cpu().numpy().view(np.uint64)).all()
@@ -499,7 +535,7 @@ def run_b200(args):
             "scaling": "weak" if cfg == "c5" else "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, N, s, R, top), "refs": N, "sketch_size": s, "reads": R,
                        "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages, "rows": args.row_dist,
-                       "passes_per_step": passes, "reads_per_pass_max": args.pass_reads or PASS_READS,
+                       "passes_per_step": passes, "reads_per_pass_max": pass_reads_eff,
                        "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass"
                              % (cnt * s * 8 / 1e9),
                        "parallelism": f"reference rows sharded over {world} GPUs, reads hashed 1/{world} per rank; NCCL all-gather of "

@@ -75,10 +75,11 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
 uint32_t skb_batch_num_groups(const skb_batch* b);
 uint64_t skb_batch_num_records(const skb_batch* b);
 uint64_t skb_batch_num_bases(const skb_batch* b); /* sum of raw record lengths (finch total_bases) */
-/* Copy the packed batch to the device now (H2D on the context's copy stream + wait). Calls that consume a batch
- * stage it on demand; staging ahead lets a caller keep inputs resident in HBM. skb_batch_add / skb_batch_stage of
- * one batch may run on another host thread while the context works on a different batch (double buffering: the
- * copy overlaps the kernels). */
+/* Start copying the packed batch to the device (H2D on the context's copy stream; the call does not wait, the kernels
+ * that read the batch do, on the device). Calls that consume a batch stage it on demand; staging ahead lets a caller
+ * keep inputs resident in HBM. skb_batch_add / skb_batch_stage of one batch may run on another host thread while the
+ * context works on a different batch (a ring of batches: packing, copy and kernels overlap). skb_batch_clear waits for
+ * the batch's copies before its page-locked buffers are reused. */
 int skb_batch_stage(skb_batch* b);
 
 /* ---- sketch (replaces `_sketch_files`, src/sketchy.rs:465-494: create_sketcher :473, process :477, to_vec :480,
@@ -119,9 +120,12 @@ int skb_predict_stream_device(skb_ctx* ctx, skb_batch* b, uint32_t k, uint32_t s
 int skb_sums_reset(skb_ctx* ctx);
 int skb_sums_download(skb_ctx* ctx, uint64_t* out /* [n_rows] */);
 int skb_sums_upload(skb_ctx* ctx, const uint64_t* in /* [n_rows] */);
-/* Reads per streaming pass: 0 = library default (4096: the streaming kernel's best fraction of the HBM roofline), up
- * to 8192 (fewer passes over the matrix: more reads per second at a lower fraction). Any value gives identical results. */
+/* Reads per streaming pass: 0 = automatic (4096 for shards of 2 GB and more: the streaming kernel's best fraction of
+ * the HBM roofline; 8192 for smaller shards, where the per-pass work that does not depend on the shard dominates), up
+ * to 8192 (fewer passes over the matrix: more reads per second at a lower fraction). Any value gives identical results.
+ * skb_pass_reads returns the size in effect. */
 int skb_set_pass_reads(skb_ctx* ctx, uint32_t max_reads_per_pass);
+uint32_t skb_pass_reads(const skb_ctx* ctx);
 /* How a pass turns its counts into every read's top-N; every mode gives identical results (tests run all of them).
  * 0 = automatic (default): brute-force ranking over all rows right after a reset, for small shards and to redo a
  * pass whose candidate lists overflowed, candidate lists from per-read lower bounds otherwise;

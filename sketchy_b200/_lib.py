@@ -46,6 +46,7 @@ SYMBOLS = [
     ("skb_sums_download", _i, [_vp, _vp]),
     ("skb_sums_upload", _i, [_vp, _vp]),
     ("skb_set_pass_reads", _i, [_vp, _u32]),
+    ("skb_pass_reads", _u32, [_vp]),
     ("skb_set_rank_mode", _i, [_vp, _i]),
     ("skb_comm_unique_id", _i, [_vp]),
     ("skb_comm_init", _i, [_vp, _vp, _i, _i]),
@@ -244,6 +245,11 @@ class Context:
 
     def set_pass_reads(self, n: int):
         self.check(self.lib.skb_set_pass_reads(self.h, n))
+
+    @property
+    def pass_reads(self) -> int:
+        """Reads per streaming pass in effect (automatic choice or set_pass_reads)."""
+        return int(self.lib.skb_pass_reads(self.h))
 
     def set_rank_mode(self, mode: int):
         """0 = automatic, 1 = candidate lists wherever possible, 2 = brute-force ranking always (same results)."""

@@ -192,7 +192,13 @@ struct SkbNccl {
 SkbNccl g_nccl;
 
 struct ProfEvent { int id; cudaEvent_t a, b; };
-#define SKB_DEFAULT_PASS_READS 4096u  // the streaming kernel runs closest to the HBM roofline here; 8192 gives more reads/s
+// Default reads per pass. A pass costs the stream of the shard plus work that does not depend on the shard (table
+// build, bounds, candidate lists: ~0.15 ms); more reads per pass always give more reads per second, at a lower
+// fraction of the HBM roofline for the streaming kernel (more hits per streamed byte). The default keeps the kernel
+// above 0.6 of the roofline where the stream dominates (shards of 2 GB and more: 4096 reads, measured 0.67 on 3.2 GB
+// and 0.74 on 10 GB) and takes the largest pass on smaller shards, where the fixed work dominates.
+#define SKB_DEFAULT_PASS_READS 4096u
+#define SKB_SMALL_SHARD_BYTES (2ull << 30)
 #define SKB_PASS_KEY_BUDGET (1ull << 18)  // query hashes per pass before the membership prefilter (which typically drops more than half of them; the 2^19-bit filter is designed for ~2^17 keys at three bits each)
 #define SKB_NSUMS 4
 #define SKB_NTRACK 3
@@ -201,6 +207,7 @@ struct ProfEvent { int id; cudaEvent_t a, b; };
 struct skb_ctx {
   int device = 0;
   int num_sms = 148;
+  int stream_ctas = 148;  // CTAs of the streaming kernel (one per SM it may take; the rest of the GPU is left to the pre-/post-pass kernels)
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // batch staging (H2D): lets skb_batch_stage overlap a predict running on `stream`
   std::string err;
@@ -230,16 +237,19 @@ struct skb_ctx {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   DevBuf qn_all, gath_idx, gath_sum, hmax_all;
+  uint64_t tau_all = 0;         // largest reference hash of any rank's shard
+  bool tau_all_valid = false;   // reset by an upload and by skb_comm_init
   uint32_t tracked_top = 0;  // 0 = invalid
   // per-group scratch (hash/select)
-  DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, cand_pool;
+  DevBuf g_tau, g_cap, g_base, g_cnt, g_kmers, g_active, g_outn, g_status, g_tiles, cand_pool;
   DevBuf sk_hashes, sk_counts;
   // predict scratch
   DevBuf q_off, qh, qread, counts, lb_sum[SKB_NTAB], lb_idx[SKB_NTAB], cand[2], cand_cnt[2], ivl[2], seg_hdr[2], seg_words[2], scal;
   DevBuf t_slots[SKB_NTAB], t_fill[SKB_NTAB], t_reads[SKB_NTAB], t_slot[SKB_NTAB], t_bloom[SKB_NTAB];
   uint32_t t_cap = 0, t_maxkeys = 0;
   DevBuf out_idx, out_sum, misc;
-  uint32_t pass_max = SKB_DEFAULT_PASS_READS;  // reads per pass (skb_set_pass_reads: up to what the kernel's shared memory holds)
+  uint32_t pass_user = 0;                      // skb_set_pass_reads (0 = automatic)
+  uint32_t pass_max = SKB_DEFAULT_PASS_READS;  // reads per pass in effect (choose_pass_max)
   uint32_t cand_cap = 0;
   // stats / profiling
   bool prof_on = false;
@@ -249,6 +259,7 @@ struct skb_ctx {
   uint64_t launches = 0;
   uint64_t st_ref_bytes = 0, st_passes = 0, st_qhashes = 0, st_cands = 0, st_members = 0;
   uint32_t* h_scal = nullptr;  // pinned, 64 bytes
+  PinBuf h_outn, h_off;        // page-locked staging of per-read arrays (query-hash counts down, list offsets up)
 };
 
 struct skb_batch {
@@ -261,11 +272,19 @@ struct skb_batch {
   uint64_t total_raw = 0;
   // device mirror
   bool staged = false;
-  DevBuf d_codes, d_nmask, d_seg_group, d_seg_chunk0, d_seg_n;
+  DevBuf d_codes, d_nmask, d_seg_group, d_seg_chunk0, d_seg_n, d_g_len;
+  PinBuf h_seg_group, h_seg_chunk0, h_seg_n, h_g_len;  // page-locked sources of the small arrays (true async copies)
+  cudaEvent_t ev_staged = nullptr;  // recorded on the copy stream behind the batch's H2D copies
   uint32_t nseg = 0;
+  uint64_t max_group_len = 0;  // longest group (bases), known once the batch is staged
 };
 
 namespace {
+
+void choose_pass_max(skb_ctx* c) {
+  if (c->pass_user) c->pass_max = std::min<uint32_t>(c->pass_user, skb_fused_max_reads(1));
+  else c->pass_max = (c->has_ref && c->ref_len * 8 < SKB_SMALL_SHARD_BYTES) ? skb_fused_max_reads(1) : SKB_DEFAULT_PASS_READS;
+}
 
 int fail(skb_ctx* c, int code, const char* fmt, ...) {
   if (c) {
@@ -324,6 +343,10 @@ int check_launch(skb_ctx* c, const char* what) {
   return SKB_OK;
 }
 
+// Enqueue the batch's H2D copies on the context's copy stream and record the batch's event behind them. Nothing here
+// waits: the kernels that read the batch wait for the event on their own stream (use_batch), so a caller's packing
+// thread goes on to its next batch while the DMA runs. The page-locked sources stay untouched until the batch is
+// cleared (skb_batch_clear waits for the event).
 int stage_batch(skb_batch* b) {
   skb_ctx* c = b->ctx;
   if (b->staged) return SKB_OK;
@@ -333,30 +356,56 @@ int stage_batch(skb_batch* b) {
   for (uint64_t i = b->cur / 16; i < ncode; ++i) b->codes.as<uint32_t>()[i] = 0;
   for (uint64_t i = b->cur / 32; i < nmask; ++i) b->nmask.as<uint32_t>()[i] = 0xFFFFFFFFu;
   // segments: <= 32 chunks of one group each
-  std::vector<uint32_t> sg, sc;
-  std::vector<uint8_t> sn;
-  for (size_t g = 0; g < b->g_first.size(); ++g) {
-    for (uint64_t ch = b->g_first[g]; ch < b->g_end[g]; ch += 32) {
-      sg.push_back((uint32_t)g);
-      sc.push_back((uint32_t)ch);
-      sn.push_back((uint8_t)std::min<uint64_t>(32, b->g_end[g] - ch));
+  const size_t G = b->g_first.size();
+  uint64_t nseg = 0;
+  b->max_group_len = 0;
+  for (size_t g = 0; g < G; ++g) {
+    nseg += (b->g_end[g] - b->g_first[g] + 31) / 32;
+    b->max_group_len = std::max(b->max_group_len, b->g_packed[g]);
+  }
+  if (nseg >= 0xFFFFFFF0ull) return fail(c, SKB_ERR_INVALID_ARG, "batch too large (segments)");
+  CU(c, b->h_seg_group.ensure(std::max<size_t>(4, nseg * 4), 0));
+  CU(c, b->h_seg_chunk0.ensure(std::max<size_t>(4, nseg * 4), 0));
+  CU(c, b->h_seg_n.ensure(std::max<size_t>(4, nseg), 0));
+  CU(c, b->h_g_len.ensure(std::max<size_t>(8, G * 8), 0));
+  uint32_t* sg = b->h_seg_group.as<uint32_t>();
+  uint32_t* sc = b->h_seg_chunk0.as<uint32_t>();
+  uint8_t* sn = b->h_seg_n.as<uint8_t>();
+  uint64_t at = 0;
+  for (size_t g = 0; g < G; ++g) {
+    for (uint64_t ch = b->g_first[g]; ch < b->g_end[g]; ch += 32, ++at) {
+      sg[at] = (uint32_t)g;
+      sc[at] = (uint32_t)ch;
+      sn[at] = (uint8_t)std::min<uint64_t>(32, b->g_end[g] - ch);
     }
   }
-  b->nseg = (uint32_t)sg.size();
+  if (G) std::memcpy(b->h_g_len.p, b->g_packed.data(), G * 8);
+  b->nseg = (uint32_t)nseg;
   CU(c, b->d_codes.ensure(ncode * 4));
   CU(c, b->d_nmask.ensure(nmask * 4));
-  CU(c, b->d_seg_group.ensure(std::max<size_t>(4, sg.size() * 4)));
-  CU(c, b->d_seg_chunk0.ensure(std::max<size_t>(4, sc.size() * 4)));
-  CU(c, b->d_seg_n.ensure(std::max<size_t>(4, sn.size())));
+  CU(c, b->d_seg_group.ensure(std::max<size_t>(4, nseg * 4)));
+  CU(c, b->d_seg_chunk0.ensure(std::max<size_t>(4, nseg * 4)));
+  CU(c, b->d_seg_n.ensure(std::max<size_t>(4, nseg)));
+  CU(c, b->d_g_len.ensure(std::max<size_t>(8, G * 8)));
+  if (!b->ev_staged) CU(c, cudaEventCreateWithFlags(&b->ev_staged, cudaEventDisableTiming));
   CU(c, cudaMemcpyAsync(b->d_codes.p, b->codes.p, ncode * 4, cudaMemcpyHostToDevice, c->copy_stream));
   CU(c, cudaMemcpyAsync(b->d_nmask.p, b->nmask.p, nmask * 4, cudaMemcpyHostToDevice, c->copy_stream));
-  if (!sg.empty()) {
-    CU(c, cudaMemcpyAsync(b->d_seg_group.p, sg.data(), sg.size() * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(c, cudaMemcpyAsync(b->d_seg_chunk0.p, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(c, cudaMemcpyAsync(b->d_seg_n.p, sn.data(), sn.size(), cudaMemcpyHostToDevice, c->copy_stream));
+  if (G) CU(c, cudaMemcpyAsync(b->d_g_len.p, b->h_g_len.p, G * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  if (nseg) {
+    CU(c, cudaMemcpyAsync(b->d_seg_group.p, sg, nseg * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(b->d_seg_chunk0.p, sc, nseg * 4, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(b->d_seg_n.p, sn, nseg, cudaMemcpyHostToDevice, c->copy_stream));
   }
-  CU(c, cudaStreamSynchronize(c->copy_stream));
+  CU(c, cudaEventRecord(b->ev_staged, c->copy_stream));
   b->staged = true;
+  return SKB_OK;
+}
+
+// stage the batch if it is not staged yet and make the context's main stream wait for its copies
+int use_batch(skb_batch* b) {
+  if (int rc = stage_batch(b)) return rc;
+  skb_ctx* c = b->ctx;
+  CU(c, cudaStreamWaitEvent(c->stream, b->ev_staged, 0));
   return SKB_OK;
 }
 
@@ -388,6 +437,59 @@ int run_hash_select(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s, uint64_t s
   h_out_n.assign(G, 0); h_kmers.assign(G, 0);
   if (G == 0) return SKB_OK;
   const double two64 = 18446744073709551616.0;
+  if (query_mode) {
+    // Fast path: one threshold for every group, so the plan (capacities, places in the pool, scratch reset) is made on
+    // the device and the host reads back only the per-read counts and one "some group needs another round" flag,
+    // through page-locked memory. A call of 100,000 reads otherwise spends a millisecond in the loop below and another in
+    // pageable copies of its arrays. A group whose candidates overflow its capacity (rare: more than four times the
+    // expected number of hashes under the threshold) sends the whole call through the general loop below.
+    const double frac = ((double)query_tau + 1.0) / two64;
+    const uint64_t pool_bound = (uint64_t)G * 96 + (uint64_t)(8.0 * frac * (double)b->total_raw) + 64;
+    CU(c, c->g_tau.ensure(G * 8)); CU(c, c->g_base.ensure(G * 8)); CU(c, c->g_cap.ensure(G * 4));
+    CU(c, c->g_cnt.ensure(G * 4)); CU(c, c->g_kmers.ensure(G * 8)); CU(c, c->g_active.ensure(G));
+    CU(c, c->g_outn.ensure(G * 4)); CU(c, c->g_status.ensure(G * 4));
+    CU(c, c->cand_pool.ensure(pool_bound * 8));
+    CU(c, c->h_outn.ensure((size_t)G * 4 + 64, 0));
+    uint32_t* d_flag = c->scal.as<uint32_t>() + 40;
+    SkbPlanArgs pa{};
+    pa.n_groups = G; pa.g_len = b->d_g_len.as<uint64_t>(); pa.tau = query_tau; pa.frac = frac;
+    pa.tau_out = c->g_tau.as<uint64_t>(); pa.base = c->g_base.as<uint64_t>(); pa.cap = c->g_cap.as<uint32_t>();
+    pa.cnt = c->g_cnt.as<uint32_t>(); pa.kmers = c->g_kmers.as<unsigned long long>(); pa.active = c->g_active.as<uint8_t>();
+    pa.status = c->g_status.as<uint32_t>(); pa.any_bad = d_flag;
+    CU(c, c->g_tiles.ensure(((size_t)G / 1024 + 1) * 8));
+    pa.tile_tot = c->g_tiles.as<unsigned long long>();
+    { ProfScope ps(c, SKB_K_SELECT, 2); skb_launch_plan_query(pa, c->stream); }
+    SkbHashArgs ha{};
+    ha.pv = view_of(b); ha.k = k; ha.seed = seed;
+    ha.tau = pa.tau_out; ha.active = pa.active;
+    ha.cand = c->cand_pool.as<uint64_t>(); ha.cand_base = pa.base; ha.cand_cap = pa.cap;
+    ha.cand_cnt = pa.cnt; ha.kmers = pa.kmers;
+    { ProfScope ps(c, SKB_K_HASH, 1); skb_launch_hash(ha, c->stream); }
+    if (int rc = check_launch(c, "hash")) return rc;
+    SkbSelectArgs sa{};
+    sa.n_groups = G; sa.cand = ha.cand; sa.cand_base = ha.cand_base; sa.cand_cap = ha.cand_cap;
+    sa.cand_cnt = ha.cand_cnt; sa.active = ha.active; sa.tau = ha.tau; sa.s = s;
+    sa.check_underfill = 0; sa.out_hashes = ha.cand; sa.out_off = ha.cand_base; sa.out_counts = nullptr;
+    sa.out_n = c->g_outn.as<uint32_t>(); sa.status = pa.status; sa.any_bad = d_flag;
+    {
+      const double n = (double)std::max<uint64_t>(b->max_group_len, 1);
+      const double est = std::min(4.0 * (n * frac) + 16.0, n) * 1.001;  // (the device plans in single precision)
+      const uint32_t want = (uint32_t)std::min<uint64_t>(16384, skb_next_pow2((uint64_t)std::max(32.0, est)));
+      if (want <= 256) { sa.threads = 32; sa.smem_elems = 256; }
+      else if (want <= 2048) { sa.threads = 256; sa.smem_elems = want; }
+      else { sa.threads = 512; sa.smem_elems = want; }
+    }
+    { ProfScope ps(c, SKB_K_SELECT, 1); skb_launch_select(sa, c->stream); }
+    if (int rc = check_launch(c, "select")) return rc;
+    uint32_t* h = c->h_outn.as<uint32_t>();
+    CU(c, cudaMemcpyAsync(h, c->g_outn.p, (size_t)G * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(h + G, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (h[G] == 0) {
+      std::memcpy(h_out_n.data(), h, (size_t)G * 4);
+      return SKB_OK;
+    }
+  }
   uint64_t pool = 0;
   for (uint32_t g = 0; g < G; ++g) {
     const double n = (double)std::max<uint64_t>(b->g_packed[g], 1);
@@ -629,7 +731,7 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   }
   // contiguous row ranges per CTA, balanced by ring tiles (a row costs at least one unit: its rank work)
   {
-    const uint32_t G = (uint32_t)c->num_sms, tile = skb_fused_tile();
+    const uint32_t G = (uint32_t)c->stream_ctas, tile = skb_fused_tile();
     std::vector<uint64_t> cum(n_rows + 1, 0);
     for (uint32_t i = 0; i < n_rows; ++i) cum[i + 1] = cum[i] + std::max<uint64_t>(1, (rlen[i] + tile - 1) / tile);
     std::vector<uint32_t> cta(G + 1, n_rows);
@@ -658,6 +760,8 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   c->tracked_cur = 0;
   CU(c, cudaStreamSynchronize(c->stream));
   c->has_ref = true;
+  c->tau_all_valid = false;
+  choose_pass_max(c);
   return SKB_OK;
 }
 
@@ -675,7 +779,8 @@ struct QuerySet {
 constexpr uint32_t kMaxPieceKeys = 65535;
 
 // qn_reads[i] = query hashes of caller read i (already on the device, compacted read after read in c->qh)
-int finish_query_set(skb_ctx* c, const std::vector<uint32_t>& qn_reads, QuerySet& qs) {
+// offsets_on_device: c->q_off already holds the offsets of the unsplit reads (the caller uploaded them)
+int finish_query_set(skb_ctx* c, const std::vector<uint32_t>& qn_reads, QuerySet& qs, bool offsets_on_device = false) {
   const uint32_t n = (uint32_t)qn_reads.size();
   bool split = false;
   for (uint32_t v : qn_reads) split = split || v > kMaxPieceKeys;
@@ -697,9 +802,14 @@ int finish_query_set(skb_ctx* c, const std::vector<uint32_t>& qn_reads, QuerySet
   for (uint32_t r = 0; r < qs.R; ++r) qs.q_off[r + 1] = qs.q_off[r] + qs.qn[r];
   const uint64_t QN = qs.q_off[qs.R];
   c->st_qhashes = QN;
-  CU(c, c->q_off.ensure(((size_t)qs.R + 1) * 8));
   CU(c, c->qread.ensure(std::max<uint64_t>(QN, 1) * 4));
-  CU(c, cudaMemcpyAsync(c->q_off.p, qs.q_off.data(), ((size_t)qs.R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  if (split || !offsets_on_device) {
+    CU(c, c->q_off.ensure(((size_t)qs.R + 1) * 8));
+    CU(c, cudaStreamSynchronize(c->stream));  // (an earlier copy out of the staging buffer may still be in flight)
+    CU(c, c->h_off.ensure(((size_t)qs.R + 1) * 8, 0));
+    std::memcpy(c->h_off.p, qs.q_off.data(), ((size_t)qs.R + 1) * 8);
+    CU(c, cudaMemcpyAsync(c->q_off.p, c->h_off.p, ((size_t)qs.R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  }
   { ProfScope ps(c, SKB_K_SELECT, 1);
     skb_launch_fill_qread(c->q_off.as<uint64_t>(), qs.R, c->qread.as<uint32_t>(), c->stream); }
   return check_launch(c, "fill_qread");
@@ -737,7 +847,7 @@ int run_passes_reported(skb_ctx* c, const QuerySet& qs, uint32_t n_reads, uint32
 int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top, int pad,
                    uint32_t* d_out_idx, uint64_t* d_out_sum) {
   if (int rc = predict_checks(c, k, s_query, top, pad)) return rc;
-  if (int rc = stage_batch(b)) return rc;
+  if (int rc = use_batch(b)) return rc;
   const uint32_t R = (uint32_t)b->g_first.size();
   c->st_passes = 0; c->st_qhashes = 0; c->st_cands = 0; c->st_ref_bytes = c->ref_len * 8;
   if (R == 0) return SKB_OK;
@@ -756,18 +866,19 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   for (uint32_t v : qn) QN += v;
   CU(c, c->qh.ensure(std::max<uint64_t>(QN, 1) * 8));
   {
-    std::vector<uint64_t> off(R + 1, 0);
+    CU(c, c->h_off.ensure(((size_t)R + 1) * 8, 0));  // page-locked; rewritten by the next call only, which starts after this one has synchronised
+    uint64_t* off = c->h_off.as<uint64_t>();
+    off[0] = 0;
     for (uint32_t r = 0; r < R; ++r) off[r + 1] = off[r] + qn[r];
     CU(c, c->q_off.ensure(((size_t)R + 1) * 8));
-    CU(c, cudaMemcpyAsync(c->q_off.p, off.data(), ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->q_off.p, off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     ProfScope ps(c, SKB_K_SELECT, 1);
     skb_launch_compact_queries(c->cand_pool.as<uint64_t>(), c->g_base.as<uint64_t>(), c->g_outn.as<uint32_t>(), c->q_off.as<uint64_t>(),
                                R, c->qh.as<uint64_t>(), c->stream);
-    CU(c, cudaStreamSynchronize(c->stream));  // `off` is a local: the copy must have read it
   }
   if (int rc = check_launch(c, "compact")) return rc;
   QuerySet qs;
-  if (int rc = finish_query_set(c, qn, qs)) return rc;
+  if (int rc = finish_query_set(c, qn, qs, true)) return rc;
   return run_passes_reported(c, qs, R, top, d_out_idx, d_out_sum);
 }
 
@@ -930,7 +1041,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     // ---- stream(i) on the main stream
     cudaStreamWaitEvent(c->stream, c->ev_pre[tab], 0);
     SkbFusedArgs fa{};
-    fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->num_sms; fa.table = t;
+    fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->stream_ctas; fa.table = t;
     fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
     fa.rowbuf = skb_fused_rowbuf(stride, fa.narrow); fa.rowbuf_log2 = fa.rowbuf == 8 ? 3 : 2;
     fa.sums_in = c->sums[s_in].as<unsigned long long>(); fa.sums_out = c->sums[s_out].as<unsigned long long>();
@@ -1064,7 +1175,7 @@ int predict_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t
   }
   if (int rc = predict_checks(c, k, s_query, top, 1)) return rc;
   if (reads_total > 0xFFFFFFF0ull) return fail(c, SKB_ERR_INVALID_ARG, "too many reads in one call");
-  if (int rc = stage_batch(b)) return rc;
+  if (int rc = use_batch(b)) return rc;
   const int W = c->world;
   const uint32_t R = (uint32_t)reads_total, R_loc = (uint32_t)b->g_first.size();
   uint64_t my_begin = 0, my_count = 0;
@@ -1075,16 +1186,21 @@ int predict_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t
   c->st_passes = 0; c->st_qhashes = 0; c->st_cands = 0; c->st_ref_bytes = c->ref_len * 8;
   if (R == 0) return SKB_OK;
   const uint32_t Rmax = (R + W - 1) / W;
-  // ---- the largest reference hash of any shard
-  CU(c, c->hmax_all.ensure((size_t)W * 8));
-  unsigned long long* d_hmax = c->hmax_all.as<unsigned long long>();
-  unsigned long long my_hmax = c->n_rows ? c->hmax : 0ull;
-  CU(c, cudaMemcpyAsync(d_hmax + c->rank, &my_hmax, 8, cudaMemcpyHostToDevice, c->stream));
-  NC(c, g_nccl.AllGather(d_hmax + c->rank, d_hmax, 1, ncclUint64, c->comm, c->stream));
-  std::vector<unsigned long long> hm(W);
-  CU(c, cudaMemcpyAsync(hm.data(), d_hmax, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  const uint64_t tau = *std::max_element(hm.begin(), hm.end());
+  // ---- the largest reference hash of any shard: exchanged once per (communicator, upload) — uploading a shard is
+  // collective in this sense: every rank uploads before the next collective predict
+  if (!c->tau_all_valid) {
+    CU(c, c->hmax_all.ensure((size_t)W * 8));
+    unsigned long long* d_hmax = c->hmax_all.as<unsigned long long>();
+    unsigned long long my_hmax = c->n_rows ? c->hmax : 0ull;
+    CU(c, cudaMemcpyAsync(d_hmax + c->rank, &my_hmax, 8, cudaMemcpyHostToDevice, c->stream));
+    NC(c, g_nccl.AllGather(d_hmax + c->rank, d_hmax, 1, ncclUint64, c->comm, c->stream));
+    std::vector<unsigned long long> hm(W);
+    CU(c, cudaMemcpyAsync(hm.data(), d_hmax, (size_t)W * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->tau_all = *std::max_element(hm.begin(), hm.end());
+    c->tau_all_valid = true;
+  }
+  const uint64_t tau = c->tau_all;
   // ---- this rank's reads: query lists
   std::vector<uint32_t> qn_loc;
   std::vector<uint64_t> kmers;
@@ -1174,6 +1290,8 @@ int skb_create(int device, skb_ctx** out) {
   skb_ctx* c = new skb_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  c->stream_ctas = c->num_sms;
+  if (const char* e = getenv("SKB_STREAM_CTAS")) c->stream_ctas = std::max(1, std::min(c->num_sms, atoi(e)));  // experiments
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1197,7 +1315,7 @@ void skb_destroy(skb_ctx* c) {
   if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   std::vector<DevBuf*> bufs = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->tile_cum, &c->memb, &c->tprefix, &c->textra,
-                               &c->g_tau, &c->g_cap, &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status,
+                               &c->g_tau, &c->g_cap, &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->g_tiles,
                                &c->cand_pool, &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->scal,
                                &c->out_idx, &c->out_sum, &c->misc, &c->dense, &c->part_idx, &c->part_sum, &c->piece_idx, &c->piece_sum, &c->piece_row, &c->qn_all, &c->gath_idx, &c->gath_sum, &c->hmax_all};
   for (auto& x : c->sums) bufs.push_back(&x);
@@ -1207,6 +1325,7 @@ void skb_destroy(skb_ctx* c) {
   for (int i = 0; i < 2; ++i)
     for (DevBuf* x : {&c->cand[i], &c->cand_cnt[i], &c->ivl[i], &c->seg_hdr[i], &c->seg_words[i]}) bufs.push_back(x);
   for (DevBuf* b : bufs) b->release();
+  c->h_outn.release(); c->h_off.release();
   if (c->h_scal) cudaFreeHost(c->h_scal);
   cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1238,13 +1357,19 @@ int skb_batch_create(skb_ctx* c, skb_batch** out) {
 void skb_batch_destroy(skb_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
+  if (b->ev_staged) { cudaEventSynchronize(b->ev_staged); cudaEventDestroy(b->ev_staged); }
   b->codes.release(); b->nmask.release();
-  b->d_codes.release(); b->d_nmask.release(); b->d_seg_group.release(); b->d_seg_chunk0.release(); b->d_seg_n.release();
+  b->h_seg_group.release(); b->h_seg_chunk0.release(); b->h_seg_n.release(); b->h_g_len.release();
+  b->d_codes.release(); b->d_nmask.release(); b->d_seg_group.release(); b->d_seg_chunk0.release(); b->d_seg_n.release(); b->d_g_len.release();
   delete b;
 }
 
 int skb_batch_clear(skb_batch* b) {
   if (!b) return SKB_ERR_INVALID_ARG;
+  if (b->staged && b->ev_staged) {  // the page-locked buffers are about to be rewritten: their copies must be over
+    cudaSetDevice(b->ctx->device);
+    cudaEventSynchronize(b->ev_staged);
+  }
   b->cur = 0; b->rec_pos.clear(); b->rec_len.clear();
   b->g_first.clear(); b->g_end.clear(); b->g_raw.clear(); b->g_packed.clear();
   b->total_raw = 0; b->staged = false; b->nseg = 0;
@@ -1346,7 +1471,7 @@ int skb_sketch(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s, uint64_t seed, 
   const uint32_t G = (uint32_t)b->g_first.size();
   if (G == 0) return SKB_OK;
   if (!out_hashes || !out_n) return fail(c, SKB_ERR_INVALID_ARG, "null output");
-  if (int rc = stage_batch(b)) return rc;
+  if (int rc = use_batch(b)) return rc;
   CU(c, c->sk_hashes.ensure((size_t)G * s * 8));
   CU(c, c->sk_counts.ensure((size_t)G * s * 4));
   std::vector<uint32_t> n;
@@ -1429,6 +1554,7 @@ int skb_comm_init(skb_ctx* c, const uint8_t* id, int rank, int world) {
   std::memcpy(&u, id, sizeof u);
   NC(c, g_nccl.CommInitRank(&c->comm, world, u, rank));
   c->rank = rank; c->world = world;
+  c->tau_all_valid = false;
   return SKB_OK;
 }
 
@@ -1528,10 +1654,12 @@ int skb_set_rank_mode(skb_ctx* c, int mode) {
 
 int skb_set_pass_reads(skb_ctx* c, uint32_t m) {
   if (!c) return SKB_ERR_INVALID_ARG;
-  c->pass_max = m ? std::min<uint32_t>(m, skb_fused_max_reads(1)) : SKB_DEFAULT_PASS_READS;
+  c->pass_user = m;
+  choose_pass_max(c);
   c->pass_proven = false;
   return SKB_OK;
 }
+uint32_t skb_pass_reads(const skb_ctx* c) { return c ? c->pass_max : 0; }
 
 // ---- shared / rank ----------------------------------------------------------------------------------------
 int skb_shared_counts(skb_ctx* c, const uint64_t* q_hashes, const uint64_t* q_off, uint32_t Q, uint64_t* out) {
@@ -1647,7 +1775,7 @@ int skb_debug_kmer_hashes(skb_ctx* c, skb_batch* b, uint32_t k, uint64_t seed, u
   if (!c || !b || b->ctx != c || !out_hash || !out_valid) return SKB_ERR_INVALID_ARG;
   cudaSetDevice(c->device);
   if (k < 1 || k > SKB_MAX_K) return fail(c, SKB_ERR_UNSUPPORTED_K, "k=%u unsupported (1..%d)", k, SKB_MAX_K);
-  if (int rc = stage_batch(b)) return rc;
+  if (int rc = use_batch(b)) return rc;
   const uint64_t n = b->cur;
   if (n == 0) return SKB_OK;
   DevBuf dh, dv;

@@ -39,8 +39,29 @@ struct SkbSelectArgs {
   uint32_t* status;         // [G]
   uint32_t threads;         // block size (32..1024, power of two)
   uint32_t smem_elems;      // power of two; sort happens in shared memory when the group fits
+  uint32_t* any_bad;        // [1] or null: set when a group ends with a status other than SKB_ST_OK
 };
 void skb_launch_select(const SkbSelectArgs& a, cudaStream_t st);
+
+// Query-mode plan on the device (one threshold for every group): candidate capacity of a group from its length
+// (4 x the expected number of hashes <= tau, + 16, a power of two >= 32, at most the length), the groups' places in the
+// pool (exclusive scan), and the per-group scratch of hash_kernel / select_kernel reset. Two launches.
+struct SkbPlanArgs {
+  uint32_t n_groups;
+  const uint64_t* g_len;  // [G] bases per group
+  uint64_t tau;
+  double frac;            // (tau + 1) / 2^64
+  uint64_t* tau_out;      // [G]
+  uint64_t* base;         // [G]
+  uint32_t* cap;          // [G]
+  uint32_t* cnt;          // [G] = 0
+  unsigned long long* kmers;  // [G] = 0
+  uint8_t* active;        // [G] = 1
+  uint32_t* status;       // [G] = 0
+  uint32_t* any_bad;      // [1] = 0
+  unsigned long long* tile_tot;  // [ceil(G / 1024)] scratch: capacity totals of the tiles of 1024 groups
+};
+void skb_launch_plan_query(const SkbPlanArgs& a, cudaStream_t st);
 
 // predict: gather every read's selected hashes into one flat list (read after read, at q_off[read])
 void skb_launch_compact_queries(const uint64_t* cand, const uint64_t* cand_base, const uint32_t* out_n,

@@ -320,7 +320,10 @@ __global__ void select_kernel(const SkbSelectArgs a) {
   if (a.active && !a.active[g]) return;
   const uint32_t cnt = a.cand_cnt[g], cap = a.cand_cap[g];
   if (cnt > cap) {
-    if (threadIdx.x == 0) { a.status[g] = SKB_ST_OVERFLOW; a.out_n[g] = 0; }
+    if (threadIdx.x == 0) {
+      a.status[g] = SKB_ST_OVERFLOW; a.out_n[g] = 0;
+      if (a.any_bad) atomicOr(a.any_bad, 1u);
+    }
     return;
   }
   uint64_t* gbuf = a.cand + a.cand_base[g];
@@ -379,8 +382,62 @@ __global__ void select_kernel(const SkbSelectArgs a) {
   }
   if (threadIdx.x == 0) {
     a.out_n[g] = n_out;
-    a.status[g] = (a.check_underfill && distinct < a.s && a.tau[g] != SKB_EMPTY_KEY) ? SKB_ST_UNDERFILL : SKB_ST_OK;
+    const uint32_t st = (a.check_underfill && distinct < a.s && a.tau[g] != SKB_EMPTY_KEY) ? SKB_ST_UNDERFILL : SKB_ST_OK;
+    a.status[g] = st;
+    if (a.any_bad && st != SKB_ST_OK) atomicOr(a.any_bad, 1u);
   }
+}
+
+// block-wide sum of one value per thread (1024 threads)
+__device__ __forceinline__ unsigned long long cta_sum_u64(unsigned long long v, unsigned long long* warp_tot) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (skb_lane() == 0) warp_tot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned long long t = 0;
+  for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) t += warp_tot[w];
+  __syncthreads();
+  return t;
+}
+
+// plan, first launch: one CTA per tile of 1024 groups. Capacities, the tile's total, the per-group scratch reset.
+__global__ void __launch_bounds__(1024) plan_caps_kernel(const SkbPlanArgs a) {
+  __shared__ unsigned long long warp_tot[32];
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cap = 0;
+  if (g < a.n_groups) {
+    const float n = fmaxf((float)a.g_len[g], 1.0f);
+    const float est = fminf(4.0f * (n * (float)a.frac) + 16.0f, n);  // (single precision: a capacity plan, not a result)
+    cap = 32;
+    while ((float)cap < est && cap < 0x80000000u) cap <<= 1;
+    a.cap[g] = cap;
+    a.tau_out[g] = a.tau;
+    a.cnt[g] = 0; a.kmers[g] = 0; a.active[g] = 1; a.status[g] = 0;
+  }
+  const unsigned long long tot = cta_sum_u64(cap, warp_tot);
+  if (threadIdx.x == 0) a.tile_tot[blockIdx.x] = tot;
+  if (g == 0) *a.any_bad = 0;
+}
+
+// plan, second launch: every group's place in the pool = the totals of the tiles before its own + an exclusive scan
+// within the tile.
+__global__ void __launch_bounds__(1024) plan_bases_kernel(const SkbPlanArgs a) {
+  __shared__ unsigned long long warp_tot[32];
+  unsigned long long before = 0;
+  for (uint32_t t = threadIdx.x; t < blockIdx.x; t += blockDim.x) before += a.tile_tot[t];
+  before = cta_sum_u64(before, warp_tot);
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, lane = skb_lane(), wid = threadIdx.x >> 5;
+  const uint32_t cap = g < a.n_groups ? a.cap[g] : 0u;
+  unsigned long long incl = cap;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)lane >= o) incl += y;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  for (uint32_t w = 0; w < wid; ++w) before += warp_tot[w];
+  if (g < a.n_groups) a.base[g] = before + incl - cap;
 }
 
 __global__ void compact_queries_kernel(const uint64_t* __restrict__ cand, const uint64_t* __restrict__ cand_base,
@@ -437,6 +494,13 @@ void skb_launch_select(const SkbSelectArgs& a, cudaStream_t st) {
   if (smem > 48 * 1024 && opt_in.needs(smem))
     cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   select_kernel<<<a.n_groups, a.threads, smem, st>>>(a);
+}
+
+void skb_launch_plan_query(const SkbPlanArgs& a, cudaStream_t st) {
+  if (a.n_groups == 0) return;
+  const unsigned tiles = (a.n_groups + 1023) / 1024;
+  plan_caps_kernel<<<tiles, 1024, 0, st>>>(a);
+  plan_bases_kernel<<<tiles, 1024, 0, st>>>(a);
 }
 
 void skb_launch_compact_queries(const uint64_t* cand, const uint64_t* cand_base, const uint32_t* out_n,

@@ -100,3 +100,19 @@ def test_avx2_block_packer_matches_the_bytewise_rule():
         t = s.copy()
         t[32 * 7 + 5] = ws
         assert fn(t.ctypes.data, t.size, codes.ctypes.data, mask.ctypes.data) == 32 * 7
+    # every byte value, at every position of a block
+    for v in range(256):
+        for pos in (v % 32, (v * 7 + 3) % 32):
+            blk = np.full(32, ord("G"), dtype=np.uint8)
+            blk[pos] = v
+            c2 = np.zeros(2, dtype=np.uint32)
+            m2 = np.zeros(1, dtype=np.uint32)
+            n = fn(blk.ctypes.data, 32, c2.ctypes.data, m2.ctypes.data)
+            if v in b" \t\r\n":
+                assert n == 0, v
+                continue
+            assert n == 32, v
+            exp = [0xAAAAAAAA, 0xAAAAAAAA]
+            exp[pos // 16] = (exp[pos // 16] & ~(3 << (2 * (pos % 16)))) | (code_of.get(v, 0) << (2 * (pos % 16)))
+            assert [int(c2[0]), int(c2[1])] == exp, v
+            assert int(m2[0]) == (0 if v in code_of else 1 << pos), v
