@@ -200,6 +200,7 @@ struct ProfEvent { int id; cudaEvent_t a, b; };
 #define SKB_DEFAULT_PASS_READS 4096u
 #define SKB_SMALL_SHARD_BYTES (2ull << 30)
 #define SKB_PASS_KEY_BUDGET (1ull << 18)  // query hashes per pass before the membership prefilter (which typically drops more than half of them; the 2^19-bit filter is designed for ~2^17 keys at three bits each)
+constexpr uint32_t kAnchorGroups = 64;   // row groups of the dense ranking's anchor launch (every 64th read)
 #define SKB_NSUMS 4
 #define SKB_NTRACK 3
 #define SKB_NTAB 3
@@ -231,7 +232,8 @@ struct skb_ctx {
   bool pass_proven = false;     // a full-size sparse pass has been checked and did not overflow: batch them
   int rank_mode = 0;            // skb_set_rank_mode
   uint32_t dense_left = 0;      // upcoming passes that are ranked densely (bounds too loose to be worth candidates)
-  DevBuf dense, part_idx, part_sum, piece_idx, piece_sum, piece_row;
+  uint32_t dense_after_reset = 0;  // dense passes after the first one of a reset (measured: the bounds from the first pass's tracked rows hold, no second dense pass is needed; SKB_DENSE_AFTER_RESET: experiments)
+  DevBuf dense, part_idx, part_sum, anch_part_idx, anch_part_sum, anch_idx, anch_sum, piece_idx, piece_sum, piece_row;
   bool pipeline = false;        // steady-state passes take their bounds from two passes back (pre-pass work enqueued next to the stream)
   // multi-GPU: one process per GPU, reference rows sharded by contiguous range, NCCL over NVLink for the exchange steps
   ncclComm_t comm = nullptr;
@@ -755,7 +757,7 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
   c->sums_cur = 0;
   c->tracked_top = 0;
   c->pass_proven = false;
-  c->dense_left = 1;  // the pass after the first (always dense) one: the tracked rows of a few thousand reads bound little
+  c->dense_left = c->dense_after_reset;  // passes after the first (always dense) one that are ranked densely too
   for (int i = 0; i < SKB_NTRACK; ++i) CU(c, c->tracked[i].ensure((SKB_MAX_TRACKED + 1) * 4));
   c->tracked_cur = 0;
   CU(c, cudaStreamSynchronize(c->stream));
@@ -922,6 +924,13 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     need(c->dense, (size_t)c->n_rows * std::max<size_t>((size_t)stride_max * 2, (size_t)std::min<uint32_t>(stride_max, skb_fused_max_reads(0)) * 4));
     need(c->part_idx, (size_t)groups_max * Bmax * top * 4);
     need(c->part_sum, (size_t)groups_max * Bmax * top * 8);
+    {
+      const size_t n_anchor = (Bmax + 63) / 64;
+      need(c->anch_part_idx, (size_t)kAnchorGroups * n_anchor * top * 4);
+      need(c->anch_part_sum, (size_t)kAnchorGroups * n_anchor * top * 8);
+      need(c->anch_idx, n_anchor * top * 4);
+      need(c->anch_sum, n_anchor * top * 8);
+    }
     if (e != cudaSuccess) return fail(c, SKB_ERR_OOM, "pass buffers: %s", cudaGetErrorString(e));
     for (int i = 0; i < 2; ++i) CU(c, cudaMemsetAsync(c->cand_cnt[i].p, 0, (size_t)Bmax * 4, c->stream));  // (a pass's last kernel clears them again)
     const uint64_t key_budget = SKB_PASS_KEY_BUDGET;
@@ -960,7 +969,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     if (!post.on) return;
     cudaStreamWaitEvent(c->side, c->ev_fused[post.fused_ev], 0);
     if (post.dense) {
-      ProfScope ps(c, SKB_K_RANK, 3, c->side);
+      ProfScope ps(c, SKB_K_RANK, 5, c->side);
       skb_launch_dense_topk(post.da, c->side);
       skb_launch_merge_topn(post.da.part_idx, post.da.part_sum, post.da.groups, post.da.n_reads, top, post.ra.out_idx, post.ra.out_sum, c->side);
       skb_launch_verdict_update(post.ra, false, c->side);
@@ -1065,6 +1074,9 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       da.groups = std::max<uint32_t>(1, std::min<uint32_t>(groups_max, (uint32_t)((8ull * c->num_sms * 64 + B - 1) / B)));
       da.sums_in = fa.sums_in; da.sums_out = fa.sums_out;
       da.part_idx = c->part_idx.as<uint32_t>(); da.part_sum = c->part_sum.as<unsigned long long>();
+      da.anchor_groups = kAnchorGroups;
+      da.anchor_part_idx = c->anch_part_idx.as<uint32_t>(); da.anchor_part_sum = c->anch_part_sum.as<unsigned long long>();
+      da.anchor_idx = c->anch_idx.as<uint32_t>(); da.anchor_sum = c->anch_sum.as<unsigned long long>();
       post.da = da;
     }
     recs.push_back({r, B, s_in, c->tracked_cur, full});
@@ -1299,6 +1311,7 @@ int skb_create(int device, skb_ctx** out) {
   for (int i = 0; ok && i < SKB_NTAB; ++i) ok = cudaEventCreateWithFlags(&c->ev_pre[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&c->ev_fused[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { delete c; return SKB_ERR_CUDA; }
+  if (const char* e = getenv("SKB_DENSE_AFTER_RESET")) c->dense_after_reset = (uint32_t)atoi(e);
   if (const char* e = getenv("SKB_PIPELINE")) c->pipeline = e[0] != '0';  // experiments: 0 = every pass waits for the one before
   if (cudaHostAlloc((void**)&c->h_scal, 64, cudaHostAllocDefault) != cudaSuccess) {
     cudaStreamDestroy(c->stream); delete c; return SKB_ERR_OOM;
@@ -1317,7 +1330,7 @@ void skb_destroy(skb_ctx* c) {
   std::vector<DevBuf*> bufs = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->tile_cum, &c->memb, &c->tprefix, &c->textra,
                                &c->g_tau, &c->g_cap, &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->g_tiles,
                                &c->cand_pool, &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->scal,
-                               &c->out_idx, &c->out_sum, &c->misc, &c->dense, &c->part_idx, &c->part_sum, &c->piece_idx, &c->piece_sum, &c->piece_row, &c->qn_all, &c->gath_idx, &c->gath_sum, &c->hmax_all};
+                               &c->out_idx, &c->out_sum, &c->misc, &c->dense, &c->part_idx, &c->part_sum, &c->anch_part_idx, &c->anch_part_sum, &c->anch_idx, &c->anch_sum, &c->piece_idx, &c->piece_sum, &c->piece_row, &c->qn_all, &c->gath_idx, &c->gath_sum, &c->hmax_all};
   for (auto& x : c->sums) bufs.push_back(&x);
   for (auto& x : c->tracked) bufs.push_back(&x);
   for (int i = 0; i < SKB_NTAB; ++i)
@@ -1620,7 +1633,7 @@ int skb_sums_reset(skb_ctx* c) {
   CU(c, cudaMemsetAsync(c->sums[c->sums_cur].p, 0, std::max<size_t>(8, (size_t)c->n_rows * 8), c->stream));
   c->tracked_top = 0;
   c->pass_proven = false;
-  c->dense_left = 1;  // the pass after the first (always dense) one: the tracked rows of a few thousand reads bound little
+  c->dense_left = c->dense_after_reset;  // passes after the first (always dense) one that are ranked densely too
   return SKB_OK;
 }
 
@@ -1641,7 +1654,7 @@ int skb_sums_upload(skb_ctx* c, const uint64_t* in) {
   CU(c, cudaStreamSynchronize(c->stream));
   c->tracked_top = 0;
   c->pass_proven = false;
-  c->dense_left = 1;
+  c->dense_left = c->dense_after_reset;
   return SKB_OK;
 }
 

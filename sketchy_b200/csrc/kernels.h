@@ -230,6 +230,16 @@ struct SkbDenseArgs {
   const unsigned long long* sums_out;  // [n_rows] after the pass (== sums_in: the row had no hit, its vector is all zero)
   uint32_t* part_idx;                  // [groups][n_reads][top]
   unsigned long long* part_sum;
+  // top <= 32: the exact lists of every 64th read are made first and give the other reads their starting thresholds
+  uint32_t anchor_groups;              // row groups of the anchor launch
+  uint32_t* anchor_part_idx;           // [anchor_groups][ceil(n_reads / 64)][top]; null = no anchor launch
+  unsigned long long* anchor_part_sum;
+  uint32_t* anchor_idx;                // [ceil(n_reads / 64)][top] merged
+  unsigned long long* anchor_sum;
+  // set by the launcher:
+  uint32_t col_stride;                 // column c of the kernel = read c * col_stride
+  const unsigned long long* thr_sum;   // starting threshold of CTA x = entry [x * top + top - 1] (or null)
+  const uint32_t* thr_idx;
 };
 void skb_launch_dense_topk(const SkbDenseArgs& a, cudaStream_t st);
 

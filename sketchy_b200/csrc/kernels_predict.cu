@@ -1073,35 +1073,59 @@ __global__ void __launch_bounds__(128) dense_topk_kernel(const SkbDenseArgs a) {
   }
 }
 
-// Dense ranking for top <= 32, the fast form: a CTA takes 64 consecutive reads and one group of rows; row tiles of
-// 32 rows x 64 reads are staged in shared memory (coalesced row segments), then every warp ranks its 8 reads with one
-// lane per row of the tile. The `top` best rows of a read so far live across the warp's lanes (lane t holds the t-th
-// best); a row enters only when it beats the current top-th entry (a ballot: almost always empty once the list has
-// warmed up), by a shuffle-insert. Same order as above: rows arrive in increasing index and must be strictly better.
+// Dense ranking for top <= 32, the fast form: a CTA takes 64 consecutive columns and one group of rows; row tiles of
+// 32 rows x 64 columns are staged in shared memory (coalesced row segments), then every warp ranks its 8 columns with
+// one lane per row of the tile. The `top` best rows of a column so far live across the warp's lanes (lane t holds the
+// t-th best); a row enters only when it beats the column's threshold (a ballot: almost always empty once the list has
+// warmed up), by a shuffle-insert. Whole keys are compared, so the order of the rows does not matter.
+// Two launches per pass (skb_launch_dense_topk):
+//   anchors  column c = read 64 c (col_stride 64): the exact top lists of every 64th read, over many small row groups.
+//   reads    column c = read c: the top-th key of the anchor read of a CTA's 64 reads is a lower bound of the top-th
+//            key of each of them (sums never decrease along the reads), so the lists start with that threshold and
+//            only the handful of rows that reach it are ever inserted. Without it every (read, row group) list warms
+//            up on its own, about top * ln(rows / top) insertions each: 80 % of the kernel's instructions.
 template <typename P>
 __global__ void __launch_bounds__(256) dense_topk_warp_kernel(const SkbDenseArgs a) {
-  constexpr int PADW = sizeof(P) == 2 ? 33 : 65;  // 32-bit words per tile row: 64 reads + one word of padding (no bank conflicts)
+  constexpr int PADW = sizeof(P) == 2 ? 33 : 65;  // 32-bit words per tile row: 64 columns + one word of padding (no bank conflicts)
   __shared__ uint32_t tile[32 * PADW];
   const uint32_t b0 = blockIdx.x * 64, g = blockIdx.y;
   const uint32_t r_lo = (uint32_t)(((uint64_t)a.n_rows * g) / gridDim.y), r_hi = (uint32_t)(((uint64_t)a.n_rows * (g + 1)) / gridDim.y);
   const uint32_t warp = threadIdx.x >> 5, lane = skb_lane(), top = a.top;
+  const uint32_t n_cols = a.col_stride == 1 ? a.n_reads : (a.n_reads + a.col_stride - 1) / a.col_stride;
   unsigned long long ks[8], thr_s[8];
   uint32_t ki[8], thr_i[8];
+  unsigned long long t0s = 0;
+  uint32_t t0i = 0xFFFFFFFFu;
+  if (a.thr_sum) {  // "at least as good as the anchor's top-th key (s, i)" == "better than (s, i + 1)"
+    const uint32_t i = a.thr_idx[(size_t)blockIdx.x * top + top - 1];
+    if (i != 0xFFFFFFFFu) { t0s = a.thr_sum[(size_t)blockIdx.x * top + top - 1]; t0i = i + 1u; }
+  }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { ks[j] = 0; ki[j] = 0xFFFFFFFFu; thr_s[j] = 0; thr_i[j] = 0xFFFFFFFFu; }
-  const uint32_t lrow = threadIdx.x >> 3, lcol = (threadIdx.x & 7u) * 8;  // tile loader: 8 threads per row, 8 reads each
+  for (int j = 0; j < 8; ++j) { ks[j] = 0; ki[j] = 0xFFFFFFFFu; thr_s[j] = t0s; thr_i[j] = t0i; }
+  const uint32_t lrow = threadIdx.x >> 3, lcol = (threadIdx.x & 7u) * 8;  // tile loader: 8 threads per row, 8 columns each
   for (uint32_t r0 = r_lo; r0 < r_hi; r0 += 32) {
     __syncthreads();  // the previous tile has been consumed
     {
       const uint32_t row = r0 + lrow;
       uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 8 values: 4 words (u16) or 8 words (u32)
       if (row < r_hi && a.sums_out[row] != a.sums_in[row]) {  // (a row without a hit in the pass: all zero, never written)
-        const P* src = reinterpret_cast<const P*>(a.dense) + (size_t)row * a.cnt_stride + b0 + lcol;
-        const uint4 x = *reinterpret_cast<const uint4*>(src);
-        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
-        if (sizeof(P) == 4) {
-          const uint4 y = *reinterpret_cast<const uint4*>(src + 4);
-          w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+        if (a.col_stride == 1) {
+          const P* src = reinterpret_cast<const P*>(a.dense) + (size_t)row * a.cnt_stride + b0 + lcol;
+          const uint4 x = *reinterpret_cast<const uint4*>(src);
+          w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+          if (sizeof(P) == 4) {
+            const uint4 y = *reinterpret_cast<const uint4*>(src + 4);
+            w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+          }
+        } else {  // gather: one value per column
+          const P* src = reinterpret_cast<const P*>(a.dense) + (size_t)row * a.cnt_stride;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t c = b0 + lcol + q;
+            const uint32_t v = c < n_cols ? (uint32_t)src[(size_t)c * a.col_stride] : 0u;
+            if (sizeof(P) == 2) w[q >> 1] |= v << (16 * (q & 1));
+            else w[q] = v;
+          }
         }
       }
       uint32_t* dst = tile + lrow * PADW + lcol * sizeof(P) / 4;
@@ -1116,7 +1140,7 @@ __global__ void __launch_bounds__(256) dense_topk_warp_kernel(const SkbDenseArgs
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t col = warp * 8 + j;
-      if (b0 + col >= a.n_reads) break;
+      if (b0 + col >= n_cols) break;
       uint32_t pv;
       if (sizeof(P) == 2) pv = (tile[lane * PADW + (col >> 1)] >> (16 * (col & 1u))) & 0xFFFFu;
       else pv = tile[lane * PADW + col];
@@ -1133,16 +1157,18 @@ __global__ void __launch_bounds__(256) dense_topk_warp_kernel(const SkbDenseArgs
         const uint32_t ui = __shfl_up_sync(0xffffffffu, ki[j], 1);
         if (lane > pos) { ks[j] = us; ki[j] = ui; }
         else if (lane == pos) { ks[j] = cs; ki[j] = ci; }
-        thr_s[j] = __shfl_sync(0xffffffffu, ks[j], top - 1);
-        thr_i[j] = __shfl_sync(0xffffffffu, ki[j], top - 1);
+        // the list's top-th entry once the list is full; never below the threshold the list started with
+        const unsigned long long ns = __shfl_sync(0xffffffffu, ks[j], top - 1);
+        const uint32_t ni = __shfl_sync(0xffffffffu, ki[j], top - 1);
+        if (skb_key_better(ns, ni, thr_s[j], thr_i[j])) { thr_s[j] = ns; thr_i[j] = ni; }
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint32_t b = b0 + warp * 8 + j;
-    if (b < a.n_reads && lane < top) {
-      const size_t o = ((size_t)g * a.n_reads + b) * top + lane;
+    if (b < n_cols && lane < top) {
+      const size_t o = ((size_t)g * n_cols + b) * top + lane;
       a.part_sum[o] = ks[j];
       a.part_idx[o] = ki[j];
     }
@@ -1318,9 +1344,24 @@ void skb_launch_rank_full(const unsigned long long* vals, uint32_t n, uint32_t t
 void skb_launch_dense_topk(const SkbDenseArgs& a, cudaStream_t st) {
   if (a.n_reads == 0 || a.groups == 0) return;
   if (a.top <= 32) {
+    SkbDenseArgs r = a;
+    r.col_stride = 1; r.thr_sum = nullptr; r.thr_idx = nullptr;
+    if (a.anchor_idx && a.n_reads > 64) {
+      // every 64th read first, over small row groups (enough CTAs for the few columns), merged into exact top lists
+      SkbDenseArgs an = a;
+      const uint32_t n_anchor = (a.n_reads + 63) / 64;
+      an.col_stride = 64; an.thr_sum = nullptr; an.thr_idx = nullptr;
+      an.groups = std::max<uint32_t>(1, std::min<uint32_t>(a.anchor_groups, a.n_rows / 64));
+      an.part_idx = a.anchor_part_idx; an.part_sum = a.anchor_part_sum;
+      const dim3 agrid((n_anchor + 63) / 64, an.groups);
+      if (a.wide) dense_topk_warp_kernel<uint32_t><<<agrid, 256, 0, st>>>(an);
+      else dense_topk_warp_kernel<uint16_t><<<agrid, 256, 0, st>>>(an);
+      skb_launch_merge_topn(an.part_idx, an.part_sum, an.groups, n_anchor, a.top, a.anchor_idx, a.anchor_sum, st);
+      r.thr_sum = a.anchor_sum; r.thr_idx = a.anchor_idx;
+    }
     const dim3 wgrid((a.n_reads + 63) / 64, a.groups);
-    if (a.wide) dense_topk_warp_kernel<uint32_t><<<wgrid, 256, 0, st>>>(a);
-    else dense_topk_warp_kernel<uint16_t><<<wgrid, 256, 0, st>>>(a);
+    if (a.wide) dense_topk_warp_kernel<uint32_t><<<wgrid, 256, 0, st>>>(r);
+    else dense_topk_warp_kernel<uint16_t><<<wgrid, 256, 0, st>>>(r);
     return;
   }
   const dim3 grid((a.n_reads + 127) / 128, a.groups);
