@@ -249,6 +249,7 @@ struct skb_ctx {
   DevBuf q_off, qh, qread, counts, lb_sum[SKB_NTAB], lb_idx[SKB_NTAB], cand[2], cand_cnt[2], ivl[2], seg_hdr[2], seg_words[2], scal;
   DevBuf t_slots[SKB_NTAB], t_fill[SKB_NTAB], t_reads[SKB_NTAB], t_slot[SKB_NTAB], t_bloom[SKB_NTAB];
   uint32_t t_cap = 0, t_maxkeys = 0;
+  uint32_t t_built[SKB_NTAB] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // keys of each table's last build (UINT32_MAX: never built, clear all)
   DevBuf out_idx, out_sum, misc;
   uint32_t pass_user = 0;                      // skb_set_pass_reads (0 = automatic)
   uint32_t pass_max = SKB_DEFAULT_PASS_READS;  // reads per pass in effect (choose_pass_max)
@@ -617,6 +618,7 @@ int ensure_table(skb_ctx* c, uint32_t max_keys) {
   }
   c->t_cap = cap;
   c->t_maxkeys = mk;
+  for (int i = 0; i < SKB_NTAB; ++i) c->t_built[i] = 0xFFFFFFFFu;  // new tables: the first build clears every slot
   return SKB_OK;
 }
 
@@ -1019,7 +1021,8 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     // ---- pre(i) on the side stream
     const SkbTable t = table_of(c, tab);
     { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1, c->side);
-      skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->side); }
+      skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->t_built[tab], c->side);
+      c->t_built[tab] = nkeys; }
     SkbRankArgs ra{};
     ra.tracked_counts = c->counts.as<uint16_t>(); ra.tracked_prefix = c->tprefix.as<uint32_t>();
     ra.tracked_extra = c->textra.as<unsigned long long>();

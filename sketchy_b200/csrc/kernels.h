@@ -116,8 +116,9 @@ struct SkbTable {
 };
 // three bits of one word per reference hash
 void skb_launch_memb_build(const struct SkbRefView& rv, uint32_t* memb, uint32_t memb_log2, cudaStream_t st);
+// n_prev = keys of the table's previous build (its slots are cleared through them), UINT32_MAX = clear every slot
 void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_t* qread, uint32_t n_keys,
-                            uint32_t read_base, cudaStream_t st);
+                            uint32_t read_base, uint32_t n_prev, cudaStream_t st);
 
 // Reference shard as laid out in HBM: row r = ref[row_start[r] .. row_start[r] + row_len[r]), row_start even
 // (16-byte aligned rows, the granularity of the bulk copies).

@@ -90,16 +90,27 @@ __global__ void __launch_bounds__(256) memb_build_kernel(const SkbRefView rv, ui
 // ---------------------------------------------------------------------------------------------------------
 // query table
 // ---------------------------------------------------------------------------------------------------------
-__global__ void table_clear_kernel(SkbTable t) {
+// A table is cleared through the keys of its previous build (a pass fills a few per cent of the slots): every slot a
+// key was put in goes back to empty. n_prev == UINT32_MAX: the table is new, every slot is cleared.
+__global__ void table_clear_kernel(SkbTable t, uint32_t n_prev) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= t.cap) {
-    reinterpret_cast<uint4*>(t.slots)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-    t.fill[i] = 0;
+  if (n_prev == 0xFFFFFFFFu) {
+    if (i <= t.cap) {
+      reinterpret_cast<uint4*>(t.slots)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+      t.fill[i] = 0;
+    }
+  } else if (i < n_prev) {
+    const uint32_t s = t.slot_of[i];
+    if (s != 0xFFFFFFFFu) {
+      reinterpret_cast<uint4*>(t.slots)[s & 0x7FFFFFFFu] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+      t.fill[s & 0x7FFFFFFFu] = 0;
+    }
   }
   if (i < SKB_BLOOM_WORDS) t.bloom[i] = 0;
   if (i == 0) *t.cursor = 0;
 }
 
+// slot_of[i] = the key's slot, bit 31 set for the key that opened the slot (it sizes the slot's read list afterwards)
 __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh, uint32_t n_keys) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
@@ -120,15 +131,20 @@ __global__ void table_insert_kernel(SkbTable t, const uint64_t* __restrict__ qh,
       slot = (slot + 1) & (t.cap - 1);
     }
   }
-  atomicAdd(&t.slots[slot].meta, 1ull);  // cnt lives in the low 13 bits; a read holds a hash at most once
-  t.slot_of[i] = slot;
+  // cnt lives in the low bits; a read holds a hash at most once. The first to count opened the slot.
+  const bool opened = SKB_SLOT_CNT(atomicAdd(&t.slots[slot].meta, 1ull)) == 0u;
+  t.slot_of[i] = slot | (opened ? 0x80000000u : 0u);
   const uint32_t lo = (uint32_t)h;
   atomicOr(&t.bloom[bloom_word(lo)], bloom_mask(lo, (uint32_t)(h >> 32)));
 }
 
-__global__ void table_alloc_kernel(SkbTable t) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s > t.cap) return;
+// read lists longer than the inline ids get their place in `reads`: done by the key that opened the slot
+__global__ void table_alloc_kernel(SkbTable t, uint32_t n_keys) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keys) return;
+  const uint32_t so = t.slot_of[i];
+  if (so == 0xFFFFFFFFu || !(so & 0x80000000u)) return;
+  const uint32_t s = so & 0x7FFFFFFFu;
   const unsigned long long m = t.slots[s].meta;
   const uint32_t c = SKB_SLOT_CNT(m);
   if (c > SKB_SLOT_INLINE) t.slots[s].meta = m | ((unsigned long long)atomicAdd(t.cursor, c) << SKB_SLOT_CNT_BITS);
@@ -138,8 +154,9 @@ __global__ void table_fill_kernel(SkbTable t, const uint32_t* __restrict__ qread
                                   uint32_t read_base) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
-  const uint32_t s = t.slot_of[i];
-  if (s == 0xFFFFFFFFu) return;  // dropped by the membership prefilter
+  const uint32_t so = t.slot_of[i];
+  if (so == 0xFFFFFFFFu) return;  // dropped by the membership prefilter
+  const uint32_t s = so & 0x7FFFFFFFu;
   const uint32_t rd = qread[i] - read_base;
   // cnt (and, for long lists, the start) are final here; only the inline id bits are still being OR-ed in
   const unsigned long long m = *reinterpret_cast<volatile unsigned long long*>(&t.slots[s].meta);
@@ -1262,13 +1279,14 @@ __global__ void __launch_bounds__(256) shared_kernel(const SkbRefView rv, const 
 // launch wrappers
 // =========================================================================================================
 void skb_launch_table_build(const SkbTable& t, const uint64_t* qh, const uint32_t* qread, uint32_t n_keys,
-                            uint32_t read_base, cudaStream_t st) {
+                            uint32_t read_base, uint32_t n_prev, cudaStream_t st) {
   const int th = 256;
-  const uint32_t n_clear = t.cap + 1 > SKB_BLOOM_WORDS ? t.cap + 1 : SKB_BLOOM_WORDS;
-  table_clear_kernel<<<(n_clear + th - 1) / th, th, 0, st>>>(t);
+  uint32_t n_clear = n_prev == 0xFFFFFFFFu ? t.cap + 1 : n_prev;
+  if (n_clear < SKB_BLOOM_WORDS) n_clear = SKB_BLOOM_WORDS;
+  table_clear_kernel<<<(n_clear + th - 1) / th, th, 0, st>>>(t, n_prev);
   if (n_keys == 0) return;
   table_insert_kernel<<<(n_keys + th - 1) / th, th, 0, st>>>(t, qh, n_keys);
-  table_alloc_kernel<<<(t.cap + 1 + th - 1) / th, th, 0, st>>>(t);
+  table_alloc_kernel<<<(n_keys + th - 1) / th, th, 0, st>>>(t, n_keys);
   table_fill_kernel<<<(n_keys + th - 1) / th, th, 0, st>>>(t, qread, n_keys, read_base);
 }
 

@@ -5,12 +5,5 @@ d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 r = d['roofline']
 print('$1', 'value', round(d['value']), 'ms/step', round(d['ms_per_step'], 2), 'kernel_ms', round(r['avg_launch_ms'], 4), 'frac', round(r['frac'], 3), 'passes', d['predict_stats']['passes'], 'B', d['config']['reads_per_pass_max'], 'crc', d['result_crc32'], 'launches', d['gpu_launches'], 'kms', {k: round(v, 2) for k, v in d['kernel_ms_per_step'].items()})" || echo "$1 FAILED"; }
 run base
-AB_ARGS="--rank-mode 2 --refs 5000" run dense5000
-timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:"dense|merge" -c 6 --csv --log-file gpurun_out/r02c_dense.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > /dev/null 2>&1
-python - <<'PY'
-import csv
-rows=[r for r in csv.reader(open('gpurun_out/r02c_dense.csv')) if len(r)>5]
-h=rows[0]
-for r in rows[1:]:
-    print(r[h.index('Kernel Name')][:50], r[h.index('Grid Size')], r[h.index('Metric Name')], r[h.index('Metric Value')])
-PY
+AB_ARGS="--refs 5000" run r5000
+AB_ARGS="--config c4" run c4
