@@ -72,6 +72,14 @@ int skb_batch_clear(skb_batch* b);
  * removed, everything else breaks k-mer windows. nthreads host threads do the packing (0 = all cores). */
 int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, const uint32_t* groups, uint64_t n,
                   uint32_t nthreads);
+/* What a group's total_bases counts (finch `total_bases_and_kmers`, src/sketchy.rs:481 -> `.msh` length / `info`):
+ * SKB_BASES_RAW (default) = the bytes of the record's sequence as the reader hands them over, line breaks of a
+ * multi-line FASTA record included (needletail 0.4.1 passes its raw slice on);
+ * SKB_BASES_STRIPPED = the bases left after blanks, tabs, CR and LF are removed. Hashes never depend on it.
+ * Set on an empty batch. */
+#define SKB_BASES_RAW 0
+#define SKB_BASES_STRIPPED 1
+int skb_batch_set_base_count(skb_batch* b, int mode);
 uint32_t skb_batch_num_groups(const skb_batch* b);
 uint64_t skb_batch_num_records(const skb_batch* b);
 uint64_t skb_batch_num_bases(const skb_batch* b); /* sum of raw record lengths (finch total_bases) */
@@ -207,6 +215,13 @@ int skb_last_predict_stats(const skb_ctx* ctx, uint64_t* ref_bytes_per_pass, uin
 uint64_t skb_last_predict_member_hashes(const skb_ctx* ctx);
 
 /* ---- debug / parity hooks (used only by tests) --------------------------------------------------------------- */
+
+/* Internal knobs for tests and experiments (every setting gives identical results): "cand_budget" = candidate
+ * records per pass over all reads (forces overflow / redo paths), "trace_passes" = one stderr line per checkpoint,
+ * "dense_after_reset" = brute-force ranked passes after the first one of a reset, "pipeline" = bounds taken two passes
+ * back, "stream_ctas" = CTAs of the streaming kernel (takes effect at the next upload). The same names, upper-cased
+ * with an SKB_ prefix, are read from the environment once when the context is created. */
+int skb_debug_set(skb_ctx* ctx, const char* key, uint64_t value);
 
 /* Hash of the canonical k-mer starting at every packed position of the batch; valid[p] = 0 where the window holds
  * a non-ACGT base or crosses a record end. Arrays are [skb_batch_packed_len(b)]. */

@@ -45,6 +45,8 @@ SYMBOLS = [
     ("skb_sums_reset", _i, [_vp]),
     ("skb_sums_download", _i, [_vp, _vp]),
     ("skb_sums_upload", _i, [_vp, _vp]),
+    ("skb_batch_set_base_count", _i, [_vp, _i]),
+    ("skb_debug_set", _i, [_vp, C.c_char_p, _u64]),
     ("skb_set_pass_reads", _i, [_vp, _u32]),
     ("skb_pass_reads", _u32, [_vp]),
     ("skb_set_rank_mode", _i, [_vp, _i]),
@@ -306,6 +308,11 @@ class Context:
                 "candidates": int(d.value), "member_hashes": int(self.lib.skb_last_predict_member_hashes(self.h))}
 
     # -- debug
+    def debug_set(self, key: str, value: int):
+        """Internal knobs for tests / experiments (results never depend on them); value 0 restores the default of
+        "cand_budget" and "stream_ctas"."""
+        self.check(self.lib.skb_debug_set(self.h, key.encode(), int(value)))
+
     def debug_kmer_hashes(self, batch: "Batch", k: int, seed: int = 0):
         n = batch.packed_len
         oh = np.zeros(max(n, 1), dtype=np.uint64)
@@ -325,6 +332,12 @@ class Batch:
 
     def clear(self):
         self.ctx.check(self.ctx.lib.skb_batch_clear(self.h))
+
+    def set_base_count(self, stripped: bool):
+        """total_bases of a group: raw sequence bytes (default, what the reference's reader passes on) or the bases
+        left after whitespace is removed. Call on an empty batch."""
+        self.ctx.check(self.ctx.lib.skb_batch_set_base_count(self.h, 1 if stripped else 0))
+        return self
 
     def add(self, blob: np.ndarray, offsets: np.ndarray, groups=None, nthreads: int = 0):
         blob = np.ascontiguousarray(blob, dtype=np.uint8)

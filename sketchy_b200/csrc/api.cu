@@ -118,7 +118,8 @@ const pack_blocks_fn kPackBlocks = choose_pack_blocks();
 
 // Pack one record at base position P (multiple of 32); everything up to Pnext (multiple of 32) not covered by a
 // valid base is marked invalid. The words touched belong to this record alone.
-void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uint32_t* codes, uint32_t* nmask) {
+// Returns the number of bases the record keeps (its length without the removed bytes).
+uint64_t pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uint32_t* codes, uint32_t* nmask) {
   uint64_t pos = P;
   uint32_t cw = 0, mw = 0;
   for (uint64_t i = 0; i < len; ++i) {
@@ -137,6 +138,7 @@ void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uin
     if ((pos & 15) == 0) { codes[(pos >> 4) - 1] = cw; cw = 0; }
     if ((pos & 31) == 0) { nmask[(pos >> 5) - 1] = mw; mw = 0; }
   }
+  const uint64_t kept = pos - P;
   // finish the current 32-base block as invalid, then whole invalid blocks
   while (pos < Pnext && (pos & 31)) {
     mw |= 1u << (pos & 31);
@@ -148,6 +150,7 @@ void pack_record(const uint8_t* s, uint64_t len, uint64_t P, uint64_t Pnext, uin
     codes[pos >> 4] = 0; codes[(pos >> 4) + 1] = 0;
     nmask[pos >> 5] = 0xFFFFFFFFu;
   }
+  return kept;
 }
 
 }  // namespace
@@ -254,9 +257,12 @@ struct skb_ctx {
   uint32_t pass_user = 0;                      // skb_set_pass_reads (0 = automatic)
   uint32_t pass_max = SKB_DEFAULT_PASS_READS;  // reads per pass in effect (choose_pass_max)
   uint32_t cand_cap = 0;
+  uint64_t cand_budget = SKB_CAND_BUDGET;  // candidate records per pass over all reads (SKB_CAND_BUDGET: tests)
+  bool trace_passes = false;               // SKB_TRACE_PASSES: one line per checkpoint on stderr
   // stats / profiling
   bool prof_on = false;
   std::vector<ProfEvent> pending;
+  std::vector<cudaEvent_t> ev_pool;  // timing events ready for reuse
   double prof_ms[SKB_K_COUNT] = {0};
   uint64_t prof_n[SKB_K_COUNT] = {0};
   uint64_t launches = 0;
@@ -273,6 +279,7 @@ struct skb_batch {
   std::vector<uint64_t> g_first, g_end;  // chunk ranges
   std::vector<uint64_t> g_raw, g_packed; // raw bytes, packed bases
   uint64_t total_raw = 0;
+  int base_count = SKB_BASES_RAW;  // what total_bases counts (skb_batch_set_base_count)
   // device mirror
   bool staged = false;
   DevBuf d_codes, d_nmask, d_seg_group, d_seg_chunk0, d_seg_n, d_g_len;
@@ -315,8 +322,11 @@ struct ProfScope {
   ProfScope(skb_ctx* ctx, int kid, int n_launches, cudaStream_t on = nullptr) : c(ctx), id(kid), st(on ? on : ctx->stream) {
     c->launches += n_launches;
     c->prof_n[id] += n_launches;
-    if (c->prof_on) {
-      cudaEventCreate(&a); cudaEventCreate(&b);
+    if (c->prof_on) {  // timing events come from a pool: creating a pair per scope costs more host time than the launches it brackets
+      for (cudaEvent_t* e : {&a, &b}) {
+        if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+        else cudaEventCreate(e);
+      }
       cudaEventRecord(a, st);
     }
   }
@@ -335,7 +345,7 @@ void prof_resolve(skb_ctx* c) {
   for (auto& e : c->pending) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.id] += ms;
-    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b);
   }
   c->pending.clear();
 }
@@ -690,10 +700,12 @@ int upload_ref_common(skb_ctx* c, const uint64_t* hashes, bool on_device, const 
       }
       cudaError_t e = doff.ensure(((size_t)n_rows + 1) * 8);
       if (e != cudaSuccess) { tmp.release(); return fail(c, SKB_ERR_OOM, "relayout: %s", cudaGetErrorString(e)); }
-      cudaMemcpyAsync(doff.p, off, ((size_t)n_rows + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-      { ProfScope ps(c, SKB_K_MISC, 1);
-        skb_launch_relayout(src, doff.as<uint64_t>(), c->ref.as<uint64_t>(), c->row_start.as<uint64_t>(), n_rows, c->stream); }
-      e = cudaStreamSynchronize(c->stream);
+      e = cudaMemcpyAsync(doff.p, off, ((size_t)n_rows + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) {
+        ProfScope ps(c, SKB_K_MISC, 1);
+        skb_launch_relayout(src, doff.as<uint64_t>(), c->ref.as<uint64_t>(), c->row_start.as<uint64_t>(), n_rows, c->stream);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       tmp.release(); doff.release();
       if (e != cudaSuccess) return fail(c, SKB_ERR_CUDA, "relayout: %s", cudaGetErrorString(e));
     }
@@ -901,8 +913,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
   CU(c, cudaMemsetAsync(d_dense_ovf, 0, 4, c->stream));
 
   // ---- every buffer a pass may need, sized once for the largest pass: nothing is (re)allocated while passes are in flight
-  uint64_t budget = SKB_CAND_BUDGET;
-  if (const char* eb = getenv("SKB_CAND_BUDGET")) budget = std::max<uint64_t>(64, strtoull(eb, nullptr, 10));  // tests only
+  const uint64_t budget = c->cand_budget;
   const uint32_t Bmax = std::max<uint32_t>(1, std::min<uint32_t>(c->pass_max, R));
   const uint32_t stride_max = (uint32_t)round_up(Bmax, 512);
   // dense ranking: row groups so that (reads x groups) threads fill the GPU, bounded by the part lists' size
@@ -967,9 +978,12 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
   // (a small shard's prefix-sum vectors are a few MB: dense ranking costs less than the sparse launch train)
   const bool small_shard = c->rank_mode == 2 || (c->rank_mode == 0 && (uint64_t)c->n_rows * stride_max * 2 <= (32ull << 20));
 
+  // event records / waits between the two streams: the first error is kept and ends the loop at its next iteration
+  cudaError_t ev_err = cudaSuccess;
+#define EV(call) do { const cudaError_t e__ = (call); if (ev_err == cudaSuccess) ev_err = e__; } while (0)
   auto enqueue_post = [&]() {  // post(i) on the side stream, behind stream(i)
     if (!post.on) return;
-    cudaStreamWaitEvent(c->side, c->ev_fused[post.fused_ev], 0);
+    EV(cudaStreamWaitEvent(c->side, c->ev_fused[post.fused_ev], 0));
     if (post.dense) {
       ProfScope ps(c, SKB_K_RANK, 5, c->side);
       skb_launch_dense_topk(post.da, c->side);
@@ -988,10 +1002,11 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     return e;
   };
   // the side stream starts behind whatever the main stream has done so far (hashing, selection, resets)
-  cudaEventRecord(c->ev_join, c->stream);
-  cudaStreamWaitEvent(c->side, c->ev_join, 0);
+  EV(cudaEventRecord(c->ev_join, c->stream));
+  EV(cudaStreamWaitEvent(c->side, c->ev_join, 0));
 
   while (r < R) {
+    if (ev_err != cudaSuccess) { rc_final = fail(c, SKB_ERR_CUDA, "predict pass (stream ordering): %s", cudaGetErrorString(ev_err)); break; }
     const bool need_init = c->tracked_top != top;  // no tracked rows yet (first pass after an upload / a reset, or `top` changed)
     const bool dense = small_shard || need_init || c->dense_left > 0 || r < dense_until;
     uint32_t B = std::min<uint32_t>(c->pass_max, R - r);
@@ -1047,11 +1062,11 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       if (lag2) skb_launch_tracked_totals(rv, ra.tracked, ra.n_tracked, table_of(c, tab_prev), ra.tracked_extra, c->side);
       skb_launch_rank_bounds(rv, t, ra, nkeys != 0, c->side);
     }
-    cudaEventRecord(c->ev_pre[tab], c->side);
+    EV(cudaEventRecord(c->ev_pre[tab], c->side));
     if (lag2) enqueue_post();  // post(i-1) behind pre(i): it runs next to stream(i)
 
     // ---- stream(i) on the main stream
-    cudaStreamWaitEvent(c->stream, c->ev_pre[tab], 0);
+    EV(cudaStreamWaitEvent(c->stream, c->ev_pre[tab], 0));
     SkbFusedArgs fa{};
     fa.rv = rv; fa.cta_row = c->cta_row.as<uint32_t>(); fa.num_ctas = c->stream_ctas; fa.table = t;
     fa.n_reads = B; fa.cnt_stride = stride; fa.narrow = narrow ? 1 : 0; fa.skip_stream = nkeys == 0; fa.row_base = c->row_base;
@@ -1066,7 +1081,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     fa.tpr = std::max(1u, (c->uniform_len + skb_fused_tile() - 1) / skb_fused_tile());
     fa.tpr_magic = (uint32_t)((0x100000000ull + fa.tpr - 1) / fa.tpr);
     { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
-    cudaEventRecord(c->ev_fused[qs], c->stream);
+    EV(cudaEventRecord(c->ev_fused[qs], c->stream));
     if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
     post.on = true; post.dense = dense; post.ra = ra; post.fused_ev = qs;
     if (dense) {
@@ -1103,7 +1118,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       break;
     }
     prev_pipelined = false;  // everything is finished: the next pass may use S_{i-1} and U_{i-1} directly
-    if (getenv("SKB_TRACE_PASSES"))
+    if (c->trace_passes)
       fprintf(stderr, "[skb] checkpoint after %zu pass(es), last %s at read %u with %u reads: fullest bucket %u of %u, intervals %u, segment records %u%s\n",
               recs.size(), dense ? "dense" : "sparse", recs.back().r, recs.back().B, h_total[2], c->cand_cap, h_total[3], h_total[4],
               h_total[0] || h_total[8] ? " OVERFLOW" : "");
@@ -1115,13 +1130,13 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       dense_until = std::max(dense_until, pr.r + pr.B);
       dense_max_reads = 256;  // 255 * 256 < 2^16: cannot overflow
       recs.clear();
-      cudaEventRecord(c->ev_join, c->stream);
-      cudaStreamWaitEvent(c->side, c->ev_join, 0);
+      EV(cudaEventRecord(c->ev_join, c->stream));
+      EV(cudaStreamWaitEvent(c->side, c->ev_join, 0));
       continue;
     }
     if (h_total[0] != 0) {  // more contenders than a bucket / a record list holds, in the sparse pass numbered h_total[1]
       const PassRec pr = recs[recs.size() - (seq - h_total[1])];
-      if (getenv("SKB_TRACE_PASSES"))
+      if (c->trace_passes)
         fprintf(stderr, "[skb] pass at read %u with %u reads overflowed (fullest bucket %u of %u, intervals %u of %u, segment records %u of %u): redo dense\n", pr.r, pr.B,
                 h_total[2], c->cand_cap, h_total[3], (unsigned)SKB_IVL_CAP, h_total[4], (unsigned)SKB_SEG_CAP);
       c->st_passes -= (seq - h_total[1]) - 1;  // the passes behind the failed one did nothing (the failed one did stream)
@@ -1137,8 +1152,8 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       c->dense_left = 1;  // and the pass after it: its bounds would be as loose
       c->pass_proven = false;
       recs.clear();
-      cudaEventRecord(c->ev_join, c->stream);
-      cudaStreamWaitEvent(c->side, c->ev_join, 0);
+      EV(cudaEventRecord(c->ev_join, c->stream));
+      EV(cudaStreamWaitEvent(c->side, c->ev_join, 0));
       continue;
     }
     if (dense) {
@@ -1149,6 +1164,8 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     }
     recs.clear();
   }
+#undef EV
+  if (!rc_final && ev_err != cudaSuccess) rc_final = fail(c, SKB_ERR_CUDA, "predict pass (stream ordering): %s", cudaGetErrorString(ev_err));
   if (rc_final) {  // leave nothing in flight behind an error
     cudaStreamSynchronize(c->side);
     cudaStreamSynchronize(c->stream);
@@ -1314,6 +1331,9 @@ int skb_create(int device, skb_ctx** out) {
   for (int i = 0; ok && i < SKB_NTAB; ++i) ok = cudaEventCreateWithFlags(&c->ev_pre[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&c->ev_fused[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { delete c; return SKB_ERR_CUDA; }
+  // environment switches are read once, here (tests and experiments; never inside the pass loop)
+  if (const char* e = getenv("SKB_CAND_BUDGET")) c->cand_budget = std::max<uint64_t>(64, strtoull(e, nullptr, 10));
+  if (const char* e = getenv("SKB_TRACE_PASSES")) c->trace_passes = e[0] != '0';
   if (const char* e = getenv("SKB_DENSE_AFTER_RESET")) c->dense_after_reset = (uint32_t)atoi(e);
   if (const char* e = getenv("SKB_PIPELINE")) c->pipeline = e[0] != '0';  // experiments: 0 = every pass waits for the one before
   if (cudaHostAlloc((void**)&c->h_scal, 64, cudaHostAllocDefault) != cudaSuccess) {
@@ -1330,6 +1350,7 @@ void skb_destroy(skb_ctx* c) {
   if (c->side) cudaStreamSynchronize(c->side);
   if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   std::vector<DevBuf*> bufs = {&c->ref, &c->row_start, &c->row_len, &c->cta_row, &c->tile_cum, &c->memb, &c->tprefix, &c->textra,
                                &c->g_tau, &c->g_cap, &c->g_base, &c->g_cnt, &c->g_kmers, &c->g_active, &c->g_outn, &c->g_status, &c->g_tiles,
                                &c->cand_pool, &c->sk_hashes, &c->sk_counts, &c->q_off, &c->qh, &c->qread, &c->counts, &c->scal,
@@ -1409,6 +1430,7 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
       if (groups[r] < groups[r - 1]) return fail(c, SKB_ERR_INVALID_ARG, "groups must be non-decreasing");
   }
   const uint64_t first_rec = b->rec_pos.size();
+  const uint64_t first_group_of_call = b->g_first.size();  // (groups == NULL: record r opens group first_group_of_call + r)
   uint64_t cur = b->cur;
   for (uint64_t r = 0; r < n; ++r) {
     const uint64_t len = offsets[r + 1] - offsets[r];
@@ -1433,11 +1455,13 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
   const uint64_t total_bytes = offsets[n] - offsets[0];
   if (total_bytes < (1u << 20) || n < 2) T = 1;
   T = (uint32_t)std::min<uint64_t>(T, n);
+  std::vector<uint64_t> kept(b->base_count == SKB_BASES_STRIPPED ? n : 0);
   auto work = [&](uint64_t r0, uint64_t r1) {
     for (uint64_t r = r0; r < r1; ++r) {
       const uint64_t P = b->rec_pos[first_rec + r];
       const uint64_t Pn = (first_rec + r + 1 < b->rec_pos.size()) ? b->rec_pos[first_rec + r + 1] : cur;
-      pack_record(blob + offsets[r], offsets[r + 1] - offsets[r], P, Pn, codes, nmask);
+      const uint64_t kp = pack_record(blob + offsets[r], offsets[r + 1] - offsets[r], P, Pn, codes, nmask);
+      if (!kept.empty()) kept[r] = kp;
     }
   };
   if (T <= 1) {
@@ -1456,7 +1480,24 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
     }
     for (auto& th : pool) th.join();
   }
+  if (!kept.empty()) {  // total_bases without the removed bytes: take the difference back out of the groups' counts
+    uint64_t gid = b->g_first.size() - 1;
+    for (uint64_t r = n; r-- > 0;) {
+      if (groups) gid = groups[r];
+      else gid = first_group_of_call + r;
+      const uint64_t removed = (offsets[r + 1] - offsets[r]) - kept[r];
+      b->g_raw[gid] -= removed;
+      b->total_raw -= removed;
+    }
+  }
   b->cur = cur;
+  return SKB_OK;
+}
+
+int skb_batch_set_base_count(skb_batch* b, int mode) {
+  if (!b || (mode != SKB_BASES_RAW && mode != SKB_BASES_STRIPPED)) return SKB_ERR_INVALID_ARG;
+  if (!b->rec_pos.empty()) return fail(b->ctx, SKB_ERR_STATE, "set the base count mode on an empty batch");
+  b->base_count = mode;
   return SKB_OK;
 }
 
@@ -1699,14 +1740,17 @@ int skb_shared_counts(skb_ctx* c, const uint64_t* q_hashes, const uint64_t* q_of
       (e = dout.ensure(pairs * 8)) != cudaSuccess) {
     rc = fail(c, SKB_ERR_OOM, "shared buffers: %s", cudaGetErrorString(e));
   } else {
-    if (qlen) cudaMemcpyAsync(dq.p, q_hashes, qlen * 8, cudaMemcpyHostToDevice, c->stream);
-    cudaMemcpyAsync(dqo.p, q_off, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-    { ProfScope ps(c, SKB_K_SHARED, 1);
-      skb_launch_shared(ref_view(c), dq.as<uint64_t>(), dqo.as<uint64_t>(), Q, dout.as<unsigned long long>(), c->stream); }
-    rc = check_launch(c, "shared");
+    if (qlen) e = cudaMemcpyAsync(dq.p, q_hashes, qlen * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dqo.p, q_off, ((size_t)Q + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) rc = fail(c, SKB_ERR_CUDA, "shared: %s", cudaGetErrorString(e));
     if (!rc) {
-      cudaMemcpyAsync(out, dout.p, pairs * 8, cudaMemcpyDeviceToHost, c->stream);
-      e = cudaStreamSynchronize(c->stream);
+      { ProfScope ps(c, SKB_K_SHARED, 1);
+        skb_launch_shared(ref_view(c), dq.as<uint64_t>(), dqo.as<uint64_t>(), Q, dout.as<unsigned long long>(), c->stream); }
+      rc = check_launch(c, "shared");
+    }
+    if (!rc) {
+      e = cudaMemcpyAsync(out, dout.p, pairs * 8, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       if (e != cudaSuccess) rc = fail(c, SKB_ERR_CUDA, "shared: %s", cudaGetErrorString(e));
     }
   }
@@ -1787,6 +1831,19 @@ uint64_t skb_last_predict_member_hashes(const skb_ctx* c) {
 }
 
 // ---- debug ------------------------------------------------------------------------------------------------
+int skb_debug_set(skb_ctx* c, const char* key, uint64_t value) {
+  if (!c || !key) return SKB_ERR_INVALID_ARG;
+  const std::string k(key);
+  if (k == "cand_budget") c->cand_budget = value ? std::max<uint64_t>(64, value) : SKB_CAND_BUDGET;
+  else if (k == "trace_passes") c->trace_passes = value != 0;
+  else if (k == "dense_after_reset") c->dense_after_reset = (uint32_t)value;
+  else if (k == "pipeline") c->pipeline = value != 0;
+  else if (k == "stream_ctas") c->stream_ctas = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c->num_sms, value ? value : (uint64_t)c->num_sms));
+  else return fail(c, SKB_ERR_INVALID_ARG, "unknown debug key '%s'", key);
+  c->pass_proven = false;
+  return SKB_OK;
+}
+
 int skb_debug_kmer_hashes(skb_ctx* c, skb_batch* b, uint32_t k, uint64_t seed, uint64_t* out_hash, uint8_t* out_valid) {
   if (!c || !b || b->ctx != c || !out_hash || !out_valid) return SKB_ERR_INVALID_ARG;
   cudaSetDevice(c->device);
@@ -1800,17 +1857,18 @@ int skb_debug_kmer_hashes(skb_ctx* c, skb_batch* b, uint32_t k, uint64_t seed, u
   if ((e = dh.ensure(n * 8)) != cudaSuccess || (e = dv.ensure(n)) != cudaSuccess) {
     rc = fail(c, SKB_ERR_OOM, "debug buffers: %s", cudaGetErrorString(e));
   } else {
-    cudaMemsetAsync(dh.p, 0, n * 8, c->stream);
-    cudaMemsetAsync(dv.p, 0, n, c->stream);
+    e = cudaMemsetAsync(dh.p, 0, n * 8, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dv.p, 0, n, c->stream);
+    if (e != cudaSuccess) { dh.release(); dv.release(); return fail(c, SKB_ERR_CUDA, "hash(dump): %s", cudaGetErrorString(e)); }
     SkbHashArgs ha{};
     ha.pv = view_of(b); ha.k = k; ha.seed = seed;
     ha.dump_hash = dh.as<uint64_t>(); ha.dump_valid = dv.as<uint8_t>();
     { ProfScope ps(c, SKB_K_HASH, 1); skb_launch_hash(ha, c->stream); }
     rc = check_launch(c, "hash(dump)");
     if (!rc) {
-      cudaMemcpyAsync(out_hash, dh.p, n * 8, cudaMemcpyDeviceToHost, c->stream);
-      cudaMemcpyAsync(out_valid, dv.p, n, cudaMemcpyDeviceToHost, c->stream);
-      e = cudaStreamSynchronize(c->stream);
+      e = cudaMemcpyAsync(out_hash, dh.p, n * 8, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out_valid, dv.p, n, cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
       if (e != cudaSuccess) rc = fail(c, SKB_ERR_CUDA, "hash(dump): %s", cudaGetErrorString(e));
     }
   }

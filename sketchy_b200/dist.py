@@ -35,24 +35,3 @@ def all_gather_topn(idx, sums, group=None):
         dist.all_gather(ls, sums.contiguous(), group=group)
         g_idx, g_sum = torch.stack(li), torch.stack(ls)
     return g_idx, g_sum
-
-
-class ShardedPredictor:
-    """Streaming predict over a reference sharded across the ranks of a process group (GPU path)."""
-
-    def __init__(self, ctx, top: int, world: int):
-        self.ctx, self.top, self.world = ctx, top, world
-
-    def predict(self, batch, k: int, s_query: int, seed: int, n_reads: int, bufs: dict):
-        """bufs: preallocated torch tensors d_idx/d_sum [R, top], m_idx/m_sum [R, top] on this rank's GPU."""
-        import torch
-        c = self.ctx
-        c.predict_stream_device(batch, k, s_query, seed, self.top, bufs["d_idx"].data_ptr(), bufs["d_sum"].data_ptr(),
-                                pad=self.world > 1)
-        if self.world == 1:
-            return bufs["d_idx"], bufs["d_sum"]
-        g_idx, g_sum = all_gather_topn(bufs["d_idx"], bufs["d_sum"])
-        torch.cuda.current_stream().synchronize()
-        c.merge_topn_device(g_idx.data_ptr(), g_sum.data_ptr(), self.world, n_reads, self.top,
-                            bufs["m_idx"].data_ptr(), bufs["m_sum"].data_ptr())
-        return bufs["m_idx"], bufs["m_sum"]

@@ -93,6 +93,29 @@ def test_sketch_parity(ctx, k, s, seed):
     b.close()
 
 
+def test_total_bases_raw_or_stripped(ctx):
+    """total_bases counts the raw sequence bytes by default (line breaks of a multi-line record
+    included, as the reference's reader hands them over) or, as a named switch, the bases left after whitespace is
+    removed. Hashes and k-mer counts are the same either way."""
+    rng = random.Random(5)
+    body = _rand_dna(rng, 1000)
+    multi = b"\n".join(body[i:i + 60] for i in range(0, len(body), 60)) + b"\r\n"
+    recs = [multi, body, b"AC GT\tACGTNACGTACGTACGTTTGACCA"]
+    res = {}
+    for stripped in (False, True):
+        b = ctx.batch().set_base_count(stripped)
+        b.add_records(recs, np.asarray([0, 1, 2], dtype=np.uint32))
+        sk, bases, kmers = ctx.sketch(b, 16, 50, 0)
+        res[stripped] = (sk, bases.tolist(), kmers.tolist())
+        b.close()
+    assert res[False][1] == [len(r) for r in recs]
+    assert res[True][1] == [len(oracle.normalize(r)) for r in recs]
+    assert res[False][2] == res[True][2]
+    for g in range(3):
+        assert res[False][0][g][0].tolist() == res[True][0][g][0].tolist()
+    assert res[True][0][0][0].tolist() == res[True][0][1][0].tolist()   # line breaks do not change the sketch
+
+
 def _world(seed, n_lineages, per_lineage, glen, s, n_reads, rlen, k=16, hseed=0, ragged=False):
     base = [synth.random_genome(glen, seed * 1000 + l) for l in range(n_lineages)]
     genomes = []
@@ -176,10 +199,10 @@ def test_predict_medium_scale(ctx):
     _check_predict(ctx, ref, off, blob, roff, 16, 1000, 0, 10, 0)
 
 
-def test_predict_more_contenders_than_a_bucket(ctx, monkeypatch):
+def test_predict_more_contenders_than_a_bucket(ctx):
     """4500 references beat the tracked row at once while the candidate budget is forced tiny: buckets overflow and the
     pass is redone with the brute-force ranking."""
-    monkeypatch.setenv("SKB_CAND_BUDGET", "4096")
+    ctx.debug_set("cand_budget", 4096)
     ga = synth.random_genome(20_000, 901)
     gb = synth.random_genome(20_000, 902)
     sk, _, _ = oracle.sketch_groups([ga.tobytes(), gb.tobytes()], [0, 1], 2, 16, 300, 0)
@@ -188,8 +211,11 @@ def test_predict_more_contenders_than_a_bucket(ctx, monkeypatch):
     off[1:] = np.cumsum([r.size for r in rows])
     ref = np.concatenate(rows)
     blob, roff, _ = synth.sample_reads([gb], 24, 1500, 77, sub=0.0, ins=0.0, dele=0.0)
-    for top in (1, 3):
-        _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, top, 8)
+    try:
+        for top in (1, 3):
+            _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, top, 8)
+    finally:
+        ctx.debug_set("cand_budget", 0)
 
 
 def test_shared_counts_and_rank(ctx):
@@ -466,12 +492,12 @@ def test_membership_prefilter_does_not_change_results(monkeypatch):
     assert 0 < out[0][3]["member_hashes"] < out[0][3]["query_hashes"]       # reads carry errors: novel k-mers are dropped
 
 
-def test_overflow_inside_a_batch_of_passes_rolls_back(ctx, monkeypatch):
+def test_overflow_inside_a_batch_of_passes_rolls_back(ctx):
     """Steady state (passes enqueued eight at a time, checked on the host afterwards): the stream switches from lineage A
     to lineage B, whose 3,000 identical rows overtake the tracked rows at the same read and overflow every bucket. The
     device marks the failing pass, the passes queued behind it do nothing, the host rolls back to it and redoes it with
     the brute-force ranking. Results must still equal the oracle's."""
-    monkeypatch.setenv("SKB_CAND_BUDGET", str(16 * 512))
+    ctx.debug_set("cand_budget", 16 * 512)
     ga = [synth.random_genome(20_000, 910 + i) for i in range(3)]
     gb = synth.random_genome(20_000, 920)
     sk, _, _ = oracle.sketch_groups([g.tobytes() for g in ga] + [gb.tobytes()], [0, 1, 2, 3], 4, 16, 300, 0)
@@ -483,5 +509,8 @@ def test_overflow_inside_a_batch_of_passes_rolls_back(ctx, monkeypatch):
     blob_b, roff_b, _ = synth.sample_reads([gb], 260, 1200, 6, sub=0.0, ins=0.0, dele=0.0)
     blob = np.concatenate([blob_a, blob_b])
     roff = np.concatenate([roff_a, roff_b[1:] + roff_a[-1]])
-    _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, 3, 16, modes=(1,))
-    assert ctx.last_predict_stats()["passes"] > (460 + 15) // 16     # a pass streamed twice: once overflowing, once dense
+    try:
+        _check_predict(ctx, ref, off, blob, roff, 16, 300, 0, 3, 16, modes=(1,))
+        assert ctx.last_predict_stats()["passes"] > (460 + 15) // 16     # a pass streamed twice: once overflowing, once dense
+    finally:
+        ctx.debug_set("cand_budget", 0)
