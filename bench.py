@@ -397,19 +397,23 @@ def run_b200(args):
         # a streaming caller feeds reads in chunks of whole passes: chunk i+1 is normalised + 2-bit packed into pinned
         # memory by the library's host threads and copied to the device while the GPU works on chunk i (two batches,
         # double buffered). With N ranks every rank packs, copies and hashes 1/N of each chunk.
-        # The first chunks are short (one pass, then two): the GPU starts after 4 % of the packing instead of 20 %.
+        # Chunks double in size (1, 2, 4, 8 passes, then 10 at most): the GPU starts after 4 % of the packing, and the
+        # later calls are few (a call costs ~0.4 ms of host round trips on top of its passes).
         P = ctx.pass_reads
-        chunk_reads = (10 if R >= 500_000 else 5) * P
-        chunks, c_lo = [], 0
-        for n_pass in (1, 2):
-            if c_lo + n_pass * P < R:
-                chunks.append((c_lo, c_lo + n_pass * P))
-                c_lo += n_pass * P
-        chunks += [(x, min(x + chunk_reads, R)) for x in range(c_lo, R, chunk_reads)]
+        chunks, c_lo, n_pass = [], 0, 1
+        while c_lo < R:
+            c_hi = min(R, c_lo + n_pass * P)
+            if R - c_hi < P // 2:        # do not leave a sliver for a call of its own
+                c_hi = R
+            chunks.append((c_lo, c_hi))
+            c_lo = c_hi
+            n_pass = min(2 * n_pass, 10)
+        chunk_reads = max(b1 - b0 for b0, b1 in chunks)
         pack_s = [0.0]
         NB = 3                                  # ring of batches: one being packed, one being copied, one being read by the kernels
         hbs = [ctx.batch() for _ in range(NB)]
-        pack_threads = max(1, (os.cpu_count() or 1) // world)   # the ranks of one box share its host cores
+        # the ranks of one box share its host cores; two are left to the thread that drives the GPU and to the reader
+        pack_threads = max(1, ((os.cpu_count() or 1) - 2 * world) // world) if not os.environ.get("SKB_BENCH_PACK_ALL") else max(1, (os.cpu_count() or 1) // world)
         gt = genotype_table(N, args.lineages).astype(np.int16) if args.consensus else None
         calls = [np.zeros((R, gt.shape[1]), dtype=np.int16) if gt is not None else None]
         from concurrent.futures import ThreadPoolExecutor
@@ -486,7 +490,7 @@ def run_b200(args):
         h2d = (packed // 4 + packed // 8 + (packed // 1024 + R) * 9 + R * 8) // world
         e2e = {"value": R / dt, "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(R * top * 12), "ms_per_step": dt * 1e3,
-               "includes": f"host normalise + 2-bit pack into pinned memory (chunks of {P}, {2 * P}, then {chunk_reads} reads, each rank its 1/{world} "
+               "includes": f"host normalise + 2-bit pack into pinned memory (chunks of {P}, {2 * P}, {4 * P} ... up to {chunk_reads} reads, each rank its 1/{world} "
                            f"of a chunk; a reader thread packs up to {NB - 1} chunks ahead, copies run on the copy stream), all kernels, "
                            + ("the NCCL exchanges, " if world > 1 else "") + "D2H of the top-N into page-locked host arrays"
                            + (", the per-read genotype consensus on the host" if gt is not None else ""),

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -863,6 +864,8 @@ int run_passes_reported(skb_ctx* c, const QuerySet& qs, uint32_t n_reads, uint32
 int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint64_t seed, uint32_t top, int pad,
                    uint32_t* d_out_idx, uint64_t* d_out_sum) {
   if (int rc = predict_checks(c, k, s_query, top, pad)) return rc;
+  const auto t_0 = std::chrono::steady_clock::now();
+  auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   if (int rc = use_batch(b)) return rc;
   const uint32_t R = (uint32_t)b->g_first.size();
   c->st_passes = 0; c->st_qhashes = 0; c->st_cands = 0; c->st_ref_bytes = c->ref_len * 8;
@@ -878,6 +881,7 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   std::vector<uint64_t> kmers;
   SelectPlan plan;
   if (int rc = run_hash_select(c, b, k, s_query, seed, true, c->hmax, nullptr, nullptr, qn, kmers, plan)) return rc;
+  const double t_hash = ms_since(t_0);
   uint64_t QN = 0;
   for (uint32_t v : qn) QN += v;
   CU(c, c->qh.ensure(std::max<uint64_t>(QN, 1) * 8));
@@ -895,7 +899,12 @@ int predict_device(skb_ctx* c, skb_batch* b, uint32_t k, uint32_t s_query, uint6
   if (int rc = check_launch(c, "compact")) return rc;
   QuerySet qs;
   if (int rc = finish_query_set(c, qn, qs, true)) return rc;
-  return run_passes_reported(c, qs, R, top, d_out_idx, d_out_sum);
+  const double t_query = ms_since(t_0);
+  const int rc = run_passes_reported(c, qs, R, top, d_out_idx, d_out_sum);
+  if (c->trace_passes)
+    fprintf(stderr, "[skb] predict call: %u reads, host clock: query lists ready at %.3f ms (hash + select %.3f), passes done at %.3f ms (%llu passes)\n",
+            R, t_query, t_hash, ms_since(t_0), (unsigned long long)c->st_passes);
+  return rc;
 }
 
 int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx, uint64_t* d_out_sum) {
