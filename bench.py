@@ -693,6 +693,8 @@ def sketch_leg(ctx, args, device):
     assert all((osk[g][0] == sk_out[g][0]).all() for g in range(n_cpu)), "GPU sketches differ from the oracle"
     kern_gbp = gbp / ((hash_ms + sel_ms) / n_it * 1e-3)
     bound = 600.0   # ~30 IMAD + ~25 ALU per k-mer at 64 lanes/clk/SM x 148 SMs x 1.965 GHz
+    inst_per_kmer = 86.0   # ncu: smsp__inst_executed.sum x 32 / k-mers (profiles/r02_hash_kernel_ncu.md); SASS body: 75
+    issue_bound = 148 * 4 * 1.965 * 32 / inst_per_kmer   # Gbp/s at one warp instruction per cycle per scheduler
     return {"workload": f"C2 sample: {ng} x 2.8 Mbp assemblies, k=16, s=1000",
             "kernel_gbp_per_s": kern_gbp, "hash_kernel_ms": hash_ms / n_it, "select_kernel_ms": sel_ms / n_it,
             "resident_call_gbp_per_s": gbp / dt_res, "resident_call_ms": dt_res * 1e3,
@@ -700,8 +702,11 @@ def sketch_leg(ctx, args, device):
             "host_call_includes": "normalise + 2-bit pack into pinned memory (all host threads), H2D, kernels, D2H of the sketches",
             "cli_fasta_to_msh": cli,
             "roofline": {"bound": "integer pipes", "achieved": kern_gbp, "peak": bound, "unit": "Gbp/s", "frac": kern_gbp / bound,
-                         "peak_source": "estimate (SURVEY App. D.2 instruction count at the 1965 MHz maximum clock); pipe "
-                                        "utilisation from ncu in profiles/r02_hash_kernel_ncu.md"},
+                         "peak_source": "estimate (SURVEY App. D.2: 55 instructions per k-mer at the 1965 MHz maximum clock)",
+                         "issue_bound_gbp_per_s": issue_bound, "frac_of_issue_bound": kern_gbp / issue_bound,
+                         "issue_bound_source": f"{inst_per_kmer:.0f} warp instructions per 32 k-mers executed (ncu), one per cycle per "
+                                               "scheduler, 148 SMs x 4 schedulers x 1.965 GHz; pipe utilisation (ALU 65 %, FMA 40 %, "
+                                               "issue 71 %) in profiles/r02_hash_kernel_ncu.md"},
             "cpu_baseline": {"value": n_cpu * GENOME_LEN / 1e9 / dt_cpu, "unit": "Gbp/s", "cores": ncores, "kind": "port",
                              "sample": f"{n_cpu} of the assemblies, one file per host thread as rayon does "
                                        f"(src/sketchy.rs:470-472), {dt_cpu:.1f}s; sketches equal the GPU's"}}

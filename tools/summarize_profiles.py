@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn the ncu artefacts in gpurun_out/ into the tracked summaries under profiles/.
 
-usage: tools/summarize_profiles.py <round-tag> <launches.csv> <fused_full.ncu-rep>
+usage: tools/summarize_profiles.py <round-tag> <launches.csv> <fused_full.ncu-rep> [<hash_full.ncu-rep>]
 """
 import collections
 import csv
@@ -54,4 +54,23 @@ with open(f"profiles/{tag}_fused_kernel_ncu.md", "w") as f:
         if w in h:
             i = h.index(w)
             f.write(f"| {w} | {r[i]} | {u[i]} |\n")
+if len(sys.argv) > 4:
+    out = subprocess.run(["ncu", "-i", sys.argv[4], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(out.split("\n")))
+    h, u, r = rr[0], rr[1], rr[2]
+    want_h = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "sm__cycles_elapsed.avg",
+              "smsp__issue_active.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+              "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+              "launch__registers_per_thread", "launch__grid_size", "dram__bytes_read.sum",
+              "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+    want_h += [x for x in h if "issue_stalled" in x and x.endswith("per_issue_active.ratio") and "not_issued" not in x]
+    with open(f"profiles/{tag}_hash_kernel_ncu.md", "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none` of hash_kernel<K16, seed 0> (sketch leg: 64 x 2.8 Mbp assemblies = 179.2 M k-mers, k=16)\n\n")
+        f.write("instructions per k-mer = smsp__inst_executed.sum x 32 / 179.2 M\n\n| metric | value | unit |\n|---|---:|---|\n")
+        for w in want_h:
+            if w in h:
+                i = h.index(w)
+                f.write(f"| {w} | {r[i]} | {u[i]} |\n")
 print("written")
