@@ -231,6 +231,8 @@ struct skb_ctx {
   int tracked_cur = 0;
   DevBuf tprefix, textra;
   cudaStream_t side = nullptr;  // pre-pass / post-pass kernels, overlapping the streaming kernel of the neighbouring passes
+  cudaStream_t tabs = nullptr;  // query-table builds: table(i) is built next to the post-pass kernels of pass i-1
+  cudaEvent_t ev_tab[SKB_NTAB] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_pre[SKB_NTAB] = {nullptr, nullptr, nullptr}, ev_fused[2] = {nullptr, nullptr}, ev_join = nullptr;
   int tab_cur = 0;              // slot of the newest query table
   bool pass_proven = false;     // a full-size sparse pass has been checked and did not overflow: batch them
@@ -343,6 +345,7 @@ void prof_resolve(skb_ctx* c) {
   if (c->pending.empty()) return;
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->side);
+  if (c->tabs) cudaStreamSynchronize(c->tabs);
   for (auto& e : c->pending) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->prof_ms[e.id] += ms;
@@ -981,6 +984,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
   struct Pending { bool on = false, dense = false; SkbRankArgs ra; SkbDenseArgs da; int fused_ev = 0; } post;
   const uint32_t kBatch = 8;
   bool prev_pipelined = false;  // the previous pass of this call was enqueued in steady state (S_{i-2}, T_{i-1} are its inputs)
+  bool have_fused = false;      // a streaming kernel of this call has been enqueued (its event orders the next table build)
   uint32_t seq = 0, r = 0, dense_until = 0, dense_max_reads = Bmax;
   int rc_final = SKB_OK, tracked_prev = c->tracked_cur;
   const SkbRefView rv = ref_view(c);
@@ -1013,6 +1017,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
   // the side stream starts behind whatever the main stream has done so far (hashing, selection, resets)
   EV(cudaEventRecord(c->ev_join, c->stream));
   EV(cudaStreamWaitEvent(c->side, c->ev_join, 0));
+  EV(cudaStreamWaitEvent(c->tabs, c->ev_join, 0));
 
   while (r < R) {
     if (ev_err != cudaSuccess) { rc_final = fail(c, SKB_ERR_CUDA, "predict pass (stream ordering): %s", cudaGetErrorString(ev_err)); break; }
@@ -1042,11 +1047,16 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     const int x_in = lag2 ? tracked_prev : c->tracked_cur, x_out = (c->tracked_cur + 1) % SKB_NTRACK;
     if (!lag2) enqueue_post();  // X_i = U_{i-1}: post(i-1) first
 
-    // ---- pre(i) on the side stream
+    // ---- table(i) on its own stream: it needs nothing of pass i-1 but the end of its streaming kernel (every earlier
+    // user of the table's slot is over by then), so it runs next to post(i-1) instead of behind it
     const SkbTable t = table_of(c, tab);
-    { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1, c->side);
-      skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->t_built[tab], c->side);
+    EV(cudaStreamWaitEvent(c->tabs, have_fused ? c->ev_fused[(seq + 1) & 1] : c->ev_join, 0));
+    { ProfScope ps(c, SKB_K_TABLE, nkeys ? 4 : 1, c->tabs);
+      skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->t_built[tab], c->tabs);
       c->t_built[tab] = nkeys; }
+    EV(cudaEventRecord(c->ev_tab[tab], c->tabs));
+    // ---- pre(i) on the side stream
+    EV(cudaStreamWaitEvent(c->side, c->ev_tab[tab], 0));
     SkbRankArgs ra{};
     ra.tracked_counts = c->counts.as<uint16_t>(); ra.tracked_prefix = c->tprefix.as<uint32_t>();
     ra.tracked_extra = c->textra.as<unsigned long long>();
@@ -1091,6 +1101,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     fa.tpr_magic = (uint32_t)((0x100000000ull + fa.tpr - 1) / fa.tpr);
     { ProfScope ps(c, SKB_K_STREAM, 1); skb_launch_fused(fa, c->stream); }
     EV(cudaEventRecord(c->ev_fused[qs], c->stream));
+    have_fused = true;
     if (int rc = check_launch(c, "predict pass")) { rc_final = rc; break; }
     post.on = true; post.dense = dense; post.ra = ra; post.fused_ev = qs;
     if (dense) {
@@ -1141,6 +1152,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       recs.clear();
       EV(cudaEventRecord(c->ev_join, c->stream));
       EV(cudaStreamWaitEvent(c->side, c->ev_join, 0));
+      EV(cudaStreamWaitEvent(c->tabs, c->ev_join, 0));
       continue;
     }
     if (h_total[0] != 0) {  // more contenders than a bucket / a record list holds, in the sparse pass numbered h_total[1]
@@ -1163,6 +1175,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       recs.clear();
       EV(cudaEventRecord(c->ev_join, c->stream));
       EV(cudaStreamWaitEvent(c->side, c->ev_join, 0));
+      EV(cudaStreamWaitEvent(c->tabs, c->ev_join, 0));
       continue;
     }
     if (dense) {
@@ -1176,6 +1189,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
 #undef EV
   if (!rc_final && ev_err != cudaSuccess) rc_final = fail(c, SKB_ERR_CUDA, "predict pass (stream ordering): %s", cudaGetErrorString(ev_err));
   if (rc_final) {  // leave nothing in flight behind an error
+    cudaStreamSynchronize(c->tabs);
     cudaStreamSynchronize(c->side);
     cudaStreamSynchronize(c->stream);
     return rc_final;
@@ -1336,8 +1350,10 @@ int skb_create(int device, skb_ctx** out) {
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->tabs, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < SKB_NTAB; ++i) ok = cudaEventCreateWithFlags(&c->ev_pre[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < SKB_NTAB; ++i) ok = cudaEventCreateWithFlags(&c->ev_tab[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&c->ev_fused[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { delete c; return SKB_ERR_CUDA; }
   // environment switches are read once, here (tests and experiments; never inside the pass loop)
@@ -1357,6 +1373,7 @@ void skb_destroy(skb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->side) cudaStreamSynchronize(c->side);
+  if (c->tabs) cudaStreamSynchronize(c->tabs);
   if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
   for (auto& e : c->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1376,6 +1393,8 @@ void skb_destroy(skb_ctx* c) {
   cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->side) cudaStreamDestroy(c->side);
+  if (c->tabs) cudaStreamDestroy(c->tabs);
+  for (int i = 0; i < SKB_NTAB; ++i) if (c->ev_tab[i]) cudaEventDestroy(c->ev_tab[i]);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (cudaEvent_t e : c->ev_pre) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_fused) if (e) cudaEventDestroy(e);
