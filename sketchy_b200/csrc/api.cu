@@ -1267,10 +1267,14 @@ int predict_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t
   CU(c, cudaMemsetAsync(d_qn + (size_t)c->rank * Rmax, 0, (size_t)Rmax * 4, c->stream));
   if (R_loc) CU(c, cudaMemcpyAsync(d_qn + (size_t)c->rank * Rmax, c->g_outn.p, (size_t)R_loc * 4, cudaMemcpyDeviceToDevice, c->stream));
   NC(c, g_nccl.AllGather(d_qn + (size_t)c->rank * Rmax, d_qn, Rmax, ncclUint32, c->comm, c->stream));
-  std::vector<uint32_t> qn_pad((size_t)W * Rmax), qn(R);
-  CU(c, cudaMemcpyAsync(qn_pad.data(), d_qn, qn_pad.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<uint32_t> qn(R);
+  CU(c, c->h_outn.ensure((size_t)W * Rmax * 4 + 64, 0));   // page-locked staging, as in the single-GPU path
+  CU(c, c->h_off.ensure(((size_t)R + 1) * 8, 0));
+  const uint32_t* qn_pad = c->h_outn.as<uint32_t>();
+  uint64_t* off = c->h_off.as<uint64_t>();
+  CU(c, cudaMemcpyAsync(c->h_outn.p, d_qn, (size_t)W * Rmax * 4, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  std::vector<uint64_t> off(R + 1, 0);
+  off[0] = 0;
   for (int g = 0; g < W; ++g) {
     uint64_t gb, gc;
     dist_range(R, g, W, &gb, &gc);
@@ -1280,7 +1284,7 @@ int predict_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t
   const uint64_t QN = off[R];
   CU(c, c->qh.ensure(std::max<uint64_t>(QN, 1) * 8));
   CU(c, c->q_off.ensure(((size_t)R + 1) * 8));
-  CU(c, cudaMemcpyAsync(c->q_off.p, off.data(), ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->q_off.p, off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   if (R_loc) {
     ProfScope ps(c, SKB_K_SELECT, 1);
     skb_launch_compact_queries(c->cand_pool.as<uint64_t>(), c->g_base.as<uint64_t>(), c->g_outn.as<uint32_t>(),
@@ -1299,9 +1303,8 @@ int predict_dist_device(skb_ctx* c, skb_batch* b, uint64_t reads_total, uint32_t
     if (r != ncclSuccess) { g_nccl.GroupEnd(); return fail(c, SKB_ERR_COMM, "ncclBroadcast: %s", g_nccl.GetErrorString(r)); }
   }
   NC(c, g_nccl.GroupEnd());
-  CU(c, cudaStreamSynchronize(c->stream));  // `off` is a local: its copy must be done; and the exchange is complete
-  QuerySet qs;
-  if (int rc = finish_query_set(c, qn, qs)) return rc;
+  QuerySet qs;   // (the offsets are on the device already; the passes are stream-ordered behind the exchange)
+  if (int rc = finish_query_set(c, qn, qs, true)) return rc;
   // ---- passes of every read against this rank's rows, then the exchange of the local top-N lists
   CU(c, c->out_idx.ensure(std::max<size_t>(4, (size_t)R * top * 4)));
   CU(c, c->out_sum.ensure(std::max<size_t>(8, (size_t)R * top * 8)));
