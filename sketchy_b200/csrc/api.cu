@@ -232,7 +232,7 @@ struct skb_ctx {
   DevBuf tprefix, textra;
   cudaStream_t side = nullptr;  // pre-pass / post-pass kernels, overlapping the streaming kernel of the neighbouring passes
   cudaStream_t tabs = nullptr;  // query-table builds: table(i) is built next to the post-pass kernels of pass i-1
-  cudaEvent_t ev_tab[SKB_NTAB] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_tab[SKB_NTAB] = {nullptr, nullptr, nullptr}, ev_post = nullptr;
   cudaEvent_t ev_pre[SKB_NTAB] = {nullptr, nullptr, nullptr}, ev_fused[2] = {nullptr, nullptr}, ev_join = nullptr;
   int tab_cur = 0;              // slot of the newest query table
   bool pass_proven = false;     // a full-size sparse pass has been checked and did not overflow: batch them
@@ -985,6 +985,7 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
   const uint32_t kBatch = 8;
   bool prev_pipelined = false;  // the previous pass of this call was enqueued in steady state (S_{i-2}, T_{i-1} are its inputs)
   bool have_fused = false;      // a streaming kernel of this call has been enqueued (its event orders the next table build)
+  bool have_post = false;       // a post-pass sequence of this call has been enqueued (ev_post is behind the newest one)
   uint32_t seq = 0, r = 0, dense_until = 0, dense_max_reads = Bmax;
   int rc_final = SKB_OK, tracked_prev = c->tracked_cur;
   const SkbRefView rv = ref_view(c);
@@ -1007,6 +1008,8 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       skb_launch_rank_expand(post.ra, c->side); skb_launch_rank_select(post.ra, c->side);
       skb_launch_verdict_update(post.ra, true, c->side);  // (the update is skipped on the device after an overflow)
     }
+    EV(cudaEventRecord(c->ev_post, c->side));
+    have_post = true;
     post.on = false;
   };
   auto join_streams = [&]() -> cudaError_t {  // main stream waits for everything enqueued on the side stream
@@ -1055,8 +1058,14 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
       skb_launch_table_build(t, c->qh.as<uint64_t>() + q_off[r], c->qread.as<uint32_t>() + q_off[r], nkeys, r, c->t_built[tab], c->tabs);
       c->t_built[tab] = nkeys; }
     EV(cudaEventRecord(c->ev_tab[tab], c->tabs));
-    // ---- pre(i) on the side stream
-    EV(cudaStreamWaitEvent(c->side, c->ev_tab[tab], 0));
+    // ---- pre(i): on the side stream behind post(i-1), whose tracked rows it uses; with bounds taken two passes back
+    // (lag2) it needs nothing of post(i-1) and follows the table build on the table stream, next to post(i-1)
+    cudaStream_t pre_st = lag2 ? c->tabs : c->side;
+    if (lag2) {
+      if (have_post) EV(cudaStreamWaitEvent(c->tabs, c->ev_post, 0));  // U_{i-2} (and every post before it) is complete
+    } else {
+      EV(cudaStreamWaitEvent(c->side, c->ev_tab[tab], 0));
+    }
     SkbRankArgs ra{};
     ra.tracked_counts = c->counts.as<uint16_t>(); ra.tracked_prefix = c->tprefix.as<uint32_t>();
     ra.tracked_extra = c->textra.as<unsigned long long>();
@@ -1075,14 +1084,14 @@ int run_passes(skb_ctx* c, const QuerySet& qs, uint32_t top, uint32_t* d_out_idx
     ra.abort = d_abort; ra.seq = seq;
     cudaError_t e = cudaSuccess;
     if (!dense) {
-      e = cudaMemsetAsync(c->textra.p, 0, (size_t)SKB_MAX_TRACKED * 8, c->side);
+      e = cudaMemsetAsync(c->textra.p, 0, (size_t)SKB_MAX_TRACKED * 8, pre_st);
       if (e != cudaSuccess) { rc_final = fail(c, SKB_ERR_CUDA, "predict pass: %s", cudaGetErrorString(e)); break; }
-      ProfScope ps(c, SKB_K_RANK, 2 + (lag2 ? 1 : 0), c->side);
-      if (lag2) skb_launch_tracked_totals(rv, ra.tracked, ra.n_tracked, table_of(c, tab_prev), ra.tracked_extra, c->side);
-      skb_launch_rank_bounds(rv, t, ra, nkeys != 0, c->side);
+      ProfScope ps(c, SKB_K_RANK, 2 + (lag2 ? 1 : 0), pre_st);
+      if (lag2) skb_launch_tracked_totals(rv, ra.tracked, ra.n_tracked, table_of(c, tab_prev), ra.tracked_extra, pre_st);
+      skb_launch_rank_bounds(rv, t, ra, nkeys != 0, pre_st);
     }
-    EV(cudaEventRecord(c->ev_pre[tab], c->side));
-    if (lag2) enqueue_post();  // post(i-1) behind pre(i): it runs next to stream(i)
+    EV(cudaEventRecord(c->ev_pre[tab], pre_st));
+    if (lag2) enqueue_post();  // post(i-1) on the side stream, next to pre(i)
 
     // ---- stream(i) on the main stream
     EV(cudaStreamWaitEvent(c->stream, c->ev_pre[tab], 0));
@@ -1357,6 +1366,7 @@ int skb_create(int device, skb_ctx** out) {
             cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < SKB_NTAB; ++i) ok = cudaEventCreateWithFlags(&c->ev_pre[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < SKB_NTAB; ++i) ok = cudaEventCreateWithFlags(&c->ev_tab[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_post, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreateWithFlags(&c->ev_fused[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { delete c; return SKB_ERR_CUDA; }
   // environment switches are read once, here (tests and experiments; never inside the pass loop)
@@ -1398,6 +1408,7 @@ void skb_destroy(skb_ctx* c) {
   if (c->side) cudaStreamDestroy(c->side);
   if (c->tabs) cudaStreamDestroy(c->tabs);
   for (int i = 0; i < SKB_NTAB; ++i) if (c->ev_tab[i]) cudaEventDestroy(c->ev_tab[i]);
+  if (c->ev_post) cudaEventDestroy(c->ev_post);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   for (cudaEvent_t e : c->ev_pre) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_fused) if (e) cudaEventDestroy(e);
