@@ -8,7 +8,9 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstring>
 #include <exception>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -17,9 +19,21 @@
 
 namespace ingest {
 
+// allocator that leaves new elements uninitialised: a blob of a gigabyte is sized in one step and then filled by many
+// threads (a zero-filling resize would touch every page on one thread first)
+template <class T>
+struct DefaultInit : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInit<U>; };
+  DefaultInit() = default;
+  template <class U> DefaultInit(const DefaultInit<U>&) {}
+  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using Bytes = std::vector<uint8_t, DefaultInit<uint8_t>>;
+
 // records of a batch as skb_batch_add takes them: one blob, offsets[n + 1], group of every record
 struct Blob {
-  std::vector<uint8_t> bytes;
+  Bytes bytes;
   std::vector<uint64_t> off{0};
   std::vector<uint32_t> grp;
   void add(const std::string& s, uint32_t g) {
@@ -87,16 +101,36 @@ inline Blob read_files(const std::vector<std::string>& files, size_t g0, size_t 
   }
   for (size_t i = 0; i < n; ++i)
     if (errs[i]) std::rethrow_exception(errs[i]);
+  // concatenation in file order: offsets first, then the bytes of the parts are copied by the same number of threads
+  // into a blob that is sized without being touched
   Blob out;
   uint64_t total = 0;
   size_t recs = 0;
-  for (const Blob& p : parts) { total += p.bytes.size(); recs += p.n(); }
-  out.bytes.reserve(total);
+  std::vector<uint64_t> at(n + 1, 0);
+  for (size_t i = 0; i < n; ++i) { at[i + 1] = at[i] + parts[i].bytes.size(); recs += parts[i].n(); }
+  total = at[n];
+  out.bytes.resize(total);
   out.off.reserve(recs + 1);
   out.grp.reserve(recs);
-  for (Blob& p : parts) {
-    out.append(p);
-    Blob().bytes.swap(p.bytes);  // release as we go
+  for (size_t i = 0; i < n; ++i) {
+    for (size_t j = 1; j < parts[i].off.size(); ++j) out.off.push_back(at[i] + parts[i].off[j]);
+    out.grp.insert(out.grp.end(), parts[i].grp.begin(), parts[i].grp.end());
+  }
+  std::atomic<size_t> nextc{0};
+  auto copy = [&]() {
+    for (;;) {
+      const size_t i = nextc.fetch_add(1);
+      if (i >= n) return;
+      if (!parts[i].bytes.empty()) std::memcpy(out.bytes.data() + at[i], parts[i].bytes.data(), parts[i].bytes.size());
+      Bytes().swap(parts[i].bytes);  // release as we go
+    }
+  };
+  if (T <= 1) {
+    copy();
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; ++t) pool.emplace_back(copy);
+    for (auto& th : pool) th.join();
   }
   return out;
 }

@@ -103,16 +103,17 @@ int env_int(std::initializer_list<const char*> names, int dflt) {
 struct Ctx {
   skb_ctx* c = nullptr;
   int rank = 0, world = 1;
-  Ctx() {
+  // with_comm = false: a sub-command whose ranks exchange nothing on the device (`sketch`) skips the NCCL set-up
+  explicit Ctx(bool with_comm = true) {
     rank = env_int({"SKETCHY_B200_RANK", "RANK", "OMPI_COMM_WORLD_RANK"}, 0);
     world = env_int({"SKETCHY_B200_WORLD", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE"}, 1);
     if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad rank / world size in the environment");
     const int dev = env_int({"SKETCHY_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, 0);
     const int rc = skb_create(dev, &c);
     if (rc != SKB_OK) throw std::runtime_error("no B200 (sm_100) device: the B200 build has no CPU fallback");
-    if (world > 1) join();
+    if (world > 1 && with_comm) join();
   }
-  ~Ctx() { if (c) { skb_comm_destroy(c); skb_destroy(c); } }
+  ~Ctx() { if (c) { if (skb_comm_world(c) > 1) skb_comm_destroy(c); skb_destroy(c); } }
   void check(int rc) const { if (rc != SKB_OK) throw std::runtime_error(skb_last_error(c)); }
   void join() {
     // stdout carries the result rows: whatever NCCL prints while the communicator is set up (its version banner goes to
@@ -144,6 +145,35 @@ struct Ctx {
       }
     }
     check(skb_comm_init(c, id, rank, world));
+  }
+  // Host-side gather without a communicator: every rank but 0 publishes its bytes as <SKETCHY_B200_COMM_FILE>.<tag>.<rank>
+  // (written under a temporary name, then renamed), rank 0 collects them in rank order (and removes the files).
+  void gather_files(const char* tag, const std::vector<uint8_t>& mine, std::vector<uint8_t>& all) const {
+    const char* path = getenv("SKETCHY_B200_COMM_FILE");
+    if (!path) throw std::runtime_error("multi-GPU run: set SKETCHY_B200_COMM_FILE to a path every rank can reach");
+    auto name = [&](int r) { return std::string(path) + "." + tag + "." + std::to_string(r); };
+    if (rank != 0) {
+      const std::string tmp = name(rank) + ".tmp";
+      FILE* fp = fopen(tmp.c_str(), "wb");
+      if (!fp || (mine.size() && fwrite(mine.data(), 1, mine.size(), fp) != mine.size())) throw std::runtime_error("cannot write the rank's result file");
+      fclose(fp);
+      if (rename(tmp.c_str(), name(rank).c_str()) != 0) throw std::runtime_error("cannot publish the rank's result file");
+      return;
+    }
+    all.assign(mine.size() * (size_t)world, 0);
+    if (!mine.empty()) memcpy(all.data(), mine.data(), mine.size());
+    for (int r = 1; r < world; ++r) {
+      for (int waited = 0;; ++waited) {
+        FILE* fp = fopen(name(r).c_str(), "rb");
+        if (fp) {
+          const size_t n = mine.empty() ? 0 : fread(all.data() + (size_t)r * mine.size(), 1, mine.size(), fp);
+          fclose(fp);
+          if (n == mine.size()) { remove(name(r).c_str()); break; }
+        }
+        if (waited > 360000) throw std::runtime_error("timed out waiting for a rank's result file");
+        usleep(10000);
+      }
+    }
   }
   // contiguous share of n items of this rank
   void range(uint64_t n, uint64_t& begin, uint64_t& count) const { skb_dist_range(n, rank, world, &begin, &count); }
@@ -249,6 +279,8 @@ void upload_reference(const Ctx& c, const msh::File& ref) {
 }
 
 // ---- sub-commands -----------------------------------------------------------------------------------------------
+constexpr uint64_t kWindowBytes = 256ull << 20;  // files of one skb_sketch call (on disk); the next window is read meanwhile
+
 int cmd_sketch(const Args& a) {
   if (!a.has("output")) throw std::runtime_error("error: The following required arguments were not provided: --output <output>");
   const std::string out = a.one("output");
@@ -261,7 +293,7 @@ int cmd_sketch(const Args& a) {
   std::vector<std::string> files;
   if (a.has("input")) files = a.opt.at("input");
   else for (std::string l; std::getline(std::cin, l);) if (!l.empty()) files.push_back(l);  // src/sketchy.rs:137-146
-  Ctx c;
+  Ctx c(false);  // the ranks sketch their files independently: no communicator
   if (c.rank == 0) {
     FILE* fp = fopen(out.c_str(), "wb");  // created before sketching, like the reference (:153)
     if (!fp) throw std::runtime_error("failed to open file");
@@ -269,8 +301,10 @@ int cmd_sketch(const Args& a) {
   }
   // The reference runs its files on a rayon pool, one sketcher per file (src/sketchy.rs:470-473). Here: the files are
   // partitioned over the GPUs by contiguous range (no collective in the hashing); a rank takes its files in windows
-  // (<= 1 GB on disk each): window i+1 is read, decompressed and split into records on the host threads while window
+  // (<= 256 MB on disk each): window i+1 is read, decompressed and split into records on the host threads while window
   // i is packed, copied and sketched, one skb_sketch call per window; results are kept in file order.
+  // the ranks of one box share its host cores
+  const unsigned host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, c.world));
   const uint32_t G = (uint32_t)files.size();
   uint64_t f_lo = 0, f_cnt = 0;
   c.range(G, f_lo, f_cnt);
@@ -284,18 +318,18 @@ int cmd_sketch(const Args& a) {
   {
     Blob cur, nxt;
     std::exception_ptr err;
-    size_t g0 = f_lo, g1 = ingest::window_end(files, g0, 1ull << 30);
+    size_t g0 = f_lo, g1 = ingest::window_end(files, g0, kWindowBytes);
     const size_t g_end = f_lo + f_cnt;
     if (g1 > g_end) g1 = g_end;
-    if (g0 < g_end) cur = ingest::read_files(files, g0, g1);
+    if (g0 < g_end) cur = ingest::read_files(files, g0, g1, host_threads);
     while (g0 < g_end) {
-      size_t n0 = g1, n1 = n0 < g_end ? std::min(g_end, ingest::window_end(files, n0, 1ull << 30)) : n0;
+      size_t n0 = g1, n1 = n0 < g_end ? std::min(g_end, ingest::window_end(files, n0, kWindowBytes)) : n0;
       std::thread reader;
-      if (n0 < g_end) reader = std::thread([&]() { try { nxt = ingest::read_files(files, n0, n1); } catch (...) { err = std::current_exception(); } });
+      if (n0 < g_end) reader = std::thread([&]() { try { nxt = ingest::read_files(files, n0, n1, host_threads); } catch (...) { err = std::current_exception(); } });
       const uint32_t W = (uint32_t)(g1 - g0);
       for (uint32_t& g : cur.grp) g -= (uint32_t)g0;  // groups of a window start at 0
       c.check(skb_batch_clear(b));
-      if (cur.n()) c.check(skb_batch_add(b, cur.bytes.data(), cur.off.data(), cur.grp.data(), cur.n(), 0));
+      if (cur.n()) c.check(skb_batch_add(b, cur.bytes.data(), cur.off.data(), cur.grp.data(), cur.n(), host_threads));
       const uint32_t have = skb_batch_num_groups(b);  // trailing empty files have no group
       std::vector<uint64_t> hs((size_t)W * s), bases(W, 0), kmers(W, 0);
       std::vector<uint32_t> cnt((size_t)W * s), n(W, 0);
@@ -316,10 +350,7 @@ int cmd_sketch(const Args& a) {
   }
   skb_batch_destroy(b);
   std::vector<uint8_t> all;
-  if (c.world > 1) {
-    all.resize(mine.size() * c.world);
-    c.check(skb_comm_allgather_host(c.c, mine.data(), all.data(), mine.size()));
-  }
+  if (c.world > 1) c.gather_files("sketch", mine, all);
   if (c.rank != 0) return 0;
   msh::File f;
   f.kmer_size = k; f.sketch_size = 0; f.hash_seed = seed;  // minHashesPerWindow = the largest sketch, as finch writes it [RECALLED]

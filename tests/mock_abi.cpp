@@ -80,6 +80,8 @@ int skb_predict_stream(skb_ctx*, skb_batch* b, uint32_t k, uint32_t s_query, uin
 int skb_comm_unique_id(uint8_t* id) { memset(id, 0, SKB_COMM_ID_BYTES); return SKB_OK; }
 int skb_comm_init(skb_ctx*, const uint8_t*, int rank, int world) { logf("comm_init %d %d\n", rank, world); return SKB_OK; }
 int skb_comm_destroy(skb_ctx*) { return SKB_OK; }
+int skb_comm_rank(const skb_ctx*) { return 0; }
+int skb_comm_world(const skb_ctx*) { return 1; }
 void skb_dist_range(uint64_t n, int rank, int world, uint64_t* begin, uint64_t* count) {
   const uint64_t per = (n + world - 1) / world;
   const uint64_t b = per * rank < n ? per * rank : n, e = per * (rank + 1) < n ? per * (rank + 1) : n;
