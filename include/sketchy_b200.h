@@ -72,6 +72,11 @@ int skb_batch_clear(skb_batch* b);
  * removed, everything else breaks k-mer windows. nthreads host threads do the packing (0 = all cores). */
 int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, const uint32_t* groups, uint64_t n,
                   uint32_t nthreads);
+/* The same with the records given one by one: record r = lens[r] bytes at recs[r], anywhere in host memory (slices of
+ * file buffers read in place: a FASTA file goes from the page cache to the packer without an intermediate copy, which
+ * is how the `sketch` host reads its files where the reference iterates needletail records, src/sketchy.rs:474-478). */
+int skb_batch_add_records(skb_batch* b, const uint8_t* const* recs, const uint64_t* lens, const uint32_t* groups,
+                          uint64_t n, uint32_t nthreads);
 /* What a group's total_bases counts (finch `total_bases_and_kmers`, src/sketchy.rs:481 -> `.msh` length / `info`):
  * SKB_BASES_RAW (default) = the bytes of the record's sequence as the reader hands them over, line breaks of a
  * multi-line FASTA record included (needletail 0.4.1 passes its raw slice on);

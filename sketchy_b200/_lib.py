@@ -32,6 +32,7 @@ SYMBOLS = [
     ("skb_batch_destroy", None, [_vp]),
     ("skb_batch_clear", _i, [_vp]),
     ("skb_batch_add", _i, [_vp, _vp, _vp, _vp, _u64, _u32]),
+    ("skb_batch_add_records", _i, [_vp, _vp, _vp, _vp, _u64, _u32]),
     ("skb_batch_num_groups", _u32, [_vp]),
     ("skb_batch_num_records", _u64, [_vp]),
     ("skb_batch_num_bases", _u64, [_vp]),
@@ -351,6 +352,14 @@ class Batch:
 
     def add_records(self, records, groups=None, nthreads: int = 0):
         arrs = [np.frombuffer(bytes(r), dtype=np.uint8) if not isinstance(r, np.ndarray) else r for r in records]
+        if arrs and sum(a.size for a in arrs) >= 65536 * len(arrs):
+            # few long records (assemblies): handed over where they lie (skb_batch_add_records), no concatenation
+            arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in arrs]
+            ptrs = np.array([a.__array_interface__["data"][0] for a in arrs], dtype=np.uint64)
+            lens = np.array([a.size for a in arrs], dtype=np.uint64)
+            g = None if groups is None else np.ascontiguousarray(groups, dtype=np.uint32)
+            self.ctx.check(self.ctx.lib.skb_batch_add_records(self.h, _ptr(ptrs), _ptr(lens), _ptr(g), len(arrs), nthreads))
+            return self
         off = np.zeros(len(arrs) + 1, dtype=np.uint64)
         if arrs:
             off[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)

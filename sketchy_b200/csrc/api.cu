@@ -1455,16 +1455,11 @@ int skb_batch_clear(skb_batch* b) {
   return SKB_OK;
 }
 
-int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, const uint32_t* groups, uint64_t n,
-                  uint32_t nthreads) {
-  if (!b) return SKB_ERR_INVALID_ARG;
+namespace {
+// records given one by one (pointer + length each): what both entry points below come down to
+int batch_add_impl(skb_batch* b, const uint8_t* const* recs, const uint64_t* lens, const uint32_t* groups, uint64_t n,
+                   uint32_t nthreads) {
   skb_ctx* c = b->ctx;
-  cudaSetDevice(c->device);  // the pinned staging buffers belong to this context's device (callers may use any thread)
-  if (b->staged) return fail(c, SKB_ERR_STATE, "batch already staged; clear it before adding");
-  if (n == 0) return SKB_OK;
-  if (!offsets || (!blob && offsets[n] != offsets[0])) return fail(c, SKB_ERR_INVALID_ARG, "null blob/offsets");
-  for (uint64_t r = 0; r < n; ++r)
-    if (offsets[r + 1] < offsets[r]) return fail(c, SKB_ERR_INVALID_ARG, "record offsets must be non-decreasing");
   if (groups) {
     const uint64_t ng = b->g_first.size();
     if (ng && groups[0] + 1 < ng) return fail(c, SKB_ERR_INVALID_ARG, "groups must continue from the last group");
@@ -1474,8 +1469,10 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
   const uint64_t first_rec = b->rec_pos.size();
   const uint64_t first_group_of_call = b->g_first.size();  // (groups == NULL: record r opens group first_group_of_call + r)
   uint64_t cur = b->cur;
+  std::vector<uint64_t> before(n + 1, 0);  // bytes of the call's records in front of record r (the threads' shares go by bytes)
   for (uint64_t r = 0; r < n; ++r) {
-    const uint64_t len = offsets[r + 1] - offsets[r];
+    const uint64_t len = lens[r];
+    before[r + 1] = before[r] + len;
     const uint64_t next = round_up(cur + len + 1, 32);
     const uint64_t gid = groups ? groups[r] : b->g_first.size();
     while (b->g_first.size() <= gid) {  // open new (possibly empty) groups
@@ -1494,7 +1491,7 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
   uint32_t* codes = b->codes.as<uint32_t>();
   uint32_t* nmask = b->nmask.as<uint32_t>();
   uint32_t T = nthreads ? nthreads : std::max(1u, std::thread::hardware_concurrency());
-  const uint64_t total_bytes = offsets[n] - offsets[0];
+  const uint64_t total_bytes = before[n];
   if (total_bytes < (1u << 20) || n < 2) T = 1;
   T = (uint32_t)std::min<uint64_t>(T, n);
   std::vector<uint64_t> kept(b->base_count == SKB_BASES_STRIPPED ? n : 0);
@@ -1502,7 +1499,7 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
     for (uint64_t r = r0; r < r1; ++r) {
       const uint64_t P = b->rec_pos[first_rec + r];
       const uint64_t Pn = (first_rec + r + 1 < b->rec_pos.size()) ? b->rec_pos[first_rec + r + 1] : cur;
-      const uint64_t kp = pack_record(blob + offsets[r], offsets[r + 1] - offsets[r], P, Pn, codes, nmask);
+      const uint64_t kp = pack_record(recs[r], lens[r], P, Pn, codes, nmask);
       if (!kept.empty()) kept[r] = kp;
     }
   };
@@ -1513,8 +1510,8 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
     uint64_t r0 = 0;
     for (uint32_t t = 0; t < T; ++t) {
       // split by bytes so long and short records balance
-      const uint64_t target = offsets[0] + total_bytes * (t + 1) / T;
-      uint64_t r1 = (t + 1 == T) ? n : (uint64_t)(std::upper_bound(offsets + r0, offsets + n, target) - offsets);
+      const uint64_t target = total_bytes * (t + 1) / T;
+      uint64_t r1 = (t + 1 == T) ? n : (uint64_t)(std::upper_bound(before.begin() + r0, before.begin() + n, target) - before.begin());
       if (r1 > n) r1 = n;
       if (r1 < r0) r1 = r0;
       pool.emplace_back(work, r0, r1);
@@ -1527,13 +1524,43 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, co
     for (uint64_t r = n; r-- > 0;) {
       if (groups) gid = groups[r];
       else gid = first_group_of_call + r;
-      const uint64_t removed = (offsets[r + 1] - offsets[r]) - kept[r];
+      const uint64_t removed = lens[r] - kept[r];
       b->g_raw[gid] -= removed;
       b->total_raw -= removed;
     }
   }
   b->cur = cur;
   return SKB_OK;
+}
+}  // namespace
+
+int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* offsets, const uint32_t* groups, uint64_t n,
+                  uint32_t nthreads) {
+  if (!b) return SKB_ERR_INVALID_ARG;
+  skb_ctx* c = b->ctx;
+  cudaSetDevice(c->device);  // the pinned staging buffers belong to this context's device (callers may use any thread)
+  if (b->staged) return fail(c, SKB_ERR_STATE, "batch already staged; clear it before adding");
+  if (n == 0) return SKB_OK;
+  if (!offsets || (!blob && offsets[n] != offsets[0])) return fail(c, SKB_ERR_INVALID_ARG, "null blob/offsets");
+  for (uint64_t r = 0; r < n; ++r)
+    if (offsets[r + 1] < offsets[r]) return fail(c, SKB_ERR_INVALID_ARG, "record offsets must be non-decreasing");
+  std::vector<const uint8_t*> recs(n);
+  std::vector<uint64_t> lens(n);
+  for (uint64_t r = 0; r < n; ++r) { recs[r] = blob + offsets[r]; lens[r] = offsets[r + 1] - offsets[r]; }
+  return batch_add_impl(b, recs.data(), lens.data(), groups, n, nthreads);
+}
+
+int skb_batch_add_records(skb_batch* b, const uint8_t* const* recs, const uint64_t* lens, const uint32_t* groups,
+                          uint64_t n, uint32_t nthreads) {
+  if (!b) return SKB_ERR_INVALID_ARG;
+  skb_ctx* c = b->ctx;
+  cudaSetDevice(c->device);
+  if (b->staged) return fail(c, SKB_ERR_STATE, "batch already staged; clear it before adding");
+  if (n == 0) return SKB_OK;
+  if (!recs || !lens) return fail(c, SKB_ERR_INVALID_ARG, "null record pointers/lengths");
+  for (uint64_t r = 0; r < n; ++r)
+    if (!recs[r] && lens[r]) return fail(c, SKB_ERR_INVALID_ARG, "null record with a non-zero length");
+  return batch_add_impl(b, recs, lens, groups, n, nthreads);
 }
 
 int skb_batch_set_base_count(skb_batch* b, int mode) {

@@ -261,7 +261,70 @@ class XzDecoder : public Decoder {
   bool live_ = false, done_ = false;
 };
 
+// what the first bytes of a file say about its compression (needletail sniffs the same way, not by file name)
+enum class Packing { Plain, Gzip, Bzip2, Xz };
+inline Packing sniff(const uint8_t* magic, size_t got) {
+  if (got >= 2 && magic[0] == 0x1F && magic[1] == 0x8B) return Packing::Gzip;
+  if (got >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') return Packing::Bzip2;
+  if (got >= 6 && std::memcmp(magic, "\xFD" "7zXZ\0", 6) == 0) return Packing::Xz;
+  return Packing::Plain;
+}
+inline std::unique_ptr<Decoder> sniff_decoder(RawInput& in) {
+  uint8_t magic[6] = {0, 0, 0, 0, 0, 0};
+  const size_t got = in.peek(magic, 6);
+  switch (sniff(magic, got)) {
+    case Packing::Gzip: return std::unique_ptr<Decoder>(new GzDecoder(in));
+    case Packing::Bzip2: return std::unique_ptr<Decoder>(new Bz2Decoder(in));
+    case Packing::Xz: return std::unique_ptr<Decoder>(new XzDecoder(in));
+    default: return std::unique_ptr<Decoder>(new PlainDecoder(in));
+  }
+}
+
 // ---- records -----------------------------------------------------------------------------------------------------
+// The records of a whole (decoded) FASTA / FASTQ file that is held in memory, as slices of that memory: the same
+// records, in the same order and with the same raw sequence bytes, as Reader::next yields for the file, without copying
+// a byte. (`sketchy sketch` reads its files this way; the streaming reader below serves stdin and live streams.)
+struct Slice { size_t start, len; };
+inline void parse_in_place(const uint8_t* p, size_t n, std::vector<Slice>& out) {
+  size_t pos = 0;
+  while (pos < n && (p[pos] == '\n' || p[pos] == '\r')) ++pos;
+  if (pos >= n) return;
+  const bool fasta = p[pos] == '>';
+  if (!fasta && p[pos] != '@') throw open_error();
+  // next line = [b, e): without its '\n' and without one '\r' in front of it; false at the end of the input
+  auto line = [&](size_t& b, size_t& e) {
+    if (pos >= n) return false;
+    const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(p + pos, '\n', n - pos));
+    b = pos;
+    e = nl ? (size_t)(nl - p) : n;
+    pos = nl ? e + 1 : n;
+    if (e > b && p[e - 1] == '\r') --e;
+    return true;
+  };
+  for (;;) {
+    size_t b, e;
+    do { if (!line(b, e)) return; } while (e == b);  // blank lines in front of a header
+    if (fasta) {
+      if (p[b] != '>') throw open_error();
+      const size_t s0 = pos;  // the raw slice runs to the next line that starts with '>' (or the end), line breaks inside kept
+      while (pos < n && p[pos] != '>') {
+        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(p + pos, '\n', n - pos));
+        pos = nl ? (size_t)(nl - p) + 1 : n;
+      }
+      size_t s1 = pos;
+      while (s1 > s0 && (p[s1 - 1] == '\n' || p[s1 - 1] == '\r')) --s1;
+      out.push_back({s0, s1 - s0});
+    } else {
+      if (p[b] != '@') throw open_error();
+      size_t sb, se, pb, pe, qb, qe;
+      if (!line(sb, se)) throw open_error();
+      if (!line(pb, pe) || pe == pb || p[pb] != '+' || !line(qb, qe)) throw open_error();
+      if (qe - qb != se - sb) throw open_error();  // needletail rejects a record whose quality length differs
+      out.push_back({sb, se - sb});
+    }
+  }
+}
+
 class Reader {
  public:
   explicit Reader(const std::string& path) {
@@ -271,12 +334,7 @@ class Reader {
       if (fd < 0) throw open_error();
     }
     in_.reset(new RawInput(fd, path != "-"));
-    uint8_t magic[6] = {0, 0, 0, 0, 0, 0};
-    const size_t got = in_->peek(magic, 6);
-    if (got >= 2 && magic[0] == 0x1F && magic[1] == 0x8B) dec_.reset(new GzDecoder(*in_));
-    else if (got >= 3 && magic[0] == 'B' && magic[1] == 'Z' && magic[2] == 'h') dec_.reset(new Bz2Decoder(*in_));
-    else if (got >= 6 && std::memcmp(magic, "\xFD" "7zXZ\0", 6) == 0) dec_.reset(new XzDecoder(*in_));
-    else dec_.reset(new PlainDecoder(*in_));
+    dec_ = sniff_decoder(*in_);
     fill();
     while (pos_ < len_ && (buf_[pos_] == '\n' || buf_[pos_] == '\r')) ++pos_;
     if (pos_ < len_) {

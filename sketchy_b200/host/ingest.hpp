@@ -4,6 +4,7 @@
 // splitting the files into records. Files are read in windows (bounded memory), every file of a window on its own
 // thread, and handed on in file order: the batch the GPU sees is the same as with one reader.
 #pragma once
+#include <sys/mman.h>
 #include <sys/stat.h>
 
 #include <atomic>
@@ -133,6 +134,122 @@ inline Blob read_files(const std::vector<std::string>& files, size_t g0, size_t 
     for (auto& th : pool) th.join();
   }
   return out;
+}
+
+// ---- files held in memory, records as slices (the `sketch` path) ------------------------------------------------------
+// A window of files as they are on disk: plain files are read, every file by one read loop, straight into one arena
+// that is reused from window to window (no page faults after the first window); compressed files are decoded into a
+// buffer of their own. Records are slices of those buffers (fastx::parse_in_place), handed to skb_batch_add_records as
+// they lie: the only copy of a plain FASTA file between the page cache and the 2-bit packer is the read itself.
+struct Files {
+  Bytes arena;                  // plain files back to back
+  std::vector<Bytes> decoded;   // file i of the window when it is compressed, not a regular file, or grew while being read
+  std::vector<const uint8_t*> rec;
+  std::vector<uint64_t> len;
+  std::vector<uint32_t> grp;    // the file's index in the window
+  size_t n() const { return rec.size(); }
+  void clear() { rec.clear(); len.clear(); grp.clear(); decoded.clear(); }
+};
+
+inline void decode_all(fastx::RawInput& in, Bytes& out, bool plain = false) {
+  std::unique_ptr<fastx::Decoder> dec = plain ? std::unique_ptr<fastx::Decoder>(new fastx::PlainDecoder(in)) : fastx::sniff_decoder(in);
+  size_t have = out.size();
+  for (;;) {
+    if (out.size() < have + (4u << 20)) out.resize(std::max<size_t>(out.size() * 2, have + (4u << 20)));
+    const size_t got = dec->read(out.data() + have, out.size() - have);
+    if (got == 0) break;
+    have += got;
+  }
+  out.resize(have);
+}
+
+// files[g0, g1) into `w` (whose arena is reused); up to `nthreads` files are read and split into records at a time
+// (0 = all host threads). Errors as read_files reports them.
+inline void load_files(const std::vector<std::string>& files, size_t g0, size_t g1, unsigned nthreads, Files& w) {
+  const size_t n = g1 - g0;
+  w.clear();
+  w.decoded.resize(n);
+  std::vector<uint64_t> at(n + 1, 0);
+  std::vector<uint64_t> size(n, 0);
+  for (size_t i = 0; i < n; ++i) { size[i] = file_size_or_zero(files[g0 + i]); at[i + 1] = at[i] + size[i]; }
+  if (w.arena.size() < at[n]) {
+    Bytes().swap(w.arena);               // nothing of the last window is kept: no copy into the larger arena
+    w.arena.resize(at[n] + at[n] / 8);   // some room: windows of one budget differ by a file's size at most
+    // first touch of a fresh arena is the dearest part of the first window: ask for huge pages (a hint; ignored where
+    // transparent huge pages are off)
+    const uintptr_t lo = ((uintptr_t)w.arena.data() + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+    const uintptr_t hi = ((uintptr_t)w.arena.data() + w.arena.size()) & ~(uintptr_t)((2u << 20) - 1);
+    if (hi > lo) ::madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+  }
+  std::vector<std::vector<fastx::Slice>> slices(n);
+  std::vector<const uint8_t*> base(n, nullptr);
+  std::vector<std::exception_ptr> errs(n);
+  unsigned T = nthreads ? nthreads : std::max(1u, std::thread::hardware_concurrency());
+  T = (unsigned)std::min<size_t>(T, std::max<size_t>(n, 1));
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= n) return;
+      try {
+        const std::string& path = files[g0 + i];
+        const int fd = path == "-" ? 0 : ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw fastx::open_error();
+        uint8_t magic[6];
+        ssize_t got = size[i] ? ::pread(fd, magic, 6, 0) : -1;  // size 0: not a regular file (or empty): the streaming way
+        uint64_t have = 0;
+        bool in_arena = got >= 0 && fastx::sniff(magic, (size_t)got) == fastx::Packing::Plain;
+        if (in_arena) {
+          uint8_t* dst = w.arena.data() + at[i];
+          while (have < size[i]) {
+            const ssize_t r = ::read(fd, dst + have, size[i] - have);
+            if (r < 0) { if (errno == EINTR) continue; ::close(fd); throw fastx::open_error(); }
+            if (r == 0) break;  // shorter than stat said: what is there
+            have += (uint64_t)r;
+          }
+          uint8_t extra;
+          ssize_t r;
+          do r = ::read(fd, &extra, 1); while (r < 0 && errno == EINTR);
+          if (r == 1) {  // the file grew since stat: the rest goes behind a copy of what was read
+            in_arena = false;
+            Bytes& d = w.decoded[i];
+            d.resize(have + 1);
+            std::memcpy(d.data(), dst, have);
+            d[have] = extra;
+            fastx::RawInput in(fd, path != "-");
+            decode_all(in, d, true);  // plain bytes from here on (the magic was sniffed above)
+          } else if (path != "-") {
+            ::close(fd);
+          }
+          if (in_arena) { base[i] = dst; fastx::parse_in_place(dst, have, slices[i]); }
+        } else {
+          fastx::RawInput in(fd, path != "-");
+          decode_all(in, w.decoded[i]);
+        }
+        if (!in_arena) { base[i] = w.decoded[i].data(); fastx::parse_in_place(base[i], w.decoded[i].size(), slices[i]); }
+      } catch (...) {
+        errs[i] = std::current_exception();
+      }
+    }
+  };
+  if (T <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; ++t) pool.emplace_back(work);
+    for (auto& th : pool) th.join();
+  }
+  for (size_t i = 0; i < n; ++i)
+    if (errs[i]) std::rethrow_exception(errs[i]);
+  size_t recs = 0;
+  for (size_t i = 0; i < n; ++i) recs += slices[i].size();
+  w.rec.reserve(recs); w.len.reserve(recs); w.grp.reserve(recs);
+  for (size_t i = 0; i < n; ++i)
+    for (const fastx::Slice& sl : slices[i]) {
+      w.rec.push_back(base[i] + sl.start);
+      w.len.push_back(sl.len);
+      w.grp.push_back((uint32_t)i);
+    }
 }
 
 }  // namespace ingest

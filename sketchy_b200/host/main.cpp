@@ -2,6 +2,7 @@
 // and error texts as the reference CLI (src/cli.rs:23-133, src/main.rs:17-68, src/sketchy.rs), with the hot path on the
 // GPU through the C ABI. `info` and the hidden `msh-*` helpers need no GPU.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -104,10 +105,13 @@ struct Ctx {
   skb_ctx* c = nullptr;
   int rank = 0, world = 1;
   // with_comm = false: a sub-command whose ranks exchange nothing on the device (`sketch`) skips the NCCL set-up
-  explicit Ctx(bool with_comm = true) {
+  static void rank_from_env(int& rank, int& world) {
     rank = env_int({"SKETCHY_B200_RANK", "RANK", "OMPI_COMM_WORLD_RANK"}, 0);
     world = env_int({"SKETCHY_B200_WORLD", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE"}, 1);
     if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad rank / world size in the environment");
+  }
+  explicit Ctx(bool with_comm = true) {
+    rank_from_env(rank, world);
     const int dev = env_int({"SKETCHY_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, 0);
     const int rc = skb_create(dev, &c);
     if (rc != SKB_OK) throw std::runtime_error("no B200 (sm_100) device: the B200 build has no CPU fallback");
@@ -278,8 +282,16 @@ void upload_reference(const Ctx& c, const msh::File& ref) {
   c.check(skb_ref_upload(c.c, flat.data(), off.data(), (uint32_t)cnt, (uint32_t)lo));
 }
 
+// A finished single-GPU command leaves without tearing the CUDA context down piece by piece (freeing the device and
+// page-locked buffers one by one and the runtime's exit handlers cost a short run more than its kernels): the
+// results are flushed, the process ends, the driver reclaims everything.
+[[noreturn]] void leave(int rc) {
+  fflush(nullptr);
+  _exit(rc);
+}
+
 // ---- sub-commands -----------------------------------------------------------------------------------------------
-constexpr uint64_t kWindowBytes = 256ull << 20;  // files of one skb_sketch call (on disk); the next window is read meanwhile
+constexpr uint64_t kWindowBytes = 128ull << 20;  // files of one skb_sketch call (on disk); the next window is read meanwhile
 
 int cmd_sketch(const Args& a) {
   if (!a.has("output")) throw std::runtime_error("error: The following required arguments were not provided: --output <output>");
@@ -293,65 +305,98 @@ int cmd_sketch(const Args& a) {
   std::vector<std::string> files;
   if (a.has("input")) files = a.opt.at("input");
   else for (std::string l; std::getline(std::cin, l);) if (!l.empty()) files.push_back(l);  // src/sketchy.rs:137-146
-  Ctx c(false);  // the ranks sketch their files independently: no communicator
-  if (c.rank == 0) {
+  const auto t_main = std::chrono::steady_clock::now();
+  int rank = 0, world = 1;
+  Ctx::rank_from_env(rank, world);
+  if (rank == 0) {
     FILE* fp = fopen(out.c_str(), "wb");  // created before sketching, like the reference (:153)
     if (!fp) throw std::runtime_error("failed to open file");
     fclose(fp);
   }
   // The reference runs its files on a rayon pool, one sketcher per file (src/sketchy.rs:470-473). Here: the files are
   // partitioned over the GPUs by contiguous range (no collective in the hashing); a rank takes its files in windows
-  // (<= 256 MB on disk each): window i+1 is read, decompressed and split into records on the host threads while window
-  // i is packed, copied and sketched, one skb_sketch call per window; results are kept in file order.
+  // (<= 128 MB on disk each): window i+1 is read into memory (plain files as they are, compressed ones decoded) and
+  // split into record slices on the host threads while window i is packed from those slices, copied and sketched, one
+  // skb_sketch call per window; results are kept in file order.
   // the ranks of one box share its host cores
-  const unsigned host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, c.world));
+  const unsigned host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, world));
   const uint32_t G = (uint32_t)files.size();
   uint64_t f_lo = 0, f_cnt = 0;
-  c.range(G, f_lo, f_cnt);
+  skb_dist_range(G, rank, world, &f_lo, &f_cnt);
   const size_t per_file = 24 + (size_t)s * 12;  // n, bases, kmers, hashes[s], counts[s]
   uint64_t share = 0, dummy = 0;
-  skb_dist_range(G, 0, c.world, &dummy, &share);  // the largest share: the fixed record size of the exchange
+  skb_dist_range(G, 0, world, &dummy, &share);  // the largest share: the fixed record size of the exchange
   std::vector<uint8_t> mine((size_t)share * per_file, 0);
   auto rec = [&](std::vector<uint8_t>& buf, size_t i) { return buf.data() + i * per_file; };
+  ingest::Files cur, nxt;  // two windows of files in memory: one being packed and sketched, one being read
+  std::exception_ptr err;
+  size_t g0 = f_lo, g1 = ingest::window_end(files, g0, kWindowBytes);
+  const size_t g_end = f_lo + f_cnt;
+  if (g1 > g_end) g1 = g_end;
+  // the first window is read while the CUDA context comes up (the larger part of a short run's wall time)
+  std::thread first;
+  if (g0 < g_end) first = std::thread([&]() { try { ingest::load_files(files, g0, g1, host_threads, cur); } catch (...) { err = std::current_exception(); } });
+  std::unique_ptr<Ctx> ctx;
+  try {
+    ctx.reset(new Ctx(false));  // the ranks sketch their files independently: no communicator
+  } catch (...) {
+    if (first.joinable()) first.join();
+    throw;
+  }
+  Ctx& c = *ctx;
+  const auto t_ctx = std::chrono::steady_clock::now();
+  if (first.joinable()) first.join();
+  if (err) std::rethrow_exception(err);
+  if (getenv("SKB_TRACE_SKETCH"))
+    fprintf(stderr, "[sketch rank %d] context ready %.1f ms after main, first window in memory after %.1f ms\n", rank,
+            std::chrono::duration<double, std::milli>(t_ctx - t_main).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_main).count());
   skb_batch* b = nullptr;
   c.check(skb_batch_create(c.c, &b));
   {
-    Blob cur, nxt;
-    std::exception_ptr err;
-    size_t g0 = f_lo, g1 = ingest::window_end(files, g0, kWindowBytes);
-    const size_t g_end = f_lo + f_cnt;
-    if (g1 > g_end) g1 = g_end;
-    if (g0 < g_end) cur = ingest::read_files(files, g0, g1, host_threads);
+    std::vector<uint64_t> hs, bases, kmers;
+    std::vector<uint32_t> cnt, n;
+    const bool trace = getenv("SKB_TRACE_SKETCH") != nullptr;
     while (g0 < g_end) {
       size_t n0 = g1, n1 = n0 < g_end ? std::min(g_end, ingest::window_end(files, n0, kWindowBytes)) : n0;
       std::thread reader;
-      if (n0 < g_end) reader = std::thread([&]() { try { nxt = ingest::read_files(files, n0, n1, host_threads); } catch (...) { err = std::current_exception(); } });
+      struct Join { std::thread& t; ~Join() { if (t.joinable()) t.join(); } } join_on_exit{reader};  // also when a call below throws
+      if (n0 < g_end) reader = std::thread([&]() { try { ingest::load_files(files, n0, n1, host_threads, nxt); } catch (...) { err = std::current_exception(); } });
       const uint32_t W = (uint32_t)(g1 - g0);
-      for (uint32_t& g : cur.grp) g -= (uint32_t)g0;  // groups of a window start at 0
+      const auto t_a = std::chrono::steady_clock::now();
       c.check(skb_batch_clear(b));
-      if (cur.n()) c.check(skb_batch_add(b, cur.bytes.data(), cur.off.data(), cur.grp.data(), cur.n(), host_threads));
+      if (cur.n()) c.check(skb_batch_add_records(b, cur.rec.data(), cur.len.data(), cur.grp.data(), cur.n(), host_threads));
+      const auto t_b = std::chrono::steady_clock::now();
       const uint32_t have = skb_batch_num_groups(b);  // trailing empty files have no group
-      std::vector<uint64_t> hs((size_t)W * s), bases(W, 0), kmers(W, 0);
-      std::vector<uint32_t> cnt((size_t)W * s), n(W, 0);
+      hs.resize((size_t)W * s); cnt.resize((size_t)W * s);
+      bases.assign(W, 0); kmers.assign(W, 0); n.assign(W, 0);
       if (have) c.check(skb_sketch(c.c, b, k, s, seed, hs.data(), cnt.data(), n.data(), bases.data(), kmers.data()));
+      const auto t_c = std::chrono::steady_clock::now();
       for (uint32_t g = 0; g < W; ++g) {
         uint8_t* r = rec(mine, g0 - f_lo + g);
         const uint64_t nn = n[g];
         memcpy(r, &nn, 8); memcpy(r + 8, &bases[g], 8); memcpy(r + 16, &kmers[g], 8);
-        memcpy(r + 24, &hs[(size_t)g * s], (size_t)s * 8);
-        memcpy(r + 24 + (size_t)s * 8, &cnt[(size_t)g * s], (size_t)s * 4);
+        memcpy(r + 24, &hs[(size_t)g * s], (size_t)nn * 8);
+        memcpy(r + 24 + (size_t)s * 8, &cnt[(size_t)g * s], (size_t)nn * 4);
       }
       if (reader.joinable()) reader.join();
+      if (trace) {  // SKB_TRACE_SKETCH=1: where a window's time goes (stderr; stdout carries nothing for `sketch`)
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[sketch rank %d] files %zu-%zu: pack %.2f ms, sketch call %.2f ms, wait for the next window %.2f ms\n",
+                rank, g0, g1, ms(t_a, t_b), ms(t_b, t_c), ms(t_c, std::chrono::steady_clock::now()));
+      }
       if (err) std::rethrow_exception(err);
-      cur = std::move(nxt);
-      nxt.clear();
+      std::swap(cur, nxt);
       g0 = n0; g1 = n1;
     }
   }
   skb_batch_destroy(b);
+  if (getenv("SKB_TRACE_SKETCH"))
+    fprintf(stderr, "[sketch rank %d] all windows done %.1f ms after main\n", rank,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_main).count());
   std::vector<uint8_t> all;
   if (c.world > 1) c.gather_files("sketch", mine, all);
-  if (c.rank != 0) return 0;
+  if (c.rank != 0) leave(0);
   msh::File f;
   f.kmer_size = k; f.sketch_size = 0; f.hash_seed = seed;  // minHashesPerWindow = the largest sketch, as finch writes it [RECALLED]
   for (uint32_t g = 0; g < G; ++g) {
@@ -369,7 +414,10 @@ int cmd_sketch(const Args& a) {
     f.sketches.push_back(std::move(sk));
   }
   msh::write_file(out, f);
-  return 0;
+  if (getenv("SKB_TRACE_SKETCH"))
+    fprintf(stderr, "[sketch rank %d] .msh written %.1f ms after main\n", rank,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_main).count());
+  leave(0);
 }
 
 int cmd_info(const Args& a) {

@@ -39,7 +39,7 @@ const char* skb_last_error(const skb_ctx* c) { return c ? c->err.c_str() : "null
 int skb_batch_create(skb_ctx* c, skb_batch** out) { *out = new skb_batch(); (*out)->ctx = c; return SKB_OK; }
 void skb_batch_destroy(skb_batch* b) { delete b; }
 int skb_batch_clear(skb_batch* b) { b->groups = 0; b->records = 0; b->bases = 0; b->last_group = -1; logf("batch_clear\n"); return SKB_OK; }
-int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* off, const uint32_t* groups, uint64_t n, uint32_t) {
+static int add_impl(skb_batch* b, const uint8_t* const* recs, const uint64_t* lens, const uint32_t* groups, uint64_t n) {
   // one line per record: group, length, checksum of the raw slice
   logf("batch_add n=%llu groups=%s\n", (unsigned long long)n, groups ? "given" : "null");
   for (uint64_t r = 0; r < n; ++r) {
@@ -47,11 +47,21 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* off, const 
     if (g < b->last_group) { b->ctx->err = "groups must be non-decreasing"; return SKB_ERR_INVALID_ARG; }
     if (g != b->last_group) b->groups = (uint32_t)g + 1;
     b->last_group = g;
-    logf("  rec group=%ld len=%llu fnv=%llu\n", g, (unsigned long long)(off[r + 1] - off[r]), fnv(blob + off[r], off[r + 1] - off[r]));
-    b->bases += off[r + 1] - off[r];
+    if (getenv("MOCK_ABI_LOG")) logf("  rec group=%ld len=%llu fnv=%llu\n", g, (unsigned long long)lens[r], fnv(recs[r], lens[r]));
+    b->bases += lens[r];
   }
   b->records += n;
   return SKB_OK;
+}
+int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* off, const uint32_t* groups, uint64_t n, uint32_t) {
+  std::vector<const uint8_t*> recs(n);
+  std::vector<uint64_t> lens(n);
+  for (uint64_t r = 0; r < n; ++r) { recs[r] = blob + off[r]; lens[r] = off[r + 1] - off[r]; }
+  return add_impl(b, recs.data(), lens.data(), groups, n);
+}
+// the same records one by one: logged like skb_batch_add (the tests check WHAT reaches the library, not through which door)
+int skb_batch_add_records(skb_batch* b, const uint8_t* const* recs, const uint64_t* lens, const uint32_t* groups, uint64_t n, uint32_t) {
+  return add_impl(b, recs, lens, groups, n);
 }
 uint32_t skb_batch_num_groups(const skb_batch* b) { return b->groups; }
 int skb_sketch(skb_ctx*, skb_batch* b, uint32_t k, uint32_t s, uint64_t seed, uint64_t* oh, uint32_t* oc, uint32_t* on,

@@ -13,10 +13,20 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = r'''
-#include "fastx.hpp"
+#include "ingest.hpp"
 #include <cstdio>
 int main(int argc, char** argv) {
   try {
+    if (argc > 2 && std::string(argv[2]) == "slices") {   // the whole file in memory, records as slices of it
+      ingest::Files w;
+      ingest::load_files({argv[1]}, 0, 1, 1, w);
+      for (size_t i = 0; i < w.n(); ++i) {
+        unsigned long long h = 1469598103934665603ull;
+        for (size_t j = 0; j < w.len[i]; ++j) { h ^= w.rec[i][j]; h *= 1099511628211ull; }
+        std::printf("%zu\t%llu\n", (size_t)w.len[i], h);
+      }
+      return 0;
+    }
     fastx::Reader rd(argc > 1 ? argv[1] : "-");
     fastx::Record r;
     while (rd.next(r)) {
@@ -38,7 +48,7 @@ def harness(tmp_path_factory):
     src = d / "h.cpp"
     src.write_text(HARNESS)
     exe = d / "h"
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "sketchy_b200", "host"), str(src), "-o",
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "sketchy_b200", "host"), str(src), "-o",
                            str(exe), "-lz", "-ldl"])
     return str(exe)
 
@@ -118,6 +128,8 @@ def test_compressed_inputs_yield_the_same_records(harness, tmp_path, kind):
         path.write_bytes(blob)
         rc, got, err = _run(harness, path=str(path))
         assert rc == 0 and got == want, (name, err)
+        p = subprocess.run([harness, str(path), "slices"], capture_output=True)   # the `sketch` path: slices of the file in memory
+        assert p.returncode == 0 and p.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in want.splitlines()), (name, "slices")
         rc, got, err = _run(harness, data=blob)   # stdin
         assert rc == 0 and got == want, (name, "stdin", err)
 
@@ -166,7 +178,8 @@ INGEST_HARNESS = r'''
 #include "ingest.hpp"
 #include <cstdio>
 #include <cstdlib>
-// usage: h <threads> <window-budget-bytes> file...   -> one line per window: g0 g1 records bytes fnv(bytes) fnv(off) fnv(grp)
+// usage: h <threads> <window-budget-bytes> file...   -> two lines per window (copying reader, in-place loader):
+//        g0 g1 records bytes fnv(bytes) fnv(off) fnv(grp)
 static unsigned long long fnv(const void* p, size_t n) {
   unsigned long long h = 1469598103934665603ull;
   for (size_t i = 0; i < n; ++i) { h ^= ((const unsigned char*)p)[i]; h *= 1099511628211ull; }
@@ -177,11 +190,24 @@ int main(int argc, char** argv) {
     const unsigned T = (unsigned)atoi(argv[1]);
     const unsigned long long budget = strtoull(argv[2], nullptr, 10);
     std::vector<std::string> files(argv + 3, argv + argc);
+    ingest::Files w;  // reused from window to window, as the CLI does
     for (size_t g0 = 0; g0 < files.size();) {
       const size_t g1 = ingest::window_end(files, g0, budget);
       const ingest::Blob b = ingest::read_files(files, g0, g1, T);
       std::printf("%zu %zu %zu %zu %llu %llu %llu\n", g0, g1, b.n(), b.bytes.size(), fnv(b.bytes.data(), b.bytes.size()),
                   fnv(b.off.data(), b.off.size() * 8), fnv(b.grp.data(), b.grp.size() * 4));
+      // the same window through the in-place loader (record slices of the files in memory), brought to the same form
+      ingest::load_files(files, g0, g1, T, w);
+      std::vector<unsigned char> bytes;
+      std::vector<uint64_t> off{0};
+      std::vector<uint32_t> grp;
+      for (size_t r = 0; r < w.n(); ++r) {
+        bytes.insert(bytes.end(), w.rec[r], w.rec[r] + w.len[r]);
+        off.push_back(bytes.size());
+        grp.push_back(w.grp[r] + (uint32_t)g0);
+      }
+      std::printf("%zu %zu %zu %zu %llu %llu %llu\n", g0, g1, w.n(), bytes.size(), fnv(bytes.data(), bytes.size()),
+                  fnv(off.data(), off.size() * 8), fnv(grp.data(), grp.size() * 4));
       g0 = g1;
     }
   } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
@@ -213,9 +239,13 @@ def test_parallel_file_reader_equals_the_sequential_one(tmp_path):
         assert p.returncode == 0, p.stderr
         outs[t] = p.stdout
     assert outs[1] == outs[3] == outs[16] and outs[1].split()[:2] == ["0", "14"]
+    a, b = outs[1].splitlines()
+    assert a == b, "the in-place loader and the copying reader disagree"
     # a tiny budget: one window per file, still every file exactly once and in order
     p = subprocess.run([exe, "4", "1"] + files, capture_output=True, text=True)
-    wins = [l.split() for l in p.stdout.splitlines()]
+    both = p.stdout.splitlines()
+    assert both[0::2] == both[1::2], "the in-place loader and the copying reader disagree"
+    wins = [l.split() for l in both[0::2]]
     assert [(int(w[0]), int(w[1])) for w in wins] == [(g, g + 1) for g in range(14)]
     assert sum(int(w[2]) for w in wins) == int(outs[1].split()[2])
     # unreadable files: the reference's error text
@@ -232,3 +262,27 @@ def test_fastq_quality_length_must_match(harness, tmp_path):
     assert rc == 0 and out.count(b"\n") == 2
     rc, out, err = _run(harness, data=good + b"@b\nACGT\n+\nIII\n")
     assert rc != 0
+
+
+def test_slices_of_a_file_in_memory_equal_the_streamed_records(harness, tmp_path):
+    """fastx::parse_in_place (the `sketch` path) against fastx::Reader on the awkward shapes: no final line break, blank
+    lines, a header at the end of the file, CRLF, leading blank lines, empty sequences, records that fail."""
+    rng = random.Random(5)
+    cases = [b">a\nACGT", b">a\nACGT\n", b">a\r\nAC\r\nGT\r\n>b\r\n\r\n", b"\n\n>a\nAC\n\nGT\n\n\n>b\nTT\n>c", b">a\n>b\n>c\nA\n",
+             b">a\n\n\n", b">", b">\n", b"\r\n>a x y\nacgtnN\n", b"@r\nACGT\n+\nIIII", b"@r\nACGT\n+\nIIII\n\n\n@s\nAC\n+r\nII\n",
+             b"@r\r\nACGT\r\n+\r\nIIII\r\n", b"@r\nACGT\n+\nIII\n", b"@r\nACGT\n", b"@r\nACGT\nIIII\nIIII\n", b"@r\n\n+\n\n",
+             b"x\n>a\nAC\n", b">a\nAC\n@r\nAC\n+\nII\n"]
+    for _ in range(200):   # random line soups over a small alphabet: whatever the reader does, the slices must do
+        marker = rng.choice([b">", b"@"])
+        lines = [rng.choice([b"", b"AC", b"ACGTN", marker + b"id", b"+", b"II", b"IIIII", b"\r", b"AC\r"]) for _ in range(rng.randint(0, 12))]
+        cases.append(marker + b"x\n" + b"\n".join(lines) + rng.choice([b"", b"\n", b"\r\n"]))
+    for i, raw in enumerate(cases):
+        f = tmp_path / f"c{i}"
+        f.write_bytes(raw)
+        a = subprocess.run([harness, str(f)], capture_output=True)
+        b = subprocess.run([harness, str(f), "slices"], capture_output=True)
+        assert (a.returncode == 0) == (b.returncode == 0), (raw, a.stderr, b.stderr)
+        if a.returncode == 0:
+            assert b.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in a.stdout.splitlines()), raw
+        else:
+            assert a.stderr == b.stderr, raw

@@ -57,5 +57,14 @@ for w in worlds:
         ref_bytes = b
     out["runs"].append({"ranks": w, "wall_s": round(dt, 3), "gbp_per_s": round(gbp / dt, 3), "ok": ok, "same_msh_as_1_rank": b == ref_bytes,
                         "stderr": "" if ok else outs[0][1][-300:].decode(errors="replace")})
+    if os.environ.get("SKB_TRACE_SKETCH"):
+        sys.stderr.write(f"--- {w} rank(s) ---\n" + "".join(o[1].decode(errors="replace") for o in outs))
+# what of the wall time is process start + CUDA context creation: the same binary on one file
+t1 = time.perf_counter()
+subprocess.run([skb_build.CLI, "sketch", "-k", "16", "-s", "1000", "-o", os.path.join(tmp, "one.msh"), "-i", paths[0]],
+               capture_output=True, timeout=900)
+out["one_file_wall_s"] = round(time.perf_counter() - t1, 3)
+for r in out["runs"]:
+    r["gbp_per_s_beyond_start_up"] = round(gbp / max(r["wall_s"] - out["one_file_wall_s"], 1e-9), 3)
 shutil.rmtree(tmp, ignore_errors=True)
 print(json.dumps(out))
