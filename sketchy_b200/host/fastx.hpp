@@ -69,6 +69,23 @@ class RawInput {  // buffered reads from a file descriptor
   }
   const uint8_t* data() const { return buf_.data() + pos_; }
   void consume(size_t n) { pos_ += n; }
+  // up to cap bytes straight into `out`: what is buffered first, otherwise one read of the descriptor without the
+  // stop in this object's buffer (0 = end of input)
+  size_t read_into(uint8_t* out, size_t cap) {
+    if (pos_ < end_) {
+      const size_t n = std::min(cap, end_ - pos_);
+      std::memcpy(out, buf_.data() + pos_, n);
+      pos_ += n;
+      return n;
+    }
+    if (eof_) return 0;
+    for (;;) {
+      const ssize_t n = ::read(fd_, out, cap);
+      if (n < 0) { if (errno == EINTR) continue; throw open_error(); }
+      if (n == 0) eof_ = true;
+      return (size_t)n;
+    }
+  }
   // true when a read would block right now: nothing buffered, not at the end, and the descriptor has nothing to give
   // (a live pipe whose writer is pausing; a regular file is always readable)
   bool would_block() const {
@@ -93,12 +110,7 @@ class Decoder {
 class PlainDecoder : public Decoder {
  public:
   explicit PlainDecoder(RawInput& in) : in_(in) {}
-  size_t read(uint8_t* out, size_t cap) override {
-    const size_t n = std::min(cap, in_.ensure());
-    std::memcpy(out, in_.data(), n);
-    in_.consume(n);
-    return n;
-  }
+  size_t read(uint8_t* out, size_t cap) override { return in_.read_into(out, cap); }
 
  private:
   RawInput& in_;
@@ -285,44 +297,86 @@ inline std::unique_ptr<Decoder> sniff_decoder(RawInput& in) {
 // records, in the same order and with the same raw sequence bytes, as Reader::next yields for the file, without copying
 // a byte. (`sketchy sketch` reads its files this way; the streaming reader below serves stdin and live streams.)
 struct Slice { size_t start, len; };
-inline void parse_in_place(const uint8_t* p, size_t n, std::vector<Slice>& out) {
-  size_t pos = 0;
-  while (pos < n && (p[pos] == '\n' || p[pos] == '\r')) ++pos;
-  if (pos >= n) return;
-  const bool fasta = p[pos] == '>';
-  if (!fasta && p[pos] != '@') throw open_error();
-  // next line = [b, e): without its '\n' and without one '\r' in front of it; false at the end of the input
-  auto line = [&](size_t& b, size_t& e) {
-    if (pos >= n) return false;
-    const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(p + pos, '\n', n - pos));
-    b = pos;
+struct ParseState { bool started = false, fasta = true; };
+
+// Parses complete records of p[pos, n) — a piece of the decoded input that starts where the last call stopped —
+// appending their sequence slices (offsets into p) and moving pos behind them. With eof = false a record counts as
+// complete only when the bytes behind it prove it (a FASTQ record: its four line ends; a FASTA record: the next line
+// that starts with '>'), so that the caller can read on and call again with more data behind the same pos. Stops early
+// after max_records records or once the slices of this call hold max_seq_bytes bytes.
+inline void parse_some(const uint8_t* p, size_t n, bool eof, ParseState& st, size_t& pos, std::vector<Slice>& out,
+                       size_t max_records, uint64_t max_seq_bytes) {
+  if (!st.started) {
+    while (pos < n && (p[pos] == '\n' || p[pos] == '\r')) ++pos;
+    if (pos >= n) return;
+    st.fasta = p[pos] == '>';
+    if (!st.fasta && p[pos] != '@') throw open_error();
+    st.started = true;
+  }
+  // next line = [b, e): without its '\n' and without one '\r' in front of it. 1 = a line, 0 = the input has ended,
+  // -1 = the line's end has not arrived yet
+  auto line = [&](size_t& cur, size_t& b, size_t& e) {
+    if (cur >= n) return eof ? 0 : -1;
+    const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(p + cur, '\n', n - cur));
+    if (!nl && !eof) return -1;
+    b = cur;
     e = nl ? (size_t)(nl - p) : n;
-    pos = nl ? e + 1 : n;
+    cur = nl ? e + 1 : n;
     if (e > b && p[e - 1] == '\r') --e;
-    return true;
+    return 1;
   };
-  for (;;) {
-    size_t b, e;
-    do { if (!line(b, e)) return; } while (e == b);  // blank lines in front of a header
-    if (fasta) {
+  uint64_t bytes = 0;
+  const size_t first = out.size();
+  while (out.size() - first < max_records && bytes < max_seq_bytes) {
+    size_t cur = pos, b = 0, e = 0;
+    for (;;) {  // blank lines in front of a header
+      const size_t c0 = cur;
+      const int r = line(cur, b, e);
+      if (r <= 0) { pos = c0; return; }
+      if (e != b) break;
+    }
+    const size_t rec_start = b;
+    if (st.fasta) {
       if (p[b] != '>') throw open_error();
-      const size_t s0 = pos;  // the raw slice runs to the next line that starts with '>' (or the end), line breaks inside kept
-      while (pos < n && p[pos] != '>') {
-        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(p + pos, '\n', n - pos));
-        pos = nl ? (size_t)(nl - p) + 1 : n;
+      const size_t s0 = cur;  // the raw slice runs to the next line that starts with '>' (or the end), line breaks inside kept
+      bool complete = false;
+      for (;;) {
+        if (cur >= n) { complete = eof; break; }
+        if (p[cur] == '>') { complete = true; break; }
+        const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(p + cur, '\n', n - cur));
+        if (!nl) { cur = n; complete = eof; break; }
+        cur = (size_t)(nl - p) + 1;
       }
-      size_t s1 = pos;
+      if (!complete) { pos = rec_start; return; }
+      size_t s1 = cur;
       while (s1 > s0 && (p[s1 - 1] == '\n' || p[s1 - 1] == '\r')) --s1;
       out.push_back({s0, s1 - s0});
+      bytes += s1 - s0;
     } else {
       if (p[b] != '@') throw open_error();
-      size_t sb, se, pb, pe, qb, qe;
-      if (!line(sb, se)) throw open_error();
-      if (!line(pb, pe) || pe == pb || p[pb] != '+' || !line(qb, qe)) throw open_error();
+      size_t sb = 0, se = 0, pb = 0, pe = 0, qb = 0, qe = 0;
+      int r = line(cur, sb, se);
+      if (r < 0) { pos = rec_start; return; }
+      if (r == 0) throw open_error();
+      r = line(cur, pb, pe);
+      if (r < 0) { pos = rec_start; return; }
+      if (r == 0 || pe == pb || p[pb] != '+') throw open_error();
+      r = line(cur, qb, qe);
+      if (r < 0) { pos = rec_start; return; }
+      if (r == 0) throw open_error();
       if (qe - qb != se - sb) throw open_error();  // needletail rejects a record whose quality length differs
       out.push_back({sb, se - sb});
+      bytes += se - sb;
     }
+    pos = cur;
   }
+}
+
+// The records of a whole (decoded) file held in memory.
+inline void parse_in_place(const uint8_t* p, size_t n, std::vector<Slice>& out) {
+  ParseState st;
+  size_t pos = 0;
+  parse_some(p, n, true, st, pos, out, SIZE_MAX, UINT64_MAX);
 }
 
 class Reader {

@@ -8,6 +8,9 @@
 #include <sys/stat.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <exception>
@@ -136,6 +139,41 @@ inline Blob read_files(const std::vector<std::string>& files, size_t g0, size_t 
   return out;
 }
 
+// ---- a bounded queue between the stages of a host pipeline (reader -> packer -> GPU caller -> printer) -----------------
+// push blocks while the queue is full, pop while it is empty; close() = no more items (pop drains what is queued, then
+// returns false); abort() = stop now (both ends return false at once; used when a stage failed).
+template <class T>
+class Channel {
+ public:
+  explicit Channel(size_t cap) : cap_(cap) {}
+  bool push(T v) {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+    if (closed_) return false;
+    q_.push_back(std::move(v));
+    cv_.notify_all();
+    return true;
+  }
+  bool pop(T& v) {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    v = std::move(q_.front());
+    q_.pop_front();
+    cv_.notify_all();
+    return true;
+  }
+  void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_.notify_all(); }
+  void abort() { std::lock_guard<std::mutex> l(m_); closed_ = true; q_.clear(); cv_.notify_all(); }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
+  size_t cap_;
+  bool closed_ = false;
+};
+
 // ---- files held in memory, records as slices (the `sketch` path) ------------------------------------------------------
 // A window of files as they are on disk: plain files are read, every file by one read loop, straight into one arena
 // that is reused from window to window (no page faults after the first window); compressed files are decoded into a
@@ -150,6 +188,13 @@ struct Files {
   size_t n() const { return rec.size(); }
   void clear() { rec.clear(); len.clear(); grp.clear(); decoded.clear(); }
 };
+
+// a hint for a large buffer that is about to be touched for the first time (ignored where transparent huge pages are off)
+inline void huge_pages(void* p, size_t n) {
+  const uintptr_t lo = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+  const uintptr_t hi = ((uintptr_t)p + n) & ~(uintptr_t)((2u << 20) - 1);
+  if (hi > lo) ::madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+}
 
 inline void decode_all(fastx::RawInput& in, Bytes& out, bool plain = false) {
   std::unique_ptr<fastx::Decoder> dec = plain ? std::unique_ptr<fastx::Decoder>(new fastx::PlainDecoder(in)) : fastx::sniff_decoder(in);
@@ -177,9 +222,7 @@ inline void load_files(const std::vector<std::string>& files, size_t g0, size_t 
     w.arena.resize(at[n] + at[n] / 8);   // some room: windows of one budget differ by a file's size at most
     // first touch of a fresh arena is the dearest part of the first window: ask for huge pages (a hint; ignored where
     // transparent huge pages are off)
-    const uintptr_t lo = ((uintptr_t)w.arena.data() + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
-    const uintptr_t hi = ((uintptr_t)w.arena.data() + w.arena.size()) & ~(uintptr_t)((2u << 20) - 1);
-    if (hi > lo) ::madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+    huge_pages(w.arena.data(), w.arena.size());
   }
   std::vector<std::vector<fastx::Slice>> slices(n);
   std::vector<const uint8_t*> base(n, nullptr);
@@ -251,5 +294,77 @@ inline void load_files(const std::vector<std::string>& files, size_t g0, size_t 
       w.grp.push_back((uint32_t)i);
     }
 }
+
+// ---- a stream of reads in chunks, records as slices (the streaming `predict` path) ----------------------------------------
+// The input (file, stdin, pipe; plain or compressed) is decoded block by block straight into a chunk's buffer and split
+// into records where it lies. A chunk ends after max_reads reads or max_seq_bytes sequence bytes — a rule of the content
+// alone, so that the ranks of a multi-GPU run cut the same file into the same chunks — or, on request, when a live input
+// pauses with nothing half-read (a sequencer writing to a pipe: what has arrived is predicted at once, as the
+// reference prints a row per read as it comes, src/sketchy.rs:328-355). The unfinished tail moves to the next chunk.
+struct Chunk {
+  Bytes buf;
+  std::vector<const uint8_t*> rec;
+  std::vector<uint64_t> len;
+  size_t n() const { return rec.size(); }
+};
+
+class ChunkReader {
+ public:
+  explicit ChunkReader(const std::string& path, size_t block = 1u << 20) : block_(block) {
+    int fd = 0;
+    if (path != "-") {
+      fd = ::open(path.c_str(), O_RDONLY);
+      if (fd < 0) throw fastx::open_error();
+    }
+    in_.reset(new fastx::RawInput(fd, path != "-"));
+    dec_ = fastx::sniff_decoder(*in_);
+  }
+  // false: the input has ended and the chunk is empty
+  bool next(Chunk& c, size_t max_reads, uint64_t max_seq_bytes, bool stop_when_idle) {
+    c.rec.clear(); c.len.clear();
+    slices_.clear();
+    size_t have = carry_.size(), pos = 0;
+    // a chunk's buffer is sized once for the usual case (FASTQ: two bytes of input per base) and reused as it circulates
+    const size_t want = have + block_ + (size_t)std::min<uint64_t>(2 * max_seq_bytes, 192ull << 20);
+    if (c.buf.size() < want) {
+      Bytes().swap(c.buf);  // nothing in it is live: no copy into the larger buffer
+      c.buf.resize(want);
+      huge_pages(c.buf.data(), c.buf.size());
+    }
+    if (have) std::memcpy(c.buf.data(), carry_.data(), have);
+    carry_.clear();
+    uint64_t seq = 0;
+    size_t counted = 0;
+    for (;;) {
+      if (max_reads > slices_.size() && seq < max_seq_bytes)
+        fastx::parse_some(c.buf.data(), have, eof_, st_, pos, slices_, max_reads - slices_.size(), max_seq_bytes - seq);
+      for (; counted < slices_.size(); ++counted) seq += slices_[counted].len;
+      if (slices_.size() >= max_reads || seq >= max_seq_bytes || eof_) break;
+      if (stop_when_idle && !slices_.empty() && pos == have && in_->would_block()) break;
+      if (c.buf.size() - have < block_) {  // grow keeping what is there (a record longer than the buffer, or a long chunk)
+        Bytes bigger;
+        bigger.resize(std::max(c.buf.size() * 2, have + block_));
+        std::memcpy(bigger.data(), c.buf.data(), have);
+        bigger.swap(c.buf);
+      }
+      const size_t got = dec_->read(c.buf.data() + have, block_);
+      if (got == 0) eof_ = true;
+      have += got;
+    }
+    carry_.assign(c.buf.data() + pos, c.buf.data() + have);
+    c.rec.reserve(slices_.size()); c.len.reserve(slices_.size());
+    for (const fastx::Slice& sl : slices_) { c.rec.push_back(c.buf.data() + sl.start); c.len.push_back(sl.len); }
+    return !slices_.empty();
+  }
+
+ private:
+  size_t block_;
+  std::unique_ptr<fastx::RawInput> in_;
+  std::unique_ptr<fastx::Decoder> dec_;
+  fastx::ParseState st_;
+  std::vector<fastx::Slice> slices_;
+  Bytes carry_;
+  bool eof_ = false;
+};
 
 }  // namespace ingest

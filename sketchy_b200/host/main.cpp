@@ -8,8 +8,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <thread>
@@ -241,33 +244,69 @@ std::string join_tab(const std::vector<std::string>& v) {
 }
 
 // src/sketchy.rs:358-413; consensus ties go to the value met first in rank order (the reference's HashMap order is
-// nondeterministic there — DESIGN.md §2)
-void print_results(const msh::File& ref, const Genotypes& g, uint64_t read, const uint32_t* idx, const uint64_t* sum,
-                   uint32_t top, bool consensus) {
-  if (consensus) {
-    std::vector<const std::vector<std::string>*> gs;
-    for (uint32_t t = 0; t < top; ++t) gs.push_back(&g.map.at(ref.sketches[idx[t]].name));
-    std::string out = std::to_string(read) + "\t-\t-\t";
-    const size_t nf = gs.empty() ? 0 : gs[0]->size();
-    for (size_t j = 0; j < nf; ++j) {
-      std::string best;
-      size_t best_n = 0;
-      for (uint32_t t = 0; t < top; ++t) {
-        size_t c = 0;
-        for (uint32_t u = 0; u < top; ++u) c += (*gs[u])[j] == (*gs[t])[j];
-        if (c > best_n) { best_n = c; best = (*gs[t])[j]; }
+// nondeterministic there — DESIGN.md §2). The parts of a row that depend on the reference sketch alone (its name, its
+// genotype columns joined, the columns as small integers for the consensus vote) are made once; a row is then an
+// append of the read number, two ready strings and the count (streaming predict prints reads x top rows).
+struct RowTable {
+  std::vector<std::string> name_part, geno_part;        // "\t" + name + "\t",  "\t" + genotype columns + "\n"
+  size_t n_features = 0;
+  std::vector<uint32_t> value_id;                       // [sketch][feature]: index into values[feature]
+  std::vector<std::vector<std::string>> values;         // distinct values of a feature
+  RowTable(const msh::File& ref, const Genotypes& g) {
+    const size_t N = ref.sketches.size();
+    name_part.reserve(N); geno_part.reserve(N);
+    n_features = N ? g.map.at(ref.sketches[0].name).size() : 0;
+    values.resize(n_features);
+    value_id.assign(N * n_features, 0);
+    std::vector<std::unordered_map<std::string, uint32_t>> seen(n_features);
+    static const std::string none;
+    for (size_t i = 0; i < N; ++i) {
+      const std::string& name = ref.sketches[i].name;
+      const std::vector<std::string>& cols = g.map.at(name);
+      name_part.push_back("\t" + name + "\t");
+      geno_part.push_back("\t" + join_tab(cols) + "\n");
+      for (size_t j = 0; j < n_features; ++j) {
+        const std::string& v = j < cols.size() ? cols[j] : none;
+        auto it = seen[j].find(v);
+        if (it == seen[j].end()) { it = seen[j].emplace(v, (uint32_t)values[j].size()).first; values[j].push_back(v); }
+        value_id[i * n_features + j] = it->second;
       }
-      out += (j ? "\t" : "") + best;
-    }
-    puts(out.c_str());
-  } else {
-    for (uint32_t t = 0; t < top; ++t) {
-      const std::string& name = ref.sketches[idx[t]].name;
-      printf("%llu\t%s\t%llu\t%s\n", (unsigned long long)read, name.c_str(), (unsigned long long)sum[t],
-             join_tab(g.map.at(name)).c_str());
     }
   }
-}
+  static void put(std::string& out, uint64_t v) {
+    char buf[24];
+    int n = 0;
+    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) out.push_back(buf[--n]);
+  }
+  // the rows of one read, appended to `out`
+  void rows(std::string& out, uint64_t read, const uint32_t* idx, const uint64_t* sum, uint32_t top, bool consensus) const {
+    if (consensus) {
+      put(out, read);
+      out += "\t-\t-\t";
+      for (size_t j = 0; j < n_features; ++j) {
+        uint32_t best = 0;
+        size_t best_n = 0;
+        for (uint32_t t = 0; t < top; ++t) {
+          const uint32_t v = value_id[(size_t)idx[t] * n_features + j];
+          size_t c = 0;
+          for (uint32_t u = 0; u < top; ++u) c += value_id[(size_t)idx[u] * n_features + j] == v;
+          if (c > best_n) { best_n = c; best = v; }
+        }
+        if (j) out.push_back('\t');
+        if (best_n) out += values[j][best];
+      }
+      out.push_back('\n');
+    } else {
+      for (uint32_t t = 0; t < top; ++t) {
+        put(out, read);
+        out += name_part[idx[t]];
+        put(out, sum[t]);
+        out += geno_part[idx[t]];
+      }
+    }
+  }
+};
 
 // this rank's contiguous range of the reference sketches (all of them on one GPU); indices reported by the library are global
 void upload_reference(const Ctx& c, const msh::File& ref) {
@@ -328,69 +367,102 @@ int cmd_sketch(const Args& a) {
   skb_dist_range(G, 0, world, &dummy, &share);  // the largest share: the fixed record size of the exchange
   std::vector<uint8_t> mine((size_t)share * per_file, 0);
   auto rec = [&](std::vector<uint8_t>& buf, size_t i) { return buf.data() + i * per_file; };
-  ingest::Files cur, nxt;  // two windows of files in memory: one being packed and sketched, one being read
-  std::exception_ptr err;
-  size_t g0 = f_lo, g1 = ingest::window_end(files, g0, kWindowBytes);
+  // Three stages, each on its own thread, joined by bounded queues: (1) the loader reads window i+2 into memory (its
+  // own pool of threads); (2) the packer normalises and 2-bit packs window i+1 from the record slices into one of two
+  // batches and starts its copy to the device; (3) this thread calls skb_sketch on window i and files the results.
+  // Three windows of files and two batches circulate; nothing is allocated once they have been round once.
+  struct Loaded { ingest::Files* f; size_t g0, g1; };
+  struct Packed { skb_batch* b; size_t g0, g1; double pack_ms; };
+  std::vector<std::pair<size_t, size_t>> wins;
   const size_t g_end = f_lo + f_cnt;
-  if (g1 > g_end) g1 = g_end;
-  // the first window is read while the CUDA context comes up (the larger part of a short run's wall time)
-  std::thread first;
-  if (g0 < g_end) first = std::thread([&]() { try { ingest::load_files(files, g0, g1, host_threads, cur); } catch (...) { err = std::current_exception(); } });
-  std::unique_ptr<Ctx> ctx;
-  try {
-    ctx.reset(new Ctx(false));  // the ranks sketch their files independently: no communicator
-  } catch (...) {
-    if (first.joinable()) first.join();
-    throw;
+  uint64_t window_bytes = kWindowBytes;
+  if (const char* e = getenv("SKETCHY_B200_WINDOW_BYTES")) window_bytes = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+  for (size_t g0 = f_lo; g0 < g_end;) {
+    const size_t g1 = std::min(g_end, ingest::window_end(files, g0, window_bytes));
+    wins.emplace_back(g0, g1);
+    g0 = g1;
   }
-  Ctx& c = *ctx;
-  const auto t_ctx = std::chrono::steady_clock::now();
-  if (first.joinable()) first.join();
-  if (err) std::rethrow_exception(err);
-  if (getenv("SKB_TRACE_SKETCH"))
-    fprintf(stderr, "[sketch rank %d] context ready %.1f ms after main, first window in memory after %.1f ms\n", rank,
-            std::chrono::duration<double, std::milli>(t_ctx - t_main).count(),
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_main).count());
-  skb_batch* b = nullptr;
-  c.check(skb_batch_create(c.c, &b));
-  {
+  ingest::Files pool[3];
+  ingest::Channel<ingest::Files*> free_files(3);
+  for (auto& f : pool) free_files.push(&f);
+  ingest::Channel<Loaded> loaded(2);
+  ingest::Channel<Packed> packed(1);
+  ingest::Channel<skb_batch*> free_batches(2);
+  std::mutex err_m;
+  std::exception_ptr err;
+  auto failed = [&]() {  // a stage failed: the first error is kept, every queue lets go of its waiters
+    { std::lock_guard<std::mutex> l(err_m); if (!err) err = std::current_exception(); }
+    free_files.abort(); loaded.abort(); packed.abort(); free_batches.abort();
+  };
+  const bool trace = getenv("SKB_TRACE_SKETCH") != nullptr;
+  auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+  // the first windows are read while the CUDA context comes up (the larger part of a short run's wall time)
+  std::thread loader([&]() {
+    try {
+      for (const auto& w : wins) {
+        ingest::Files* f = nullptr;
+        if (!free_files.pop(f)) return;
+        ingest::load_files(files, w.first, w.second, host_threads, *f);
+        if (!loaded.push({f, w.first, w.second})) return;
+      }
+      loaded.close();
+    } catch (...) { failed(); }
+  });
+  struct Join { std::thread& t; std::function<void()> before; ~Join() { if (t.joinable()) { if (before) before(); t.join(); } } };
+  Join join_loader{loader, [&]() { free_files.abort(); loaded.abort(); }};  // also when something below throws
+  Ctx c(false);  // the ranks sketch their files independently: no communicator
+  if (trace) fprintf(stderr, "[sketch rank %d] context ready %.1f ms after main\n", rank, ms_since(t_main));
+  skb_batch* batches[2] = {nullptr, nullptr};
+  for (auto& b : batches) { c.check(skb_batch_create(c.c, &b)); free_batches.push(b); }
+  std::thread packer([&]() {
+    try {
+      Loaded L;
+      while (loaded.pop(L)) {
+        skb_batch* b = nullptr;
+        if (!free_batches.pop(b)) return;
+        const auto t0 = std::chrono::steady_clock::now();
+        c.check(skb_batch_clear(b));
+        if (L.f->n()) c.check(skb_batch_add_records(b, L.f->rec.data(), L.f->len.data(), L.f->grp.data(), L.f->n(), host_threads));
+        if (skb_batch_num_groups(b)) c.check(skb_batch_stage(b));
+        const double pack_ms = ms_since(t0);
+        if (!free_files.push(L.f)) return;  // the slices have been read: the window's memory goes back to the loader
+        if (!packed.push({b, L.g0, L.g1, pack_ms})) return;
+      }
+      packed.close();
+    } catch (...) { failed(); }
+  });
+  Join join_packer{packer, [&]() { loaded.abort(); packed.abort(); free_batches.abort(); free_files.abort(); }};
+  try {
     std::vector<uint64_t> hs, bases, kmers;
     std::vector<uint32_t> cnt, n;
-    const bool trace = getenv("SKB_TRACE_SKETCH") != nullptr;
-    while (g0 < g_end) {
-      size_t n0 = g1, n1 = n0 < g_end ? std::min(g_end, ingest::window_end(files, n0, kWindowBytes)) : n0;
-      std::thread reader;
-      struct Join { std::thread& t; ~Join() { if (t.joinable()) t.join(); } } join_on_exit{reader};  // also when a call below throws
-      if (n0 < g_end) reader = std::thread([&]() { try { ingest::load_files(files, n0, n1, host_threads, nxt); } catch (...) { err = std::current_exception(); } });
-      const uint32_t W = (uint32_t)(g1 - g0);
-      const auto t_a = std::chrono::steady_clock::now();
-      c.check(skb_batch_clear(b));
-      if (cur.n()) c.check(skb_batch_add_records(b, cur.rec.data(), cur.len.data(), cur.grp.data(), cur.n(), host_threads));
-      const auto t_b = std::chrono::steady_clock::now();
-      const uint32_t have = skb_batch_num_groups(b);  // trailing empty files have no group
+    Packed P;
+    auto t_wait = std::chrono::steady_clock::now();
+    while (packed.pop(P)) {
+      const double wait_ms = ms_since(t_wait);
+      const auto t0 = std::chrono::steady_clock::now();
+      const uint32_t W = (uint32_t)(P.g1 - P.g0);
+      const uint32_t have = skb_batch_num_groups(P.b);  // trailing empty files have no group
       hs.resize((size_t)W * s); cnt.resize((size_t)W * s);
       bases.assign(W, 0); kmers.assign(W, 0); n.assign(W, 0);
-      if (have) c.check(skb_sketch(c.c, b, k, s, seed, hs.data(), cnt.data(), n.data(), bases.data(), kmers.data()));
-      const auto t_c = std::chrono::steady_clock::now();
+      if (have) c.check(skb_sketch(c.c, P.b, k, s, seed, hs.data(), cnt.data(), n.data(), bases.data(), kmers.data()));
       for (uint32_t g = 0; g < W; ++g) {
-        uint8_t* r = rec(mine, g0 - f_lo + g);
+        uint8_t* r = rec(mine, P.g0 - f_lo + g);
         const uint64_t nn = n[g];
         memcpy(r, &nn, 8); memcpy(r + 8, &bases[g], 8); memcpy(r + 16, &kmers[g], 8);
         memcpy(r + 24, &hs[(size_t)g * s], (size_t)nn * 8);
         memcpy(r + 24 + (size_t)s * 8, &cnt[(size_t)g * s], (size_t)nn * 4);
       }
-      if (reader.joinable()) reader.join();
-      if (trace) {  // SKB_TRACE_SKETCH=1: where a window's time goes (stderr; stdout carries nothing for `sketch`)
-        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[sketch rank %d] files %zu-%zu: pack %.2f ms, sketch call %.2f ms, wait for the next window %.2f ms\n",
-                rank, g0, g1, ms(t_a, t_b), ms(t_b, t_c), ms(t_c, std::chrono::steady_clock::now()));
-      }
-      if (err) std::rethrow_exception(err);
-      std::swap(cur, nxt);
-      g0 = n0; g1 = n1;
+      if (trace)  // SKB_TRACE_SKETCH=1: where a window's time goes (stderr; stdout carries nothing for `sketch`)
+        fprintf(stderr, "[sketch rank %d] files %zu-%zu: waited %.2f ms for the packed window (its pack + copy start took %.2f ms), sketch call %.2f ms\n",
+                rank, P.g0, P.g1, wait_ms, P.pack_ms, ms_since(t0));
+      free_batches.push(P.b);
+      t_wait = std::chrono::steady_clock::now();
     }
-  }
-  skb_batch_destroy(b);
+  } catch (...) { failed(); }
+  loader.join();
+  packer.join();
+  if (err) std::rethrow_exception(err);
+  for (auto& b : batches) skb_batch_destroy(b);
   if (getenv("SKB_TRACE_SKETCH"))
     fprintf(stderr, "[sketch rank %d] all windows done %.1f ms after main\n", rank,
             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_main).count());
@@ -489,59 +561,120 @@ int cmd_predict(const Args& a) {
   Ctx c;
   if (c.world > 1 && !a.has("input")) throw std::runtime_error("a multi-GPU run reads its reads from a file (-i): stdin cannot be shared by the ranks");
   const bool speaker = c.rank == 0;  // rank 0 prints; every rank computes
-  fastx::Reader rd(a.has("input") ? a.one("input") : std::string("-"));
+  ingest::ChunkReader reads(a.has("input") ? a.one("input") : std::string("-"));
   const Genotypes g = read_genotypes(a.one("genotypes"));
   for (const auto& s : ref.sketches)
     if (!g.map.count(s.name)) throw std::runtime_error("reference sketch identifier " + s.name + " has no genotype row");
   if (header && speaker) printf("reads\tsketch_id\tshared_hashes\t%s\n", g.header.c_str());
   if (top > ref.sketches.size()) throw std::runtime_error("--top exceeds the number of reference sketches");
   upload_reference(c, ref);
-  skb_batch* b = nullptr;
-  c.check(skb_batch_create(c.c, &b));
-  fastx::Record r;
-  Blob blob;
+  const RowTable table(ref, g);
+  const unsigned host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, c.world));
+  constexpr size_t kChunkReads = 65536;
+  constexpr uint64_t kChunkBytes = 64ull << 20;  // sequence bytes of a chunk (its buffer: about twice that for FASTQ)
   if (stream) {  // src/sketchy.rs:317-356
-    uint64_t read = 1;
-    bool more = true;
-    std::vector<uint32_t> idx;
-    std::vector<uint64_t> sum;
-    while (more) {
-      blob.clear();
-      while (blob.n() < 65536 && (more = rd.next(r))) {
-        blob.add(r.seq, 0);
-        if (limit && read + blob.n() - 1 == limit) { more = false; break; }
-        if (c.world == 1 && rd.input_idle()) break;  // a live stream that is pausing: predict what has arrived instead of waiting for 65536 reads
+    // Four stages on their own threads, joined by bounded queues: (1) the reader decodes the input into a chunk's buffer
+    // and splits it into record slices; (2) the packer normalises and 2-bit packs this rank's share of the chunk into
+    // one of two batches and starts its copy; (3) this thread runs the (collective) predict call of the chunk;
+    // (4) the printer formats and writes the rows of the chunk before. Three chunks and two batches circulate.
+    struct Packed { skb_batch* b; uint64_t n; };
+    struct Result { std::vector<uint32_t> idx; std::vector<uint64_t> sum; uint64_t first, n; };
+    ingest::Chunk chunk_pool[3];
+    ingest::Channel<ingest::Chunk*> free_chunks(3), loaded(2);
+    for (auto& ch : chunk_pool) free_chunks.push(&ch);
+    ingest::Channel<Packed> packed(1);
+    ingest::Channel<skb_batch*> free_batches(2);
+    ingest::Channel<Result> results(2);
+    std::mutex err_m;
+    std::exception_ptr err;
+    auto failed = [&]() {
+      { std::lock_guard<std::mutex> l(err_m); if (!err) err = std::current_exception(); }
+      free_chunks.abort(); loaded.abort(); packed.abort(); free_batches.abort(); results.abort();
+    };
+    skb_batch* batches[2] = {nullptr, nullptr};
+    for (auto& b : batches) { c.check(skb_batch_create(c.c, &b)); free_batches.push(b); }
+    std::thread reader([&]() {
+      try {
+        uint64_t fed = 0;
+        for (;;) {
+          ingest::Chunk* ch = nullptr;
+          if (!free_chunks.pop(ch)) return;
+          const size_t want = limit ? (size_t)std::min<uint64_t>(kChunkReads, limit - fed) : kChunkReads;  // -l: stop feeding reads (:350-353)
+          // a live stream that is pausing: predict what has arrived instead of waiting for a full chunk (one rank only:
+          // the ranks of a multi-GPU run must cut the same chunks)
+          if (want == 0 || !reads.next(*ch, want, kChunkBytes, c.world == 1)) break;
+          fed += ch->n();
+          if (!loaded.push(ch)) return;
+        }
+        loaded.close();
+      } catch (...) { failed(); }
+    });
+    std::thread packer([&]() {
+      try {
+        ingest::Chunk* ch = nullptr;
+        while (loaded.pop(ch)) {
+          skb_batch* b = nullptr;
+          if (!free_batches.pop(b)) return;
+          // every rank has parsed the chunk; it packs, copies and hashes only its share of it
+          uint64_t lo = 0, cnt = 0;
+          c.range(ch->n(), lo, cnt);
+          c.check(skb_batch_clear(b));
+          if (cnt) {
+            c.check(skb_batch_add_records(b, ch->rec.data() + lo, ch->len.data() + lo, nullptr, cnt, host_threads));
+            c.check(skb_batch_stage(b));
+          }
+          const uint64_t n = ch->n();
+          if (!free_chunks.push(ch)) return;
+          if (!packed.push({b, n})) return;
+        }
+        packed.close();
+      } catch (...) { failed(); }
+    });
+    std::thread printer([&]() {
+      try {
+        Result r;
+        std::string out;
+        while (results.pop(r)) {
+          out.clear();
+          for (uint64_t i = 0; i < r.n; ++i) table.rows(out, r.first + i, &r.idx[i * top], &r.sum[i * top], top, consensus);
+          if (fwrite(out.data(), 1, out.size(), stdout) != out.size()) throw std::runtime_error("failed to write to stdout");
+          fflush(stdout);  // the reference's println! reaches a pipe line by line: a consumer of the live stream sees each chunk at once
+        }
+      } catch (...) { failed(); }
+    });
+    try {
+      uint64_t read = 1;
+      Packed P;
+      while (packed.pop(P)) {
+        Result r;
+        r.first = read; r.n = P.n;
+        if (speaker) { r.idx.resize(P.n * top); r.sum.resize(P.n * top); }
+        c.check(skb_predict_stream_dist(c.c, P.b, P.n, k, s_query, seed, top, speaker ? r.idx.data() : nullptr, speaker ? r.sum.data() : nullptr));
+        free_batches.push(P.b);
+        read += P.n;
+        if (speaker && !results.push(std::move(r))) break;
       }
-      if (!blob.n()) break;
-      // every rank has parsed the chunk; it packs, copies and hashes only its share of it
-      uint64_t lo = 0, cnt = 0;
-      c.range(blob.n(), lo, cnt);
-      std::vector<uint64_t> off(blob.off.begin() + lo, blob.off.begin() + lo + cnt + 1);
-      c.check(skb_batch_clear(b));
-      if (cnt) c.check(skb_batch_add(b, blob.bytes.data(), off.data(), nullptr, cnt, 0));
-      idx.resize(blob.n() * top); sum.resize(blob.n() * top);
-      c.check(skb_predict_stream_dist(c.c, b, blob.n(), k, s_query, seed, top, speaker ? idx.data() : nullptr, speaker ? sum.data() : nullptr));
-      if (speaker) {
-        for (size_t i = 0; i < blob.n(); ++i) print_results(ref, g, read + i, &idx[i * top], &sum[i * top], top, consensus);
-        fflush(stdout);  // the reference's println! reaches a pipe line by line: a consumer of the live stream sees each chunk at once
-      }
-      read += blob.n();
-    }
+      results.close();
+    } catch (...) { failed(); }
+    reader.join(); packer.join(); printer.join();
+    if (err) std::rethrow_exception(err);
+    for (auto& b : batches) skb_batch_destroy(b);
+    if (c.world == 1) leave(0);
+    return 0;
   } else {  // src/sketchy.rs:281-315: one sketcher for all reads
+    skb_batch* b = nullptr;
+    c.check(skb_batch_create(c.c, &b));
     uint64_t read = 0;
-    c.check(skb_batch_clear(b));
     bool any = false;
+    ingest::Chunk ch;
+    std::vector<uint32_t> zeros;
     for (;;) {
-      blob.clear();
-      bool stop = false;
-      while (blob.bytes.size() < (256u << 20)) {
-        if (!rd.next(r)) { stop = true; break; }
-        blob.add(r.seq, 0);
-        read += 1;
-        if (read == limit) { stop = true; break; }
-      }
-      if (blob.n()) { c.check(skb_batch_add(b, blob.bytes.data(), blob.off.data(), blob.grp.data(), blob.n(), 0)); any = true; }
-      if (stop) break;
+      const size_t want = limit ? (size_t)std::min<uint64_t>(1u << 20, limit - read) : (size_t)1 << 20;
+      if (want == 0 || !reads.next(ch, want, 256ull << 20, false)) break;
+      zeros.assign(ch.n(), 0);  // every read joins group 0
+      c.check(skb_batch_add_records(b, ch.rec.data(), ch.len.data(), zeros.data(), ch.n(), host_threads));
+      any = true;
+      read += ch.n();
     }
     std::vector<uint64_t> q(s_query);
     uint32_t qn = 0;
@@ -574,9 +707,13 @@ int cmd_predict(const Args& a) {
       std::sort(cand.begin(), cand.end(), [](const auto& x, const auto& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
       for (uint32_t t = 0; t < top; ++t) { sum[t] = cand[t].first; idx[t] = cand[t].second; }
     }
-    if (speaker) print_results(ref, g, read, idx.data(), sum.data(), top, consensus);
+    if (speaker) {
+      std::string out;
+      table.rows(out, read, idx.data(), sum.data(), top, consensus);
+      fwrite(out.data(), 1, out.size(), stdout);
+    }
+    skb_batch_destroy(b);
   }
-  skb_batch_destroy(b);
   return 0;
 }
 

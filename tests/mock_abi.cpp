@@ -63,6 +63,7 @@ int skb_batch_add(skb_batch* b, const uint8_t* blob, const uint64_t* off, const 
 int skb_batch_add_records(skb_batch* b, const uint8_t* const* recs, const uint64_t* lens, const uint32_t* groups, uint64_t n, uint32_t) {
   return add_impl(b, recs, lens, groups, n);
 }
+int skb_batch_stage(skb_batch*) { return SKB_OK; }  // (not logged: the copy is an overlap detail, not part of what is handed over)
 uint32_t skb_batch_num_groups(const skb_batch* b) { return b->groups; }
 int skb_sketch(skb_ctx*, skb_batch* b, uint32_t k, uint32_t s, uint64_t seed, uint64_t* oh, uint32_t* oc, uint32_t* on,
                uint64_t* ob, uint64_t* ok) {

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HARNESS = r'''
 #include "ingest.hpp"
 #include <cstdio>
+#include <cstdlib>
 int main(int argc, char** argv) {
   try {
     if (argc > 2 && std::string(argv[2]) == "slices") {   // the whole file in memory, records as slices of it
@@ -24,6 +25,19 @@ int main(int argc, char** argv) {
         unsigned long long h = 1469598103934665603ull;
         for (size_t j = 0; j < w.len[i]; ++j) { h ^= w.rec[i][j]; h *= 1099511628211ull; }
         std::printf("%zu\t%llu\n", (size_t)w.len[i], h);
+      }
+      return 0;
+    }
+    if (argc > 2 && std::string(argv[2]) == "chunks") {   // the streaming predict path: chunks of record slices
+      ingest::ChunkReader cr(argv[1], (size_t)atol(argv[3]));
+      ingest::Chunk c;
+      while (cr.next(c, (size_t)atol(argv[4]), (uint64_t)atol(argv[5]), false)) {
+        for (size_t i = 0; i < c.n(); ++i) {
+          unsigned long long h = 1469598103934665603ull;
+          for (size_t j = 0; j < c.len[i]; ++j) { h ^= c.rec[i][j]; h *= 1099511628211ull; }
+          std::printf("%zu\t%llu\n", (size_t)c.len[i], h);
+        }
+        if (argc > 6) std::printf("chunk %zu\n", c.n());
       }
       return 0;
     }
@@ -130,6 +144,11 @@ def test_compressed_inputs_yield_the_same_records(harness, tmp_path, kind):
         assert rc == 0 and got == want, (name, err)
         p = subprocess.run([harness, str(path), "slices"], capture_output=True)   # the `sketch` path: slices of the file in memory
         assert p.returncode == 0 and p.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in want.splitlines()), (name, "slices")
+        for block, reads, nbytes in ((1 << 20, 1 << 16, 1 << 30), (4099, 7, 1 << 30), (64, 1000, 5000)):   # the streaming `predict` path
+            p = subprocess.run([harness, str(path), "chunks", str(block), str(reads), str(nbytes)], capture_output=True)
+            assert p.returncode == 0 and p.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in want.splitlines()), (name, "chunks", block)
+        p = subprocess.run([harness, "-", "chunks", "1000", "50", "100000"], input=blob, capture_output=True)
+        assert p.returncode == 0 and p.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in want.splitlines()), (name, "chunks", "stdin")
         rc, got, err = _run(harness, data=blob)   # stdin
         assert rc == 0 and got == want, (name, "stdin", err)
 
@@ -280,9 +299,10 @@ def test_slices_of_a_file_in_memory_equal_the_streamed_records(harness, tmp_path
         f = tmp_path / f"c{i}"
         f.write_bytes(raw)
         a = subprocess.run([harness, str(f)], capture_output=True)
-        b = subprocess.run([harness, str(f), "slices"], capture_output=True)
-        assert (a.returncode == 0) == (b.returncode == 0), (raw, a.stderr, b.stderr)
-        if a.returncode == 0:
-            assert b.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in a.stdout.splitlines()), raw
-        else:
-            assert a.stderr == b.stderr, raw
+        for mode in (["slices"], ["chunks", "1", "3", "1000000"], ["chunks", "5", "1", "1000000"], ["chunks", "4096", "1000", "6"]):
+            b = subprocess.run([harness, str(f)] + mode, capture_output=True)
+            assert (a.returncode == 0) == (b.returncode == 0), (raw, mode, a.stderr, b.stderr)
+            if a.returncode == 0:
+                assert b.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in a.stdout.splitlines()), (raw, mode)
+            else:
+                assert a.stderr == b.stderr, (raw, mode)

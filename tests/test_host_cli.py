@@ -243,6 +243,53 @@ def test_sketch_host_hands_every_record_to_the_library_in_file_order(mock_cli, t
         assert dec["k"] == 21 and dec["seed"] == 9
 
 
+def test_sketch_host_pipelines_windows_of_files_in_order(mock_cli, tmp_path):
+    """`sketch` with many windows (loader, packer and GPU caller on their own threads): every window is cleared, filled
+    with its files' records (groups counted from the window's first file) and sketched once, windows in file order;
+    an unreadable file in a late window ends the run with the reference's error and no stuck thread."""
+    rng = random.Random(8)
+    files, per_file = [], []
+    for g in range(12):
+        recs = ["".join(rng.choice("ACGT") for _ in range(rng.randint(50, 200))) for _ in range(rng.randint(1, 3))]
+        p = tmp_path / f"w{g}.fa"
+        p.write_text("".join(f">c{i}\n{s}\n" for i, s in enumerate(recs)))
+        files.append(str(p))
+        per_file.append([f"len={len(r)} fnv={_fnv(r.encode())}" for r in recs])
+    out = tmp_path / "o.msh"
+    budget = os.path.getsize(files[0]) + os.path.getsize(files[1]) + os.path.getsize(files[2])   # ~3 files per window
+    exe = mock_cli.exe
+    log = tmp_path / "calls.log"
+    p = subprocess.run([exe, "sketch", "-i", *files, "-o", str(out), "-s", "50"], capture_output=True,
+                       env=dict(os.environ, MOCK_ABI_LOG=str(log), SKETCHY_B200_WINDOW_BYTES=str(budget)))
+    assert p.returncode == 0, p.stderr
+    lines = log.read_text().splitlines()
+    # the packer and the caller log from two threads: per kind of call the order is fixed
+    adds = [l for l in lines if l.startswith("batch_add")]
+    sketches = [l for l in lines if l.startswith("sketch ")]
+    assert len(adds) == len(sketches) >= 3 and lines.count("batch_clear") == len(adds)
+    got, g = [], 0
+    recs = [l.split() for l in lines if l.startswith("  rec")]
+    i = 0
+    for a, sk in zip(adds, sketches):
+        n = int(a.split()[1].split("=")[1])
+        win = recs[i:i + n]
+        i += n
+        groups = sorted({int(r[1].split("=")[1]) for r in win})
+        assert groups == list(range(len(groups)))                      # groups of a window start at 0
+        assert f"groups={len(groups)} records={n}" in sk
+        for j in groups:
+            assert [" ".join(r[2:]) for r in win if r[1] == f"group={j}"] == per_file[g + j]
+        g += len(groups)
+    assert g == 12 and i == len(recs)
+    dec = capnp_py.decode_msh(out.read_bytes())
+    assert [s["name"] for s in dec["sketches"]] == [f"w{g}.fa" for g in range(12)]
+    # a bad file in the last window: clean error, no hang
+    (tmp_path / "bad.fa").write_bytes(b"no sequence here\n")
+    p = subprocess.run([exe, "sketch", "-i", *files, str(tmp_path / "bad.fa"), "-o", str(out), "-s", "50"], capture_output=True, timeout=60,
+                       env=dict(os.environ, SKETCHY_B200_WINDOW_BYTES=str(budget)))
+    assert p.returncode == 1 and b"failed to open Fastx file or record with Needletail" in p.stderr
+
+
 def test_predict_host_batches_reads_and_follows_a_live_stream(mock_cli, tmp_path):
     """streaming `predict`: every read is its own group (one sketcher per read, src/sketchy.rs:331), `-l` stops feeding
     reads (:350-353), rows are numbered from 1; when a live stdin pauses, the reads that have arrived are predicted at
