@@ -570,7 +570,8 @@ int cmd_predict(const Args& a) {
   upload_reference(c, ref);
   const RowTable table(ref, g);
   const unsigned host_threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, c.world));
-  constexpr size_t kChunkReads = 65536;
+  size_t kChunkReads = 65536;
+  if (const char* e = getenv("SKETCHY_B200_CHUNK_READS")) kChunkReads = std::max<size_t>(1, strtoull(e, nullptr, 10));  // (tests: many small chunks)
   constexpr uint64_t kChunkBytes = 64ull << 20;  // sequence bytes of a chunk (its buffer: about twice that for FASTQ)
   if (stream) {  // src/sketchy.rs:317-356
     // Four stages on their own threads, joined by bounded queues: (1) the reader decodes the input into a chunk's buffer

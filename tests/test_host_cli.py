@@ -27,8 +27,8 @@ def cli():
     return CLI
 
 
-def run(*args, stdin=None, ok=True):
-    p = subprocess.run([cli(), *args], input=stdin, capture_output=True, text=True)
+def run(*args, stdin=None, ok=True, env=None):
+    p = subprocess.run([cli(), *args], input=stdin, capture_output=True, text=True, env=None if env is None else dict(os.environ, **env))
     if ok:
         assert p.returncode == 0, p.stderr
     return p
@@ -158,6 +158,15 @@ def test_cli_sketch_shared_predict_match_oracle(tmp_path):
         assert gz_rows == exp_lines, ext
     lim = run("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "3", "-s", "-l", "5").stdout.splitlines()
     assert lim == exp_lines[1:1 + 15]
+    # many small chunks through the reader / packer / predict / printer threads (the sums carry over from call to call),
+    # with and without -l, and windows of one file in `sketch`: the same rows, the same file
+    for extra in ([], ["-l", "17"]):
+        small = run("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "3", "-s", "-H", *extra,
+                    env={"SKETCHY_B200_CHUNK_READS": "7"}).stdout.splitlines()
+        assert small == (exp_lines if not extra else exp_lines[:1 + 17 * 3])
+    ref_w = tmp_path / "ref_w.msh"
+    run("sketch", "-i", *[p for p, _ in paths], "-o", str(ref_w), "-s", str(s_), "-k", str(k), "-e", str(seed), env={"SKETCHY_B200_WINDOW_BYTES": "1"})
+    assert ref_w.read_bytes() == ref.read_bytes()
     n, ri, rs, _ = oracle.predict_readset(np.concatenate(rows), off, reads, k, s_, seed, 3)
     got = run("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "3").stdout.splitlines()
     assert got == [f"{n}\tg{int(i)}.fa\t{int(s)}\t" + "\t".join(gm[f"g{int(i)}.fa"]) for i, s in zip(ri, rs)]

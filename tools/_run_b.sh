@@ -1,2 +1,1 @@
-SKB_TRACE_SKETCH=1 timeout 600 python tools/sketch_scale.py 256 1 > gpurun_out/r02_sketch_cli_256.json 2> gpurun_out/r02_sketch_cli_256.log; cat gpurun_out/r02_sketch_cli_256.json; grep -v "files " gpurun_out/r02_sketch_cli_256.log | tail; grep "files " gpurun_out/r02_sketch_cli_256.log | head -3
-echo CVD; CUDA_VISIBLE_DEVICES=0 SKB_TRACE_SKETCH=1 timeout 600 python tools/sketch_scale.py 256 1 > gpurun_out/r02_sketch_cli_256_cvd.json 2> gpurun_out/r02_sketch_cli_256_cvd.log; cat gpurun_out/r02_sketch_cli_256_cvd.json; grep -v "files " gpurun_out/r02_sketch_cli_256_cvd.log | tail; nvidia-smi -L | wc -l
+timeout 600 python tools/predict_cli_rate.py 100000 10 > gpurun_out/r02_predict_cli.json 2> gpurun_out/r02_predict_cli.log; cat gpurun_out/r02_predict_cli.json; tail -5 gpurun_out/r02_predict_cli.log
