@@ -1,18 +1,22 @@
 // kernels_predict.cu — streaming predict on sm_100a.
 //
-//   table_*       : per-pass hash set of the batch's query hashes: a global open-addressing table of 16-byte
-//                   slots (L2 resident) plus a 128 KB bit filter that every CTA keeps in shared memory.
+//   table_*       : per-pass hash set of the pass's query hashes: a global open-addressing table of 16-byte slots
+//                   (L2 resident; a slot holds the key, its count and up to three read ids inline) plus a 64 KB bit
+//                   filter (three bits per key in one 32-bit word) that every CTA keeps in shared memory. A table is
+//                   cleared through the keys of its previous build.
 //   fused_kernel  : the HBM-bound kernel. Persistent, one CTA per SM, each owning a contiguous range of reference
-//                   rows. 16 consumer warps each stream their share of the rows (256-hash sub-tiles, round robin)
-//                   through a PRIVATE 4-stage cp.async.bulk (TMA) + mbarrier staging ring that the warp refills
-//                   itself, probe every streamed hash against the filter, verify the few passers against the table
-//                   with loads issued a sub-tile ahead of their use, and count hits per read in shared memory; two
-//                   rank warps turn a finished row's counts into cumulative sums over the reads of the pass, test
-//                   them against the per-read bounds and emit top-N candidates. Warps only meet at row granularity
-//                   (4 rows in flight), so one warp's passers never stall the others' streams.
+//                   rows. A row is cut into claims of two 256-hash sub-tiles; the CTA's 32 warps take claims in order
+//                   from a shared counter and stream them through a PRIVATE two-stage cp.async.bulk (TMA) + mbarrier
+//                   ring that the warp refills itself. A warp probes every staged hash against the filter and
+//                   resolves the few passers on the spot: the lanes that hold one look the hash up in the table (one
+//                   16-byte load) and add the key's reads to the row's counters in shared memory. The warp whose
+//                   claim completes a row does the row's rank step (new running sum; lane segments of reads that
+//                   reach their bound are copied out as records / intervals for the post-pass kernels) and hands
+//                   the counter buffer back; 4 or 8 rows are in flight. No FIFO, no rank warps, no polling.
 //                   HBM traffic per pass = the reference matrix, once.
-//   rank_*        : bounds from the tracked rows, candidate grouping, exact per-read top-N by
-//                   (sum desc, index asc).
+//   rank_*        : bounds from the tracked rows, candidate lists from the records and intervals, exact per-read
+//                   top-N by (sum desc, index asc); brute-force ranking from prefix sums for the first pass after
+//                   a reset, small shards and redone passes.
 //
 // Replaces `_common_hashes` x N + `sum[i] += shared` + stable sort + `[..top]`
 // (reference src/sketchy.rs:337-348, 391, 419-459). Rows are strictly increasing (checked at upload) and each
