@@ -73,6 +73,50 @@ def _files(rng):
     return files
 
 
+def test_records_where_they_lie_equal_the_blob(ctx):
+    """skb_batch_add_records (pointer + length per record: how `sketchy sketch` hands over the slices of its file buffers)
+    against skb_batch_add (one blob + offsets): the same packed batch — every position's hash and validity, the
+    records' places, the totals — with and without explicit groups, on dirty and empty records and in both base
+    count modes; a second call appends."""
+    import ctypes as C
+    rng = random.Random(77)
+    recs = list(DIRTY) + [_rand_dna(rng, rng.randint(0, 3000), b"ACGTACGTACGTNacgt\n") for _ in range(60)] + [_rand_dna(rng, 70000)]
+    groups = np.sort(np.array([rng.randint(0, 9) for _ in recs], dtype=np.uint32))
+    groups[0] = 0
+    keep = [np.frombuffer(r, dtype=np.uint8) if r else np.zeros(0, dtype=np.uint8) for r in recs]   # scattered buffers
+    ptrs = np.array([a.__array_interface__["data"][0] if a.size else 0 for a in keep], dtype=np.uint64)
+    lens = np.array([a.size for a in keep], dtype=np.uint64)
+    blob = np.concatenate(keep)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    for g in (None, groups):
+        for stripped in (False, True):
+            a = ctx.batch().set_base_count(stripped).add(blob, off, g)
+            b = ctx.batch().set_base_count(stripped)
+            half = len(recs) // 2
+            gp = None if g is None else g.ctypes.data_as(C.c_void_p)
+            gp2 = None if g is None else C.c_void_p(g.ctypes.data + 4 * half)
+            ctx.check(ctx.lib.skb_batch_add_records(b.h, C.c_void_p(ptrs.ctypes.data), C.c_void_p(lens.ctypes.data), gp, half, 3))
+            ctx.check(ctx.lib.skb_batch_add_records(b.h, C.c_void_p(ptrs.ctypes.data + 8 * half), C.c_void_p(lens.ctypes.data + 8 * half),
+                                                    gp2, len(recs) - half, 0))
+            assert (a.num_groups, a.num_records, a.num_bases, a.packed_len) == (b.num_groups, b.num_records, b.num_bases, b.packed_len)
+            assert all(a.record_start(r) == b.record_start(r) for r in range(len(recs)))
+            ha, va = ctx.debug_kmer_hashes(a, 16, 42)
+            hb, vb = ctx.debug_kmer_hashes(b, 16, 42)
+            assert (va == vb).all() and (ha[va == 1] == hb[vb == 1]).all()
+            ska, ba, ka = ctx.sketch(a, 16, 200, 42)
+            skb_, bb, kb = ctx.sketch(b, 16, 200, 42)
+            assert list(ba) == list(bb) and list(ka) == list(kb)
+            assert all((x[0] == y[0]).all() and (x[1] == y[1]).all() for x, y in zip(ska, skb_))
+            a.close(); b.close()
+    # a null record with a length is refused
+    b = ctx.batch()
+    bad_p = np.array([0], dtype=np.uint64)
+    bad_l = np.array([5], dtype=np.uint64)
+    assert ctx.lib.skb_batch_add_records(b.h, C.c_void_p(bad_p.ctypes.data), C.c_void_p(bad_l.ctypes.data), None, 1, 1) != 0
+    b.close()
+
+
 @pytest.mark.parametrize("k,s,seed", [(16, 1000, 0), (16, 100, 42), (21, 500, 42), (16, 10000, 0), (31, 64, 7)])
 def test_sketch_parity(ctx, k, s, seed):
     """K1+K2 == finch MashSketcher per file: hashes, occurrence counts, total_bases, total_kmers."""
