@@ -115,7 +115,15 @@ struct Ctx {
   }
   explicit Ctx(bool with_comm = true) {
     rank_from_env(rank, world);
-    const int dev = env_int({"SKETCHY_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, 0);
+    int dev = env_int({"SKETCHY_B200_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, 0);
+    // One process per GPU: a rank that can see every GPU of the box initialises all of them, and the ranks' start-ups
+    // queue behind each other in the driver (two ranks: 1.1 s until the context is ready, against 0.5 s when each sees
+    // only its own GPU — profiles/r02_sketch_cli_trace.txt). So unless the caller has chosen the visible devices, the
+    // rank binds itself to its GPU before the first CUDA call. SKETCHY_B200_NO_DEVICE_BINDING=1 leaves the process alone.
+    if (world > 1 && !getenv("CUDA_VISIBLE_DEVICES") && !getenv("SKETCHY_B200_NO_DEVICE_BINDING")) {
+      setenv("CUDA_VISIBLE_DEVICES", std::to_string(dev).c_str(), 1);
+      dev = 0;
+    }
     const int rc = skb_create(dev, &c);
     if (rc != SKB_OK) throw std::runtime_error("no B200 (sm_100) device: the B200 build has no CPU fallback");
     if (world > 1 && with_comm) join();

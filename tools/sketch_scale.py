@@ -47,6 +47,8 @@ for w in worlds:
     procs = []
     for r in range(w):
         env = dict(os.environ, SKETCHY_B200_RANK=str(r), SKETCHY_B200_WORLD=str(w), SKETCHY_B200_DEVICE=str(r), SKETCHY_B200_COMM_FILE=comm)
+        if os.environ.get("SKB_SCALE_CVD"):   # every rank sees its own GPU only (what a job launcher's GPU binding does)
+            env.update(CUDA_VISIBLE_DEVICES=str(r), SKETCHY_B200_DEVICE="0")
         procs.append(subprocess.Popen([skb_build.CLI, "sketch", "-k", "16", "-s", "1000", "-o", msh, "-i", *paths], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE))
     outs = [p.communicate(timeout=900) for p in procs]
