@@ -558,8 +558,10 @@ int cmd_predict(const Args& a) {
   const uint64_t limit = std::stoull(a.one("limit", "0"));
   const bool stream = a.has("stream"), consensus = a.has("consensus"), header = a.has("header");
   if (consensus && top % 2 != 1) throw std::runtime_error("--top must be an odd number when using --consensus");
-  if (top < 1 || top > SKB_MAX_TOP)  // checked before anything is printed (the reference has no such limit)
-    throw std::runtime_error("--top must be between 1 and " + std::to_string(SKB_MAX_TOP) + " in the B200 build");
+  // checked before anything is printed (the reference has no such limit). The limit is the streaming kernels'; the
+  // read-set mode ranks once, and beyond the limit it ranks its count vector on the host.
+  if (top < 1 || (stream && top > SKB_MAX_TOP))
+    throw std::runtime_error("--top must be between 1 and " + std::to_string(SKB_MAX_TOP) + " for streaming predict in the B200 build");
   require_msh(a.one("reference"));
   const msh::File ref = msh::read_file(a.one("reference"));
   if (ref.sketches.empty()) throw std::runtime_error("reference sketch file holds no sketches");
@@ -698,7 +700,15 @@ int cmd_predict(const Args& a) {
     const uint32_t ltop = (uint32_t)std::min<uint64_t>(top, cnt);
     std::vector<uint32_t> idx(top, 0xFFFFFFFFu);
     std::vector<uint64_t> sum(top, 0);
-    if (ltop) c.check(skb_rank_counts(c.c, counts.data(), (uint32_t)cnt, ltop, idx.data(), sum.data()));
+    if (ltop && ltop <= SKB_MAX_TOP) {
+      c.check(skb_rank_counts(c.c, counts.data(), (uint32_t)cnt, ltop, idx.data(), sum.data()));
+    } else if (ltop) {  // a longer list than the device ranks: the same order (count desc, index asc) on the host
+      std::vector<uint32_t> order(cnt);
+      for (uint32_t i = 0; i < cnt; ++i) order[i] = i;
+      std::partial_sort(order.begin(), order.begin() + ltop, order.end(),
+                        [&](uint32_t x, uint32_t y) { return counts[x] != counts[y] ? counts[x] > counts[y] : x < y; });
+      for (uint32_t t = 0; t < ltop; ++t) { idx[t] = order[t]; sum[t] = counts[order[t]]; }
+    }
     for (uint32_t t = 0; t < ltop; ++t) idx[t] += (uint32_t)lo;
     if (c.world > 1) {
       std::vector<uint8_t> mine((size_t)top * 12), all((size_t)top * 12 * c.world);

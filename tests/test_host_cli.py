@@ -356,6 +356,31 @@ def test_predict_host_batches_reads_and_follows_a_live_stream(mock_cli, tmp_path
     assert calls == ["batch_add n=2 groups=null", "batch_add n=1 groups=null"]
 
 
+def test_readset_predict_ranks_long_lists_on_the_host(mock_cli, tmp_path):
+    """The device ranks up to SKB_MAX_TOP (128) rows; the reference has no such limit (src/sketchy.rs:310, :391). Read-set
+    mode, which ranks once, takes a longer `--top` through a host ranking in the same order (count desc, index asc);
+    streaming mode refuses it before anything is printed."""
+    rng = random.Random(12)
+    f = _file(rng, n=200, s=6)
+    for s in f["sketches"]:
+        s["hashes"] = sorted(rng.sample(range(1, 2**63), 4)); s["counts"] = [1] * 4
+    (tmp_path / "ref.txt").write_text(_to_text(f))
+    ref = tmp_path / "ref.msh"
+    run("msh-from-text", str(tmp_path / "ref.txt"), str(ref))
+    geno = tmp_path / "g.tsv"
+    geno.write_text("id\tst\n" + "".join(f"{s['name']}\tST{i % 5}\n" for i, s in enumerate(f["sketches"])))
+    fq = tmp_path / "r.fq"
+    fq.write_text("@r0\nACGTACGTACGTACGTACGTAA\n+\n" + "I" * 22 + "\n")
+    names = [s["name"] for s in f["sketches"]]
+    p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "150")
+    assert p.returncode == 0, p.stderr
+    assert not any(l.startswith("rank_counts") for l in log)
+    # the stand-in's shared count of row i is i: the best 150 are rows 199 ... 50
+    assert p.stdout.decode().splitlines() == [f"1\t{names[i]}\t{i}\tST{i % 5}" for i in range(199, 49, -1)]
+    p, log = mock_cli("predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "150", "-s")
+    assert p.returncode == 1 and p.stdout == b"" and b"--top must be between 1 and 128 for streaming predict" in p.stderr
+
+
 @pytest.mark.gpu
 def test_cli_on_the_c1_shapes_matches_oracle(tmp_path):
     """BASELINE.json configs[0] at full size through the C++ host: sketch 100 synthetic 2.8 Mbp assemblies (4 lineages x
