@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsketchy_b200.so")
 SOURCES = ["api.cu", "kernels_sketch.cu", "kernels_predict.cu"]
-HEADERS = ["common.cuh", "kernels.h", "pack_avx2.cpp", os.path.join("..", "..", "include", "sketchy_b200.h")]
+HEADERS = ["common.cuh", "kernels.h", "pack_avx2.cpp", "pack_avx512.cpp", os.path.join("..", "..", "include", "sketchy_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr"]
 
@@ -54,6 +54,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cxx = shutil.which("g++") or "g++"
     subprocess.check_call([cxx, "-O3", "-mavx2", "-fPIC", "-std=c++17", "-Wall", "-c", os.path.join(CSRC, "pack_avx2.cpp"), "-o", pobj])
     objs.append(pobj)
+    pobj5 = os.path.join(HERE, "build", "pack_avx512.o")   # likewise: only this file is built with the AVX-512 flags
+    subprocess.check_call([cxx, "-O3", "-mavx512f", "-mavx512bw", "-mavx512vbmi", "-fPIC", "-std=c++17", "-Wall", "-c",
+                           os.path.join(CSRC, "pack_avx512.cpp"), "-o", pobj5])
+    objs.append(pobj5)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
