@@ -320,9 +320,12 @@ class ChunkReader {
     dec_ = fastx::sniff_decoder(*in_);
   }
   // false: the input has ended and the chunk is empty
+  // A malformed record ends the stream the way it does in the reference, which handles record after record: the reads
+  // in front of it still come out (as a last, short chunk), the call after that throws the reader's error.
   bool next(Chunk& c, size_t max_reads, uint64_t max_seq_bytes, bool stop_when_idle) {
     c.rec.clear(); c.len.clear();
     slices_.clear();
+    if (pending_) std::rethrow_exception(pending_);
     size_t have = carry_.size(), pos = 0;
     // a chunk's buffer is sized once for the usual case (FASTQ: two bytes of input per base) and reused as it circulates
     const size_t want = have + block_ + (size_t)std::min<uint64_t>(2 * max_seq_bytes, 192ull << 20);
@@ -336,8 +339,16 @@ class ChunkReader {
     uint64_t seq = 0;
     size_t counted = 0;
     for (;;) {
-      if (max_reads > slices_.size() && seq < max_seq_bytes)
-        fastx::parse_some(c.buf.data(), have, eof_, st_, pos, slices_, max_reads - slices_.size(), max_seq_bytes - seq);
+      if (max_reads > slices_.size() && seq < max_seq_bytes) {
+        try {
+          fastx::parse_some(c.buf.data(), have, eof_, st_, pos, slices_, max_reads - slices_.size(), max_seq_bytes - seq);
+        } catch (...) {
+          if (slices_.empty()) throw;
+          pending_ = std::current_exception();
+          pos = have;  // nothing behind the bad record is used
+          break;
+        }
+      }
       for (; counted < slices_.size(); ++counted) seq += slices_[counted].len;
       if (slices_.size() >= max_reads || seq >= max_seq_bytes || eof_) break;
       if (stop_when_idle && !slices_.empty() && pos == have && in_->would_block()) break;
@@ -365,6 +376,7 @@ class ChunkReader {
   std::vector<fastx::Slice> slices_;
   Bytes carry_;
   bool eof_ = false;
+  std::exception_ptr pending_;
 };
 
 }  // namespace ingest

@@ -618,7 +618,12 @@ int cmd_predict(const Args& a) {
           if (!loaded.push(ch)) return;
         }
         loaded.close();
-      } catch (...) { failed(); }
+      } catch (...) {
+        // a bad record: the chunks in front of it run through the stages and are printed, as the reference prints every
+        // read it has handled before it stops; the error is reported when the pipeline has drained
+        { std::lock_guard<std::mutex> l(err_m); if (!err) err = std::current_exception(); }
+        loaded.close();
+      }
     });
     std::thread packer([&]() {
       try {

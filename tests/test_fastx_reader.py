@@ -306,3 +306,5 @@ def test_slices_of_a_file_in_memory_equal_the_streamed_records(harness, tmp_path
                 assert b.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in a.stdout.splitlines()), (raw, mode)
             else:
                 assert a.stderr == b.stderr, (raw, mode)
+                if mode[0] == "chunks":   # the records in front of the bad one still come out, as from the streaming reader
+                    assert b.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in a.stdout.splitlines()), (raw, mode)

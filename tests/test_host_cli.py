@@ -356,6 +356,29 @@ def test_predict_host_batches_reads_and_follows_a_live_stream(mock_cli, tmp_path
     assert calls == ["batch_add n=2 groups=null", "batch_add n=1 groups=null"]
 
 
+def test_streaming_predict_prints_the_reads_in_front_of_a_bad_record(mock_cli, tmp_path):
+    """The reference handles record after record (src/sketchy.rs:328-355): a malformed record stops it after the rows of
+    every read before it. The chunked pipeline does the same: the chunks in front of the bad record run through, then the
+    reader's error ends the run with status 1."""
+    rng = random.Random(14)
+    f = _file(rng, n=3, s=8)
+    for s in f["sketches"]:
+        s["hashes"] = sorted(rng.sample(range(1, 2**63), 4)); s["counts"] = [1] * 4
+    (tmp_path / "ref.txt").write_text(_to_text(f))
+    ref = tmp_path / "ref.msh"
+    run("msh-from-text", str(tmp_path / "ref.txt"), str(ref))
+    geno = tmp_path / "g.tsv"
+    geno.write_text("id\tst\n" + "".join(f"{s['name']}\tST{i}\n" for i, s in enumerate(f["sketches"])))
+    good = "".join(f"@r{i}\nACGTACGTACGTACGTACGT\n+\n{'I' * 20}\n" for i in range(11))
+    fq = tmp_path / "bad.fq"
+    fq.write_text(good + "@r11\nACGTACGT\n+\nIII\n" + "@r12\nACGT\n+\nIIII\n")      # read 12: quality shorter than the sequence
+    for chunk_reads in ("65536", "4"):
+        p = subprocess.run([mock_cli.exe, "predict", "-i", str(fq), "-r", str(ref), "-g", str(geno), "-t", "1", "-s"], capture_output=True,
+                           timeout=60, env=dict(os.environ, SKETCHY_B200_CHUNK_READS=chunk_reads))
+        assert p.returncode == 1 and b"failed to open Fastx file or record with Needletail" in p.stderr
+        assert [l.split(b"\t")[0] for l in p.stdout.splitlines()] == [str(i + 1).encode() for i in range(11)]
+
+
 def test_readset_predict_ranks_long_lists_on_the_host(mock_cli, tmp_path):
     """The device ranks up to SKB_MAX_TOP (128) rows; the reference has no such limit (src/sketchy.rs:310, :391). Read-set
     mode, which ranks once, takes a longer `--top` through a host ranking in the same order (count desc, index asc);
