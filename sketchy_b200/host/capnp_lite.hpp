@@ -11,15 +11,22 @@
 
 namespace capnp_lite {
 
+// Segments are views into the caller's buffer (a reference file of gigabytes is not copied a second time); words are
+// read with memcpy, so the buffer needs no alignment.
+struct Seg {
+  const uint8_t* p = nullptr;
+  uint64_t words = 0;
+  uint64_t size() const { return words; }
+};
 struct Message {
-  std::vector<std::vector<uint64_t>> segs;
+  std::vector<Seg> segs;
 };
 
-inline Message parse_stream(const std::vector<uint8_t>& buf) {
+inline Message parse_stream(const uint8_t* buf, size_t n) {
   auto rd32 = [&](size_t at) -> uint32_t {
-    if (at + 4 > buf.size()) throw std::runtime_error("truncated Cap'n Proto header");
+    if (at + 4 > n) throw std::runtime_error("truncated Cap'n Proto header");
     uint32_t v;
-    std::memcpy(&v, buf.data() + at, 4);
+    std::memcpy(&v, buf + at, 4);
     return v;
   };
   const uint32_t nseg = rd32(0) + 1;
@@ -32,13 +39,14 @@ inline Message parse_stream(const std::vector<uint8_t>& buf) {
   m.segs.resize(nseg);
   for (uint32_t i = 0; i < nseg; ++i) {
     const size_t bytes = (size_t)sizes[i] * 8;
-    if (at + bytes > buf.size()) throw std::runtime_error("truncated Cap'n Proto segment");
-    m.segs[i].resize(sizes[i]);
-    if (bytes) std::memcpy(m.segs[i].data(), buf.data() + at, bytes);
+    if (at + bytes > n) throw std::runtime_error("truncated Cap'n Proto segment");
+    m.segs[i].p = buf + at;
+    m.segs[i].words = sizes[i];
     at += bytes;
   }
   return m;
 }
+inline Message parse_stream(const std::vector<uint8_t>& buf) { return parse_stream(buf.data(), buf.size()); }
 
 // A resolved object location: segment + word index of the content, plus the pointer word that describes it.
 struct Loc {
@@ -55,7 +63,14 @@ class Reader {
 
   uint64_t word(uint32_t seg, uint64_t w) const {
     if (seg >= m_.segs.size() || w >= m_.segs[seg].size()) throw std::runtime_error("Cap'n Proto pointer out of bounds");
-    return m_.segs[seg][w];
+    uint64_t v;
+    std::memcpy(&v, m_.segs[seg].p + w * 8, 8);
+    return v;
+  }
+  // the bytes of `nwords` words from (seg, w) on, for bulk copies of list contents (bounds checked like word())
+  const uint8_t* bytes(uint32_t seg, uint64_t w, uint64_t nwords) const {
+    if (seg >= m_.segs.size() || w + nwords > m_.segs[seg].size()) throw std::runtime_error("Cap'n Proto pointer out of bounds");
+    return m_.segs[seg].p + w * 8;
   }
 
   // follow the pointer stored at (seg, w)
@@ -168,9 +183,8 @@ inline std::string read_text(const Reader& r, const Loc& l) {
   const ListView v = as_list(r, l);
   if (v.null || v.count == 0) return std::string();
   if (v.esize != 2) throw std::runtime_error("Text is not a byte list");
-  std::string out(v.count - 1, '\0');  // drop the NUL terminator
-  for (uint32_t i = 0; i + 1 < v.count; ++i) out[i] = (char)((r.word(v.seg, v.first + i / 8) >> (8 * (i % 8))) & 0xFF);
-  return out;
+  // (little-endian host, as everywhere in this code base: list bytes are element bytes)
+  return std::string(reinterpret_cast<const char*>(r.bytes(v.seg, v.first, ((uint64_t)v.count + 7) / 8)), v.count - 1);  // without the NUL
 }
 
 template <class T>
@@ -179,59 +193,25 @@ inline std::vector<T> read_prims(const Reader& r, const Loc& l, uint32_t expect_
   std::vector<T> out;
   if (v.null) return out;
   if (v.esize != expect_esize) throw std::runtime_error("unexpected list element size");
+  const uint64_t nbytes = (uint64_t)v.count * sizeof(T);
+  const uint8_t* src = r.bytes(v.seg, v.first, (nbytes + 7) / 8);
   out.resize(v.count);
-  const uint32_t per = 8 / sizeof(T);
-  for (uint32_t i = 0; i < v.count; ++i) {
-    const uint64_t w = r.word(v.seg, v.first + i / per);
-    out[i] = (T)(w >> (8 * sizeof(T) * (i % per)));
-  }
+  if (nbytes) std::memcpy(out.data(), src, nbytes);
   return out;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// single-segment writer
+// pointer words for a writer (msh.cpp plans the layout of a message and streams it out)
 // ---------------------------------------------------------------------------------------------------------------
-class Writer {
- public:
-  Writer() { w_.push_back(0); }  // word 0: root pointer
-  uint64_t alloc(uint64_t nwords) {
-    const uint64_t at = w_.size();
-    w_.resize(at + nwords, 0);
-    return at;
-  }
-  uint64_t& at(uint64_t i) { return w_[i]; }
-  void set_struct_ptr(uint64_t ptr_word, uint64_t target, uint32_t dwords, uint32_t pwords) {
-    const int64_t off = (int64_t)target - (int64_t)ptr_word - 1;
-    w_[ptr_word] = ((uint64_t)((uint32_t)(off << 2))) | ((uint64_t)dwords << 32) | ((uint64_t)pwords << 48);
-  }
-  void set_list_ptr(uint64_t ptr_word, uint64_t target, uint32_t esize, uint32_t count) {
-    const int64_t off = (int64_t)target - (int64_t)ptr_word - 1;
-    w_[ptr_word] = ((uint64_t)((uint32_t)(off << 2) | 1u)) | ((uint64_t)esize << 32) | ((uint64_t)count << 35);
-  }
-  void write_text(uint64_t ptr_word, const std::string& s) {
-    const uint32_t n = (uint32_t)s.size() + 1;
-    const uint64_t t = alloc((n + 7) / 8);
-    std::memcpy(reinterpret_cast<uint8_t*>(&w_[t]), s.data(), s.size());
-    set_list_ptr(ptr_word, t, 2, n);
-  }
-  template <class T>
-  void write_prims(uint64_t ptr_word, const std::vector<T>& v, uint32_t esize) {
-    const uint64_t bytes = v.size() * sizeof(T);
-    const uint64_t t = alloc((bytes + 7) / 8);
-    if (bytes) std::memcpy(reinterpret_cast<uint8_t*>(&w_[t]), v.data(), bytes);
-    set_list_ptr(ptr_word, t, esize, (uint32_t)v.size());
-  }
-  std::vector<uint8_t> to_stream() const {
-    std::vector<uint8_t> out(8 + w_.size() * 8);
-    const uint32_t zero = 0, words = (uint32_t)w_.size();
-    std::memcpy(out.data(), &zero, 4);
-    std::memcpy(out.data() + 4, &words, 4);
-    std::memcpy(out.data() + 8, w_.data(), w_.size() * 8);
-    return out;
-  }
-
- private:
-  std::vector<uint64_t> w_;
-};
+inline uint64_t struct_ptr_word(uint64_t ptr_word, uint64_t target, uint32_t dwords, uint32_t pwords) {
+  const int64_t off = (int64_t)target - (int64_t)ptr_word - 1;
+  return ((uint64_t)((uint32_t)(off << 2))) | ((uint64_t)dwords << 32) | ((uint64_t)pwords << 48);
+}
+inline uint64_t list_ptr_word(uint64_t ptr_word, uint64_t target, uint32_t esize, uint32_t count) {
+  const int64_t off = (int64_t)target - (int64_t)ptr_word - 1;
+  return ((uint64_t)((uint32_t)(off << 2) | 1u)) | ((uint64_t)esize << 32) | ((uint64_t)count << 35);
+}
+// far pointer to a one-word landing pad at word `pad` of segment `seg`
+inline uint64_t far_ptr_word(uint32_t seg, uint64_t pad) { return 2u | (pad << 3) | ((uint64_t)seg << 32); }
 
 }  // namespace capnp_lite

@@ -73,6 +73,28 @@ def test_msh_reader_follows_far_and_double_far_pointers(tmp_path):
     assert run("msh-to-text", str(out)).stdout == _to_text(f)  # ... and the C++ reader with both
 
 
+def test_msh_writer_splits_large_files_into_segments(tmp_path):
+    """A Cap'n Proto pointer reaches 2^29 words, so a reference of the C3 size (40,000 x 10,000 hashes = 4.8 GB) cannot be
+    one segment: past a segment budget the writer puts the hash and count lists into data segments behind far pointers
+    (what the builders of finch / Mash do). With the budget lowered the form shows on a small file: the independent
+    Python decoder and the C++ reader both get the content back; at the default budget a small file is one segment."""
+    import struct
+    f = _file(random.Random(13), n=9, s=40)
+    txt = tmp_path / "a.txt"
+    txt.write_text(_to_text(f))
+    one = tmp_path / "one.msh"
+    run("msh-from-text", str(txt), str(one))
+    assert struct.unpack("<I", one.read_bytes()[:4])[0] == 0
+    for budget, min_segments in ((1, 19), (64, 3), (200, 2)):
+        out = tmp_path / f"multi_{budget}.msh"
+        run("msh-from-text", str(txt), str(out), env={"SKETCHY_B200_MSH_SEGMENT_WORDS": str(budget)})
+        b = out.read_bytes()
+        assert struct.unpack("<I", b[:4])[0] + 1 >= min_segments
+        assert capnp_py.decode_msh(b) == f
+        assert run("msh-to-text", str(out)).stdout == _to_text(f)
+        assert run("info", "-i", str(out)).stdout == run("info", "-i", str(one)).stdout
+
+
 def test_info_check_and_errors(tmp_path):
     f = _file(random.Random(5), n=3)
     txt, ref = tmp_path / "r.txt", tmp_path / "r.msh"
