@@ -263,24 +263,26 @@ struct RowTable {
   RowTable(const msh::File& ref, const Genotypes& g) {
     const size_t N = ref.sketches.size();
     name_part.reserve(N); geno_part.reserve(N);
-    n_features = N ? g.map.at(ref.sketches[0].name).size() : 0;
+    for (size_t i = 0; i < N; ++i) n_features = std::max(n_features, g.map.at(ref.sketches[i].name).size());
     values.resize(n_features);
-    value_id.assign(N * n_features, 0);
+    value_id.assign(N * n_features, kNoValue);  // a row with fewer columns casts no vote for the missing ones
+    n_cols.reserve(N);
     std::vector<std::unordered_map<std::string, uint32_t>> seen(n_features);
-    static const std::string none;
     for (size_t i = 0; i < N; ++i) {
       const std::string& name = ref.sketches[i].name;
       const std::vector<std::string>& cols = g.map.at(name);
       name_part.push_back("\t" + name + "\t");
       geno_part.push_back("\t" + join_tab(cols) + "\n");
-      for (size_t j = 0; j < n_features; ++j) {
-        const std::string& v = j < cols.size() ? cols[j] : none;
-        auto it = seen[j].find(v);
-        if (it == seen[j].end()) { it = seen[j].emplace(v, (uint32_t)values[j].size()).first; values[j].push_back(v); }
+      n_cols.push_back((uint32_t)cols.size());
+      for (size_t j = 0; j < cols.size(); ++j) {
+        auto it = seen[j].find(cols[j]);
+        if (it == seen[j].end()) { it = seen[j].emplace(cols[j], (uint32_t)values[j].size()).first; values[j].push_back(cols[j]); }
         value_id[i * n_features + j] = it->second;
       }
     }
   }
+  static constexpr uint32_t kNoValue = 0xFFFFFFFFu;
+  std::vector<uint32_t> n_cols;                         // genotype columns of a sketch's row
   static void put(std::string& out, uint64_t v) {
     char buf[24];
     int n = 0;
@@ -292,11 +294,13 @@ struct RowTable {
     if (consensus) {
       put(out, read);
       out += "\t-\t-\t";
-      for (size_t j = 0; j < n_features; ++j) {
+      const size_t nf = n_cols[idx[0]];  // the best row's column count decides the width (src/sketchy.rs:368)
+      for (size_t j = 0; j < nf; ++j) {
         uint32_t best = 0;
         size_t best_n = 0;
         for (uint32_t t = 0; t < top; ++t) {
           const uint32_t v = value_id[(size_t)idx[t] * n_features + j];
+          if (v == kNoValue) continue;
           size_t c = 0;
           for (uint32_t u = 0; u < top; ++u) c += value_id[(size_t)idx[u] * n_features + j] == v;
           if (c > best_n) { best_n = c; best = v; }
