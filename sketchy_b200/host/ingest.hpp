@@ -1,8 +1,12 @@
-// ingest.hpp — host-side record batches for the C ABI and a parallel file reader for `sketchy sketch`.
-// The reference sketches its input files on a rayon pool, one finch sketcher per file (src/sketchy.rs:465-494); here the
-// hashing is one GPU call for all files, so what is left to spread over the host cores is reading, decompressing and
-// splitting the files into records. Files are read in windows (bounded memory), every file of a window on its own
-// thread, and handed on in file order: the batch the GPU sees is the same as with one reader.
+// ingest.hpp — the host side of `sketchy sketch` and `sketchy predict` between the input files and the C ABI.
+// The reference sketches its input files on a rayon pool, one finch sketcher per file (src/sketchy.rs:465-494), and
+// predicts read after read (:317-356); here the hashing is one GPU call per window of files / chunk of reads, so what
+// is left to the host cores is reading, decompressing, splitting into records and 2-bit packing. This header holds:
+//   Channel      a bounded queue between the stages of those pipelines (reader -> packer -> GPU caller -> printer)
+//   Files        a window of files held in memory, records as slices of it (load_files; the `sketch` path)
+//   ChunkReader  a stream of reads decoded block by block, records as slices of the chunk's buffer (the `predict` path)
+//   Blob         the copying form of a window (read_files, through the streaming fastx::Reader): the reference the
+//                tests hold the two slice forms against
 #pragma once
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -35,7 +39,9 @@ struct DefaultInit : std::allocator<T> {
 };
 using Bytes = std::vector<uint8_t, DefaultInit<uint8_t>>;
 
-// records of a batch as skb_batch_add takes them: one blob, offsets[n + 1], group of every record
+// records of a batch as skb_batch_add takes them: one blob, offsets[n + 1], group of every record (the copying form:
+// read_files below builds it through the streaming reader; the CLI itself works on slices — Files / Chunk further down —
+// and the tests hold the two against each other)
 struct Blob {
   Bytes bytes;
   std::vector<uint64_t> off{0};

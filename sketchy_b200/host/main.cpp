@@ -194,8 +194,6 @@ struct Ctx {
   void range(uint64_t n, uint64_t& begin, uint64_t& count) const { skb_dist_range(n, rank, world, &begin, &count); }
 };
 
-using ingest::Blob;
-
 // ---- genotype table (src/sketchy.rs:538-571): TSV with header; header minus the first column; name -> columns
 struct Genotypes {
   std::string header;
