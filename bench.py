@@ -48,7 +48,7 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def parse():
+def parse(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=5)
@@ -69,7 +69,7 @@ def parse():
     p.add_argument("--no-extras", action="store_true", help="skip the zero-hit variant and the sketch leg")
     p.add_argument("--sketch-genomes", type=int, default=128, help="genomes in the bounded sketch-throughput sample (0 = skip)")
     p.add_argument("--sketch-only", action="store_true", help="run the sketch leg alone and print its record (profiling aid)")
-    a = p.parse_args()
+    a = p.parse_args(argv)
     refs, s, reads, top, lin, dist_kind, cons = CONFIGS[a.config]
     a.refs = a.refs or refs
     a.sketch_size = a.sketch_size or s
@@ -544,13 +544,8 @@ def run_b200(args):
             "value": R / (ms_per_step * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak" if cfg == "c5" else "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, N, s, R, top), "refs": N, "sketch_size": s, "reads": R,
-                       "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages, "rows": args.row_dist,
-                       "passes_per_step": passes, "reads_per_pass_max": pass_reads_eff,
-                       "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass"
-                             % (cnt * s * 8 / 1e9),
-                       "parallelism": f"reference rows sharded over {world} GPUs, reads hashed 1/{world} per rank; NCCL all-gather of "
-                                      "the query lists and of the local top-N (library communicator)" if world > 1 else "1 GPU"},
+            "config": config_of(cfg, N, s, R, top, args, world),
+            "passes": {"per_step": passes, "reads_per_pass_max": pass_reads_eff},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -624,6 +619,17 @@ def zero_hit_variant(ctx, args, device, blob, roff, peak, how):
             "value": R / dt, "value_unit": "reads/s", "passes_per_step": st_["passes"],
             "member_hashes_per_step": st_.get("member_hashes"),
             "workload": workload_name("c3i", N, s, R, top)}
+
+
+def config_of(cfg, N, s, R, top, args, world):
+    """The `config` object of a bench line: what defines the workload and its placement, and nothing that a run
+    measures — both arms (`--impl b200`, `--impl reference`) print the same dict for the same command line."""
+    per_gpu = (N + world - 1) // world
+    return {"workload": workload_name(cfg, N, s, R, top), "refs": N, "sketch_size": s, "reads": R,
+            "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages, "rows": args.row_dist,
+            "l2": "reference matrix (%.2f GB per GPU) is larger than L2; streamed from HBM every pass" % (per_gpu * s * 8 / 1e9),
+            "parallelism": (f"reference rows sharded over {world} GPUs, reads hashed 1/{world} per rank; NCCL all-gather of "
+                            "the query lists and of the local top-N (library communicator)") if world > 1 else "1 GPU"}
 
 
 def sketch_leg(ctx, args, device):
@@ -788,10 +794,9 @@ def run_reference(args):
            "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak" if args.config == "c5" else "strong",
            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": workload_name(args.config, N_, s, R_, top), "refs": N_, "sketch_size": s, "reads": R_,
-                      "read_len": args.read_len, "k": K, "top": top, "lineages": args.lineages, "rows": args.row_dist,
-                      "sample": f"each step = a bounded sample of {n_s} consecutive reads of the workload against "
-                                + (f"the full {N} x {s} matrix" if N == N_ else f"{N} x {s} rows (one GPU's shard of the {N_}-row reference)")},
+           "config": config_of(args.config, N_, s, R_, top, args, args.gpus),   # the same dict as the GPU arm's line at this N
+           "sample": f"each step = a bounded sample of {n_s} consecutive reads of the workload against "
+                     + (f"the full {N} x {s} matrix" if N == N_ else f"{N} x {s} rows (one GPU's shard of the {N_}-row reference)"),
            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",
                             "sample": f"{n_s} reads per step vs {N}x{s} rows; C++ restatement of sketchy "
                                       f"0.6.0 (oracle/oracle.cpp), single thread like the reference's predict loop",

@@ -24,6 +24,13 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["all_cores"]["cores"] >= 1 and cb["all_cores"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("predict 64 reads vs 1000 x s=500")
+    # the same `config` object as the GPU arm prints for this command line (the driver compares the two arms' dicts):
+    # both come from bench.config_of, which holds nothing a run measures
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.parse(["--refs", "1000", "--sketch-size", "500", "--reads", "64", "--lineages", "2"])
+    assert d["config"] == bench.config_of(a.config, 1000, 500, 64, a.top, a, 1)
+    assert set(d["config"]) == {"workload", "refs", "sketch_size", "reads", "read_len", "k", "top", "lineages", "rows", "l2", "parallelism"}
 
 
 def test_reference_arm_is_silent_on_other_ranks():
