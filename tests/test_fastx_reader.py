@@ -308,3 +308,42 @@ def test_slices_of_a_file_in_memory_equal_the_streamed_records(harness, tmp_path
                 assert a.stderr == b.stderr, (raw, mode)
                 if mode[0] == "chunks":   # the records in front of the bad one still come out, as from the streaming reader
                     assert b.stdout == b"".join(l.split(b"\t", 1)[1] + b"\n" for l in a.stdout.splitlines()), (raw, mode)
+
+
+CHANNEL_HARNESS = r'''
+#include "ingest.hpp"
+#include <cstdio>
+int main() {
+  // order and completeness through a queue of 2 with a slow consumer; close() lets the consumer drain, then stop
+  ingest::Channel<int> ch(2);
+  long long sum = 0; int last = -1; bool ordered = true;
+  std::thread prod([&] { for (int i = 0; i < 10000; ++i) if (!ch.push(i)) return; ch.close(); });
+  int v;
+  while (ch.pop(v)) { ordered = ordered && v == last + 1; last = v; sum += v; }
+  prod.join();
+  if (!ordered || last != 9999 || sum != 49995000LL) { std::puts("order"); return 1; }
+  if (ch.push(1) || ch.pop(v)) { std::puts("closed"); return 1; }          // closed and empty: both ends say no
+  // abort() releases a producer blocked on a full queue and a consumer blocked on an empty one, and drops what is queued
+  ingest::Channel<int> full(1), empty(1);
+  full.push(7);
+  bool pushed = true, popped = true;
+  std::thread a([&] { pushed = full.push(8); }), b([&] { int x; popped = empty.pop(x); });
+  std::this_thread::sleep_for(std::chrono::milliseconds(50));
+  full.abort(); empty.abort();
+  a.join(); b.join();
+  if (pushed || popped || full.pop(v)) { std::puts("abort"); return 1; }
+  std::puts("ok");
+  return 0;
+}
+'''
+
+
+def test_pipeline_channel(tmp_path):
+    """ingest::Channel, the bounded queue between the stages of the CLI's host pipelines: order, back-pressure, close
+    (drain, then stop) and abort (everybody lets go at once, queued items are dropped)."""
+    (tmp_path / "c.cpp").write_text(CHANNEL_HARNESS)
+    exe = str(tmp_path / "c")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "sketchy_b200", "host"), str(tmp_path / "c.cpp"),
+                           "-o", exe, "-lz", "-ldl"])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", p.stdout
